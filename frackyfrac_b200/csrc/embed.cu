@@ -1,0 +1,287 @@
+// Bottom-up branch embedding on the device (replaces abundanceToFlatNodes +
+// normalizeFlatNodes, frcfrc/unifrac.go:32-67, for all samples at once).
+//
+// Layout: node-major.  Row v of the embedding holds node v for every sample,
+// samples contiguous, so every kernel here reads and writes fully coalesced
+// rows and a parent row is the sum (or OR) of its child rows.  Node ids are
+// pre-order, so parent < child and "children in ascending id" is file order.
+//
+// Two embeddings:
+//   fp64  E[B][ld]    exact subtree sums in the reference's order (child order
+//                     from 0.0; totals ascending id) — feeds the exact pair
+//                     kernel and, rounded once to fp32, the weighted kernel.
+//   bits  P[B][nw]    presence only (unweighted): 1 bit per (node, sample),
+//                     parent = OR of children.  32x less traffic than bytes.
+// All of it is HBM-bound streaming; the level passes touch each element once
+// as a write and once as a read ("embedding roofline").
+#include "frc_internal.h"
+
+namespace frc {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------- fp64 path
+// One warp per sample: scatter its CSR row into the leaf rows.
+__global__ void k_scatter_f64(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                              const double* __restrict__ val, int64_t n_samples, double* E,
+                              int64_t ld) {
+  int64_t s = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (s >= n_samples) return;
+  int64_t b = row_ptr[s], e = row_ptr[s + 1];
+  for (int64_t k = b + lane; k < e; k += 32) E[static_cast<int64_t>(col[k]) * ld + s] = val[k];
+}
+
+// One tree level: E[v] = ((0 + E[c1]) + E[c2]) + ... in child order.
+// grid.x = nodes of the level, grid.y * blockDim.x * 2 covers the samples.
+__global__ void k_level_sum_f64(const int32_t* __restrict__ nodes, const int32_t* __restrict__ child_ptr,
+                                const int32_t* __restrict__ child_idx, double* E, int64_t ld) {
+  int32_t v = nodes[blockIdx.x];
+  int64_t s = (static_cast<int64_t>(blockIdx.y) * blockDim.x + threadIdx.x) * 2;
+  if (s >= ld) return;  // ld is even (multiple of 128)
+  int32_t cb = child_ptr[v], ce = child_ptr[v + 1];
+  double2 acc = make_double2(0.0, 0.0);
+  for (int32_t c = cb; c < ce; ++c) {
+    const double2 x = *reinterpret_cast<const double2*>(E + static_cast<int64_t>(child_idx[c]) * ld + s);
+    acc.x = __dadd_rn(acc.x, x.x);
+    acc.y = __dadd_rn(acc.y, x.y);
+  }
+  *reinterpret_cast<double2*>(E + static_cast<int64_t>(v) * ld + s) = acc;
+}
+
+// total[s] = sum of E[v][s] over all v ascending (zeros add exactly nothing, so
+// this equals the reference's sum over its id-sorted non-zero list).
+__global__ void k_totals_f64(const double* __restrict__ E, int32_t n_nodes, int64_t ld,
+                             int64_t n_samples, double* __restrict__ total) {
+  int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= n_samples) return;
+  double acc = 0.0;
+  int32_t v = 0;
+  for (; v + 8 <= n_nodes; v += 8) {
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = E[static_cast<int64_t>(v + u) * ld + s];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, x[u]);
+  }
+  for (; v < n_nodes; ++v) acc = __dadd_rn(acc, E[static_cast<int64_t>(v) * ld + s]);
+  total[s] = acc;
+}
+
+__global__ void k_normalize_f64(double* E, int32_t n_nodes, int64_t ld, int64_t n_samples,
+                                const double* __restrict__ total) {
+  int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= n_samples) return;
+  const double t = total[s];
+  for (int32_t v = blockIdx.y; v < n_nodes; v += gridDim.y) {
+    double x = E[static_cast<int64_t>(v) * ld + s];
+    if (x != 0.0) E[static_cast<int64_t>(v) * ld + s] = __ddiv_rn(x, t);
+  }
+}
+
+// Weighted operand + per-chunk partial denominators.
+// grid.x covers samples, grid.y = node chunks; partial[chunk][s].
+__global__ void k_weighted_operand(const double* __restrict__ E, const double* __restrict__ length,
+                                   int32_t n_nodes, int64_t ld, const double* __restrict__ total,
+                                   int prescale, float* __restrict__ A, double* __restrict__ partial) {
+  int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= ld) return;
+  int32_t per = (n_nodes + gridDim.y - 1) / gridDim.y;
+  int32_t v0 = blockIdx.y * per, v1 = min(n_nodes, v0 + per);
+  const double t = total ? total[s] : 1.0;
+  double w = 0.0;
+  for (int32_t v = v0; v < v1; ++v) {
+    double x = E[static_cast<int64_t>(v) * ld + s];
+    double a = (x != 0.0 && total) ? x / t : x;
+    double la = length[v] * a;
+    w += la;
+    A[static_cast<int64_t>(v) * ld + s] = static_cast<float>(prescale ? la : a);
+  }
+  partial[static_cast<int64_t>(blockIdx.y) * ld + s] = w;
+}
+
+__global__ void k_reduce_partials(const double* __restrict__ partial, int n_chunks, int64_t ld,
+                                  int64_t n, double* __restrict__ out) {
+  int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  double acc = 0.0;
+  for (int c = 0; c < n_chunks; ++c) acc += partial[static_cast<int64_t>(c) * ld + s];
+  out[s] = acc;
+}
+
+// ---------------------------------------------------------------- bits path
+__global__ void k_scatter_bits(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                               int64_t n_samples, uint32_t* bits, int32_t nw) {
+  int64_t s = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (s >= n_samples) return;
+  int64_t b = row_ptr[s], e = row_ptr[s + 1];
+  const uint32_t m = 1u << (s & 31);
+  for (int64_t k = b + lane; k < e; k += 32)
+    atomicOr(bits + static_cast<int64_t>(col[k]) * nw + (s >> 5), m);
+}
+
+__global__ void k_level_or(const int32_t* __restrict__ nodes, const int32_t* __restrict__ child_ptr,
+                           const int32_t* __restrict__ child_idx, uint32_t* bits, int32_t nw) {
+  int32_t v = nodes[blockIdx.x];
+  int32_t w = blockIdx.y * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  int32_t cb = child_ptr[v], ce = child_ptr[v + 1];
+  uint32_t acc = 0;
+  for (int32_t c = cb; c < ce; ++c) acc |= bits[static_cast<int64_t>(child_idx[c]) * nw + w];
+  bits[static_cast<int64_t>(v) * nw + w] = acc;
+}
+
+// One warp per (word column, node chunk); lane = sample bit.
+__global__ void k_presence_rowsum(const uint32_t* __restrict__ bits, int32_t n_nodes, int32_t nw,
+                                  const double* __restrict__ lenq, double* __restrict__ partial) {
+  int32_t w = blockIdx.x;
+  int lane = threadIdx.x;
+  int32_t per = (n_nodes + gridDim.y - 1) / gridDim.y;
+  int32_t v0 = blockIdx.y * per, v1 = min(n_nodes, v0 + per);
+  double acc = 0.0;
+  for (int32_t v = v0; v < v1; ++v) {
+    uint32_t word = bits[static_cast<int64_t>(v) * nw + w];
+    if ((word >> lane) & 1u) acc += lenq[v];
+  }
+  partial[static_cast<int64_t>(blockIdx.y) * (static_cast<int64_t>(nw) * 32) + w * 32 + lane] = acc;
+}
+
+// bits -> three K-major bf16 operands.  Block = 64 nodes x 256 samples.
+__global__ void __launch_bounds__(256)
+k_expand_operands(const uint32_t* __restrict__ bits, int32_t n_nodes, int32_t nw, int32_t kp,
+                  int64_t np, const uint16_t* __restrict__ len_hi, const uint16_t* __restrict__ len_lo,
+                  uint16_t* __restrict__ P, uint16_t* __restrict__ Bh, uint16_t* __restrict__ Bl) {
+  __shared__ uint32_t words[64][9];
+  const int32_t v0 = blockIdx.x * 64;
+  const int32_t w0 = blockIdx.y * 8;
+  for (int idx = threadIdx.x; idx < 512; idx += 256) {
+    int node = idx >> 3, word = idx & 7;
+    uint32_t x = 0;
+    if (v0 + node < n_nodes && w0 + word < nw)
+      x = bits[static_cast<int64_t>(v0 + node) * nw + w0 + word];
+    words[node][word] = x;
+  }
+  __syncthreads();
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t va = v0 + 2 * lane, vb = va + 1;
+  const uint32_t wa = words[2 * lane][wi], wb = words[2 * lane + 1][wi];
+  const uint32_t ha = va < n_nodes ? len_hi[va] : 0, hb = vb < n_nodes ? len_hi[vb] : 0;
+  const uint32_t la = va < n_nodes ? len_lo[va] : 0, lb = vb < n_nodes ? len_lo[vb] : 0;
+  const int64_t s0 = (static_cast<int64_t>(w0) + wi) * 32;
+#pragma unroll 4
+  for (int it = 0; it < 32; ++it) {
+    const int64_t s = s0 + it;
+    if (s >= np) break;
+    const uint32_t ba = (wa >> it) & 1u, bb = (wb >> it) & 1u;
+    const int64_t o = s * kp + va;
+    const uint32_t ma = 0u - ba, mb = 0u - bb;  // all-ones masks
+    *reinterpret_cast<uint32_t*>(P + o) = (0x3F80u & ma) | ((0x3F80u & mb) << 16);
+    *reinterpret_cast<uint32_t*>(Bh + o) = (ha & ma) | ((hb & mb) << 16);
+    *reinterpret_cast<uint32_t*>(Bl + o) = (la & ma) | ((lb & mb) << 16);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launchers
+int launch_embed_f64(const DevTree& t, const int32_t* level_ptr, const DevCsr& a, double* E,
+                     int64_t ld, cudaStream_t s) {
+  int launches = 0;
+  cudaMemsetAsync(E, 0, sizeof(double) * ld * t.n_nodes, s);
+  if (a.n_samples > 0 && a.nnz > 0) {
+    int64_t threads = a.n_samples * 32;
+    k_scatter_f64<<<static_cast<unsigned>((threads + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+        a.row_ptr, a.col, a.val, a.n_samples, E, ld);
+    ++launches;
+  }
+  for (int32_t h = 1; h <= t.height; ++h) {
+    int32_t b = level_ptr[h], e = level_ptr[h + 1];
+    if (e == b) continue;
+    dim3 grid(static_cast<unsigned>(e - b), static_cast<unsigned>((ld / 2 + kThreads - 1) / kThreads));
+    k_level_sum_f64<<<grid, kThreads, 0, s>>>(t.level_nodes + b, t.child_ptr, t.child_idx, E, ld);
+    ++launches;
+  }
+  return launches;
+}
+
+int launch_totals_f64(const double* E, int32_t n_nodes, int64_t ld, int64_t n_samples, double* total,
+                      cudaStream_t s) {
+  if (n_samples == 0) return 0;
+  k_totals_f64<<<static_cast<unsigned>((n_samples + 127) / 128), 128, 0, s>>>(E, n_nodes, ld,
+                                                                               n_samples, total);
+  return 1;
+}
+
+int launch_normalize_f64(double* E, int32_t n_nodes, int64_t ld, int64_t n_samples,
+                         const double* total, cudaStream_t s) {
+  if (n_samples == 0) return 0;
+  dim3 grid(static_cast<unsigned>((n_samples + kThreads - 1) / kThreads),
+            static_cast<unsigned>(min(n_nodes, 512)));
+  k_normalize_f64<<<grid, kThreads, 0, s>>>(E, n_nodes, ld, n_samples, total);
+  return 1;
+}
+
+static int pick_chunks(int32_t n_nodes) {
+  int c = n_nodes / 256;
+  return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+
+int launch_weighted_operand(const double* E, const double* length, int32_t n_nodes, int32_t kp,
+                            int64_t ld, int64_t n_samples, const double* total, bool prescale,
+                            float* A, double* W, double* scratch, cudaStream_t s) {
+  int chunks = pick_chunks(n_nodes);
+  if (kp > n_nodes)
+    cudaMemsetAsync(A + static_cast<int64_t>(n_nodes) * ld, 0, sizeof(float) * ld * (kp - n_nodes), s);
+  dim3 grid(static_cast<unsigned>((ld + kThreads - 1) / kThreads), chunks);
+  k_weighted_operand<<<grid, kThreads, 0, s>>>(E, length, n_nodes, ld, total, prescale ? 1 : 0, A,
+                                               scratch);
+  k_reduce_partials<<<static_cast<unsigned>((ld + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+      scratch, chunks, ld, ld, W);
+  (void)n_samples;
+  return 2;
+}
+int weighted_scratch_chunks(int32_t n_nodes) { return pick_chunks(n_nodes); }
+
+int launch_embed_bits(const DevTree& t, const int32_t* level_ptr, const DevCsr& a, uint32_t* bits,
+                      int32_t nw, cudaStream_t s) {
+  int launches = 0;
+  cudaMemsetAsync(bits, 0, sizeof(uint32_t) * static_cast<int64_t>(nw) * t.n_nodes, s);
+  if (a.n_samples > 0 && a.nnz > 0) {
+    int64_t threads = a.n_samples * 32;
+    k_scatter_bits<<<static_cast<unsigned>((threads + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+        a.row_ptr, a.col, a.n_samples, bits, nw);
+    ++launches;
+  }
+  for (int32_t h = 1; h <= t.height; ++h) {
+    int32_t b = level_ptr[h], e = level_ptr[h + 1];
+    if (e == b) continue;
+    dim3 grid(static_cast<unsigned>(e - b), static_cast<unsigned>((nw + 127) / 128));
+    k_level_or<<<grid, 128, 0, s>>>(t.level_nodes + b, t.child_ptr, t.child_idx, bits, nw);
+    ++launches;
+  }
+  return launches;
+}
+
+int launch_presence_rowsum(const uint32_t* bits, int32_t n_nodes, int32_t nw, const double* lenq,
+                           double* r, double* scratch, cudaStream_t s) {
+  int chunks = pick_chunks(n_nodes);
+  dim3 grid(nw, chunks);
+  k_presence_rowsum<<<grid, 32, 0, s>>>(bits, n_nodes, nw, lenq, scratch);
+  int64_t ld = static_cast<int64_t>(nw) * 32;
+  k_reduce_partials<<<static_cast<unsigned>((ld + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+      scratch, chunks, ld, ld, r);
+  return 2;
+}
+
+int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, int32_t kp, int64_t np,
+                           const uint16_t* len_hi, const uint16_t* len_lo, uint16_t* P, uint16_t* Bh,
+                           uint16_t* Bl, cudaStream_t s) {
+  dim3 grid(kp / 64, static_cast<unsigned>((np + 255) / 256));
+  k_expand_operands<<<grid, 256, 0, s>>>(bits, n_nodes, nw, kp, np, len_hi, len_lo, P, Bh, Bl);
+  return 1;
+}
+
+}  // namespace frc

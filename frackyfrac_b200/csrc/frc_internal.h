@@ -1,0 +1,101 @@
+// Internal interfaces between the translation units of libfrcfrc_cuda.
+// Nothing here is part of the C ABI (include/frcfrc_cuda.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+namespace frc {
+
+constexpr int kTile = 128;   // samples per tile edge (pair tiles are kTile x kTile)
+constexpr int kKBlock = 64;  // nodes per contraction block (128 B of bf16)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+// Flat index of the first pair of row i in the lower triangle (common/common.go:21-31).
+inline int64_t tri(int64_t i) { return i * (i - 1) / 2; }
+
+// Tree arrays resident on the device.
+struct DevTree {
+  int32_t n_nodes = 0;
+  int32_t height = 0;                  // number of levels above the leaves
+  const int32_t* parent = nullptr;     // [B]
+  const double* length = nullptr;      // [B]
+  const int32_t* child_ptr = nullptr;  // [B+1]
+  const int32_t* child_idx = nullptr;  // [B-1], ascending id within a parent = file order
+  const int32_t* level_nodes = nullptr;// [B] nodes grouped by height (leaves first), ascending id
+};
+
+struct DevCsr {
+  int64_t n_samples = 0;
+  int64_t nnz = 0;
+  const int64_t* row_ptr = nullptr;
+  const int32_t* col = nullptr;
+  const double* val = nullptr;  // may be null for the presence-only path
+};
+
+// One tile of the lower triangle: rows [128*ti, +128) x cols [128*tj, +128), tj <= ti.
+struct Tile { int32_t ti, tj; };
+
+// ---- embed.cu ---------------------------------------------------------------
+// fp64 branch embedding, node-major E[B][ld] (unifrac.go:32-53): leaf rows
+// scattered from the CSR, then one pass per tree level, children summed in
+// child order starting from 0.0.  Returns launches.
+int launch_embed_f64(const DevTree& t, const int32_t* level_ptr_host, const DevCsr& a, double* E,
+                     int64_t ld, cudaStream_t s);
+// total[s] = sum over ALL nodes in ascending id order (unifrac.go:60-63).
+int launch_totals_f64(const double* E, int32_t n_nodes, int64_t ld, int64_t n_samples,
+                      double* total, cudaStream_t s);
+// E[v][s] /= total[s] for non-zero entries (unifrac.go:64-66).
+int launch_normalize_f64(double* E, int32_t n_nodes, int64_t ld, int64_t n_samples,
+                         const double* total, cudaStream_t s);
+// Weighted operand: A[v][s] = float(len[v] * E[v][s] / total[s]) (prescale) or
+// float(E[v][s] / total[s]); rows [n_nodes, kp) zero.  total == nullptr: no division (-l).
+// Also W[s] = sum_v len[v] * a[v][s] in fp64 (denominator, separable).
+int launch_weighted_operand(const double* E, const double* length, int32_t n_nodes, int32_t kp,
+                            int64_t ld, int64_t n_samples, const double* total, bool prescale,
+                            float* A, double* W, double* scratch, cudaStream_t s);
+// Rows of scratch (each ld doubles) the two partial-sum reductions need.
+int weighted_scratch_chunks(int32_t n_nodes);
+
+// Presence bits, node-major bits[B][nw] (bit s%32 of word s/32).
+int launch_embed_bits(const DevTree& t, const int32_t* level_ptr_host, const DevCsr& a,
+                      uint32_t* bits, int32_t nw, cudaStream_t s);
+// r[s] = sum_v lenq[v] * present(v, s) in fp64.
+int launch_presence_rowsum(const uint32_t* bits, int32_t n_nodes, int32_t nw, const double* lenq,
+                           double* r, double* scratch, cudaStream_t s);
+// Expand bits into the three K-major bf16 operands [np][kp]:
+// P = 0/1, Bh = P * len_hi, Bl = P * len_lo.
+int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, int32_t kp,
+                           int64_t np, const uint16_t* len_hi, const uint16_t* len_lo,
+                           uint16_t* P, uint16_t* Bh, uint16_t* Bl, cudaStream_t s);
+
+// ---- exact.cu ---------------------------------------------------------------
+// fp64 reference-order distances for pairs [first, first+count) of the triangle.
+int launch_exact_pairs(const double* E, const double* length, int32_t n_nodes, int64_t ld,
+                       bool weighted, int64_t first, int64_t count, double* out, cudaStream_t s);
+
+// ---- weighted.cu ------------------------------------------------------------
+int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
+                          const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
+                          int64_t first, double* out, cudaStream_t s);
+void weighted_setup();  // cudaFuncSetAttribute calls, once per process
+
+// ---- unweighted_tc.cu -------------------------------------------------------
+struct TcOperands;  // opaque: tensor maps
+TcOperands* tc_operands_create(const uint16_t* P, const uint16_t* Bh, const uint16_t* Bl, int64_t np,
+                               int32_t kp, std::string* err);
+void tc_operands_destroy(TcOperands* o);
+// Distances of the tiles in `tiles` into out[index - first]; the band offset of
+// every pair with d < flag_below is appended to flagged[] (count in *n_flagged;
+// capacity = pairs of the band, so it cannot overflow) for the fix-up pass.
+int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, const Tile* tiles,
+                         int32_t n_tiles, int64_t n_samples, int64_t first, double* out,
+                         double flag_below, uint32_t* flagged, unsigned long long* n_flagged,
+                         int num_sms, cudaStream_t s);
+// fp64 recompute of the flagged pairs from the presence rows and true lengths.
+int launch_unweighted_fixup(const TcOperands* ops, int32_t n_nodes, int32_t kp, const double* length,
+                            const uint32_t* flagged, const unsigned long long* n_flagged,
+                            int64_t first, double* out, int num_sms, cudaStream_t s);
+bool tc_setup(std::string* err);  // smem attribute + driver entry points, once per process
+
+}  // namespace frc

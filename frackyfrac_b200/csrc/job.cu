@@ -1,0 +1,694 @@
+// Host side of libfrcfrc_cuda: the C ABI of include/frcfrc_cuda.h.
+//
+// A job is one unifrac() call (frcfrc/unifrac.go:97-124): validate + copy the
+// flattened tree and CSR abundances, upload them in one pinned transfer, build
+// the branch embedding on the device, then compute the lower triangle in bands
+// of consecutive rows.  Bands alternate between two streams, each followed by
+// its own pinned D2H copy, and are handed to the caller strictly in flat-index
+// order by frc_next (the ordered iter.Seq of unifrac.go:209-228).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/frcfrc_cuda.h"
+#include "frc_internal.h"
+
+using namespace frc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------ arenas
+struct Arena {
+  struct Block { char* p; size_t cap, off; };
+  std::vector<Block> blocks;
+  bool pinned = false;
+  size_t min_block = 0;
+
+  void* alloc(size_t bytes, cudaError_t* err) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    for (auto& b : blocks)
+      if (b.cap - b.off >= bytes) { void* r = b.p + b.off; b.off += bytes; return r; }
+    size_t cap = std::max(bytes, min_block);
+    char* p = nullptr;
+    cudaError_t e = pinned ? cudaHostAlloc(reinterpret_cast<void**>(&p), cap, cudaHostAllocDefault)
+                           : cudaMalloc(reinterpret_cast<void**>(&p), cap);
+    if (e != cudaSuccess && cap > bytes) {  // retry without the rounding-up
+      cudaGetLastError();
+      cap = bytes;
+      e = pinned ? cudaHostAlloc(reinterpret_cast<void**>(&p), cap, cudaHostAllocDefault)
+                 : cudaMalloc(reinterpret_cast<void**>(&p), cap);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); *err = e; return nullptr; }
+    blocks.push_back({p, cap, bytes});
+    return p;
+  }
+  void reset() { for (auto& b : blocks) b.off = 0; }
+  void release() {
+    for (auto& b : blocks) { if (pinned) cudaFreeHost(b.p); else cudaFree(b.p); }
+    blocks.clear();
+  }
+};
+
+uint16_t bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>((u >> 16) | ((u & 0xFFFFu) ? 0x40u : 0u));
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+float bf16_to_float(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+constexpr int kSlots = 3;
+constexpr double kFlagBelow = 0.125;            // fast unweighted: recompute d below this exactly
+constexpr int64_t kExactWorkLimit = 1LL << 28;  // AUTO: pairs * nodes at or below this -> exact
+
+}  // namespace
+
+struct frc_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream[2] = {nullptr, nullptr};
+  Arena dev, pin;
+  bool in_use = false;
+};
+
+struct Band { int64_t row0, row1, first, count; int32_t tile_off, n_tiles; };
+
+struct Slot {
+  double* dev = nullptr;
+  double* host = nullptr;
+  uint32_t* flagged = nullptr;
+  unsigned long long* n_flagged = nullptr;  // device
+  unsigned long long* n_flagged_host = nullptr;
+  cudaEvent_t k0 = nullptr, k1 = nullptr, done = nullptr;
+  int band = -1;  // index into mine[]
+};
+
+struct frc_job {
+  frc_ctx* ctx = nullptr;
+  bool own_ctx = false;
+  frc_opts_t opts{};
+  std::string err;
+  frc_info_t info{};
+
+  int64_t N = 0, np = 0, nnz = 0;
+  int32_t B = 0, kp = 0, nw = 0;
+  bool exact = false, weighted = false, prescale = true;
+
+  std::vector<int32_t> level_ptr;  // host
+  std::vector<Band> bands;         // whole triangle
+  std::vector<int> mine;           // indices into bands
+  std::vector<Tile> tiles;         // host copy (uploaded)
+
+  // device
+  DevTree dtree;
+  DevCsr dcsr;
+  char* d_inputs = nullptr;
+  size_t input_bytes = 0;
+  Tile* d_tiles = nullptr;
+  uint16_t *d_len_hi = nullptr, *d_len_lo = nullptr;
+  double* d_lenq = nullptr;
+  float* d_lenf = nullptr;
+  double *d_E = nullptr, *d_total = nullptr, *d_W = nullptr, *d_r = nullptr, *d_scratch = nullptr;
+  float* d_A = nullptr;
+  uint32_t* d_bits = nullptr;
+  uint16_t *d_P = nullptr, *d_Bh = nullptr, *d_Bl = nullptr;
+  TcOperands* tc = nullptr;
+
+  Slot slots[kSlots];
+  int n_slots = 0;
+  size_t next_enqueue = 0, next_deliver = 0;
+  int held_slot = -1;  // slot whose buffer the caller currently reads
+  cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_embed0 = nullptr, ev_embed1 = nullptr;
+  bool embed_timed = false;
+};
+
+namespace {
+
+#define JOB_CUDA(job, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      (job)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                       \
+      cudaGetLastError();                                                                    \
+      return _e == cudaErrorMemoryAllocation ? FRC_ERR_OOM : FRC_ERR_CUDA;                   \
+    }                                                                                        \
+  } while (0)
+
+int fail(frc_job* j, int code, const std::string& msg) { j->err = msg; return code; }
+
+int64_t choose_band_rows(int64_t N, int64_t requested) {
+  if (requested > 0) return round_up(requested, kTile);
+  int64_t tile_rows = (N + kTile - 1) / kTile;
+  int64_t g = std::min<int64_t>(8, std::max<int64_t>(1, (tile_rows + 7) / 8));
+  while (g > 1 && g * kTile * N * 8 > (512LL << 20)) --g;
+  return g * kTile;
+}
+
+template <class T>
+T* dev_alloc(frc_job* j, size_t n, int* rc) {
+  cudaError_t e = cudaSuccess;
+  void* p = j->ctx->dev.alloc(n * sizeof(T), &e);
+  if (!p) {
+    j->err = "device allocation of " + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e);
+    *rc = FRC_ERR_OOM;
+  }
+  return static_cast<T*>(p);
+}
+template <class T>
+T* pin_alloc(frc_job* j, size_t n, int* rc) {
+  cudaError_t e = cudaSuccess;
+  void* p = j->ctx->pin.alloc(n * sizeof(T), &e);
+  if (!p) {
+    j->err = "pinned host allocation of " + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e);
+    *rc = FRC_ERR_OOM;
+  }
+  return static_cast<T*>(p);
+}
+
+// Queue the embedding stage on stream 0.
+int run_embedding(frc_job* j) {
+  frc_ctx* c = j->ctx;
+  cudaStream_t s = c->stream[0];
+  int launches = 0;
+  JOB_CUDA(j, cudaEventRecord(j->ev_embed0, s));
+  if (j->exact || j->weighted) {
+    launches += launch_embed_f64(j->dtree, j->level_ptr.data(), j->dcsr, j->d_E, j->np, s);
+    const bool norm = j->opts.normalize != 0;
+    if (norm) launches += launch_totals_f64(j->d_E, j->B, j->np, j->N, j->d_total, s);
+    if (j->exact) {
+      if (norm) launches += launch_normalize_f64(j->d_E, j->B, j->np, j->N, j->d_total, s);
+    } else {
+      if (norm && j->np > j->N)  // padding samples: total = 1 avoids touching garbage
+        JOB_CUDA(j, cudaMemsetAsync(j->d_total + j->N, 0, sizeof(double) * (j->np - j->N), s));
+      launches += launch_weighted_operand(j->d_E, j->dtree.length, j->B, j->kp, j->np, j->N,
+                                          norm ? j->d_total : nullptr, j->prescale, j->d_A, j->d_W,
+                                          j->d_scratch, s);
+    }
+    // write each element once, read it once when folded into its parent (+ CSR)
+    j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
+  } else {
+    launches += launch_embed_bits(j->dtree, j->level_ptr.data(), j->dcsr, j->d_bits, j->nw, s);
+    launches += launch_presence_rowsum(j->d_bits, j->B, j->nw, j->d_lenq, j->d_r, j->d_scratch, s);
+    launches += launch_expand_operands(j->d_bits, j->B, j->nw, j->kp, j->np, j->d_len_hi, j->d_len_lo,
+                                       j->d_P, j->d_Bh, j->d_Bl, s);
+    // bits written + read once per level pass, three bf16 operands written once (+ CSR cols)
+    j->info.embed_bytes = 2LL * j->B * j->nw * 4 + 3LL * j->np * j->kp * 2 + 4LL * j->nnz;
+  }
+  JOB_CUDA(j, cudaGetLastError());
+  JOB_CUDA(j, cudaEventRecord(j->ev_embed1, s));
+  JOB_CUDA(j, cudaStreamWaitEvent(c->stream[1], j->ev_embed1, 0));
+  j->info.kernel_launches += launches;
+  j->embed_timed = false;
+  return FRC_OK;
+}
+
+// Queue band mine[idx] into its slot.
+int enqueue_band(frc_job* j, size_t idx) {
+  frc_ctx* c = j->ctx;
+  const Band& b = j->bands[j->mine[idx]];
+  Slot& sl = j->slots[idx % j->n_slots];
+  cudaStream_t s = c->stream[idx % 2];
+  sl.band = static_cast<int>(idx);
+  int launches = 0;
+  JOB_CUDA(j, cudaEventRecord(sl.k0, s));
+  if (j->exact) {
+    launches += launch_exact_pairs(j->d_E, j->dtree.length, j->B, j->np, j->weighted, b.first, b.count,
+                                   sl.dev, s);
+  } else if (j->weighted) {
+    launches += launch_weighted_tiles(j->d_A, j->np, j->kp, j->d_lenf, j->prescale, j->d_W,
+                                      j->d_tiles + b.tile_off, b.n_tiles, j->N, b.first, sl.dev, s);
+  } else {
+    JOB_CUDA(j, cudaMemsetAsync(sl.n_flagged, 0, sizeof(unsigned long long), s));
+    launches += launch_unweighted_tc(j->tc, j->kp, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
+                                     b.first, sl.dev, kFlagBelow, sl.flagged, sl.n_flagged, c->num_sms, s);
+    launches += launch_unweighted_fixup(j->tc, j->B, j->kp, j->dtree.length, sl.flagged, sl.n_flagged,
+                                        b.first, sl.dev, c->num_sms, s);
+    JOB_CUDA(j, cudaMemcpyAsync(sl.n_flagged_host, sl.n_flagged, sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, s));
+  }
+  JOB_CUDA(j, cudaGetLastError());
+  JOB_CUDA(j, cudaEventRecord(sl.k1, s));
+  if (!(j->opts.flags & FRC_FLAG_NO_D2H)) {
+    JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, s));
+    j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
+  }
+  JOB_CUDA(j, cudaEventRecord(sl.done, s));
+  j->info.kernel_launches += launches;
+  return FRC_OK;
+}
+
+int start_pairs(frc_job* j) {
+  j->next_enqueue = j->next_deliver = 0;
+  j->held_slot = -1;
+  j->info.pairs_ms = 0;
+  j->info.flagged_pairs = 0;
+  j->info.d2h_bytes = 0;
+  // keep one slot free for the band the caller is still reading
+  while (j->next_enqueue < j->mine.size() && j->next_enqueue < static_cast<size_t>(j->n_slots - 1)) {
+    int rc = enqueue_band(j, j->next_enqueue);
+    if (rc) return rc;
+    ++j->next_enqueue;
+  }
+  return FRC_OK;
+}
+
+void destroy_job(frc_job* j) {
+  if (!j) return;
+  if (j->ctx) {
+    cudaSetDevice(j->ctx->device);
+    for (auto s : j->ctx->stream) if (s) cudaStreamSynchronize(s);
+    cudaGetLastError();
+  }
+  for (auto& sl : j->slots) {
+    if (sl.k0) cudaEventDestroy(sl.k0);
+    if (sl.k1) cudaEventDestroy(sl.k1);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
+  if (j->ev_h2d0) cudaEventDestroy(j->ev_h2d0);
+  if (j->ev_h2d1) cudaEventDestroy(j->ev_h2d1);
+  if (j->ev_embed0) cudaEventDestroy(j->ev_embed0);
+  if (j->ev_embed1) cudaEventDestroy(j->ev_embed1);
+  tc_operands_destroy(j->tc);
+  if (j->ctx) {
+    j->ctx->dev.reset();
+    j->ctx->pin.reset();
+    j->ctx->in_use = false;
+    if (j->own_ctx) frc_ctx_destroy(j->ctx);
+  }
+  delete j;
+}
+
+}  // namespace
+
+extern "C" {
+
+int frc_abi_version(void) { return FRC_ABI_VERSION; }
+
+const char* frc_last_error(const frc_job_t* job) { return job ? job->err.c_str() : g_create_error.c_str(); }
+
+int frc_ctx_create(int32_t device, frc_ctx_t** out) {
+  if (!out) { g_create_error = "frc_ctx_create: out is NULL"; return FRC_ERR_ARG; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
+    return FRC_ERR_CUDA;
+  }
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= count) { g_create_error = "device ordinal out of range"; return FRC_ERR_ARG; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+    return FRC_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "libfrcfrc_cuda is built for sm_100a (B200) only; device " + std::to_string(device) +
+                     " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + " (" + prop.name + ")";
+    return FRC_ERR_UNSUPPORTED;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return FRC_ERR_CUDA;
+  }
+  frc_ctx* c = new frc_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->dev.pinned = false; c->dev.min_block = 64u << 20;
+  c->pin.pinned = true;  c->pin.min_block = 8u << 20;
+  for (auto& s : c->stream)
+    if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) {
+      g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+      frc_ctx_destroy(c);
+      return FRC_ERR_CUDA;
+    }
+  std::string terr;
+  if (!tc_setup(&terr)) { g_create_error = terr; frc_ctx_destroy(c); return FRC_ERR_CUDA; }
+  weighted_setup();
+  if ((e = cudaGetLastError()) != cudaSuccess) {
+    g_create_error = std::string("kernel attribute setup: ") + cudaGetErrorString(e);
+    frc_ctx_destroy(c);
+    return FRC_ERR_CUDA;
+  }
+  *out = c;
+  return FRC_OK;
+}
+
+void frc_ctx_destroy(frc_ctx_t* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (auto s : c->stream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  c->dev.release();
+  c->pin.release();
+  cudaGetLastError();
+  delete c;
+}
+
+int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, const frc_opts_t* opts,
+               frc_job_t** out) {
+  g_create_error.clear();
+  if (!out) { g_create_error = "frc_create: out is NULL"; return FRC_ERR_ARG; }
+  *out = nullptr;
+  if (!tree || !abnd || !opts) { g_create_error = "frc_create: NULL argument"; return FRC_ERR_ARG; }
+  frc_job* j = new frc_job();
+  auto bail = [&](int rc) { g_create_error = j->err; destroy_job(j); return rc; };
+#define CREATE_CUDA(expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      cudaGetLastError();                                                                    \
+      return bail(fail(j, _e == cudaErrorMemoryAllocation ? FRC_ERR_OOM : FRC_ERR_CUDA,      \
+                       std::string(#expr) + ": " + cudaGetErrorString(_e)));                 \
+    }                                                                                        \
+  } while (0)
+  j->opts = *opts;
+
+  // ---------------------------------------------------------- validate options
+  if (opts->mode != FRC_UNWEIGHTED && opts->mode != FRC_WEIGHTED) return bail(fail(j, FRC_ERR_ARG, "bad mode"));
+  if (opts->path < FRC_PATH_AUTO || opts->path > FRC_PATH_EXACT) return bail(fail(j, FRC_ERR_ARG, "bad path"));
+  if (opts->normalize != 0 && opts->normalize != 1) return bail(fail(j, FRC_ERR_ARG, "bad normalize"));
+  if (opts->normalize == 0 && opts->mode != FRC_WEIGHTED)  // frcfrc.go:84-86
+    return bail(fail(j, FRC_ERR_ARG, "-l can only be used with weighted unifrac"));
+  int world = opts->world <= 0 ? 1 : opts->world;
+  int rank = opts->world <= 0 ? 0 : opts->rank;
+  if (rank < 0 || rank >= world) return bail(fail(j, FRC_ERR_ARG, "rank outside [0, world)"));
+  if (opts->band_rows < 0) return bail(fail(j, FRC_ERR_ARG, "band_rows < 0"));
+  j->weighted = opts->mode == FRC_WEIGHTED;
+
+  // ------------------------------------------------------------- validate tree
+  const int32_t B = tree->n_nodes;
+  if (B < 1 || !tree->parent || !tree->length) return bail(fail(j, FRC_ERR_ARG, "empty tree"));
+  if (tree->parent[0] != -1) return bail(fail(j, FRC_ERR_ARG, "parent[0] must be -1 (root has pre-order id 0)"));
+  std::vector<int32_t> child_cnt(B, 0), height(B, 0);
+  {
+    // pre-order check: parent[v] must lie on the path root..v-1
+    std::vector<int32_t> stack;
+    stack.push_back(0);
+    for (int32_t v = 1; v < B; ++v) {
+      int32_t p = tree->parent[v];
+      if (p < 0 || p >= v) return bail(fail(j, FRC_ERR_ARG, "parent[" + std::to_string(v) + "] is not a smaller node id"));
+      while (!stack.empty() && stack.back() != p) stack.pop_back();
+      if (stack.empty()) return bail(fail(j, FRC_ERR_ARG, "node ids are not a pre-order numbering (node " + std::to_string(v) + ")"));
+      stack.push_back(v);
+      child_cnt[p]++;
+    }
+  }
+  bool neg_len = false, bad_len = false;
+  for (int32_t v = 0; v < B; ++v) {
+    double l = tree->length[v];
+    if (!(l == l) || std::isinf(l)) bad_len = true;
+    else if (l < 0) neg_len = true;
+  }
+  for (int32_t v = B - 1; v >= 1; --v) height[tree->parent[v]] = std::max(height[tree->parent[v]], height[v] + 1);
+  const int32_t H = height[0];
+
+  // ------------------------------------------------------------ validate table
+  const int64_t N = abnd->n_samples;
+  if (N < 0 || (N > 0 && !abnd->row_ptr)) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
+  if (N > (1LL << 31) - 256) return bail(fail(j, FRC_ERR_UNSUPPORTED, "too many samples"));
+  const int64_t nnz = N > 0 ? abnd->row_ptr[N] : 0;
+  if (N > 0 && abnd->row_ptr[0] != 0) return bail(fail(j, FRC_ERR_ARG, "row_ptr[0] != 0"));
+  if (nnz < 0 || (nnz > 0 && (!abnd->col || !abnd->val))) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
+  {
+    std::vector<int64_t> stamp(B, 0);
+    for (int64_t s = 0; s < N; ++s) {
+      int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
+      if (e < b || e > nnz) return bail(fail(j, FRC_ERR_ARG, "row_ptr is not monotone"));
+      for (int64_t k = b; k < e; ++k) {
+        int32_t c = abnd->col[k];
+        double v = abnd->val[k];
+        if (c < 0 || c >= B) return bail(fail(j, FRC_ERR_ARG, "sample #" + std::to_string(s + 1) + ": node id out of range"));
+        if (child_cnt[c] != 0) return bail(fail(j, FRC_ERR_ARG, "sample #" + std::to_string(s + 1) + ": node " + std::to_string(c) + " is not a leaf"));
+        if (!(v > 0) || std::isinf(v)) return bail(fail(j, FRC_ERR_ARG, "sample #" + std::to_string(s + 1) + ": bad value"));
+        if (stamp[c] == s + 1) return bail(fail(j, FRC_ERR_ARG, "sample #" + std::to_string(s + 1) + ": leaf " + std::to_string(c) + " listed twice"));
+        stamp[c] = s + 1;
+      }
+    }
+  }
+
+  // --------------------------------------------------------------- choose path
+  j->N = N; j->B = B; j->nnz = nnz;
+  j->np = std::max<int64_t>(kTile, round_up(N, kTile));
+  j->kp = static_cast<int32_t>(round_up(B, kKBlock));
+  j->nw = static_cast<int32_t>(j->np / 32);
+  const int64_t n_pairs = N >= 2 ? tri(N) : 0;
+  if (opts->path == FRC_PATH_EXACT) j->exact = true;
+  else if (opts->path == FRC_PATH_FAST) j->exact = false;
+  else j->exact = n_pairs == 0 || (static_cast<double>(n_pairs) * B <= static_cast<double>(kExactWorkLimit));
+  if (!j->exact && bad_len)
+    return bail(fail(j, FRC_ERR_UNSUPPORTED, "non-finite branch length: only the exact path handles it"));
+  j->prescale = !neg_len;
+  j->info.path_taken = j->exact ? FRC_PATH_EXACT : FRC_PATH_FAST;
+  j->info.tree_height = H;
+  j->info.n_pairs_total = n_pairs;
+  j->info.n_nodes_padded = j->exact ? B : j->kp;
+
+  // ---------------------------------------------------------------------- bands
+  const int64_t band_rows = choose_band_rows(N, opts->band_rows);
+  for (int64_t r0 = 0; r0 < N; r0 += band_rows) {
+    Band b;
+    b.row0 = r0; b.row1 = std::min(N, r0 + band_rows);
+    b.first = b.row0 >= 2 ? tri(b.row0) : 0;
+    b.count = tri(b.row1) - b.first;
+    b.tile_off = 0; b.n_tiles = 0;
+    if (b.count > 0) j->bands.push_back(b);
+  }
+  int64_t max_band = 1;
+  for (size_t k = 0; k < j->bands.size(); ++k)
+    if (static_cast<int>(k % world) == rank) {
+      j->mine.push_back(static_cast<int>(k));
+      j->info.n_pairs_mine += j->bands[k].count;
+      max_band = std::max(max_band, j->bands[k].count);
+    }
+  if (max_band >= (1LL << 32)) return bail(fail(j, FRC_ERR_UNSUPPORTED, "band too large; lower band_rows"));
+  j->info.n_bands_total = static_cast<int32_t>(j->bands.size());
+  j->info.n_bands_mine = static_cast<int32_t>(j->mine.size());
+  if (!j->exact)
+    for (int k : j->mine) {
+      Band& b = j->bands[k];
+      b.tile_off = static_cast<int32_t>(j->tiles.size());
+      int32_t t0 = static_cast<int32_t>(b.row0 / kTile), t1 = static_cast<int32_t>((b.row1 - 1) / kTile);
+      // column-major inside the band: CTAs running together share the few
+      // i-tiles of the band and neighbouring j-tiles (L2 reuse of both operands)
+      for (int32_t tj = 0; tj <= t1; ++tj)
+        for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) j->tiles.push_back({ti, tj});
+      b.n_tiles = static_cast<int32_t>(j->tiles.size()) - b.tile_off;
+    }
+
+  // -------------------------------------------------------------------- context
+  int rc = FRC_OK;
+  if (ctx) {
+    if (ctx->in_use) return bail(fail(j, FRC_ERR_STATE, "context already has a live job"));
+    j->ctx = ctx;
+  } else {
+    rc = frc_ctx_create(opts->device, &j->ctx);
+    if (rc) { j->err = g_create_error; j->ctx = nullptr; return bail(rc); }
+    j->own_ctx = true;
+  }
+  frc_ctx* c = j->ctx;
+  c->in_use = true;
+  CREATE_CUDA(cudaSetDevice(c->device));
+
+  // ------------------------------------------------- pack + upload the inputs
+  const bool need_val = j->exact || j->weighted;
+  struct Seg { size_t off, bytes; };
+  size_t total = 0;
+  auto seg = [&](size_t bytes) { Seg s{total, bytes}; total += (bytes + 255) & ~size_t(255); return s; };
+  Seg s_rowptr = seg(sizeof(int64_t) * (N + 1)), s_col = seg(sizeof(int32_t) * nnz),
+      s_val = seg(need_val ? sizeof(double) * nnz : 0), s_parent = seg(sizeof(int32_t) * B),
+      s_len = seg(sizeof(double) * B), s_cptr = seg(sizeof(int32_t) * (B + 1)),
+      s_cidx = seg(sizeof(int32_t) * B), s_lvl = seg(sizeof(int32_t) * B),
+      s_hi = seg(sizeof(uint16_t) * B), s_lo = seg(sizeof(uint16_t) * B), s_lenq = seg(sizeof(double) * B),
+      s_lenf = seg(sizeof(float) * j->kp), s_tiles = seg(sizeof(Tile) * j->tiles.size());
+  char* stage = pin_alloc<char>(j, total, &rc);
+  if (!stage) return bail(rc);
+  j->d_inputs = dev_alloc<char>(j, total, &rc);
+  if (!j->d_inputs) return bail(rc);
+  j->input_bytes = total;
+  {
+    int64_t* rp = reinterpret_cast<int64_t*>(stage + s_rowptr.off);
+    if (N > 0) memcpy(rp, abnd->row_ptr, sizeof(int64_t) * (N + 1)); else rp[0] = 0;
+    if (nnz) memcpy(stage + s_col.off, abnd->col, sizeof(int32_t) * nnz);
+    if (nnz && need_val) memcpy(stage + s_val.off, abnd->val, sizeof(double) * nnz);
+    memcpy(stage + s_parent.off, tree->parent, sizeof(int32_t) * B);
+    memcpy(stage + s_len.off, tree->length, sizeof(double) * B);
+    int32_t* cptr = reinterpret_cast<int32_t*>(stage + s_cptr.off);
+    int32_t* cidx = reinterpret_cast<int32_t*>(stage + s_cidx.off);
+    cptr[0] = 0;
+    for (int32_t v = 0; v < B; ++v) cptr[v + 1] = cptr[v] + child_cnt[v];
+    std::vector<int32_t> fill(cptr, cptr + B);
+    for (int32_t v = 1; v < B; ++v) cidx[fill[tree->parent[v]]++] = v;  // ascending id = file order
+    j->level_ptr.assign(H + 2, 0);
+    for (int32_t v = 0; v < B; ++v) j->level_ptr[height[v] + 1]++;
+    for (int32_t h = 0; h <= H; ++h) j->level_ptr[h + 1] += j->level_ptr[h];
+    int32_t* lvl = reinterpret_cast<int32_t*>(stage + s_lvl.off);
+    std::vector<int32_t> lfill(j->level_ptr.begin(), j->level_ptr.end() - 1);
+    for (int32_t v = 0; v < B; ++v) lvl[lfill[height[v]]++] = v;
+    uint16_t* hi = reinterpret_cast<uint16_t*>(stage + s_hi.off);
+    uint16_t* lo = reinterpret_cast<uint16_t*>(stage + s_lo.off);
+    double* lq = reinterpret_cast<double*>(stage + s_lenq.off);
+    float* lf = reinterpret_cast<float*>(stage + s_lenf.off);
+    for (int32_t v = 0; v < B; ++v) {
+      double l = tree->length[v];
+      hi[v] = bf16_rn(static_cast<float>(l));
+      double res = l - static_cast<double>(bf16_to_float(hi[v]));
+      lo[v] = (l == l && !std::isinf(l)) ? bf16_rn(static_cast<float>(res)) : 0;
+      lq[v] = static_cast<double>(bf16_to_float(hi[v])) + static_cast<double>(bf16_to_float(lo[v]));
+      lf[v] = static_cast<float>(l);
+    }
+    for (int32_t v = B; v < j->kp; ++v) lf[v] = 0.f;
+    if (!j->tiles.empty()) memcpy(stage + s_tiles.off, j->tiles.data(), sizeof(Tile) * j->tiles.size());
+  }
+  CREATE_CUDA(cudaEventCreate(&j->ev_h2d0));
+  CREATE_CUDA(cudaEventCreate(&j->ev_h2d1));
+  CREATE_CUDA(cudaEventCreate(&j->ev_embed0));
+  CREATE_CUDA(cudaEventCreate(&j->ev_embed1));
+  CREATE_CUDA(cudaEventRecord(j->ev_h2d0, c->stream[0]));
+  CREATE_CUDA(cudaMemcpyAsync(j->d_inputs, stage, total, cudaMemcpyHostToDevice, c->stream[0]));
+  CREATE_CUDA(cudaEventRecord(j->ev_h2d1, c->stream[0]));
+  j->info.h2d_bytes = static_cast<int64_t>(total);
+  char* d = j->d_inputs;
+  j->dcsr.n_samples = N; j->dcsr.nnz = nnz;
+  j->dcsr.row_ptr = reinterpret_cast<int64_t*>(d + s_rowptr.off);
+  j->dcsr.col = reinterpret_cast<int32_t*>(d + s_col.off);
+  j->dcsr.val = need_val ? reinterpret_cast<double*>(d + s_val.off) : nullptr;
+  j->dtree.n_nodes = B; j->dtree.height = H;
+  j->dtree.parent = reinterpret_cast<int32_t*>(d + s_parent.off);
+  j->dtree.length = reinterpret_cast<double*>(d + s_len.off);
+  j->dtree.child_ptr = reinterpret_cast<int32_t*>(d + s_cptr.off);
+  j->dtree.child_idx = reinterpret_cast<int32_t*>(d + s_cidx.off);
+  j->dtree.level_nodes = reinterpret_cast<int32_t*>(d + s_lvl.off);
+  j->d_len_hi = reinterpret_cast<uint16_t*>(d + s_hi.off);
+  j->d_len_lo = reinterpret_cast<uint16_t*>(d + s_lo.off);
+  j->d_lenq = reinterpret_cast<double*>(d + s_lenq.off);
+  j->d_lenf = reinterpret_cast<float*>(d + s_lenf.off);
+  j->d_tiles = reinterpret_cast<Tile*>(d + s_tiles.off);
+
+  // ------------------------------------------------------------ device buffers
+  const int chunks = weighted_scratch_chunks(B);
+  if (j->exact || j->weighted) {
+    if (!(j->d_E = dev_alloc<double>(j, static_cast<size_t>(B) * j->np, &rc))) return bail(rc);
+    if (!(j->d_total = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
+    if (!j->exact) {
+      if (!(j->d_A = dev_alloc<float>(j, static_cast<size_t>(j->kp) * j->np, &rc))) return bail(rc);
+      if (!(j->d_W = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
+      if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
+    }
+  } else {
+    if (!(j->d_bits = dev_alloc<uint32_t>(j, static_cast<size_t>(B) * j->nw, &rc))) return bail(rc);
+    const size_t opsz = static_cast<size_t>(j->np) * j->kp;
+    if (!(j->d_P = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
+    if (!(j->d_Bh = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
+    if (!(j->d_Bl = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
+    if (!(j->d_r = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
+    if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
+    std::string terr;
+    j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, &terr);
+    if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
+  }
+  j->n_slots = static_cast<int>(std::min<size_t>(kSlots, std::max<size_t>(2, j->mine.size() + 1)));
+  if (j->mine.empty()) j->n_slots = 0;
+  for (int k = 0; k < j->n_slots; ++k) {
+    Slot& sl = j->slots[k];
+    if (!(sl.dev = dev_alloc<double>(j, max_band, &rc))) return bail(rc);
+    if (!(opts->flags & FRC_FLAG_NO_D2H) && !(sl.host = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
+    if (!j->exact && !j->weighted) {
+      if (!(sl.flagged = dev_alloc<uint32_t>(j, max_band, &rc))) return bail(rc);
+      if (!(sl.n_flagged = dev_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
+      if (!(sl.n_flagged_host = pin_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
+      *sl.n_flagged_host = 0;
+    }
+    cudaError_t e;
+    if ((e = cudaEventCreate(&sl.k0)) != cudaSuccess || (e = cudaEventCreate(&sl.k1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess)
+      return bail(fail(j, FRC_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e)));
+  }
+
+  // ----------------------------------------------------------------- go
+  if ((rc = run_embedding(j)) != FRC_OK) return bail(rc);
+  if ((rc = start_pairs(j)) != FRC_OK) return bail(rc);
+  *out = j;
+  return FRC_OK;
+#undef CREATE_CUDA
+}
+
+int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* count) {
+  if (!j || !data || !first_index || !count) return FRC_ERR_ARG;
+  *data = nullptr; *first_index = 0; *count = 0;
+  JOB_CUDA(j, cudaSetDevice(j->ctx->device));
+  // the band handed out by the previous call is released now
+  if (j->held_slot >= 0) {
+    j->held_slot = -1;
+    if (j->next_enqueue < j->mine.size()) {
+      int rc = enqueue_band(j, j->next_enqueue);
+      if (rc) return rc;
+      ++j->next_enqueue;
+    }
+  }
+  if (j->next_deliver >= j->mine.size()) return FRC_OK;  // end of stream
+  if (j->next_deliver >= j->next_enqueue) {               // only when n_slots == 2 and first call
+    int rc = enqueue_band(j, j->next_enqueue);
+    if (rc) return rc;
+    ++j->next_enqueue;
+  }
+  const size_t idx = j->next_deliver;
+  Slot& sl = j->slots[idx % j->n_slots];
+  JOB_CUDA(j, cudaEventSynchronize(sl.done));
+  float ms = 0.f;
+  JOB_CUDA(j, cudaEventElapsedTime(&ms, sl.k0, sl.k1));
+  j->info.pairs_ms += ms;
+  if (sl.n_flagged_host) j->info.flagged_pairs += static_cast<int64_t>(*sl.n_flagged_host);
+  const Band& b = j->bands[j->mine[idx]];
+  *data = (j->opts.flags & FRC_FLAG_NO_D2H) ? sl.dev : sl.host;
+  *first_index = b.first;
+  *count = b.count;
+  j->held_slot = static_cast<int>(idx % j->n_slots);
+  ++j->next_deliver;
+  return FRC_OK;
+}
+
+int frc_restart(frc_job_t* j) {
+  if (!j) return FRC_ERR_ARG;
+  JOB_CUDA(j, cudaSetDevice(j->ctx->device));
+  for (auto s : j->ctx->stream) JOB_CUDA(j, cudaStreamSynchronize(s));
+  j->info.kernel_launches = 0;
+  // stream 0 must not start before stream 1 drained (it did: both are idle)
+  int rc = run_embedding(j);
+  if (rc) return rc;
+  return start_pairs(j);
+}
+
+int frc_job_info(const frc_job_t* cj, frc_info_t* info) {
+  if (!cj || !info) return FRC_ERR_ARG;
+  frc_job* j = const_cast<frc_job*>(cj);
+  if (!j->embed_timed && j->ev_embed1) {
+    cudaSetDevice(j->ctx->device);
+    if (cudaEventSynchronize(j->ev_embed1) == cudaSuccess) {
+      float a = 0.f, b = 0.f;
+      if (cudaEventElapsedTime(&a, j->ev_h2d0, j->ev_h2d1) == cudaSuccess) j->info.h2d_ms = a;
+      if (cudaEventElapsedTime(&b, j->ev_embed0, j->ev_embed1) == cudaSuccess) j->info.embed_ms = b;
+      j->embed_timed = true;
+    }
+    cudaGetLastError();
+  }
+  *info = j->info;
+  return FRC_OK;
+}
+
+void frc_destroy(frc_job_t* j) { destroy_job(j); }
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// Unweighted UniFrac pair tiles on the tcgen05 tensor cores (replaces
+// unifracDistUnweighted, frcfrc/unifrac.go:144-171, for 128 x 128 sample pairs
+// per output tile).
+//
+// For presence P (0/1) and branch lengths len:
+//     shared(i,j) = sum_k len_k P_ik P_jk          (the reference's `common`)
+//     r_i         = sum_k len_k P_ik
+//     unique(i,j) = r_i + r_j - 2 shared           (the reference's `result`)
+//     d(i,j)      = unique / (unique + shared) = (R - 2s) / (R - s),  R = r_i + r_j
+// so the pairwise part is the dense contraction S = P diag(len) P^T: a GEMM.
+// P is exact in bf16; len is split len ~= hi + lo (two bf16 planes, relative
+// error <= 2^-18), the products P*hi and P*lo are exact in the fp32 accumulator,
+// and r is computed in fp64 from the SAME quantised lengths so that the
+// subtraction R - 2s cancels consistently.  Pairs whose distance comes out
+// small (where the subtraction loses relative accuracy) are flagged and
+// recomputed in fp64 from the presence rows by k_unweighted_fixup.
+//
+// Kernel structure (one CTA per SM, persistent over a tile list):
+//   warp 0     TMA producer: per 64-node block loads A = P[i-tile],
+//              Bh = (P*hi)[j-tile], Bl = (P*lo)[j-tile] (128-byte swizzle) into a
+//              4-stage ring, mbarrier complete_tx.
+//   warp 1     allocates TMEM, issues tcgen05.mma (M128 N128 K16, bf16 -> fp32):
+//              8 MMAs per stage (4 k-steps x 2 planes sharing A), tcgen05.commit
+//              frees the stage; one commit per K-chunk publishes the accumulator.
+//   warps 2-5  epilogue: tcgen05.ld the fp32 partial accumulator of each
+//              K-chunk into registers and add (two-level accumulation bounds the
+//              fp32 error over contractions of 10^5..10^6 terms), then the
+//              fused ratio epilogue in fp64 and direct stores into the flat
+//              lower-triangle band buffer.
+// Two TMEM accumulators (2 x 128 columns) let the MMAs of chunk c+1 overlap the
+// drain of chunk c, and the next tile's mainloop overlap this tile's epilogue.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "frc_internal.h"
+#include "ptx.cuh"
+
+namespace frc {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+constexpr int NUM_BARS = 2 * STAGES + 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_BARS * 8 + 16 + 1024;
+constexpr int THREADS = 192;
+constexpr uint32_t TMEM_COLS = 2 * BN;
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapBh,
+                const __grid_constant__ CUtensorMap mapBl, int32_t n_kblocks, int32_t chunk_kblocks,
+                const double* __restrict__ r, const Tile* __restrict__ tiles, int32_t n_tiles,
+                int64_t n_samples, int64_t first, double* __restrict__ out, double flag_below,
+                uint32_t* __restrict__ flagged, unsigned long long* __restrict__ n_flagged) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw + pad;  // 1024-aligned: required by SWIZZLE_128B
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapP);
+    ptx::prefetch_tensormap(&mapBh);
+    ptx::prefetch_tensormap(&mapBl);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar(b), 1);
+      ptx::mbar_init(tempty_bar(b), 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<1>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+    ptx::tmem_relinquish<1>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_chunks = (n_kblocks + chunk_kblocks - 1) / chunk_kblocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const Tile tile = tiles[t];
+        const int row_a = tile.ti * BM, row_b = tile.tj * BN;
+        for (int kb = 0; kb < n_kblocks; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          ptx::mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          ptx::tma_load_2d(sa, &mapP, full_bar(stage), kb * BK, row_a);
+          ptx::tma_load_2d(sa + A_BYTES, &mapBh, full_bar(stage), kb * BK, row_b);
+          ptx::tma_load_2d(sa + A_BYTES + B_BYTES, &mapBl, full_bar(stage), kb * BK, row_b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t chunk = 0;  // running chunk counter over all tiles of this CTA
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
+          const uint32_t buf = chunk & 1u;
+          ptx::mbar_wait(tempty_bar(buf), ((chunk >> 1) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          const int kb_end = min(n_kblocks, (ch + 1) * chunk_kblocks);
+          for (int kb = ch * chunk_kblocks; kb < kb_end; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            const uint64_t da = ptx::umma_desc_k_sw128(sa);
+            const uint64_t dh = ptx::umma_desc_k_sw128(sa + A_BYTES);
+            const uint64_t dl = ptx::umma_desc_k_sw128(sa + A_BYTES + B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              // advancing 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the
+              // (>>4) start-address field
+              ptx::umma_bf16<1>(d_tmem, da + 2u * k, dh + 2u * k, idesc,
+                                (kb > ch * chunk_kblocks || k > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k)
+              ptx::umma_bf16<1>(d_tmem, da + 2u * k, dl + 2u * k, idesc, 1u);
+            ptx::umma_commit(empty_bar(stage));  // stage reusable once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          ptx::umma_commit(tfull_bar(buf));  // accumulator of this chunk complete
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t chunk = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const Tile tile = tiles[t];
+      float acc[BN];
+#pragma unroll
+      for (int n = 0; n < BN; ++n) acc[n] = 0.f;
+      for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
+        const uint32_t buf = chunk & 1u;
+        ptx::mbar_wait(tfull_bar(buf), (chunk >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + cc * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) acc[cc * 32 + x] += __uint_as_float(v[x]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
+      }
+      // fused ratio epilogue, fp64
+      const int64_t i = static_cast<int64_t>(tile.ti) * BM + q * 32 + lane;
+      if (i < n_samples) {
+        const double ri = r[i];
+        const int64_t rowoff = i * (i - 1) / 2 - first;
+        const int64_t j0 = static_cast<int64_t>(tile.tj) * BN;
+#pragma unroll
+        for (int n = 0; n < BN; ++n) {
+          const int64_t j = j0 + n;
+          if (j < i) {
+            const double R = ri + r[j];
+            const double s = static_cast<double>(acc[n]);
+            const double d = (R - 2.0 * s) / (R - s);
+            out[rowoff + j] = d;
+            if (d < flag_below) {
+              unsigned long long slot = atomicAdd(n_flagged, 1ULL);
+              flagged[slot] = static_cast<uint32_t>(rowoff + j);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc<1>(tmem_base, TMEM_COLS);
+  }
+}
+
+// Exact recompute of flagged pairs from the bf16 presence rows: one warp per
+// pair, fp64, true branch lengths.  Identical samples give exactly 0.
+__global__ void __launch_bounds__(256)
+k_unweighted_fixup(const uint16_t* __restrict__ P, int32_t n_nodes, int32_t kp,
+                   const double* __restrict__ length, const uint32_t* __restrict__ flagged,
+                   const unsigned long long* __restrict__ n_flagged, int64_t first,
+                   double* __restrict__ out) {
+  const unsigned long long total = *n_flagged;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+  for (unsigned long long w = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+       w < total; w += warps) {
+    const uint32_t off = flagged[w];
+    const int64_t p = first + off;
+    int64_t i = static_cast<int64_t>((1.0 + sqrt(1.0 + 8.0 * static_cast<double>(p))) * 0.5);
+    while (i * (i - 1) / 2 > p) --i;
+    while ((i + 1) * i / 2 <= p) ++i;
+    const int64_t j = p - i * (i - 1) / 2;
+    const uint4* pi = reinterpret_cast<const uint4*>(P + i * kp);
+    const uint4* pj = reinterpret_cast<const uint4*>(P + j * kp);
+    double uniq = 0.0, comm = 0.0;
+    for (int32_t c = lane; c * 8 < n_nodes; c += 32) {
+      const uint4 a = pi[c], b = pj[c];
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        const int32_t k = c * 8 + h;
+        if (k < n_nodes) {
+          const bool pa = ((aw[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu) != 0;
+          const bool pb = ((bw[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu) != 0;
+          if (pa && pb) comm += length[k];
+          else if (pa || pb) uniq += length[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      uniq += __shfl_xor_sync(0xffffffffu, uniq, o);
+      comm += __shfl_xor_sync(0xffffffffu, comm, o);
+    }
+    if (lane == 0) out[off] = uniq / (uniq + comm);
+  }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled g_encode = nullptr;
+
+bool make_map(CUtensorMap* m, const void* base, int64_t rows, int32_t kp, int box_rows,
+              std::string* err) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp) * 2};
+  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(rc));
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+struct TcOperands {
+  CUtensorMap mapP, mapBh, mapBl;
+  const uint16_t* P;
+};
+
+bool tc_setup(std::string* err) {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
+    return false;
+  }
+  g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+  e = cudaFuncSetAttribute(k_unweighted_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("cudaFuncSetAttribute(k_unweighted_tc): ") + cudaGetErrorString(e);
+    g_encode = nullptr;
+    return false;
+  }
+  return true;
+}
+
+TcOperands* tc_operands_create(const uint16_t* P, const uint16_t* Bh, const uint16_t* Bl, int64_t np,
+                               int32_t kp, std::string* err) {
+  if (!tc_setup(err)) return nullptr;
+  TcOperands* o = new TcOperands();
+  o->P = P;
+  if (!make_map(&o->mapP, P, np, kp, BM, err) || !make_map(&o->mapBh, Bh, np, kp, BN, err) ||
+      !make_map(&o->mapBl, Bl, np, kp, BN, err)) {
+    delete o;
+    return nullptr;
+  }
+  return o;
+}
+void tc_operands_destroy(TcOperands* o) { delete o; }
+
+static int tc_chunk_kblocks() {
+  static int v = [] {
+    const char* e = getenv("FRC_TC_CHUNK_KBLOCKS");
+    int x = e ? atoi(e) : 32;  // 32 blocks = 2048 nodes per fp32 TMEM accumulation run
+    return x < 1 ? 1 : x;
+  }();
+  return v;
+}
+
+int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, const Tile* tiles,
+                         int32_t n_tiles, int64_t n_samples, int64_t first, double* out,
+                         double flag_below, uint32_t* flagged, unsigned long long* n_flagged,
+                         int num_sms, cudaStream_t s) {
+  if (n_tiles <= 0) return 0;
+  int grid = n_tiles < num_sms ? n_tiles : num_sms;
+  k_unweighted_tc<<<grid, THREADS, SMEM_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, kp / BK,
+                                                    tc_chunk_kblocks(), r, tiles, n_tiles, n_samples,
+                                                    first, out, flag_below, flagged, n_flagged);
+  return 1;
+}
+
+int launch_unweighted_fixup(const TcOperands* ops, int32_t n_nodes, int32_t kp, const double* length,
+                            const uint32_t* flagged, const unsigned long long* n_flagged,
+                            int64_t first, double* out, int num_sms, cudaStream_t s) {
+  k_unweighted_fixup<<<num_sms * 4, 256, 0, s>>>(ops->P, n_nodes, kp, length, flagged, n_flagged, first,
+                                                 out);
+  return 1;
+}
+
+}  // namespace frc

@@ -1,0 +1,158 @@
+// Weighted UniFrac pair tiles on the FP32 CUDA cores (replaces
+// unifracDistWeighted, frcfrc/unifrac.go:174-205, for 128 x 128 sample pairs
+// per CTA).
+//
+//   d(i,j) = sum_k len_k |a_ik - a_jk|  /  sum_k len_k (a_ik + a_jk)
+//
+// The denominator is separable (W_i + W_j, computed once per sample in fp64 by
+// the embedding stage), so the pair kernel only accumulates the numerator: an
+// L1 distance between two columns of the node-major operand A[kp][ld].  With
+// non-negative branch lengths the operand is pre-scaled (A = len * a), so the
+// inner loop is exactly two FP32 instructions per (pair, node): FADD d = a - b,
+// FADD acc = acc + |d| (|.| is a free source modifier).  Negative lengths use
+// the FFMA form with len staged next to the tile.
+//
+// Tiling: CTA = 128 x 128 pairs, 256 threads, each an 8 x 8 register block
+// (two 4-wide groups per side, so every shared-memory read is a conflict-free
+// LDS.128).  The contraction is staged through shared memory in 32-node slabs
+// with a 3-deep cp.async ring.  Accumulation is two-level (flush the 64
+// running sums into 64 totals every 256 nodes) to keep fp32 summation error
+// well under the 1e-5 budget for contractions of 10^5..10^6 nodes.
+#include "frc_internal.h"
+
+namespace frc {
+namespace {
+
+constexpr int KT = 32;        // nodes per smem slab
+constexpr int STAGES = 3;
+constexpr int FLUSH = 8;      // slabs between flushes (256 nodes)
+constexpr int SLAB_FLOATS = KT * kTile;           // one operand side
+constexpr int STAGE_FLOATS = 2 * SLAB_FLOATS + KT;  // + per-node lengths
+constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool kPrescaled>
+__global__ void __launch_bounds__(256, 1)
+k_weighted_tiles(const float* __restrict__ A, int64_t ld, int32_t kp, const float* __restrict__ lenf,
+                 const double* __restrict__ W, const Tile* __restrict__ tiles, int64_t n_samples,
+                 int64_t first, double* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const Tile tile = tiles[blockIdx.x];
+  const int64_t i0 = static_cast<int64_t>(tile.ti) * kTile;
+  const int64_t j0 = static_cast<int64_t>(tile.tj) * kTile;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int n_slabs = kp / KT;
+
+  auto load_slab = [&](int slab, int stage) {
+    float* sa = smem + stage * STAGE_FLOATS;
+    float* sb = sa + SLAB_FLOATS;
+    const float* ga = A + static_cast<int64_t>(slab) * KT * ld + i0;
+    const float* gb = A + static_cast<int64_t>(slab) * KT * ld + j0;
+    // 32 rows x 128 floats per side = 1024 16-byte chunks per side
+#pragma unroll
+    for (int c = tid; c < KT * (kTile / 4); c += 256) {
+      int row = c >> 5, q = c & 31;
+      cp_async16(sa + row * kTile + q * 4, ga + static_cast<int64_t>(row) * ld + q * 4);
+      cp_async16(sb + row * kTile + q * 4, gb + static_cast<int64_t>(row) * ld + q * 4);
+    }
+    if (!kPrescaled && tid < KT) cp_async4(sb + SLAB_FLOATS + tid, lenf + slab * KT + tid);
+  };
+
+  float acc[8][8], tot[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { acc[a][b] = 0.f; tot[a][b] = 0.f; }
+
+  for (int p = 0; p < STAGES - 1; ++p) {
+    if (p < n_slabs) load_slab(p, p);
+    cp_async_commit();
+  }
+  for (int slab = 0; slab < n_slabs; ++slab) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nxt = slab + STAGES - 1;
+      if (nxt < n_slabs) load_slab(nxt, nxt % STAGES);
+      cp_async_commit();
+    }
+    const float* sa = smem + (slab % STAGES) * STAGE_FLOATS;
+    const float* sb = sa + SLAB_FLOATS;
+    const float* sl = sb + SLAB_FLOATS;
+#pragma unroll 4
+    for (int kk = 0; kk < KT; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(sa + kk * kTile + ty * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(sa + kk * kTile + 64 + ty * 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + kk * kTile + tx * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(sb + kk * kTile + 64 + tx * 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      if (kPrescaled) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) acc[a][b] += fabsf(av[a] - bv[b]);
+      } else {
+        const float l = sl[kk];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(l, fabsf(av[a] - bv[b]), acc[a][b]);
+      }
+    }
+    if ((slab % FLUSH) == FLUSH - 1) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { tot[a][b] += acc[a][b]; acc[a][b] = 0.f; }
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int64_t i = i0 + (a < 4 ? ty * 4 + a : 64 + ty * 4 + (a - 4));
+    if (i >= n_samples) continue;
+    const double wi = W[i];
+    double* orow = out + (i * (i - 1) / 2 - first);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int64_t j = j0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
+      if (j < i) orow[j] = static_cast<double>(tot[a][b] + acc[a][b]) / (wi + W[j]);
+    }
+  }
+}
+
+}  // namespace
+
+void weighted_setup() {
+  cudaFuncSetAttribute(k_weighted_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaFuncSetAttribute(k_weighted_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
+                          const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
+                          int64_t first, double* out, cudaStream_t s) {
+  if (n_tiles <= 0) return 0;
+  if (prescaled)
+    k_weighted_tiles<true><<<n_tiles, 256, SMEM_BYTES, s>>>(A, ld, kp, lenf, W, tiles, n_samples, first, out);
+  else
+    k_weighted_tiles<false><<<n_tiles, 256, SMEM_BYTES, s>>>(A, ld, kp, lenf, W, tiles, n_samples, first, out);
+  return 1;
+}
+
+}  // namespace frc

@@ -1,0 +1,215 @@
+"""ctypes binding of libfrcfrc_cuda (include/frcfrc_cuda.h).
+
+This is the Python face of the drop-in boundary: `unifrac()` mirrors the
+reference's `unifrac(abnd, tree, weighted)` (frcfrc/unifrac.go:97) over a
+flattened tree and CSR abundances, and yields the flat lower-triangle vector in
+IterPairs order (common/common.go:21-31).  There is no CPU path: if the CUDA
+library is missing or no sm_100 device is present this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libfrcfrc_cuda.so")
+
+UNWEIGHTED, WEIGHTED = 0, 1
+PATH_AUTO, PATH_FAST, PATH_EXACT = -1, 0, 1
+FLAG_NO_D2H = 1
+
+EXPORTS = ["frc_abi_version", "frc_ctx_create", "frc_ctx_destroy", "frc_create", "frc_next",
+           "frc_restart", "frc_job_info", "frc_destroy", "frc_last_error"]
+
+
+class FrcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libfrcfrc_cuda error {code}: {msg}")
+        self.code = code
+
+
+class _Tree(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("parent", C.c_void_p), ("length", C.c_void_p)]
+
+
+class _Csr(C.Structure):
+    _fields_ = [("n_samples", C.c_int64), ("row_ptr", C.c_void_p), ("col", C.c_void_p),
+                ("val", C.c_void_p)]
+
+
+class _Opts(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("normalize", C.c_int32), ("path", C.c_int32),
+                ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("band_rows", C.c_int64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _Info(C.Structure):
+    _fields_ = [("path_taken", C.c_int32), ("n_bands_total", C.c_int32), ("n_bands_mine", C.c_int32),
+                ("tree_height", C.c_int32), ("n_pairs_total", C.c_int64), ("n_pairs_mine", C.c_int64),
+                ("n_nodes_padded", C.c_int64), ("kernel_launches", C.c_int64), ("h2d_ms", C.c_double),
+                ("embed_ms", C.c_double), ("pairs_ms", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("embed_bytes", C.c_int64), ("flagged_pairs", C.c_int64)]
+
+
+@dataclass
+class JobInfo:
+    path_taken: int
+    n_bands_total: int
+    n_bands_mine: int
+    tree_height: int
+    n_pairs_total: int
+    n_pairs_mine: int
+    n_nodes_padded: int
+    kernel_launches: int
+    h2d_ms: float
+    embed_ms: float
+    pairs_ms: float
+    h2d_bytes: int
+    d2h_bytes: int
+    embed_bytes: int
+    flagged_pairs: int
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FrcError(-1, f"{LIB_PATH} is missing: build it with `python -m frackyfrac_b200.build` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.frc_abi_version.restype = C.c_int
+        L.frc_ctx_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
+        L.frc_ctx_destroy.argtypes = [C.c_void_p]
+        L.frc_ctx_destroy.restype = None
+        L.frc_create.argtypes = [C.c_void_p, C.POINTER(_Tree), C.POINTER(_Csr), C.POINTER(_Opts),
+                                 C.POINTER(C.c_void_p)]
+        L.frc_next.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.frc_restart.argtypes = [C.c_void_p]
+        L.frc_job_info.argtypes = [C.c_void_p, C.POINTER(_Info)]
+        L.frc_destroy.argtypes = [C.c_void_p]
+        L.frc_destroy.restype = None
+        L.frc_last_error.argtypes = [C.c_void_p]
+        L.frc_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+class Context:
+    """Reusable device context (streams + memory pools)."""
+
+    def __init__(self, device: int = -1):
+        h = C.c_void_p()
+        rc = lib().frc_ctx_create(device, C.byref(h))
+        if rc:
+            raise FrcError(rc, lib().frc_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().frc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Job:
+    """One unifrac() call.  Iterate `chunks()` for (first_index, ndarray) runs."""
+
+    def __init__(self, parent, length, row_ptr, col, val, *, weighted: bool, normalize: bool = True,
+                 path: int = PATH_AUTO, ctx: Context | None = None, device: int = -1, rank: int = 0,
+                 world: int = 1, band_rows: int = 0, flags: int = 0):
+        self._keep = [np.ascontiguousarray(parent, np.int32), np.ascontiguousarray(length, np.float64),
+                      np.ascontiguousarray(row_ptr, np.int64), np.ascontiguousarray(col, np.int32),
+                      np.ascontiguousarray(val, np.float64)]
+        p, l, rp, c, v = self._keep
+        if len(p) != len(l):
+            raise ValueError("parent and length differ in size")
+        if len(c) != len(v) or (len(rp) and rp[-1] != len(c)):
+            raise ValueError("CSR arrays are inconsistent")
+        t = _Tree(len(p), p.ctypes.data, l.ctypes.data)
+        a = _Csr(max(len(rp) - 1, 0), rp.ctypes.data if len(rp) else None, c.ctypes.data, v.ctypes.data)
+        o = _Opts(WEIGHTED if weighted else UNWEIGHTED, 1 if normalize else 0, path, device, rank, world,
+                  band_rows, flags, 0)
+        self.h = C.c_void_p()
+        self.flags = flags
+        self.ctx = ctx
+        rc = lib().frc_create(ctx.h if ctx else None, C.byref(t), C.byref(a), C.byref(o), C.byref(self.h))
+        if rc:
+            self.h = None
+            raise FrcError(rc, lib().frc_last_error(None).decode())
+        self._keep = None  # inputs were copied
+
+    def next_raw(self):
+        """(address, first_index, count) of the next chunk; count == 0 at the end."""
+        d, f, n = C.c_void_p(), C.c_int64(), C.c_int64()
+        rc = lib().frc_next(self.h, C.byref(d), C.byref(f), C.byref(n))
+        if rc:
+            raise FrcError(rc, lib().frc_last_error(self.h).decode())
+        return d.value, f.value, n.value
+
+    def chunks(self, copy: bool = True):
+        if self.flags & FLAG_NO_D2H:
+            raise RuntimeError("chunks() needs host output; this job keeps distances in HBM")
+        while True:
+            addr, first, n = self.next_raw()
+            if n == 0:
+                return
+            a = np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_double)), shape=(n,))
+            yield first, (a.copy() if copy else a)
+
+    def drain(self) -> int:
+        """Runs the stream to its end without touching the data; returns pairs seen."""
+        total = 0
+        while True:
+            _, _, n = self.next_raw()
+            if n == 0:
+                return total
+            total += n
+
+    def restart(self):
+        rc = lib().frc_restart(self.h)
+        if rc:
+            raise FrcError(rc, lib().frc_last_error(self.h).decode())
+
+    def info(self) -> JobInfo:
+        i = _Info()
+        lib().frc_job_info(self.h, C.byref(i))
+        return JobInfo(*[getattr(i, f[0]) for f in _Info._fields_])
+
+    def close(self):
+        if self.h:
+            lib().frc_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def unifrac(parent, length, row_ptr, col, val, weighted: bool, normalize: bool = True, **kw) -> np.ndarray:
+    """All n(n-1)/2 distances (this rank's bands; zeros elsewhere when world > 1)."""
+    n = max(len(row_ptr) - 1, 0)
+    out = np.zeros(n * (n - 1) // 2 if n >= 2 else 0, np.float64)
+    with Job(parent, length, row_ptr, col, val, weighted=weighted, normalize=normalize, **kw) as job:
+        for first, a in job.chunks(copy=False):
+            out[first:first + len(a)] = a
+    return out

@@ -1,0 +1,158 @@
+// C++ stand-in for the Go `frcfrc` binary (frcfrc/frcfrc.go): same flags, same
+// validation and error behaviour, same stdout / -o bytes.  It exists because
+// this image has no Go toolchain; INTEGRATION.md shows the cgo patch that makes
+// the real Go main call the same C ABI.  The only thing replaced is the body
+// of unifrac() (frcfrc.go:58): it now pulls ordered chunks from libfrcfrc_cuda.
+#include <cerrno>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "frcfrc_cuda.h"
+#include "hostlib.hpp"
+
+namespace {
+
+const char* kUsage =
+    "FrackyFrac calculates UniFrac on the given abundance table.\n"
+    "Outputs one distance per line in the order (1,2),(1,3),(2,3)...(1,n)...(n-1,n).\n"
+    "\n"
+    "Params:\n";
+// flag.PrintDefaults() layout for the flags of frcfrc.go:18-27 (sorted by name).
+const char* kDefaults =
+    "  -i string\n    \tPath to input file (default stdin)\n"
+    "  -l\tLeave abundance values unnormalized (default normalize each sample to sum up to 1)\n"
+    "  -o string\n    \tPath to output file (default stdout)\n"
+    "  -p int\n    \tNumber of threads (default 1)\n"
+    "  -s\tInput is in sparse format\n"
+    "  -t string\n    \tPath to tree file, required\n"
+    "  -w\tUse weighted UniFrac (default unweighted)\n";
+
+[[noreturn]] void die(const std::string& msg) {  // common.ExitIfError (common/common.go:13-18)
+  fprintf(stderr, "ERROR: %s\n", msg.c_str());
+  exit(2);
+}
+void usage() { fputs(kUsage, stderr); fputs(kDefaults, stderr); }
+
+std::string slurp(const std::string& path) {
+  FILE* f = path.empty() ? stdin : fopen(path.c_str(), "rb");
+  if (!f) die("open " + path + ": " + strerror(errno));
+  std::string out;
+  char buf[1 << 16];
+  size_t r;
+  while ((r = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, r);
+  if (!path.empty()) fclose(f);
+  return out;
+}
+
+struct Flags {
+  std::string fin, fout, ftree;
+  bool wgt = false, sparse = false, nnorm = false;
+  long nt = 1;
+};
+
+bool parse_bool(const std::string& v, bool* out) {
+  if (v == "1" || v == "t" || v == "T" || v == "true" || v == "TRUE" || v == "True") { *out = true; return true; }
+  if (v == "0" || v == "f" || v == "F" || v == "false" || v == "FALSE" || v == "False") { *out = false; return true; }
+  return false;
+}
+
+// Go's flag package: -x, --x, -x=v, -x v; parsing stops at the first non-flag or "--".
+Flags parse_flags(int argc, char** argv) {
+  Flags f;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a.size() < 2 || a[0] != '-') break;
+    size_t d = a[1] == '-' ? 2 : 1;
+    if (a.size() == 2 && d == 2) break;  // "--"
+    std::string name = a.substr(d), val;
+    bool has_val = false;
+    size_t eq = name.find('=');
+    if (eq != std::string::npos) { val = name.substr(eq + 1); name = name.substr(0, eq); has_val = true; }
+    auto bad = [&](const std::string& m) { fprintf(stderr, "%s\n", m.c_str()); usage(); exit(2); };
+    if (name == "h" || name == "help") { usage(); exit(0); }
+    bool* bp = name == "w" ? &f.wgt : name == "s" ? &f.sparse : name == "l" ? &f.nnorm : nullptr;
+    if (bp) {
+      if (!has_val) *bp = true;
+      else if (!parse_bool(val, bp)) bad("invalid boolean value \"" + val + "\" for -" + name + ": parse error");
+      continue;
+    }
+    if (name != "i" && name != "o" && name != "t" && name != "p") bad("flag provided but not defined: -" + name);
+    if (!has_val) {
+      if (i + 1 >= argc) bad("flag needs an argument: -" + name);
+      val = argv[++i];
+    }
+    if (name == "i") f.fin = val;
+    else if (name == "o") f.fout = val;
+    else if (name == "t") f.ftree = val;
+    else {
+      char* end = nullptr;
+      errno = 0;
+      f.nt = strtol(val.c_str(), &end, 0);
+      if (val.empty() || *end || errno) bad("invalid value \"" + val + "\" for flag -p: parse error");
+    }
+  }
+  return f;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc == 1) { usage(); return 0; }  // frcfrc.go:71-74
+  Flags fl = parse_flags(argc, argv);
+  if (fl.ftree.empty()) die("please provide a tree file with -t");
+  if (fl.nt < 1) die("bad number of threads: " + std::to_string(fl.nt));
+  if (fl.nnorm && !fl.wgt) die("-l can only be used with weighted unifrac");
+
+  auto t0 = std::chrono::steady_clock::now();
+  try {
+    fputs("Reading tree\n", stderr);
+    std::string tt = slurp(fl.ftree);
+    frchost::FlatTree tree = frchost::parse_newick(tt.data(), tt.size());
+    fputs("Loading abundances\n", stderr);
+    std::string it = slurp(fl.fin);
+    frchost::Table tab = frchost::parse_table(it.data(), it.size(), fl.sparse);
+    fputs("Validating\n", stderr);
+    frchost::Csr csr = frchost::resolve(tab, tree);
+
+    FILE* w = fl.fout.empty() ? stdout : fopen(fl.fout.c_str(), "wb");
+    if (!w) die("open " + fl.fout + ": " + strerror(errno));
+
+    fputs("Converting abundances\n", stderr);
+    frc_tree_t ft{static_cast<int32_t>(tree.parent.size()), tree.parent.data(), tree.length.data()};
+    frc_csr_t fc{tab.n_samples(), csr.row_ptr.data(), csr.col.data(), csr.val.data()};
+    frc_opts_t fo{};
+    fo.mode = fl.wgt ? FRC_WEIGHTED : FRC_UNWEIGHTED;
+    fo.normalize = fl.nnorm ? 0 : 1;
+    fo.path = FRC_PATH_AUTO;
+    if (const char* e = getenv("FRCFRC_PATH")) fo.path = !strcmp(e, "exact") ? FRC_PATH_EXACT : !strcmp(e, "fast") ? FRC_PATH_FAST : FRC_PATH_AUTO;
+    fo.device = -1;
+    fo.world = 1;
+    frc_job_t* job = nullptr;
+    if (frc_create(nullptr, &ft, &fc, &fo, &job) != FRC_OK) die(frc_last_error(nullptr));
+    fputs("Calculating distances\n", stderr);
+    std::string text;
+    for (;;) {
+      const double* d; int64_t first, n;
+      if (frc_next(job, &d, &first, &n) != FRC_OK) { std::string m = frc_last_error(job); frc_destroy(job); die(m); }
+      if (n == 0) break;
+      text.clear();
+      frchost::append_lines(d, n, text);
+      if (fwrite(text.data(), 1, text.size(), w) != text.size()) {  // frcfrc.go:59-63
+        std::string m = std::string("write: ") + strerror(errno);
+        frc_destroy(job);
+        die(m);
+      }
+    }
+    frc_destroy(job);
+    if (!fl.fout.empty()) fclose(w); else fflush(w);
+  } catch (const std::exception& e) {
+    die(e.what());
+  }
+  double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  fprintf(stderr, "Took %.6gs\nDone\n", sec);
+  return 0;
+}

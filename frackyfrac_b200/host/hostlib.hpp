@@ -1,0 +1,54 @@
+// Host side above the C ABI, in C++ because the reference host is compiled Go
+// and this image has no Go toolchain.  It mirrors what frackyfrac keeps on the
+// host: the Newick reader (third-party biostuff/formats/newick, used at
+// frcfrc/frcfrc.go:109-114), the dense / sparse table readers
+// (parser/parser.go:21-140), species validation (frcfrc/unifrac.go:70-93),
+// the flattening enumerateNodes performs (unifrac.go:127-133), and the
+// fmt.Fprintln writer (frcfrc.go:58-62).  No distance arithmetic lives here.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace frchost {
+
+struct FlatTree {
+  std::vector<int32_t> parent;     // pre-order ids, root = 0, parent[0] = -1
+  std::vector<double> length;      // node.Distance (0 when absent)
+  std::vector<std::string> name;   // "" when absent
+  std::vector<int32_t> n_children;
+};
+
+// First tree of the text (frcfrc.go:109-114).  Throws std::runtime_error.
+FlatTree parse_newick(const char* text, size_t len);
+
+// One map per sample, as parser.ParseAbundance / ParseSparseAbundance deliver
+// them, with species names interned.  Entry order = first assignment.
+struct Table {
+  std::vector<std::string> species;              // id -> name
+  std::vector<int64_t> row_ptr{0};               // per sample
+  std::vector<int32_t> sp;                       // species id
+  std::vector<double> val;
+  int64_t n_samples() const { return static_cast<int64_t>(row_ptr.size()) - 1; }
+};
+Table parse_table(const char* text, size_t len, bool sparse);
+
+// validateSpecies + name -> leaf resolution.  Output is the frc_csr_t payload:
+// every leaf carrying the name gets the value (unifrac.go:38-43), names that
+// only match internal nodes are dropped.  Throws with the reference's message
+// (unifrac.go:85-88) when a species is not in the tree.
+struct Csr {
+  std::vector<int64_t> row_ptr;
+  std::vector<int32_t> col;
+  std::vector<double> val;
+};
+Csr resolve(const Table& t, const FlatTree& tree);
+
+// Go's fmt %v for float64, no newline.  Returns the length written (<= 32).
+int format_go(double v, char* buf);
+
+// One distance per line, exactly as `fmt.Fprintln(w, f)`; appends to `out`.
+void append_lines(const double* d, int64_t n, std::string& out);
+
+}  // namespace frchost

@@ -1,0 +1,149 @@
+/*
+ * libfrcfrc_cuda — C ABI of the B200 (sm_100a) UniFrac engine.
+ *
+ * This is the drop-in boundary for the one hot path of fluhus/frackyfrac:
+ * the call `unifrac(abnd, tree, *wgt)` at frcfrc/frcfrc.go:58, i.e. everything
+ * in frcfrc/unifrac.go (embedding :32-67,:97-124; pair distances :144-228).
+ * Everything that touches strings (flags, Newick, TSV / sparse tables, species
+ * validation, text output) stays on the host side of this boundary.
+ *
+ * Conventions
+ *   - plain C, no CUDA / torch types; all pointers are HOST pointers unless a
+ *     parameter says "device".
+ *   - every entry point returns an frc_status (0 = ok) except frc_destroy,
+ *     frc_ctx_destroy, frc_last_error and frc_abi_version.
+ *   - inputs are borrowed and fully copied before frc_create returns (cgo
+ *     forbids retaining Go pointers).
+ *   - failures (bad argument, CUDA error, out of memory) are errors; there is
+ *     no CPU fallback anywhere behind this ABI.
+ *   - entry points of one job/context must be called from one host thread at a
+ *     time.
+ */
+#ifndef FRCFRC_CUDA_H
+#define FRCFRC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRC_ABI_VERSION 1
+
+typedef enum {
+  FRC_OK = 0,
+  FRC_ERR_ARG = 1,         /* invalid tree / table / option                    */
+  FRC_ERR_CUDA = 2,        /* a CUDA runtime or driver call failed             */
+  FRC_ERR_OOM = 3,         /* device or pinned host memory exhausted           */
+  FRC_ERR_STATE = 4,       /* call sequence violated                           */
+  FRC_ERR_UNSUPPORTED = 5  /* device is not sm_100 / problem exceeds a limit   */
+} frc_status;
+
+/* Replaces the `weighted bool` argument of unifrac() (frcfrc/unifrac.go:97),
+ * set from flag -w (frcfrc/frcfrc.go:22). */
+typedef enum { FRC_UNWEIGHTED = 0, FRC_WEIGHTED = 1 } frc_mode;
+
+/* Which pair kernel runs.
+ *   AUTO : EXACT when n_pairs * n_nodes is small (bit-exact testdata .want files),
+ *          otherwise FAST.
+ *   FAST : unweighted -> tcgen05 bf16 hi/lo GEMM; weighted -> FP32 L1 tiles.
+ *          Within 1e-5 relative of the reference.
+ *   EXACT: fp64, the reference's summation order (ascending node id, separate
+ *          multiply and add): bit-identical to frcfrc/unifrac.go:144-205. */
+typedef enum { FRC_PATH_AUTO = -1, FRC_PATH_FAST = 0, FRC_PATH_EXACT = 1 } frc_path;
+
+/* The flattened tree: what enumerateNodes (frcfrc/unifrac.go:127-133) and the
+ * treeDists loop (:117-120) produce.  Node ids are PRE-ORDER indices, root = 0,
+ * so parent[v] < v for v > 0 and siblings appear in file order. */
+typedef struct {
+  int32_t n_nodes;
+  const int32_t *parent;  /* [n_nodes], parent[0] = -1                          */
+  const double *length;   /* [n_nodes], node.Distance verbatim, root included   */
+} frc_tree_t;
+
+/* One row per sample: the per-sample map[string]float64 of frcfrc.go:41-51
+ * after name resolution.  col = id of a LEAF node carrying that species name
+ * (a name carried by several leaves is expanded to all of them, a name that
+ * only matches internal nodes is dropped: unifrac.go:38-43).  val > 0, finite.
+ * A leaf may appear at most once per row; order within a row is free. */
+typedef struct {
+  int64_t n_samples;
+  const int64_t *row_ptr; /* [n_samples + 1], row_ptr[0] = 0                    */
+  const int32_t *col;     /* [row_ptr[n_samples]]                               */
+  const double *val;      /* [row_ptr[n_samples]]                               */
+} frc_csr_t;
+
+#define FRC_FLAG_NO_D2H 1u /* keep distances in HBM: frc_next returns DEVICE
+                              pointers (kernel-only timing, GPU consumers)     */
+
+typedef struct {
+  int32_t mode;       /* frc_mode                                               */
+  int32_t normalize;  /* 1 = default; 0 = flag -l (frcfrc.go:25, unifrac.go:108) */
+  int32_t path;       /* frc_path                                               */
+  int32_t device;     /* CUDA device ordinal; -1 = current device               */
+  int32_t rank;       /* tile-band sharding: this job yields the bands b with   */
+  int32_t world;      /*   b % world == rank (one process per GPU). 0/1 = all   */
+  int64_t band_rows;  /* rows of the lower triangle per output chunk; 0 = auto  */
+  uint32_t flags;     /* FRC_FLAG_*                                             */
+  uint32_t reserved;
+} frc_opts_t;
+
+typedef struct frc_ctx frc_ctx_t; /* device + streams + reusable memory pools  */
+typedef struct frc_job frc_job_t; /* one unifrac() call                         */
+
+/* What a finished or running job did; for benchmarks and tests. */
+typedef struct {
+  int32_t path_taken;      /* FRC_PATH_FAST / FRC_PATH_EXACT                    */
+  int32_t n_bands_total;   /* bands of the whole triangle                       */
+  int32_t n_bands_mine;    /* bands this rank yields                            */
+  int32_t tree_height;     /* level-synchronous passes of the embedding         */
+  int64_t n_pairs_total;   /* n(n-1)/2                                          */
+  int64_t n_pairs_mine;
+  int64_t n_nodes_padded;  /* contraction length the pair kernel runs over      */
+  int64_t kernel_launches; /* kernels of this library launched so far           */
+  double h2d_ms, embed_ms, pairs_ms; /* device time (CUDA events) of finished stages;
+                                        pairs_ms = sum over finished bands      */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t embed_bytes;     /* algorithmic HBM bytes of the embedding stage      */
+  int64_t flagged_pairs;   /* fast unweighted: pairs recomputed exactly (d tiny) */
+} frc_info_t;
+
+int frc_abi_version(void);
+
+/* Optional reusable context.  A job created with ctx == NULL owns a private
+ * one.  Reusing a context across jobs reuses its device / pinned allocations. */
+int frc_ctx_create(int32_t device, frc_ctx_t **out);
+void frc_ctx_destroy(frc_ctx_t *ctx);
+
+/* Replaces the body of unifrac() (frcfrc/unifrac.go:97-124): validates, copies
+ * and uploads the inputs, builds the branch embedding on the device and queues
+ * the first tile bands.  Returns without waiting for the device. */
+int frc_create(frc_ctx_t *ctx, const frc_tree_t *tree, const frc_csr_t *abnd,
+               const frc_opts_t *opts, frc_job_t **out);
+
+/* Replaces ranging over the iter.Seq[float64] that unifrac() returns
+ * (frcfrc/frcfrc.go:58-62, unifrac.go:209-228).  Yields contiguous runs of the
+ * flat lower-triangle vector, index(i,j) = i(i-1)/2 + j for j < i
+ * (common/common.go:21-31), in strictly increasing index order.  `*data` is
+ * engine-owned pinned host memory (device memory with FRC_FLAG_NO_D2H), valid
+ * until the next call on this job.  *count == 0 means the stream has ended. */
+int frc_next(frc_job_t *job, const double **data, int64_t *first_index, int64_t *count);
+
+/* Re-runs embedding + pair stage on the inputs already resident in HBM
+ * (benchmarking the device path without the host→device copy). */
+int frc_restart(frc_job_t *job);
+
+int frc_job_info(const frc_job_t *job, frc_info_t *info);
+
+/* Legal at any time, also mid-stream (the consumer's `break`, frcfrc.go:59-61). */
+void frc_destroy(frc_job_t *job);
+
+/* Message of the last failed call on this job; with job == NULL, of the last
+ * failed frc_create / frc_ctx_create on the calling thread. */
+const char *frc_last_error(const frc_job_t *job);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRCFRC_CUDA_H */
