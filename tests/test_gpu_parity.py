@@ -1,0 +1,202 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (GPU box only)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import kat
+from tests.helpers import gpu_flat, oracle_flat, rel_err
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _read(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return f.read()
+
+
+# ------------------------------------------------------------------ known answers
+@pytest.mark.parametrize("case", kat.UNIT, ids=[c["name"] for c in kat.UNIT])
+def test_unit_kat_bit_exact(gpu_ctx, case):
+    """frcfrc/unifrac_test.go: reflect.DeepEqual on float64, i.e. bit-exact."""
+    from frackyfrac_b200 import engine, hostlib
+
+    tree = hostlib.Tree(case["tree"])
+    tab = hostlib.Table(kat.sparse_text(case["abnd"]), True)
+    rp, col, val = tab.resolve(tree)
+    got = engine.unifrac(tree.parent, tree.length, rp, col, val, case["weighted"], ctx=gpu_ctx)
+    assert got.tolist() == case["want"]
+
+
+@pytest.mark.parametrize("fixture,sparse,weighted", kat.CLI)
+def test_cli_golden_through_abi(gpu_ctx, fixture, sparse, weighted):
+    """testdata/run.sh: output text must equal *.want byte for byte."""
+    from frackyfrac_b200 import engine, hostlib
+
+    tree = hostlib.Tree(_read(fixture + ".tree"))
+    tab = hostlib.Table(_read(fixture + (".sparse" if sparse else ".dense")), sparse)
+    rp, col, val = tab.resolve(tree)
+    got = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, ctx=gpu_ctx)
+    text = "".join(hostlib.format_go(v) + "\n" for v in got)
+    assert text == _read(fixture + ".want")
+
+
+@pytest.mark.parametrize("fixture,sparse,weighted", kat.CLI)
+def test_cli_binary_golden(built, tmp_path, fixture, sparse, weighted):
+    """The C++ stand-in for the Go binary, run exactly as testdata/run.sh runs frcfrc."""
+    from frackyfrac_b200 import hostlib
+
+    out = tmp_path / "got"
+    cmd = [hostlib.CLI_PATH, "-i", os.path.join(GOLDEN, fixture + (".sparse" if sparse else ".dense")),
+           "-t", os.path.join(GOLDEN, fixture + ".tree"), "-o", str(out)]
+    if sparse:
+        cmd.insert(1, "-s")
+    if weighted:
+        cmd.insert(1, "-w")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == _read(fixture + ".want")
+
+
+# ------------------------------------------------------------------ exact path
+@pytest.mark.parametrize("weighted,normalize", [(False, 1), (True, 1), (True, 2)])
+@pytest.mark.parametrize("shape", ["random", "caterpillar", "balanced"])
+def test_exact_path_bit_identical(gpu_ctx, weighted, normalize, shape):
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(300, 11, shape=shape)
+    csr = synth.random_table(tree, 40, 0.05, 12, integer_counts=False)
+    want = oracle_flat(tree, csr, weighted, normalize)
+    got = gpu_flat(tree, csr, weighted, normalize == 1, path=engine.PATH_EXACT, ctx=gpu_ctx)
+    assert np.array_equal(got, want), f"max rel err {rel_err(got, want).max()}"
+
+
+def test_exact_multifurcating_and_shared_names(gpu_ctx):
+    """Children are summed in file order; a name on several leaves feeds all of them (A6)."""
+    from frackyfrac_b200 import engine, hostlib
+    from oracle import oracle as orc
+
+    nwk = "((a:0.1,b:0.25,c:0.7,a:0.3)x:0.5,(d:1.5,(e:0.125,f:0.3):0.2,x:0.9):0.05,g:2)r:0.75;"
+    tab_text = "a:0.3 d:7 x:5\nb:1.1 e:2 g:0.01\nc:3 f:1e-3 a:2\n\nd:1 e:1 f:1 g:1 x:2\n"
+    tree = hostlib.Tree(nwk)
+    tab = hostlib.Table(tab_text, True)
+    rp, col, val = tab.resolve(tree)
+    otree, otab = orc.Tree.parse(nwk), orc.Table.parse(tab_text, True)
+    for weighted in (False, True):
+        want = orc.unifrac(otab, otree, weighted, 1, 1)
+        got = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, path=engine.PATH_EXACT, ctx=gpu_ctx)
+        assert np.array_equal(got, want, equal_nan=True)
+        assert np.isnan(want).sum() == 0 and len(want) == 10
+
+
+def test_empty_samples_give_nan(gpu_ctx):
+    """Two empty samples: 0/0 = NaN (A8); empty vs non-empty = 1."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(50, 3)
+    rp, col, val = synth.random_table(tree, 4, 0.1, 4)
+    m = rp[1]
+    rp = np.array([0, m, m, 2 * m, 2 * m], np.int64)  # samples 1 and 3 empty
+    for weighted in (False, True):
+        for path in (engine.PATH_EXACT, engine.PATH_FAST):
+            got = engine.unifrac(tree.parent, tree.length, rp, col[:2 * m], val[:2 * m], weighted, path=path, ctx=gpu_ctx)
+            want = oracle_flat(tree, (rp, col[:2 * m], val[:2 * m]), weighted)
+            assert np.isnan(want[4]) and np.isnan(got[4])  # pair (3,1)
+            assert rel_err(got, want).max() < 1e-5
+
+
+# ------------------------------------------------------------------- fast paths
+@pytest.mark.parametrize("weighted,normalize", [(False, 1), (True, 1), (True, 2)])
+def test_fast_path_within_tolerance(gpu_ctx, weighted, normalize):
+    """north_star: every distance within 1e-5 relative of the reference."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(1000, 21)
+    csr = synth.random_table(tree, 300, 0.02, 22)
+    want = oracle_flat(tree, csr, weighted, normalize)
+    got = gpu_flat(tree, csr, weighted, normalize == 1, path=engine.PATH_FAST, ctx=gpu_ctx)
+    e = rel_err(got, want)
+    assert e.max() < 1e-5, f"max rel err {e.max():.3e}"
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_fast_path_identical_and_near_identical_samples(gpu_ctx, weighted):
+    """Identical samples must give exactly 0; near-identical ones stay within 1e-5 relative."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(800, 31)
+    rp, col, val = synth.random_table(tree, 130, 0.03, 32)
+    m = rp[1]
+    col[m:2 * m] = col[:m]          # sample 1 == sample 0
+    val[m:2 * m] = val[:m]
+    col[2 * m:3 * m] = col[:m]      # sample 2 = sample 0 with one leaf swapped
+    val[2 * m:3 * m] = val[:m]
+    others = np.setdiff1d(tree.leaf_ids, col[:m])
+    col[2 * m] = others[0]
+    want = oracle_flat(tree, (rp, col, val), weighted)
+    got = gpu_flat(tree, (rp, col, val), weighted, path=engine.PATH_FAST, ctx=gpu_ctx)
+    assert want[0] == 0.0 and got[0] == 0.0
+    assert rel_err(got, want).max() < 1e-5
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_fast_path_multi_band_and_sharded(gpu_ctx, weighted):
+    """Band streaming order, and world=2 band sharding: union of ranks == single rank, same bytes."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(500, 41)
+    rp, col, val = synth.random_table(tree, 700, 0.02, 42)
+    want = oracle_flat(tree, (rp, col, val), weighted)
+    one = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, path=engine.PATH_FAST, band_rows=128, ctx=gpu_ctx)
+    assert rel_err(one, want).max() < 1e-5
+    parts = [engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, path=engine.PATH_FAST, band_rows=128,
+                            rank=r, world=2, ctx=gpu_ctx) for r in range(2)]
+    assert np.array_equal(parts[0] + parts[1], one)
+    assert ((parts[0] != 0) & (parts[1] != 0)).sum() == 0
+    whole = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, path=engine.PATH_FAST, band_rows=1024, ctx=gpu_ctx)
+    assert np.array_equal(whole, one), "results must not depend on the band decomposition"
+
+
+def test_stream_order_and_early_destroy(gpu_ctx):
+    """frc_next yields strictly increasing contiguous runs; destroying mid-stream is legal."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(200, 51)
+    rp, col, val = synth.random_table(tree, 600, 0.05, 52)
+    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=True, path=engine.PATH_FAST, band_rows=128, ctx=gpu_ctx) as job:
+        expect = 0
+        for first, a in job.chunks():
+            assert first == expect
+            expect += len(a)
+        assert expect == 600 * 599 // 2
+        info = job.info()
+        assert info.n_bands_mine == 5 and info.kernel_launches > 0
+    job = engine.Job(tree.parent, tree.length, rp, col, val, weighted=False, path=engine.PATH_FAST, band_rows=128, ctx=gpu_ctx)
+    next(job.chunks())
+    job.close()  # the consumer's `break`
+    again = engine.unifrac(tree.parent, tree.length, rp, col, val, False, ctx=gpu_ctx)
+    assert len(again) == 600 * 599 // 2
+
+
+def test_bad_arguments_are_errors(gpu_ctx):
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(20, 61)
+    rp, col, val = synth.random_table(tree, 3, 0.2, 62)
+    internal = int(np.setdiff1d(np.arange(tree.n_nodes), tree.leaf_ids)[0])
+    bad_col = col.copy(); bad_col[0] = internal
+    with pytest.raises(engine.FrcError):
+        engine.unifrac(tree.parent, tree.length, rp, bad_col, val, False, ctx=gpu_ctx)
+    bad_val = val.copy(); bad_val[1] = 0.0
+    with pytest.raises(engine.FrcError):
+        engine.unifrac(tree.parent, tree.length, rp, col, bad_val, True, ctx=gpu_ctx)
+    bad_parent = tree.parent.copy(); bad_parent[3] = 7
+    with pytest.raises(engine.FrcError):
+        engine.unifrac(bad_parent, tree.length, rp, col, val, False, ctx=gpu_ctx)
+    with pytest.raises(engine.FrcError):  # -l only with -w (frcfrc.go:84-86)
+        engine.unifrac(tree.parent, tree.length, rp, col, val, False, normalize=False, ctx=gpu_ctx)
+    ok = engine.unifrac(tree.parent, tree.length, rp, col, val, False, ctx=gpu_ctx)
+    assert len(ok) == 3
