@@ -92,7 +92,7 @@ struct Slot {
   uint32_t* flagged = nullptr;
   unsigned long long* n_flagged = nullptr;  // device
   unsigned long long* n_flagged_host = nullptr;
-  cudaEvent_t k0 = nullptr, k1 = nullptr, done = nullptr;
+  cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr, done = nullptr;
   int band = -1;  // index into mine[]
 };
 
@@ -132,6 +132,8 @@ struct frc_job {
   size_t next_enqueue = 0, next_deliver = 0;
   int held_slot = -1;  // slot whose buffer the caller currently reads
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_embed0 = nullptr, ev_embed1 = nullptr;
+  cudaEvent_t ev_run1 = nullptr, ev_join = nullptr;
+  bool run_timed = false;
   bool embed_timed = false;
 };
 
@@ -149,10 +151,20 @@ namespace {
 
 int fail(frc_job* j, int code, const std::string& msg) { j->err = msg; return code; }
 
-int64_t choose_band_rows(int64_t N, int64_t requested) {
+// Band b of the triangle costs ~b (its rows have ~b*band_rows columns), so
+// ranks take bands in boustrophedon order: 0..G-1, G-1..0, ... which pairs a
+// cheap band with an expensive one and balances to within one band.
+int band_owner(size_t b, int world) {
+  size_t m = b % (2 * static_cast<size_t>(world));
+  return static_cast<int>(m < static_cast<size_t>(world) ? m : 2 * world - 1 - m);
+}
+
+int64_t choose_band_rows(int64_t N, int64_t requested, int world) {
   if (requested > 0) return round_up(requested, kTile);
   int64_t tile_rows = (N + kTile - 1) / kTile;
-  int64_t g = std::min<int64_t>(8, std::max<int64_t>(1, (tile_rows + 7) / 8));
+  // at least ~8 bands per rank (D2H overlap, load balance), at most 8 tile rows
+  // per band (L2 reuse of the j-side operand across the band's i-tiles)
+  int64_t g = std::min<int64_t>(8, std::max<int64_t>(1, tile_rows / (8 * static_cast<int64_t>(world))));
   while (g > 1 && g * kTile * N * 8 > (512LL << 20)) --g;
   return g * kTile;
 }
@@ -234,19 +246,27 @@ int enqueue_band(frc_job* j, size_t idx) {
     JOB_CUDA(j, cudaMemsetAsync(sl.n_flagged, 0, sizeof(unsigned long long), s));
     launches += launch_unweighted_tc(j->tc, j->kp, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
                                      b.first, sl.dev, kFlagBelow, sl.flagged, sl.n_flagged, c->num_sms, s);
+    JOB_CUDA(j, cudaEventRecord(sl.k1, s));
     launches += launch_unweighted_fixup(j->tc, j->B, j->kp, j->dtree.length, sl.flagged, sl.n_flagged,
                                         b.first, sl.dev, c->num_sms, s);
     JOB_CUDA(j, cudaMemcpyAsync(sl.n_flagged_host, sl.n_flagged, sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, s));
   }
   JOB_CUDA(j, cudaGetLastError());
-  JOB_CUDA(j, cudaEventRecord(sl.k1, s));
+  if (j->exact || j->weighted) JOB_CUDA(j, cudaEventRecord(sl.k1, s));
+  JOB_CUDA(j, cudaEventRecord(sl.k2, s));
   if (!(j->opts.flags & FRC_FLAG_NO_D2H)) {
     JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, s));
     j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
   }
   JOB_CUDA(j, cudaEventRecord(sl.done, s));
   j->info.kernel_launches += launches;
+  if (idx + 1 == j->mine.size()) {
+    // last band queued: join both streams and stamp the end of the run on stream 0
+    JOB_CUDA(j, cudaEventRecord(j->ev_join, c->stream[1]));
+    JOB_CUDA(j, cudaStreamWaitEvent(c->stream[0], j->ev_join, 0));
+    JOB_CUDA(j, cudaEventRecord(j->ev_run1, c->stream[0]));
+  }
   return FRC_OK;
 }
 
@@ -254,6 +274,9 @@ int start_pairs(frc_job* j) {
   j->next_enqueue = j->next_deliver = 0;
   j->held_slot = -1;
   j->info.pairs_ms = 0;
+  j->info.fixup_ms = 0;
+  j->info.run_ms = 0;
+  j->run_timed = false;
   j->info.flagged_pairs = 0;
   j->info.d2h_bytes = 0;
   // keep one slot free for the band the caller is still reading
@@ -275,12 +298,15 @@ void destroy_job(frc_job* j) {
   for (auto& sl : j->slots) {
     if (sl.k0) cudaEventDestroy(sl.k0);
     if (sl.k1) cudaEventDestroy(sl.k1);
+    if (sl.k2) cudaEventDestroy(sl.k2);
     if (sl.done) cudaEventDestroy(sl.done);
   }
   if (j->ev_h2d0) cudaEventDestroy(j->ev_h2d0);
   if (j->ev_h2d1) cudaEventDestroy(j->ev_h2d1);
   if (j->ev_embed0) cudaEventDestroy(j->ev_embed0);
   if (j->ev_embed1) cudaEventDestroy(j->ev_embed1);
+  if (j->ev_run1) cudaEventDestroy(j->ev_run1);
+  if (j->ev_join) cudaEventDestroy(j->ev_join);
   tc_operands_destroy(j->tc);
   if (j->ctx) {
     j->ctx->dev.reset();
@@ -458,7 +484,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->info.n_nodes_padded = j->exact ? B : j->kp;
 
   // ---------------------------------------------------------------------- bands
-  const int64_t band_rows = choose_band_rows(N, opts->band_rows);
+  const int64_t band_rows = choose_band_rows(N, opts->band_rows, world);
   for (int64_t r0 = 0; r0 < N; r0 += band_rows) {
     Band b;
     b.row0 = r0; b.row1 = std::min(N, r0 + band_rows);
@@ -469,7 +495,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   }
   int64_t max_band = 1;
   for (size_t k = 0; k < j->bands.size(); ++k)
-    if (static_cast<int>(k % world) == rank) {
+    if (band_owner(k, world) == rank) {
       j->mine.push_back(static_cast<int>(k));
       j->info.n_pairs_mine += j->bands[k].count;
       max_band = std::max(max_band, j->bands[k].count);
@@ -557,6 +583,8 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   CREATE_CUDA(cudaEventCreate(&j->ev_h2d1));
   CREATE_CUDA(cudaEventCreate(&j->ev_embed0));
   CREATE_CUDA(cudaEventCreate(&j->ev_embed1));
+  CREATE_CUDA(cudaEventCreate(&j->ev_run1));
+  CREATE_CUDA(cudaEventCreateWithFlags(&j->ev_join, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventRecord(j->ev_h2d0, c->stream[0]));
   CREATE_CUDA(cudaMemcpyAsync(j->d_inputs, stage, total, cudaMemcpyHostToDevice, c->stream[0]));
   CREATE_CUDA(cudaEventRecord(j->ev_h2d1, c->stream[0]));
@@ -614,6 +642,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     }
     cudaError_t e;
     if ((e = cudaEventCreate(&sl.k0)) != cudaSuccess || (e = cudaEventCreate(&sl.k1)) != cudaSuccess ||
+        (e = cudaEventCreate(&sl.k2)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess)
       return bail(fail(j, FRC_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e)));
   }
@@ -651,6 +680,14 @@ int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* c
   float ms = 0.f;
   JOB_CUDA(j, cudaEventElapsedTime(&ms, sl.k0, sl.k1));
   j->info.pairs_ms += ms;
+  JOB_CUDA(j, cudaEventElapsedTime(&ms, sl.k1, sl.k2));
+  j->info.fixup_ms += ms;
+  if (j->next_deliver + 1 == j->mine.size() && !j->run_timed) {
+    JOB_CUDA(j, cudaEventSynchronize(j->ev_run1));
+    JOB_CUDA(j, cudaEventElapsedTime(&ms, j->ev_embed0, j->ev_run1));
+    j->info.run_ms = ms;
+    j->run_timed = true;
+  }
   if (sl.n_flagged_host) j->info.flagged_pairs += static_cast<int64_t>(*sl.n_flagged_host);
   const Band& b = j->bands[j->mine[idx]];
   *data = (j->opts.flags & FRC_FLAG_NO_D2H) ? sl.dev : sl.host;

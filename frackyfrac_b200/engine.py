@@ -50,7 +50,8 @@ class _Info(C.Structure):
     _fields_ = [("path_taken", C.c_int32), ("n_bands_total", C.c_int32), ("n_bands_mine", C.c_int32),
                 ("tree_height", C.c_int32), ("n_pairs_total", C.c_int64), ("n_pairs_mine", C.c_int64),
                 ("n_nodes_padded", C.c_int64), ("kernel_launches", C.c_int64), ("h2d_ms", C.c_double),
-                ("embed_ms", C.c_double), ("pairs_ms", C.c_double), ("h2d_bytes", C.c_int64),
+                ("embed_ms", C.c_double), ("pairs_ms", C.c_double), ("fixup_ms", C.c_double),
+                ("run_ms", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("embed_bytes", C.c_int64), ("flagged_pairs", C.c_int64)]
 
 
@@ -67,6 +68,8 @@ class JobInfo:
     h2d_ms: float
     embed_ms: float
     pairs_ms: float
+    fixup_ms: float
+    run_ms: float
     h2d_bytes: int
     d2h_bytes: int
     embed_bytes: int

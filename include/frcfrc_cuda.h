@@ -82,8 +82,8 @@ typedef struct {
   int32_t normalize;  /* 1 = default; 0 = flag -l (frcfrc.go:25, unifrac.go:108) */
   int32_t path;       /* frc_path                                               */
   int32_t device;     /* CUDA device ordinal; -1 = current device               */
-  int32_t rank;       /* tile-band sharding: this job yields the bands b with   */
-  int32_t world;      /*   b % world == rank (one process per GPU). 0/1 = all   */
+  int32_t rank;       /* tile-band sharding over `world` processes (one per GPU): */
+  int32_t world;      /*   bands are dealt 0..G-1,G-1..0,...; 0/1 = all bands     */
   int64_t band_rows;  /* rows of the lower triangle per output chunk; 0 = auto  */
   uint32_t flags;     /* FRC_FLAG_*                                             */
   uint32_t reserved;
@@ -102,8 +102,11 @@ typedef struct {
   int64_t n_pairs_mine;
   int64_t n_nodes_padded;  /* contraction length the pair kernel runs over      */
   int64_t kernel_launches; /* kernels of this library launched so far           */
-  double h2d_ms, embed_ms, pairs_ms; /* device time (CUDA events) of finished stages;
-                                        pairs_ms = sum over finished bands      */
+  double h2d_ms, embed_ms;  /* device time (CUDA events) of the upload / embedding */
+  double pairs_ms;          /* sum over delivered bands of the pair kernel's time  */
+  double fixup_ms;          /* same for the exact fix-up pass (fast unweighted)    */
+  double run_ms;            /* embedding start -> last band (and its D2H) done;
+                               valid once the stream has been read to its end      */
   int64_t h2d_bytes, d2h_bytes;
   int64_t embed_bytes;     /* algorithmic HBM bytes of the embedding stage      */
   int64_t flagged_pairs;   /* fast unweighted: pairs recomputed exactly (d tiny) */
