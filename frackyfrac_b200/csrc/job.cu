@@ -728,4 +728,25 @@ int frc_job_info(const frc_job_t* cj, frc_info_t* info) {
 
 void frc_destroy(frc_job_t* j) { destroy_job(j); }
 
+int64_t frc_plan_bands(int64_t n_samples, int64_t band_rows, int32_t rank, int32_t world,
+                       int64_t* first_index, int64_t* count, int64_t cap) {
+  if (world <= 0) { world = 1; rank = 0; }
+  if (n_samples < 0 || band_rows < 0 || rank < 0 || rank >= world) return -FRC_ERR_ARG;
+  const int64_t rows = choose_band_rows(n_samples, band_rows, world);
+  int64_t n = 0;
+  size_t k = 0;
+  for (int64_t r0 = 0; r0 < n_samples; r0 += rows) {
+    const int64_t r1 = std::min(n_samples, r0 + rows);
+    const int64_t first = r0 >= 2 ? tri(r0) : 0;
+    const int64_t cnt = tri(r1) - first;
+    if (cnt <= 0) continue;
+    if (band_owner(k, world) == rank) {
+      if (n < cap && first_index && count) { first_index[n] = first; count[n] = cnt; }
+      ++n;
+    }
+    ++k;
+  }
+  return n;
+}
+
 }  // extern "C"

@@ -22,7 +22,7 @@ PATH_AUTO, PATH_FAST, PATH_EXACT = -1, 0, 1
 FLAG_NO_D2H = 1
 
 EXPORTS = ["frc_abi_version", "frc_ctx_create", "frc_ctx_destroy", "frc_create", "frc_next",
-           "frc_restart", "frc_job_info", "frc_destroy", "frc_last_error"]
+           "frc_restart", "frc_job_info", "frc_destroy", "frc_last_error", "frc_plan_bands"]
 
 
 class FrcError(RuntimeError):
@@ -100,6 +100,8 @@ def lib():
         L.frc_destroy.restype = None
         L.frc_last_error.argtypes = [C.c_void_p]
         L.frc_last_error.restype = C.c_char_p
+        L.frc_plan_bands.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+        L.frc_plan_bands.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -206,6 +208,17 @@ class Job:
             self.close()
         except Exception:
             pass
+
+
+def plan_bands(n_samples: int, rank: int = 0, world: int = 1, band_rows: int = 0):
+    """(first_index, count) of the bands `rank` yields, in stream order (host-only helper)."""
+    n = lib().frc_plan_bands(n_samples, band_rows, rank, world, None, None, 0)
+    if n < 0:
+        raise FrcError(-n, "bad band plan arguments")
+    first = np.zeros(n, np.int64)
+    count = np.zeros(n, np.int64)
+    lib().frc_plan_bands(n_samples, band_rows, rank, world, first.ctypes.data, count.ctypes.data, n)
+    return first, count
 
 
 def unifrac(parent, length, row_ptr, col, val, weighted: bool, normalize: bool = True, **kw) -> np.ndarray:

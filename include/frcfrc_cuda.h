@@ -139,6 +139,15 @@ int frc_restart(frc_job_t *job);
 
 int frc_job_info(const frc_job_t *job, frc_info_t *info);
 
+/* Pure host helper (no device needed): the band decomposition frc_create uses.
+ * Writes, for the bands that `rank` of `world` yields (all bands when world
+ * <= 1), the flat index of their first pair and their pair count, in stream
+ * order; returns the number of such bands (also when it exceeds `cap`), or a
+ * negative frc_status.  Lets a multi-process host merge the per-rank streams
+ * back into IterPairs order. */
+int64_t frc_plan_bands(int64_t n_samples, int64_t band_rows, int32_t rank, int32_t world,
+                       int64_t *first_index, int64_t *count, int64_t cap);
+
 /* Legal at any time, also mid-stream (the consumer's `break`, frcfrc.go:59-61). */
 void frc_destroy(frc_job_t *job);
 

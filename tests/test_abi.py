@@ -1,0 +1,89 @@
+"""The C-ABI library loads, exports what include/frcfrc_cuda.h declares, and its structs match
+the Python binding (CPU; no compute calls)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "frcfrc_cuda.h")
+
+
+def test_exports_every_declared_symbol(built):
+    from frackyfrac_b200 import engine
+
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(frc_[a-z_]+)\s*\(", src)))
+    assert set(declared) == set(engine.EXPORTS)
+    L = engine.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.frc_abi_version() == 1
+
+
+def test_struct_layout_matches_binding(built, tmp_path):
+    from frackyfrac_b200 import engine
+
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "frcfrc_cuda.h"\n'
+                    'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(frc_tree_t), sizeof(frc_csr_t), sizeof(frc_opts_t),'
+                    ' sizeof(frc_info_t), offsetof(frc_opts_t, band_rows), offsetof(frc_info_t, flagged_pairs));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    got = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()))
+    want = [C.sizeof(engine._Tree), C.sizeof(engine._Csr), C.sizeof(engine._Opts), C.sizeof(engine._Info),
+            engine._Opts.band_rows.offset, engine._Info.flagged_pairs.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback(built):
+    """Without an sm_100 device the product path must fail loudly, never compute."""
+    import torch
+
+    from frackyfrac_b200 import engine
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the loud-failure path is exercised on the CPU box")
+    with pytest.raises(engine.FrcError):
+        engine.Context(0)
+    with pytest.raises(engine.FrcError):
+        engine.unifrac(np.array([-1, 0, 0], np.int32), np.array([0, 1, 1.0]), np.array([0, 1, 2], np.int64),
+                       np.array([1, 2], np.int32), np.array([1.0, 1.0]), False)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under frackyfrac_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "frackyfrac_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath or "__pycache__" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+
+
+def test_band_plan_covers_the_triangle(built):
+    from frackyfrac_b200 import engine
+
+    for n in (0, 1, 2, 127, 128, 129, 1000, 5000, 14142):
+        total = n * (n - 1) // 2 if n >= 2 else 0
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                f, c = engine.plan_bands(n, r, world)
+                assert (np.diff(f) > 0).all()
+                seen += list(zip(f.tolist(), c.tolist()))
+            seen.sort()
+            pos = 0
+            for f, c in seen:
+                assert f == pos and c > 0
+                pos += c
+            assert pos == total
+    # boustrophedon dealing keeps per-rank pair counts within one band of each other
+    per = [engine.plan_bands(14142, r, 8)[1].sum() for r in range(8)]
+    assert max(per) - min(per) <= engine.plan_bands(14142, 0, 1)[1].max()

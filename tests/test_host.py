@@ -1,0 +1,100 @@
+"""The C++ host side above the C ABI against the oracle's independent readers (CPU)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import kat
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_newick_flattening_matches_oracle(built):
+    from frackyfrac_b200 import hostlib, synth
+    from oracle import oracle as orc
+
+    texts = ["(s2:3,s1:1,s3:5);", "((s1:1,s2:3):2,(s3:2,s4:5):1);", " ( a : 1.5 ,\n(b:2e-3,c)x:4 [comment] )root:0.25 ;",
+             "('it''s':1,b:2);", "((a,b),(c,(d,e)));", "x;"]
+    for shape in ("random", "caterpillar", "balanced"):
+        texts.append(synth.to_newick(synth.random_tree(257, 9, shape=shape)))
+    for txt in texts:
+        h = hostlib.Tree(txt)
+        p, l = orc.Tree.parse(txt).flatten()
+        assert np.array_equal(h.parent, p) and np.array_equal(h.length, l), txt[:40]
+        assert h.parent[0] == -1 and (h.parent[1:] < np.arange(1, len(p))).all()
+    assert hostlib.Tree("('it''s':1,b:2);").names()[1] == "it's"
+    for bad in ["(a,b)", "(a,b));", "((a,b);", "(a:x,b);", ""]:
+        with pytest.raises(hostlib.HostError):
+            hostlib.Tree(bad)
+        with pytest.raises(orc.OracleError):
+            orc.Tree.parse(bad)
+
+
+def test_table_readers_match_reference_tests_and_oracle(built):
+    from frackyfrac_b200 import hostlib
+    from oracle import oracle as orc
+
+    dense = "   aa  bbbb    \n1\t2\n 3  \t  4 \t\n"            # parser_test.go:10
+    sparse = "a:11 b:222  \n  b:32 c:7\n\nd:1\tc:4\ta:10\n"    # parser_test.go:29
+    assert hostlib.Table(dense, False).maps() == [{"aa": 1, "bbbb": 2}, {"aa": 3, "bbbb": 4}]
+    assert hostlib.Table(sparse, True).maps() == [{"a": 11, "b": 222}, {"b": 32, "c": 7}, {}, {"d": 1, "c": 4, "a": 10}]
+    rng = np.random.default_rng(3)
+    names = [f"sp{k}" for k in range(30)] + ["w:x", "dup", "dup"]
+    for _ in range(20):
+        rows = []
+        for _ in range(rng.integers(1, 6)):
+            rows.append(" ".join(f"{names[k]}:{rng.integers(1, 99)}" for k in rng.integers(0, len(names), rng.integers(0, 9))))
+        txt = "\n".join(rows) + "\n"
+        assert hostlib.Table(txt, True).maps() == orc.Table.parse(txt, True).maps()
+        hdr = " ".join(names[:6] + ["dup", "dup"])
+        body = "\n".join(" ".join(str(rng.integers(0, 4)) for _ in range(8)) for _ in range(4))
+        txt = hdr + "\n" + body + "\r\n"
+        assert hostlib.Table(txt, False).maps() == orc.Table.parse(txt, False).maps()
+    for bad, sp in [("a\n", True), (":\n", True), ("a:0\n", True), ("a:-1\n", True), ("a:nan\n", True),
+                    ("\n1 2\n", False), ("a b\n1\n", False), ("a b\n1 -2\n", False), ("a b\n\n", False)]:
+        with pytest.raises(hostlib.HostError):
+            hostlib.Table(bad, sp)
+
+
+def test_resolve_semantics(built):
+    """Names -> leaf ids: every leaf with the name (A6), internal-only names dropped (A2),
+    unknown names are the reference's validation error (unifrac.go:85-88)."""
+    from frackyfrac_b200 import hostlib
+
+    tree = hostlib.Tree("((x:1,y:1)in:1,(x:1,z:1):1);")
+    rp, col, val = hostlib.Table("x:3 in:9\nz:2\n\n", True).resolve(tree)
+    assert rp.tolist() == [0, 2, 3, 3] and col.tolist() == [2, 5, 6] and val.tolist() == [3, 3, 2]
+    with pytest.raises(hostlib.HostError, match=r'sample #2 has value 0.5 for species "nope" which is not in the tree'):
+        hostlib.Table("x:1\nnope:0.5\n", True).resolve(tree)
+
+
+def test_go_format_matches_oracle(built):
+    from frackyfrac_b200 import hostlib
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(11)
+    vals = np.concatenate([rng.random(3000), rng.random(1000) * 10.0 ** rng.integers(-12, 3, 1000),
+                           [0.0, 1.0, np.nan, 1e-5, 1e-4, 2 / 3, 22 / 36, 0.1 + 0.2]])
+    for v in vals:
+        assert hostlib.format_go(float(v)) == orc.format_go(float(v))
+
+
+def test_cli_flag_rules(built):
+    """frcfrc.go:70-88 and common.go:13-18: usage exit 0 without args; ERROR: ... exit 2."""
+    from frackyfrac_b200 import hostlib
+
+    r = subprocess.run([hostlib.CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "" and r.stderr.startswith("FrackyFrac calculates UniFrac")
+    assert "  -t string\n    \tPath to tree file, required\n" in r.stderr
+    for args, msg in [(["-w"], "ERROR: please provide a tree file with -t\n"),
+                      (["-t", "x", "-p", "0"], "ERROR: bad number of threads: 0\n"),
+                      (["-t", "x", "-l"], "ERROR: -l can only be used with weighted unifrac\n")]:
+        r = subprocess.run([hostlib.CLI_PATH] + args, capture_output=True, text=True)
+        assert r.returncode == 2 and r.stderr == msg and r.stdout == ""
+    r = subprocess.run([hostlib.CLI_PATH, "-q"], capture_output=True, text=True)
+    assert r.returncode == 2 and r.stderr.startswith("flag provided but not defined: -q\n")
+    # validation errors surface as the reference's message with exit status 2, before any device work
+    tree = os.path.join(GOLDEN, "wtd.tree")
+    r = subprocess.run([hostlib.CLI_PATH, "-t", tree, "-s"], input="nope:1\n", capture_output=True, text=True)
+    assert r.returncode == 2 and 'species "nope" which is not in the tree' in r.stderr
