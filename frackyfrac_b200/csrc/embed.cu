@@ -184,6 +184,118 @@ k_expand_operands(const uint32_t* __restrict__ bits, int32_t n_nodes, int32_t nw
   }
 }
 
+
+// ------------------------------------------------- fused presence embedding
+// One launch for the whole unweighted embedding stage.  Samples are
+// independent, so a CTA that owns one word column (32 samples) can run the
+// entire bottom-up pass for them with block-level barriers only: its column of
+// the presence matrix (one 32-bit word per node) lives in shared memory (or in
+// a private global scratch column when the tree is too large for that).
+//   phase 1  scatter the 32 CSR rows into leaf words (shared-memory atomics)
+//   phase 2  per tree level: word(v) = OR of the children's words
+//   phase 3  r[s] = sum_v lenq[v] * present(v, s), fp64, fixed summation order
+//   phase 4  write the three K-major bf16 operand rows of the 32 samples
+//            (P, P*len_hi, P*len_lo): 16-byte stores, a warp covers 512
+//            contiguous bytes of one row — this phase is the HBM-bound part.
+template <bool kSmem>
+__global__ void __launch_bounds__(512)
+k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                       int64_t n_samples, const int32_t* __restrict__ level_nodes,
+                       const int32_t* __restrict__ level_ptr, int32_t height,
+                       const int32_t* __restrict__ child_ptr, const int32_t* __restrict__ child_idx,
+                       int32_t n_nodes, int32_t kp, const double* __restrict__ lenq,
+                       const uint16_t* __restrict__ len_hi, const uint16_t* __restrict__ len_lo,
+                       uint32_t* __restrict__ scratch, double* __restrict__ r, uint16_t* __restrict__ P,
+                       uint16_t* __restrict__ Bh, uint16_t* __restrict__ Bl) {
+  extern __shared__ __align__(16) uint32_t smem_words[];
+  __shared__ double part[16][32];
+  const int w = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // column storage padded to a multiple of 8 words so phase 4 can read groups of 8
+  uint32_t* colw = kSmem ? smem_words : scratch + static_cast<int64_t>(w) * kp;
+
+  for (int32_t v = tid; v < kp; v += 512) colw[v] = 0u;
+  __syncthreads();
+  // phase 1
+  for (int sl = warp; sl < 32; sl += 16) {
+    const int64_t s = static_cast<int64_t>(w) * 32 + sl;
+    if (s < n_samples) {
+      const int64_t b = row_ptr[s], e = row_ptr[s + 1];
+      for (int64_t k = b + lane; k < e; k += 32) atomicOr(colw + col[k], 1u << sl);
+    }
+  }
+  __syncthreads();
+  // phase 2
+  for (int32_t h = 1; h <= height; ++h) {
+    const int32_t b = level_ptr[h], e = level_ptr[h + 1];
+    for (int32_t idx = b + tid; idx < e; idx += 512) {
+      const int32_t v = level_nodes[idx];
+      uint32_t acc = 0;
+      for (int32_t c = child_ptr[v]; c < child_ptr[v + 1]; ++c) acc |= colw[child_idx[c]];
+      colw[v] = acc;
+    }
+    __syncthreads();
+  }
+  // phase 3
+  {
+    const int32_t per = (n_nodes + 15) / 16;
+    const int32_t v0 = warp * per, v1 = min(n_nodes, v0 + per);
+    double acc = 0.0;
+    for (int32_t v = v0; v < v1; ++v)
+      if ((colw[v] >> lane) & 1u) acc += lenq[v];
+    part[warp][lane] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += part[k][lane];
+    r[static_cast<int64_t>(w) * 32 + lane] = acc;
+  }
+  // phase 4
+  for (int32_t g = tid; g * 8 < kp; g += 512) {
+    const uint4 wa = *reinterpret_cast<const uint4*>(colw + g * 8);
+    const uint4 wb = *reinterpret_cast<const uint4*>(colw + g * 8 + 4);
+    const uint32_t wd[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    uint32_t hi[8], lo[8];
+    if (g * 8 + 8 <= n_nodes) {
+      const uint4 h4 = *reinterpret_cast<const uint4*>(len_hi + g * 8);
+      const uint4 l4 = *reinterpret_cast<const uint4*>(len_lo + g * 8);
+      const uint32_t hh[4] = {h4.x, h4.y, h4.z, h4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        hi[2 * q] = hh[q] & 0xFFFFu; hi[2 * q + 1] = hh[q] >> 16;
+        lo[2 * q] = ll[q] & 0xFFFFu; lo[2 * q + 1] = ll[q] >> 16;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int32_t v = g * 8 + q;
+        hi[q] = v < n_nodes ? len_hi[v] : 0u;
+        lo[q] = v < n_nodes ? len_lo[v] : 0u;
+      }
+    }
+    const int64_t base = static_cast<int64_t>(w) * 32 * kp + static_cast<int64_t>(g) * 8;
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+      uint32_t m[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) m[q] = 0u - ((wd[q] >> it) & 1u);
+      uint4 p4, h4, l4;
+      p4.x = (0x3F80u & m[0]) | ((0x3F80u & m[1]) << 16); p4.y = (0x3F80u & m[2]) | ((0x3F80u & m[3]) << 16);
+      p4.z = (0x3F80u & m[4]) | ((0x3F80u & m[5]) << 16); p4.w = (0x3F80u & m[6]) | ((0x3F80u & m[7]) << 16);
+      h4.x = (hi[0] & m[0]) | ((hi[1] & m[1]) << 16); h4.y = (hi[2] & m[2]) | ((hi[3] & m[3]) << 16);
+      h4.z = (hi[4] & m[4]) | ((hi[5] & m[5]) << 16); h4.w = (hi[6] & m[6]) | ((hi[7] & m[7]) << 16);
+      l4.x = (lo[0] & m[0]) | ((lo[1] & m[1]) << 16); l4.y = (lo[2] & m[2]) | ((lo[3] & m[3]) << 16);
+      l4.z = (lo[4] & m[4]) | ((lo[5] & m[5]) << 16); l4.w = (lo[6] & m[6]) | ((lo[7] & m[7]) << 16);
+      const int64_t o = base + static_cast<int64_t>(it) * kp;
+      __stcs(reinterpret_cast<uint4*>(P + o), p4);
+      __stcs(reinterpret_cast<uint4*>(Bh + o), h4);
+      __stcs(reinterpret_cast<uint4*>(Bl + o), l4);
+    }
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ launchers
@@ -281,6 +393,33 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
                            uint16_t* Bl, cudaStream_t s) {
   dim3 grid(kp / 64, static_cast<unsigned>((np + 255) / 256));
   k_expand_operands<<<grid, 256, 0, s>>>(bits, n_nodes, nw, kp, np, len_hi, len_lo, P, Bh, Bl);
+  return 1;
+}
+
+
+int64_t presence_fused_scratch_words(int32_t kp, int32_t nw) {
+  return static_cast<int64_t>(kp) * 4 <= 200 * 1024 ? 0 : static_cast<int64_t>(kp) * nw;
+}
+
+int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
+                                int32_t nw, int32_t kp, const double* lenq, const uint16_t* len_hi,
+                                const uint16_t* len_lo, uint32_t* scratch, double* r, uint16_t* P,
+                                uint16_t* Bh, uint16_t* Bl, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(kp) * 4;
+  if (smem <= 200 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(k_embed_presence_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr = true;
+    }
+    k_embed_presence_fused<true><<<nw, 512, smem, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
+                                                       level_ptr_dev, t.height, t.child_ptr, t.child_idx,
+                                                       t.n_nodes, kp, lenq, len_hi, len_lo, nullptr, r, P, Bh, Bl);
+  } else {
+    k_embed_presence_fused<false><<<nw, 512, 0, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
+                                                     level_ptr_dev, t.height, t.child_ptr, t.child_idx,
+                                                     t.n_nodes, kp, lenq, len_hi, len_lo, scratch, r, P, Bh, Bl);
+  }
   return 1;
 }
 

@@ -69,6 +69,16 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
                            int64_t np, const uint16_t* len_hi, const uint16_t* len_lo,
                            uint16_t* P, uint16_t* Bh, uint16_t* Bl, cudaStream_t s);
 
+// The whole unweighted embedding stage in one launch (scatter, level passes, row
+// sums, operand expansion); one CTA per 32 samples.  `scratch` holds the
+// per-CTA presence column when it does not fit shared memory
+// (presence_fused_scratch_words(kp, nw) words, 0 when shared memory is used).
+int64_t presence_fused_scratch_words(int32_t kp, int32_t nw);
+int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
+                                int32_t nw, int32_t kp, const double* lenq, const uint16_t* len_hi,
+                                const uint16_t* len_lo, uint32_t* scratch, double* r, uint16_t* P,
+                                uint16_t* Bh, uint16_t* Bl, cudaStream_t s);
+
 // ---- exact.cu ---------------------------------------------------------------
 // fp64 reference-order distances for pairs [first, first+count) of the triangle.
 int launch_exact_pairs(const double* E, const double* length, int32_t n_nodes, int64_t ld,

@@ -7,12 +7,22 @@
 // its own pinned D2H copy, and are handed to the caller strictly in flat-index
 // order by frc_next (the ordered iter.Seq of unifrac.go:209-228).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "../../include/frcfrc_cuda.h"
 #include "frc_internal.h"
@@ -70,6 +80,61 @@ float bf16_to_float(uint16_t h) {
   return f;
 }
 
+// Small persistent worker pool (host-side validation / staging copies): waking
+// parked threads costs microseconds, spawning them per job cost ~0.5 ms.
+class Pool {
+ public:
+  explicit Pool(int n) {
+    for (int t = 0; t < n; ++t) workers_.emplace_back([this, t] { loop(t + 1); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> g(m_); stop_ = true; ++epoch_; }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  int size() const { return static_cast<int>(workers_.size()) + 1; }
+  // Runs fn(t) for t in [0, T) on T <= size() threads (t = 0 on the caller).
+  void run(int T, const std::function<void(int)>& fn) {
+    if (T <= 1) { fn(0); return; }
+    {
+      std::lock_guard<std::mutex> g(m_);
+      fn_ = &fn; active_ = T; pending_ = T - 1; ++epoch_;
+    }
+    cv_.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn = nullptr;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+        if (id < active_) fn = fn_;
+      }
+      if (fn) {
+        (*fn)(id);
+        std::lock_guard<std::mutex> g(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int active_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
 constexpr int kSlots = 3;
 constexpr double kFlagBelow = 0.125;            // fast unweighted: recompute d below this exactly
 constexpr int64_t kExactWorkLimit = 1LL << 28;  // AUTO: pairs * nodes at or below this -> exact
@@ -81,6 +146,9 @@ struct frc_ctx {
   int num_sms = 0;
   cudaStream_t stream[2] = {nullptr, nullptr};
   Arena dev, pin;
+  std::unique_ptr<Pool> pool;
+  std::vector<std::vector<int64_t>> stamps;  // per-worker duplicate-detection scratch
+  int64_t stamp_epoch = 0;
   bool in_use = false;
 };
 
@@ -118,6 +186,9 @@ struct frc_job {
   char* d_inputs = nullptr;
   size_t input_bytes = 0;
   Tile* d_tiles = nullptr;
+  int32_t* d_level_ptr = nullptr;
+  bool fused_embed = true;
+  bool zero_copy = false;
   uint16_t *d_len_hi = nullptr, *d_len_lo = nullptr;
   double* d_lenq = nullptr;
   float* d_lenf = nullptr;
@@ -212,10 +283,16 @@ int run_embedding(frc_job* j) {
     // write each element once, read it once when folded into its parent (+ CSR)
     j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
   } else {
-    launches += launch_embed_bits(j->dtree, j->level_ptr.data(), j->dcsr, j->d_bits, j->nw, s);
-    launches += launch_presence_rowsum(j->d_bits, j->B, j->nw, j->d_lenq, j->d_r, j->d_scratch, s);
-    launches += launch_expand_operands(j->d_bits, j->B, j->nw, j->kp, j->np, j->d_len_hi, j->d_len_lo,
-                                       j->d_P, j->d_Bh, j->d_Bl, s);
+    if (j->fused_embed) {
+      launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->kp, j->d_lenq,
+                                              j->d_len_hi, j->d_len_lo, j->d_bits, j->d_r, j->d_P, j->d_Bh,
+                                              j->d_Bl, s);
+    } else {
+      launches += launch_embed_bits(j->dtree, j->level_ptr.data(), j->dcsr, j->d_bits, j->nw, s);
+      launches += launch_presence_rowsum(j->d_bits, j->B, j->nw, j->d_lenq, j->d_r, j->d_scratch, s);
+      launches += launch_expand_operands(j->d_bits, j->B, j->nw, j->kp, j->np, j->d_len_hi, j->d_len_lo,
+                                         j->d_P, j->d_Bh, j->d_Bl, s);
+    }
     // bits written + read once per level pass, three bf16 operands written once (+ CSR cols)
     j->info.embed_bytes = 2LL * j->B * j->nw * 4 + 3LL * j->np * j->kp * 2 + 4LL * j->nnz;
   }
@@ -256,7 +333,8 @@ int enqueue_band(frc_job* j, size_t idx) {
   if (j->exact || j->weighted) JOB_CUDA(j, cudaEventRecord(sl.k1, s));
   JOB_CUDA(j, cudaEventRecord(sl.k2, s));
   if (!(j->opts.flags & FRC_FLAG_NO_D2H)) {
-    JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, s));
+    if (sl.dev != sl.host)
+      JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, s));
     j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
   }
   JOB_CUDA(j, cudaEventRecord(sl.done, s));
@@ -356,6 +434,13 @@ int frc_ctx_create(int32_t device, frc_ctx_t** out) {
   c->num_sms = prop.multiProcessorCount;
   c->dev.pinned = false; c->dev.min_block = 64u << 20;
   c->pin.pinned = true;  c->pin.min_block = 8u << 20;
+  {
+    int hw = static_cast<int>(std::thread::hardware_concurrency());
+    int n = std::max(1, std::min(8, hw)) - 1;
+    if (const char* e = getenv("FRC_HOST_THREADS")) n = std::max(1, atoi(e)) - 1;
+    c->pool.reset(new Pool(n));
+    c->stamps.resize(n + 1);
+  }
   for (auto& s : c->stream)
     if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) {
       g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
@@ -377,6 +462,7 @@ int frc_ctx_create(int32_t device, frc_ctx_t** out) {
 void frc_ctx_destroy(frc_ctx_t* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  c->pool.reset();
   for (auto s : c->stream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
   c->dev.release();
   c->pin.release();
@@ -392,6 +478,14 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   if (!tree || !abnd || !opts) { g_create_error = "frc_create: NULL argument"; return FRC_ERR_ARG; }
   frc_job* j = new frc_job();
   auto bail = [&](int rc) { g_create_error = j->err; destroy_job(j); return rc; };
+  const bool trace = getenv("FRC_TRACE") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[frc_create] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - tp0).count());
+    tp0 = now;
+  };
 #define CREATE_CUDA(expr)                                                                    \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
@@ -442,6 +536,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   for (int32_t v = B - 1; v >= 1; --v) height[tree->parent[v]] = std::max(height[tree->parent[v]], height[v] + 1);
   const int32_t H = height[0];
 
+  mark("validate tree");
   // ------------------------------------------------------------ validate table
   const int64_t N = abnd->n_samples;
   if (N < 0 || (N > 0 && !abnd->row_ptr)) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
@@ -449,22 +544,10 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   const int64_t nnz = N > 0 ? abnd->row_ptr[N] : 0;
   if (N > 0 && abnd->row_ptr[0] != 0) return bail(fail(j, FRC_ERR_ARG, "row_ptr[0] != 0"));
   if (nnz < 0 || (nnz > 0 && (!abnd->col || !abnd->val))) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
-  {
-    std::vector<int64_t> stamp(B, 0);
-    for (int64_t s = 0; s < N; ++s) {
-      int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
-      if (e < b || e > nnz) return bail(fail(j, FRC_ERR_ARG, "row_ptr is not monotone"));
-      for (int64_t k = b; k < e; ++k) {
-        int32_t c = abnd->col[k];
-        double v = abnd->val[k];
-        if (c < 0 || c >= B) return bail(fail(j, FRC_ERR_ARG, "sample #" + std::to_string(s + 1) + ": node id out of range"));
-        if (child_cnt[c] != 0) return bail(fail(j, FRC_ERR_ARG, "sample #" + std::to_string(s + 1) + ": node " + std::to_string(c) + " is not a leaf"));
-        if (!(v > 0) || std::isinf(v)) return bail(fail(j, FRC_ERR_ARG, "sample #" + std::to_string(s + 1) + ": bad value"));
-        if (stamp[c] == s + 1) return bail(fail(j, FRC_ERR_ARG, "sample #" + std::to_string(s + 1) + ": leaf " + std::to_string(c) + " listed twice"));
-        stamp[c] = s + 1;
-      }
-    }
-  }
+  for (int64_t s = 0; s < N; ++s)
+    if (abnd->row_ptr[s + 1] < abnd->row_ptr[s] || abnd->row_ptr[s + 1] > nnz)
+      return bail(fail(j, FRC_ERR_ARG, "row_ptr is not monotone"));
+  // (entries are validated while they are copied into the pinned staging buffer, below)
 
   // --------------------------------------------------------------- choose path
   j->N = N; j->B = B; j->nnz = nnz;
@@ -515,6 +598,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       b.n_tiles = static_cast<int32_t>(j->tiles.size()) - b.tile_off;
     }
 
+  mark("row_ptr check + bands/tiles");
   // -------------------------------------------------------------------- context
   int rc = FRC_OK;
   if (ctx) {
@@ -529,6 +613,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   c->in_use = true;
   CREATE_CUDA(cudaSetDevice(c->device));
 
+  mark("context");
   // ------------------------------------------------- pack + upload the inputs
   const bool need_val = j->exact || j->weighted;
   struct Seg { size_t off, bytes; };
@@ -539,7 +624,8 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       s_len = seg(sizeof(double) * B), s_cptr = seg(sizeof(int32_t) * (B + 1)),
       s_cidx = seg(sizeof(int32_t) * B), s_lvl = seg(sizeof(int32_t) * B),
       s_hi = seg(sizeof(uint16_t) * B), s_lo = seg(sizeof(uint16_t) * B), s_lenq = seg(sizeof(double) * B),
-      s_lenf = seg(sizeof(float) * j->kp), s_tiles = seg(sizeof(Tile) * j->tiles.size());
+      s_lenf = seg(sizeof(float) * j->kp), s_tiles = seg(sizeof(Tile) * j->tiles.size()),
+      s_lptr = seg(sizeof(int32_t) * (H + 2));
   char* stage = pin_alloc<char>(j, total, &rc);
   if (!stage) return bail(rc);
   j->d_inputs = dev_alloc<char>(j, total, &rc);
@@ -548,8 +634,60 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   {
     int64_t* rp = reinterpret_cast<int64_t*>(stage + s_rowptr.off);
     if (N > 0) memcpy(rp, abnd->row_ptr, sizeof(int64_t) * (N + 1)); else rp[0] = 0;
-    if (nnz) memcpy(stage + s_col.off, abnd->col, sizeof(int32_t) * nnz);
-    if (nnz && need_val) memcpy(stage + s_val.off, abnd->val, sizeof(double) * nnz);
+    mark("staging alloc + row_ptr copy");
+    // validate + copy the CSR entries in one pass, samples split over host threads
+    {
+      int32_t* dcol = reinterpret_cast<int32_t*>(stage + s_col.off);
+      double* dval = need_val ? reinterpret_cast<double*>(stage + s_val.off) : nullptr;
+      const int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->pool->size(), nnz / 32768)));
+      std::vector<std::string> errs(T);
+      // duplicate detection: stamp[leaf] = epoch-tagged sample id; the arrays persist in the
+      // context, so nothing is cleared between jobs
+      const int64_t tag = c->stamp_epoch;
+      c->stamp_epoch += N + 1;
+      std::function<void(int)> work = [&](int t) {
+        auto row_at = [&](int64_t target) {
+          return static_cast<int64_t>(std::lower_bound(abnd->row_ptr, abnd->row_ptr + N, target) - abnd->row_ptr);
+        };
+        const int64_t s0 = t == 0 ? 0 : row_at(nnz * t / T), s1 = t == T - 1 ? N : row_at(nnz * (t + 1) / T);
+        std::vector<int64_t>& stamp = c->stamps[t];
+        if (static_cast<int32_t>(stamp.size()) < B) stamp.assign(B, -1);
+        for (int64_t s = s0; s < s1; ++s) {
+          const int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
+          const int64_t mark_s = tag + s;
+          for (int64_t k = b; k < e; ++k) {
+            const int32_t cc = abnd->col[k];
+            const double v = abnd->val[k];
+            const char* what = nullptr;
+            if (cc < 0 || cc >= B) what = "node id out of range";
+            else if (child_cnt[cc] != 0) what = "node is not a leaf";
+            else if (!(v > 0) || std::isinf(v)) what = "bad value";
+            else if (stamp[cc] == mark_s) what = "leaf listed twice";
+            if (what) {
+              errs[t] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
+                        std::to_string(cc) + "): " + what;
+              return;
+            }
+            stamp[cc] = mark_s;
+#if defined(__x86_64__)
+            // streaming stores: the staging buffer is read next by the DMA engine, not by a core
+            _mm_stream_si32(dcol + k, cc);
+            if (dval) _mm_stream_si64(reinterpret_cast<long long*>(dval + k), static_cast<long long>(__builtin_bit_cast(int64_t, v)));
+#else
+            dcol[k] = cc;
+            if (dval) dval[k] = v;
+#endif
+          }
+        }
+#if defined(__x86_64__)
+        _mm_sfence();
+#endif
+      };
+      c->pool->run(T, work);
+      for (auto& e : errs)
+        if (!e.empty()) return bail(fail(j, FRC_ERR_ARG, e));
+    }
+    mark("validate+copy CSR entries");
     memcpy(stage + s_parent.off, tree->parent, sizeof(int32_t) * B);
     memcpy(stage + s_len.off, tree->length, sizeof(double) * B);
     int32_t* cptr = reinterpret_cast<int32_t*>(stage + s_cptr.off);
@@ -578,7 +716,9 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     }
     for (int32_t v = B; v < j->kp; ++v) lf[v] = 0.f;
     if (!j->tiles.empty()) memcpy(stage + s_tiles.off, j->tiles.data(), sizeof(Tile) * j->tiles.size());
+    memcpy(stage + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
   }
+  mark("tree arrays, hi/lo, tiles");
   CREATE_CUDA(cudaEventCreate(&j->ev_h2d0));
   CREATE_CUDA(cudaEventCreate(&j->ev_h2d1));
   CREATE_CUDA(cudaEventCreate(&j->ev_embed0));
@@ -605,7 +745,9 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->d_lenq = reinterpret_cast<double*>(d + s_lenq.off);
   j->d_lenf = reinterpret_cast<float*>(d + s_lenf.off);
   j->d_tiles = reinterpret_cast<Tile*>(d + s_tiles.off);
+  j->d_level_ptr = reinterpret_cast<int32_t*>(d + s_lptr.off);
 
+  mark("events + H2D enqueue");
   // ------------------------------------------------------------ device buffers
   const int chunks = weighted_scratch_chunks(B);
   if (j->exact || j->weighted) {
@@ -617,7 +759,13 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
     }
   } else {
-    if (!(j->d_bits = dev_alloc<uint32_t>(j, static_cast<size_t>(B) * j->nw, &rc))) return bail(rc);
+    {
+      const char* e = getenv("FRC_EMBED_LEVELS");  // 1 = the multi-launch level-synchronous path
+      j->fused_embed = !(e && atoi(e) == 1);
+      size_t words = j->fused_embed ? static_cast<size_t>(presence_fused_scratch_words(j->kp, j->nw))
+                                    : static_cast<size_t>(B) * j->nw;
+      if (!(j->d_bits = dev_alloc<uint32_t>(j, std::max<size_t>(words, 64), &rc))) return bail(rc);
+    }
     const size_t opsz = static_cast<size_t>(j->np) * j->kp;
     if (!(j->d_P = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
     if (!(j->d_Bh = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
@@ -628,12 +776,14 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, &terr);
     if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
   }
+  { const char* e = getenv("FRC_ZERO_COPY"); j->zero_copy = e && atoi(e) == 1; }
   j->n_slots = static_cast<int>(std::min<size_t>(kSlots, std::max<size_t>(2, j->mine.size() + 1)));
   if (j->mine.empty()) j->n_slots = 0;
   for (int k = 0; k < j->n_slots; ++k) {
     Slot& sl = j->slots[k];
-    if (!(sl.dev = dev_alloc<double>(j, max_band, &rc))) return bail(rc);
     if (!(opts->flags & FRC_FLAG_NO_D2H) && !(sl.host = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
+    if (j->zero_copy && sl.host) sl.dev = sl.host;  // kernels store straight into pinned host memory (UVA)
+    else if (!(sl.dev = dev_alloc<double>(j, max_band, &rc))) return bail(rc);
     if (!j->exact && !j->weighted) {
       if (!(sl.flagged = dev_alloc<uint32_t>(j, max_band, &rc))) return bail(rc);
       if (!(sl.n_flagged = dev_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
@@ -647,9 +797,11 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       return bail(fail(j, FRC_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e)));
   }
 
+  mark("device buffers, tensor maps, slots");
   // ----------------------------------------------------------------- go
   if ((rc = run_embedding(j)) != FRC_OK) return bail(rc);
   if ((rc = start_pairs(j)) != FRC_OK) return bail(rc);
+  mark("enqueue embedding + first bands");
   *out = j;
   return FRC_OK;
 #undef CREATE_CUDA

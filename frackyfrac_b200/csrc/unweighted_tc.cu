@@ -16,19 +16,27 @@
 // recomputed in fp64 from the presence rows by k_unweighted_fixup.
 //
 // Kernel structure (one CTA per SM, persistent over a tile list):
-//   warp 0     TMA producer: per 64-node block loads A = P[i-tile],
-//              Bh = (P*hi)[j-tile], Bl = (P*lo)[j-tile] (128-byte swizzle) into a
-//              4-stage ring, mbarrier complete_tx.
-//   warp 1     allocates TMEM, issues tcgen05.mma (M128 N128 K16, bf16 -> fp32):
-//              8 MMAs per stage (4 k-steps x 2 planes sharing A), tcgen05.commit
-//              frees the stage; one commit per K-chunk publishes the accumulator.
-//   warps 2-5  epilogue: tcgen05.ld the fp32 partial accumulator of each
-//              K-chunk into registers and add (two-level accumulation bounds the
-//              fp32 error over contractions of 10^5..10^6 terms), then the
-//              fused ratio epilogue in fp64 and direct stores into the flat
-//              lower-triangle band buffer.
-// Two TMEM accumulators (2 x 128 columns) let the MMAs of chunk c+1 overlap the
-// drain of chunk c, and the next tile's mainloop overlap this tile's epilogue.
+//   warp 0     TMA producer: per 64-node block loads A = P[i-tile] and, stacked
+//              right behind each other, Bh = (P*hi)[j-tile] and Bl = (P*lo)[j-tile]
+//              (128-byte swizzle) into a 4-stage ring, mbarrier complete_tx.
+//   warp 1     allocates TMEM and issues tcgen05.mma M128 N256 K16 (bf16 -> fp32):
+//              the stacked [Bh; Bl] is ONE 256-row B operand, so A is read from
+//              shared memory once per k-step and the accumulator holds the hi-plane
+//              sums in columns [0,128) and the lo-plane sums in [128,256).
+//              tcgen05.commit frees the stage; one commit per K-chunk publishes
+//              the accumulator buffer.
+//   warps 2-9  epilogue (8 warps = 4 TMEM lane quarters x 2 column halves):
+//              tcgen05.ld the partial sums of each K-chunk and add them into fp32
+//              registers, then the fused ratio epilogue in fp64 and direct stores
+//              into the flat lower-triangle band buffer.
+// Why two accumulator halves and K-chunks: the tensor core's fp32 accumulate
+// loses the addend bits below the accumulator's ulp (measured: a bias, not
+// noise).  hi-plane addends are 8-bit significands, so they add EXACTLY while the
+// running sum stays within 2^16 of them; keeping the 2^-9-smaller lo plane out of
+// that sum and restarting it every K-chunk keeps it so.  The chunk sums are then
+// added in registers with round-to-nearest.
+// Two TMEM buffers (2 x 256 columns = all of TMEM) let the MMAs of chunk c+1
+// overlap the drain of chunk c, and the next tile's mainloop this tile's epilogue.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -49,8 +57,11 @@ constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
 constexpr int NUM_BARS = 2 * STAGES + 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_BARS * 8 + 16 + 1024;
-constexpr int THREADS = 192;
-constexpr uint32_t TMEM_COLS = 2 * BN;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 2;                // warp 0: TMA producer, warp 1: MMA issuer
+constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+constexpr int DN = 2 * BN;                 // accumulator columns: [hi | lo]
+constexpr uint32_t TMEM_COLS = 2 * DN;    // two buffers: all 512 columns
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapBh,
@@ -84,7 +95,7 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tfull_bar(b), 1);
-      ptx::mbar_init(tempty_bar(b), 4);  // one arrival per epilogue warp
+      ptx::mbar_init(tempty_bar(b), EPI_WARPS);  // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -122,7 +133,7 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, DN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk = 0;  // running chunk counter over all tiles of this CTA
@@ -131,25 +142,22 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
           const uint32_t buf = chunk & 1u;
           ptx::mbar_wait(tempty_bar(buf), ((chunk >> 1) & 1u) ^ 1u);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * BN;
+          const uint32_t d_tmem = tmem_base + buf * DN;
           const int kb_end = min(n_kblocks, (ch + 1) * chunk_kblocks);
           for (int kb = ch * chunk_kblocks; kb < kb_end; ++kb) {
             ptx::mbar_wait(full_bar(stage), phase);
             ptx::tc_fence_after();
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
             const uint64_t da = ptx::umma_desc_k_sw128(sa);
-            const uint64_t dh = ptx::umma_desc_k_sw128(sa + A_BYTES);
-            const uint64_t dl = ptx::umma_desc_k_sw128(sa + A_BYTES + B_BYTES);
+            // Bh and Bl sit back to back: one 256-row K-major operand
+            const uint64_t db = ptx::umma_desc_k_sw128(sa + A_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
               // advancing 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the
               // (>>4) start-address field
-              ptx::umma_bf16<1>(d_tmem, da + 2u * k, dh + 2u * k, idesc,
+              ptx::umma_bf16<1>(d_tmem, da + 2u * k, db + 2u * k, idesc,
                                 (kb > ch * chunk_kblocks || k > 0) ? 1u : 0u);
             }
-#pragma unroll
-            for (int k = 0; k < BK / UK; ++k)
-              ptx::umma_bf16<1>(d_tmem, da + 2u * k, dl + 2u * k, idesc, 1u);
             ptx::umma_commit(empty_bar(stage));  // stage reusable once these MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -157,27 +165,30 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         }
       }
     }
-  } else {
+  } else if (warp >= EPI_WARP0) {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int half = (warp - EPI_WARP0) >> 2;  // which 64 columns of each plane it owns
     uint32_t chunk = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const Tile tile = tiles[t];
-      float acc[BN];
+      float acc[64];
 #pragma unroll
-      for (int n = 0; n < BN; ++n) acc[n] = 0.f;
+      for (int n = 0; n < 64; ++n) acc[n] = 0.f;
       for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
         const uint32_t buf = chunk & 1u;
         ptx::mbar_wait(tfull_bar(buf), (chunk >> 1) & 1u);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * DN + half * 64;
 #pragma unroll
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + cc * 32, v);
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t v[16], w[16];
+          ptx::tmem_ld_32x16(taddr + cc * 16, v);
+          ptx::tmem_ld_32x16(taddr + BN + cc * 16, w);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int x = 0; x < 32; ++x) acc[cc * 32 + x] += __uint_as_float(v[x]);
+          for (int x = 0; x < 16; ++x)  // round-to-nearest adds: unbiased
+            acc[cc * 16 + x] += __uint_as_float(v[x]) + __uint_as_float(w[x]);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -188,9 +199,9 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       if (i < n_samples) {
         const double ri = r[i];
         const int64_t rowoff = i * (i - 1) / 2 - first;
-        const int64_t j0 = static_cast<int64_t>(tile.tj) * BN;
+        const int64_t j0 = static_cast<int64_t>(tile.tj) * BN + half * 64;
 #pragma unroll
-        for (int n = 0; n < BN; ++n) {
+        for (int n = 0; n < 64; ++n) {
           const int64_t j = j0 + n;
           if (j < i) {
             const double R = ri + r[j];
@@ -321,12 +332,10 @@ TcOperands* tc_operands_create(const uint16_t* P, const uint16_t* Bh, const uint
 void tc_operands_destroy(TcOperands* o) { delete o; }
 
 static int tc_chunk_kblocks() {
-  static int v = [] {
-    const char* e = getenv("FRC_TC_CHUNK_KBLOCKS");
-    int x = e ? atoi(e) : 32;  // 32 blocks = 2048 nodes per fp32 TMEM accumulation run
-    return x < 1 ? 1 : x;
-  }();
-  return v;
+  // 64 blocks = 4096 nodes per uninterrupted fp32 TMEM accumulation run
+  const char* e = getenv("FRC_TC_CHUNK_KBLOCKS");
+  int x = e ? atoi(e) : 64;
+  return x < 1 ? 1 : x;
 }
 
 int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, const Tile* tiles,

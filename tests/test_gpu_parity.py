@@ -122,6 +122,21 @@ def test_fast_path_within_tolerance(gpu_ctx, weighted, normalize):
     assert e.max() < 1e-5, f"max rel err {e.max():.3e}"
 
 
+@pytest.mark.parametrize("shape,levels", [("caterpillar", 0), ("caterpillar", 1), ("balanced", 0), ("random", 1)])
+def test_fast_unweighted_embedding_variants(gpu_ctx, monkeypatch, shape, levels):
+    """Both embedding implementations (fused single launch / one launch per level), deep and flat trees (H9)."""
+    from frackyfrac_b200 import engine, synth
+
+    monkeypatch.setenv("FRC_EMBED_LEVELS", str(levels))
+    tree = synth.random_tree(700, 71, shape=shape)
+    csr = synth.random_table(tree, 200, 0.03, 72)
+    want = oracle_flat(tree, csr, False)
+    with engine.Job(tree.parent, tree.length, *csr, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx) as job:
+        got = np.concatenate([a for _, a in job.chunks()])
+        assert job.info().tree_height == {"caterpillar": 699, "balanced": 10, "random": job.info().tree_height}[shape]
+    assert rel_err(got, want).max() < 1e-5
+
+
 @pytest.mark.parametrize("weighted", [False, True])
 def test_fast_path_identical_and_near_identical_samples(gpu_ctx, weighted):
     """Identical samples must give exactly 0; near-identical ones stay within 1e-5 relative."""
