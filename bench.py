@@ -38,6 +38,8 @@ CONFIGS = {
     "cfg2w": ("weighted", 10_000, 5_000, 0.02, 1002, 2002),
     "cfg3": ("weighted", 50_000, 20_000, 0.02, 1003, 2003),
     "cfg3u": ("unweighted", 50_000, 20_000, 0.02, 1003, 2003),
+    "cfg4": ("unweighted", 100_000, 100_000, 0.02, 1004, 2004),
+    "cfg4s": ("unweighted", 100_000, 30_000, 0.02, 1004, 2004),
     "tiny": ("unweighted", 1_000, 512, 0.02, 1009, 2009),
 }
 
@@ -241,6 +243,10 @@ def run_ours(args, world, rank, local_rank):
     value = total_pairs * args.steps / dev_s
 
     # ---------------------------------------------- e2e: host buffers through the C ABI
+    class _NoInfo:
+        h2d_bytes = d2h_bytes = 0
+        h2d_ms = 0.0
+
     def e2e_step():
         with engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
                         rank=rank, world=world) as j:
@@ -248,17 +254,20 @@ def run_ours(args, world, rank, local_rank):
             i = j.info()
         return n, i
 
-    for _ in range(args.warmup):
-        e2e_step()
+    ei = _NoInfo()
+    if not args.no_e2e:
+        for _ in range(args.warmup):
+            e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, ei = e2e_step()
+    if not args.no_e2e:
+        for _ in range(args.steps):
+            _, ei = e2e_step()
     barrier()
     sampler.mark(t0, time.perf_counter())
-    e2e_s = maxreduce(time.perf_counter() - t0)
+    e2e_s = max(maxreduce(time.perf_counter() - t0), 1e-9)
     clocks = sampler.stop()
-    e2e = {"value": total_pairs * args.steps / e2e_s, "unit": "sample-pairs/s",
+    e2e = None if args.no_e2e else {"value": total_pairs * args.steps / e2e_s, "unit": "sample-pairs/s",
            "h2d_bytes_per_step": int(ei.h2d_bytes), "d2h_bytes_per_step": int(ei.d2h_bytes),
            "ms_per_step": 1e3 * e2e_s / args.steps,
            "timed": "host wall clock around frc_create..frc_next*..frc_destroy (includes host validation, "
@@ -266,7 +275,7 @@ def run_ours(args, world, rank, local_rank):
 
     # ---------------------------------------------- roofline of the dominant kernel (rank 0, timed alone)
     roofline, cpu = None, None
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         rj = engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
                         band_rows=1 << 20, flags=engine.FLAG_NO_D2H)
         rj.drain()
@@ -296,6 +305,7 @@ def run_ours(args, world, rank, local_rank):
                         "peak_source": f"{peaks_kind} bf16_tflops (burst; kernel timed alone, one launch over all tiles)",
                         "note": "algorithmic flops = 2*B per pair; the kernel executes 2 bf16 planes (hi/lo) and "
                                 "full diagonal tiles, reported as executed_*"}
+    if rank == 0:
         if not args.no_cpu:
             cpu = cpu_baseline(tree, csr, weighted, target_s=args.ref_seconds)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -331,6 +341,9 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--ref-seconds", type=float, default=12.0, help="CPU work per reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (configs whose output exceeds host RAM)")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-alone timing leg")
+    ap.add_argument("--min-warmup", type=int, default=3)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -341,7 +354,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:]
         os.execv(sys.executable, cmd)
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, args.min_warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args, world, rank)
     else:

@@ -105,7 +105,8 @@ int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, con
 // fp64 recompute of the flagged pairs from the presence rows and true lengths.
 int launch_unweighted_fixup(const TcOperands* ops, int32_t n_nodes, int32_t kp, const double* length,
                             const uint32_t* flagged, const unsigned long long* n_flagged,
-                            int64_t first, double* out, int num_sms, cudaStream_t s);
+                            unsigned long long* count_host, int64_t first, double* out, int num_sms,
+                            cudaStream_t s);
 bool tc_setup(std::string* err);  // smem attribute + driver entry points, once per process
 
 }  // namespace frc

@@ -135,7 +135,9 @@ class Pool {
   bool stop_ = false;
 };
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 8;                       // output ring: enough for the compute to run ahead of the D2H
+constexpr int kMinSlots = 3;
+constexpr int64_t kSlotBytesBudget = 4LL << 30;  // device (and pinned) bytes the ring may take beyond kMinSlots
 constexpr double kFlagBelow = 0.125;            // fast unweighted: recompute d below this exactly
 constexpr int64_t kExactWorkLimit = 1LL << 28;  // AUTO: pairs * nodes at or below this -> exact
 
@@ -144,7 +146,7 @@ constexpr int64_t kExactWorkLimit = 1LL << 28;  // AUTO: pairs * nodes at or bel
 struct frc_ctx {
   int device = 0;
   int num_sms = 0;
-  cudaStream_t stream[2] = {nullptr, nullptr};
+  cudaStream_t stream[3] = {nullptr, nullptr, nullptr};  // two compute streams + one copy (D2H) stream
   Arena dev, pin;
   std::unique_ptr<Pool> pool;
   std::vector<std::vector<int64_t>> stamps;  // per-worker duplicate-detection scratch
@@ -158,7 +160,6 @@ struct Slot {
   double* dev = nullptr;
   double* host = nullptr;
   uint32_t* flagged = nullptr;
-  unsigned long long* n_flagged = nullptr;  // device
   unsigned long long* n_flagged_host = nullptr;
   cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr, done = nullptr;
   int band = -1;  // index into mine[]
@@ -187,6 +188,7 @@ struct frc_job {
   size_t input_bytes = 0;
   Tile* d_tiles = nullptr;
   int32_t* d_level_ptr = nullptr;
+  unsigned long long* d_flag_counts = nullptr;  // one per band of this rank
   bool fused_embed = true;
   bool zero_copy = false;
   uint16_t *d_len_hi = nullptr, *d_len_lo = nullptr;
@@ -206,6 +208,7 @@ struct frc_job {
   cudaEvent_t ev_run1 = nullptr, ev_join = nullptr;
   bool run_timed = false;
   bool embed_timed = false;
+  std::chrono::steady_clock::time_point t_host0;
 };
 
 namespace {
@@ -230,13 +233,18 @@ int band_owner(size_t b, int world) {
   return static_cast<int>(m < static_cast<size_t>(world) ? m : 2 * world - 1 - m);
 }
 
-int64_t choose_band_rows(int64_t N, int64_t requested, int world) {
+int64_t choose_band_rows(int64_t N, int64_t requested, int world, bool d2h = true) {
   if (requested > 0) return round_up(requested, kTile);
-  int64_t tile_rows = (N + kTile - 1) / kTile;
-  // at least ~8 bands per rank (D2H overlap, load balance), at most 8 tile rows
-  // per band (L2 reuse of the j-side operand across the band's i-tiles)
-  int64_t g = std::min<int64_t>(8, std::max<int64_t>(1, tile_rows / (8 * static_cast<int64_t>(world))));
-  while (g > 1 && g * kTile * N * 8 > (512LL << 20)) --g;
+  const int64_t tile_rows = (N + kTile - 1) / kTile;
+  int64_t g;
+  if (!d2h && world == 1) {
+    g = tile_rows;  // nothing to overlap with: as few launches as memory allows
+  } else {
+    // at least ~8 bands per rank (D2H overlap, load balance), at most 12 tile rows per band
+    // (the more i-tiles run together, the more often a j-side operand tile is reused from L2)
+    g = std::min<int64_t>(12, std::max<int64_t>(1, tile_rows / (8 * static_cast<int64_t>(world))));
+  }
+  while (g > 1 && g * kTile * N * 8 > (1536LL << 20)) --g;
   return g * kTile;
 }
 
@@ -266,6 +274,9 @@ int run_embedding(frc_job* j) {
   frc_ctx* c = j->ctx;
   cudaStream_t s = c->stream[0];
   int launches = 0;
+  j->t_host0 = std::chrono::steady_clock::now();
+  if (j->d_flag_counts)
+    JOB_CUDA(j, cudaMemsetAsync(j->d_flag_counts, 0, sizeof(unsigned long long) * (j->mine.size() + 1), s));
   JOB_CUDA(j, cudaEventRecord(j->ev_embed0, s));
   if (j->exact || j->weighted) {
     launches += launch_embed_f64(j->dtree, j->level_ptr.data(), j->dcsr, j->d_E, j->np, s);
@@ -307,6 +318,9 @@ int run_embedding(frc_job* j) {
 // Queue band mine[idx] into its slot.
 int enqueue_band(frc_job* j, size_t idx) {
   frc_ctx* c = j->ctx;
+  if (getenv("FRC_TRACE"))
+    fprintf(stderr, "[host] enqueue band %zu at %.3f ms\n", idx,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - j->t_host0).count());
   const Band& b = j->bands[j->mine[idx]];
   Slot& sl = j->slots[idx % j->n_slots];
   cudaStream_t s = c->stream[idx % 2];
@@ -320,29 +334,36 @@ int enqueue_band(frc_job* j, size_t idx) {
     launches += launch_weighted_tiles(j->d_A, j->np, j->kp, j->d_lenf, j->prescale, j->d_W,
                                       j->d_tiles + b.tile_off, b.n_tiles, j->N, b.first, sl.dev, s);
   } else {
-    JOB_CUDA(j, cudaMemsetAsync(sl.n_flagged, 0, sizeof(unsigned long long), s));
+    // no copy-engine work between the kernels: a memset or an 8-byte D2H would queue behind the
+    // previous band's bulk D2H and stall this band (measured).  Counters are per band, zeroed once
+    // per run; the fix-up kernel publishes the count through mapped pinned memory.
+    unsigned long long* cnt = j->d_flag_counts + idx;
     launches += launch_unweighted_tc(j->tc, j->kp, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
-                                     b.first, sl.dev, kFlagBelow, sl.flagged, sl.n_flagged, c->num_sms, s);
+                                     b.first, sl.dev, kFlagBelow, sl.flagged, cnt, c->num_sms, s);
     JOB_CUDA(j, cudaEventRecord(sl.k1, s));
-    launches += launch_unweighted_fixup(j->tc, j->B, j->kp, j->dtree.length, sl.flagged, sl.n_flagged,
-                                        b.first, sl.dev, c->num_sms, s);
-    JOB_CUDA(j, cudaMemcpyAsync(sl.n_flagged_host, sl.n_flagged, sizeof(unsigned long long),
-                                cudaMemcpyDeviceToHost, s));
+    launches += launch_unweighted_fixup(j->tc, j->B, j->kp, j->dtree.length, sl.flagged, cnt,
+                                        sl.n_flagged_host, b.first, sl.dev, c->num_sms, s);
   }
   JOB_CUDA(j, cudaGetLastError());
   if (j->exact || j->weighted) JOB_CUDA(j, cudaEventRecord(sl.k1, s));
   JOB_CUDA(j, cudaEventRecord(sl.k2, s));
-  if (!(j->opts.flags & FRC_FLAG_NO_D2H)) {
-    if (sl.dev != sl.host)
-      JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, s));
+  // bulk D2H runs on its own stream so the compute streams never hold copy-engine work
+  // (a kernel queued behind a copy in the same stream cannot overlap that copy)
+  cudaStream_t cs = c->stream[2];
+  if (!(j->opts.flags & FRC_FLAG_NO_D2H) && sl.dev != sl.host) {
+    JOB_CUDA(j, cudaStreamWaitEvent(cs, sl.k2, 0));
+    JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, cs));
     j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
+    JOB_CUDA(j, cudaEventRecord(sl.done, cs));
+  } else {
+    JOB_CUDA(j, cudaEventRecord(sl.done, s));
   }
-  JOB_CUDA(j, cudaEventRecord(sl.done, s));
   j->info.kernel_launches += launches;
   if (idx + 1 == j->mine.size()) {
-    // last band queued: join both streams and stamp the end of the run on stream 0
+    // last band queued: join all streams and stamp the end of the run on stream 0
     JOB_CUDA(j, cudaEventRecord(j->ev_join, c->stream[1]));
     JOB_CUDA(j, cudaStreamWaitEvent(c->stream[0], j->ev_join, 0));
+    JOB_CUDA(j, cudaStreamWaitEvent(c->stream[0], sl.done, 0));
     JOB_CUDA(j, cudaEventRecord(j->ev_run1, c->stream[0]));
   }
   return FRC_OK;
@@ -567,7 +588,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->info.n_nodes_padded = j->exact ? B : j->kp;
 
   // ---------------------------------------------------------------------- bands
-  const int64_t band_rows = choose_band_rows(N, opts->band_rows, world);
+  const int64_t band_rows = choose_band_rows(N, opts->band_rows, world, !(opts->flags & FRC_FLAG_NO_D2H));
   for (int64_t r0 = 0; r0 < N; r0 += band_rows) {
     Band b;
     b.row0 = r0; b.row1 = std::min(N, r0 + band_rows);
@@ -772,12 +793,16 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (!(j->d_Bl = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
     if (!(j->d_r = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
     if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
+    if (!(j->d_flag_counts = dev_alloc<unsigned long long>(j, j->mine.size() + 1, &rc))) return bail(rc);
     std::string terr;
     j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, &terr);
     if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
   }
   { const char* e = getenv("FRC_ZERO_COPY"); j->zero_copy = e && atoi(e) == 1; }
-  j->n_slots = static_cast<int>(std::min<size_t>(kSlots, std::max<size_t>(2, j->mine.size() + 1)));
+  {
+    int64_t want = std::max<int64_t>(kMinSlots, std::min<int64_t>(kSlots, kSlotBytesBudget / (max_band * 8)));
+    j->n_slots = static_cast<int>(std::min<int64_t>(want, std::max<int64_t>(2, static_cast<int64_t>(j->mine.size()) + 1)));
+  }
   if (j->mine.empty()) j->n_slots = 0;
   for (int k = 0; k < j->n_slots; ++k) {
     Slot& sl = j->slots[k];
@@ -786,14 +811,13 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     else if (!(sl.dev = dev_alloc<double>(j, max_band, &rc))) return bail(rc);
     if (!j->exact && !j->weighted) {
       if (!(sl.flagged = dev_alloc<uint32_t>(j, max_band, &rc))) return bail(rc);
-      if (!(sl.n_flagged = dev_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
       if (!(sl.n_flagged_host = pin_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
       *sl.n_flagged_host = 0;
     }
     cudaError_t e;
     if ((e = cudaEventCreate(&sl.k0)) != cudaSuccess || (e = cudaEventCreate(&sl.k1)) != cudaSuccess ||
         (e = cudaEventCreate(&sl.k2)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess)
+        (e = cudaEventCreate(&sl.done)) != cudaSuccess)
       return bail(fail(j, FRC_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e)));
   }
 
@@ -841,6 +865,17 @@ int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* c
     j->run_timed = true;
   }
   if (sl.n_flagged_host) j->info.flagged_pairs += static_cast<int64_t>(*sl.n_flagged_host);
+  if (getenv("FRC_TRACE")) {
+    fprintf(stderr, "[host] deliver band %zu at %.3f ms\n", idx,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - j->t_host0).count());
+    float a = 0, b = 0, c2 = 0, d = 0;
+    cudaEventElapsedTime(&a, j->ev_embed0, sl.k0);
+    cudaEventElapsedTime(&b, j->ev_embed0, sl.k1);
+    cudaEventElapsedTime(&c2, j->ev_embed0, sl.k2);
+    cudaEventElapsedTime(&d, j->ev_embed0, sl.done);
+    fprintf(stderr, "[band %3zu] start %.3f kernel_end %.3f fixup_end %.3f d2h_end %.3f ms (pairs %lld)\n", idx, a, b, c2, d,
+            static_cast<long long>(j->bands[j->mine[idx]].count));
+  }
   const Band& b = j->bands[j->mine[idx]];
   *data = (j->opts.flags & FRC_FLAG_NO_D2H) ? sl.dev : sl.host;
   *first_index = b.first;

@@ -230,9 +230,10 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
 __global__ void __launch_bounds__(256)
 k_unweighted_fixup(const uint16_t* __restrict__ P, int32_t n_nodes, int32_t kp,
                    const double* __restrict__ length, const uint32_t* __restrict__ flagged,
-                   const unsigned long long* __restrict__ n_flagged, int64_t first,
-                   double* __restrict__ out) {
+                   const unsigned long long* __restrict__ n_flagged,
+                   unsigned long long* __restrict__ count_host, int64_t first, double* __restrict__ out) {
   const unsigned long long total = *n_flagged;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count_host = total;  // mapped pinned memory
   const int lane = threadIdx.x & 31;
   const unsigned long long warps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
   for (unsigned long long w = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -352,9 +353,10 @@ int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, con
 
 int launch_unweighted_fixup(const TcOperands* ops, int32_t n_nodes, int32_t kp, const double* length,
                             const uint32_t* flagged, const unsigned long long* n_flagged,
-                            int64_t first, double* out, int num_sms, cudaStream_t s) {
-  k_unweighted_fixup<<<num_sms * 4, 256, 0, s>>>(ops->P, n_nodes, kp, length, flagged, n_flagged, first,
-                                                 out);
+                            unsigned long long* count_host, int64_t first, double* out, int num_sms,
+                            cudaStream_t s) {
+  k_unweighted_fixup<<<num_sms * 4, 256, 0, s>>>(ops->P, n_nodes, kp, length, flagged, n_flagged, count_host,
+                                                 first, out);
   return 1;
 }
 
