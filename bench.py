@@ -304,7 +304,8 @@ def run_ours(args, world, rank, local_rank):
                         "executed_tflops": executed, "executed_frac": executed / peak,
                         "peak_source": f"{peaks_kind} bf16_tflops (burst; kernel timed alone, one launch over all tiles)",
                         "note": "algorithmic flops = 2*B per pair; the kernel executes 2 bf16 planes (hi/lo) and "
-                                "full diagonal tiles, reported as executed_*"}
+                                "full diagonal tiles, reported as executed_* (the CTA-pair kernel also runs one "
+                                "masked tile above each second diagonal tile, not counted)"}
     if rank == 0:
         if not args.no_cpu:
             cpu = cpu_baseline(tree, csr, weighted, target_s=args.ref_seconds)

@@ -193,28 +193,29 @@ k_expand_operands(const uint32_t* __restrict__ bits, int32_t n_nodes, int32_t nw
 // a private global scratch column when the tree is too large for that).
 //   phase 1  scatter the 32 CSR rows into leaf words (shared-memory atomics)
 //   phase 2  per tree level: word(v) = OR of the children's words
-//   phase 3  r[s] = sum_v lenq[v] * present(v, s), fp64, fixed summation order
-//   phase 4  write the three K-major bf16 operand rows of the 32 samples
-//            (P, P*len_hi, P*len_lo): 16-byte stores, a warp covers 512
-//            contiguous bytes of one row — this phase is the HBM-bound part.
+//   phase 3  publish the column to bitsT[w][kp] for k_presence_rowsum_t (r[s] =
+//            sum_v lenq[v] * present(v,s), fp64, fixed order) and k_expand_operands_t, which
+//            writes the three bf16 operands at HBM speed with thousands of CTAs
+//            (doing that from these 160 CTAs reached only 2.3 TB/s).
 template <bool kSmem>
 __global__ void __launch_bounds__(512)
 k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                        int64_t n_samples, const int32_t* __restrict__ level_nodes,
-                       const int32_t* __restrict__ level_ptr, int32_t height,
-                       const int32_t* __restrict__ child_ptr, const int32_t* __restrict__ child_idx,
+                       const int32_t* __restrict__ level_parent, const int32_t* __restrict__ level_ptr,
+                       int32_t height,
                        int32_t n_nodes, int32_t kp, const double* __restrict__ lenq,
                        const uint16_t* __restrict__ len_hi, const uint16_t* __restrict__ len_lo,
                        uint32_t* __restrict__ scratch, double* __restrict__ r, uint16_t* __restrict__ P,
                        uint16_t* __restrict__ Bh, uint16_t* __restrict__ Bl) {
   extern __shared__ __align__(16) uint32_t smem_words[];
-  __shared__ double part[16][32];
+  __shared__ int32_t lptr[128];
   const int w = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // column storage padded to a multiple of 8 words so phase 4 can read groups of 8
   uint32_t* colw = kSmem ? smem_words : scratch + static_cast<int64_t>(w) * kp;
 
   for (int32_t v = tid; v < kp; v += 512) colw[v] = 0u;
+  if (tid < 128 && tid <= height + 1) lptr[tid] = level_ptr[tid];
   __syncthreads();
   // phase 1
   for (int sl = warp; sl < 32; sl += 16) {
@@ -225,74 +226,82 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
     }
   }
   __syncthreads();
-  // phase 2
-  for (int32_t h = 1; h <= height; ++h) {
-    const int32_t b = level_ptr[h], e = level_ptr[h + 1];
+  // phase 2: every node ORs its (final) word into its parent, one tree level at a time from the
+  // leaves up.  level_nodes / level_parent are read coalesced; no dependent global loads.
+  for (int32_t h = 0; h < height; ++h) {
+    const int32_t b = h < 127 ? lptr[h] : level_ptr[h], e = h < 127 ? lptr[h + 1] : level_ptr[h + 1];
     for (int32_t idx = b + tid; idx < e; idx += 512) {
-      const int32_t v = level_nodes[idx];
-      uint32_t acc = 0;
-      for (int32_t c = child_ptr[v]; c < child_ptr[v + 1]; ++c) acc |= colw[child_idx[c]];
-      colw[v] = acc;
+      const uint32_t x = colw[level_nodes[idx]];
+      if (x) atomicOr(colw + level_parent[idx], x);
     }
     __syncthreads();
   }
-  // phase 3
-  {
-    const int32_t per = (n_nodes + 15) / 16;
-    const int32_t v0 = warp * per, v1 = min(n_nodes, v0 + per);
-    double acc = 0.0;
-    for (int32_t v = v0; v < v1; ++v)
-      if ((colw[v] >> lane) & 1u) acc += lenq[v];
-    part[warp][lane] = acc;
+  // phase 3: publish the column (already in place when it lives in global memory)
+  if (kSmem) {
+    uint32_t* dst = scratch + static_cast<int64_t>(w) * kp;
+    for (int32_t g = tid; g * 4 < kp; g += 512)
+      *reinterpret_cast<uint4*>(dst + g * 4) = *reinterpret_cast<const uint4*>(colw + g * 4);
+  }
+}
+
+// partial[c][s] = sum over the nodes of chunk c of lenq[v] * present(v, s): one warp per
+// (word column, node chunk), lane = sample; words and lengths are read as 16-byte broadcasts.
+__global__ void __launch_bounds__(32)
+k_presence_rowsum_t(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
+                    const double* __restrict__ lenq8, double* __restrict__ partial, int64_t ld) {
+  const int32_t w = blockIdx.x, lane = threadIdx.x;
+  const int32_t v0 = blockIdx.y * per, v1 = min(kp, v0 + per);  // per is a multiple of 8
+  const uint32_t* col = bitsT + static_cast<int64_t>(w) * kp;
+  double a0 = 0.0, a1 = 0.0;
+  for (int32_t v = v0; v < v1; v += 8) {
+    const uint4 wa = *reinterpret_cast<const uint4*>(col + v), wb = *reinterpret_cast<const uint4*>(col + v + 4);
+    const double2 l0 = *reinterpret_cast<const double2*>(lenq8 + v), l1 = *reinterpret_cast<const double2*>(lenq8 + v + 2);
+    const double2 l2 = *reinterpret_cast<const double2*>(lenq8 + v + 4), l3 = *reinterpret_cast<const double2*>(lenq8 + v + 6);
+    a0 += ((wa.x >> lane) & 1u) ? l0.x : 0.0;
+    a1 += ((wa.y >> lane) & 1u) ? l0.y : 0.0;
+    a0 += ((wa.z >> lane) & 1u) ? l1.x : 0.0;
+    a1 += ((wa.w >> lane) & 1u) ? l1.y : 0.0;
+    a0 += ((wb.x >> lane) & 1u) ? l2.x : 0.0;
+    a1 += ((wb.y >> lane) & 1u) ? l2.y : 0.0;
+    a0 += ((wb.z >> lane) & 1u) ? l3.x : 0.0;
+    a1 += ((wb.w >> lane) & 1u) ? l3.y : 0.0;
+  }
+  partial[static_cast<int64_t>(blockIdx.y) * ld + w * 32 + lane] = a0 + a1;
+}
+
+// Presence columns bitsT[nw][kp] (word w holds samples 32w..32w+31 of one node) -> the three
+// K-major bf16 operands [np][kp].  Block = 64 nodes x 256 samples; the only HBM-heavy kernel of
+// the embedding stage: 3 * np * kp * 2 bytes written, each warp store covers 128 contiguous bytes.
+__global__ void __launch_bounds__(256)
+k_expand_operands_t(const uint32_t* __restrict__ bitsT, int32_t n_nodes, int32_t nw, int32_t kp,
+                    int64_t np, const uint16_t* __restrict__ len_hi, const uint16_t* __restrict__ len_lo,
+                    uint16_t* __restrict__ P, uint16_t* __restrict__ Bh, uint16_t* __restrict__ Bl) {
+  __shared__ uint32_t words[8][64];
+  const int32_t v0 = blockIdx.x * 64;
+  const int32_t w0 = blockIdx.y * 8;
+  for (int idx = threadIdx.x; idx < 512; idx += 256) {
+    int word = idx >> 6, node = idx & 63;
+    uint32_t x = 0;
+    if (w0 + word < nw) x = bitsT[static_cast<int64_t>(w0 + word) * kp + v0 + node];  // kp is padded: in range
+    words[word][node] = x;
   }
   __syncthreads();
-  if (warp == 0) {
-    double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc += part[k][lane];
-    r[static_cast<int64_t>(w) * 32 + lane] = acc;
-  }
-  // phase 4
-  for (int32_t g = tid; g * 8 < kp; g += 512) {
-    const uint4 wa = *reinterpret_cast<const uint4*>(colw + g * 8);
-    const uint4 wb = *reinterpret_cast<const uint4*>(colw + g * 8 + 4);
-    const uint32_t wd[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-    uint32_t hi[8], lo[8];
-    if (g * 8 + 8 <= n_nodes) {
-      const uint4 h4 = *reinterpret_cast<const uint4*>(len_hi + g * 8);
-      const uint4 l4 = *reinterpret_cast<const uint4*>(len_lo + g * 8);
-      const uint32_t hh[4] = {h4.x, h4.y, h4.z, h4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        hi[2 * q] = hh[q] & 0xFFFFu; hi[2 * q + 1] = hh[q] >> 16;
-        lo[2 * q] = ll[q] & 0xFFFFu; lo[2 * q + 1] = ll[q] >> 16;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int32_t v = g * 8 + q;
-        hi[q] = v < n_nodes ? len_hi[v] : 0u;
-        lo[q] = v < n_nodes ? len_lo[v] : 0u;
-      }
-    }
-    const int64_t base = static_cast<int64_t>(w) * 32 * kp + static_cast<int64_t>(g) * 8;
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t va = v0 + 2 * lane, vb = va + 1;
+  const uint2 wab = *reinterpret_cast<const uint2*>(&words[wi][2 * lane]);
+  const uint32_t wa = wab.x, wb = wab.y;
+  const uint32_t ha = va < n_nodes ? len_hi[va] : 0, hb = vb < n_nodes ? len_hi[vb] : 0;
+  const uint32_t la = va < n_nodes ? len_lo[va] : 0, lb = vb < n_nodes ? len_lo[vb] : 0;
+  const int64_t s0 = (static_cast<int64_t>(w0) + wi) * 32;
 #pragma unroll 4
-    for (int it = 0; it < 32; ++it) {
-      uint32_t m[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) m[q] = 0u - ((wd[q] >> it) & 1u);
-      uint4 p4, h4, l4;
-      p4.x = (0x3F80u & m[0]) | ((0x3F80u & m[1]) << 16); p4.y = (0x3F80u & m[2]) | ((0x3F80u & m[3]) << 16);
-      p4.z = (0x3F80u & m[4]) | ((0x3F80u & m[5]) << 16); p4.w = (0x3F80u & m[6]) | ((0x3F80u & m[7]) << 16);
-      h4.x = (hi[0] & m[0]) | ((hi[1] & m[1]) << 16); h4.y = (hi[2] & m[2]) | ((hi[3] & m[3]) << 16);
-      h4.z = (hi[4] & m[4]) | ((hi[5] & m[5]) << 16); h4.w = (hi[6] & m[6]) | ((hi[7] & m[7]) << 16);
-      l4.x = (lo[0] & m[0]) | ((lo[1] & m[1]) << 16); l4.y = (lo[2] & m[2]) | ((lo[3] & m[3]) << 16);
-      l4.z = (lo[4] & m[4]) | ((lo[5] & m[5]) << 16); l4.w = (lo[6] & m[6]) | ((lo[7] & m[7]) << 16);
-      const int64_t o = base + static_cast<int64_t>(it) * kp;
-      __stcs(reinterpret_cast<uint4*>(P + o), p4);
-      __stcs(reinterpret_cast<uint4*>(Bh + o), h4);
-      __stcs(reinterpret_cast<uint4*>(Bl + o), l4);
-    }
+  for (int it = 0; it < 32; ++it) {
+    const int64_t s = s0 + it;
+    if (s >= np) break;
+    const uint32_t ma = 0u - ((wa >> it) & 1u), mb = 0u - ((wb >> it) & 1u);
+    const int64_t o = s * kp + va;
+    *reinterpret_cast<uint32_t*>(P + o) = (0x3F80u & ma) | ((0x3F80u & mb) << 16);
+    *reinterpret_cast<uint32_t*>(Bh + o) = (ha & ma) | ((hb & mb) << 16);
+    *reinterpret_cast<uint32_t*>(Bl + o) = (la & ma) | ((lb & mb) << 16);
   }
 }
 
@@ -397,14 +406,12 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 }
 
 
-int64_t presence_fused_scratch_words(int32_t kp, int32_t nw) {
-  return static_cast<int64_t>(kp) * 4 <= 200 * 1024 ? 0 : static_cast<int64_t>(kp) * nw;
-}
+int64_t presence_fused_scratch_words(int32_t kp, int32_t nw) { return static_cast<int64_t>(kp) * nw; }
 
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t kp, const double* lenq, const uint16_t* len_hi,
-                                const uint16_t* len_lo, uint32_t* scratch, double* r, uint16_t* P,
-                                uint16_t* Bh, uint16_t* Bl, cudaStream_t s) {
+                                const uint16_t* len_lo, uint32_t* scratch, double* partial, double* r,
+                                uint16_t* P, uint16_t* Bh, uint16_t* Bl, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(kp) * 4;
   if (smem <= 200 * 1024) {
     static bool attr = false;
@@ -413,14 +420,24 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
       attr = true;
     }
     k_embed_presence_fused<true><<<nw, 512, smem, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
-                                                       level_ptr_dev, t.height, t.child_ptr, t.child_idx,
-                                                       t.n_nodes, kp, lenq, len_hi, len_lo, nullptr, r, P, Bh, Bl);
+                                                       t.level_parent, level_ptr_dev, t.height,
+                                                       t.n_nodes, kp, lenq, len_hi, len_lo, scratch, r, P, Bh, Bl);
   } else {
     k_embed_presence_fused<false><<<nw, 512, 0, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
-                                                     level_ptr_dev, t.height, t.child_ptr, t.child_idx,
+                                                     t.level_parent, level_ptr_dev, t.height,
                                                      t.n_nodes, kp, lenq, len_hi, len_lo, scratch, r, P, Bh, Bl);
   }
-  return 1;
+  const int64_t np = static_cast<int64_t>(nw) * 32;
+  {
+    const int chunks = pick_chunks(t.n_nodes);
+    const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 8));
+    dim3 g(nw, chunks);
+    k_presence_rowsum_t<<<g, 32, 0, s>>>(scratch, kp, per, lenq, partial, np);
+    k_reduce_partials<<<static_cast<unsigned>((np + kThreads - 1) / kThreads), kThreads, 0, s>>>(partial, chunks, np, np, r);
+  }
+  dim3 grid(kp / 64, static_cast<unsigned>((np + 255) / 256));
+  k_expand_operands_t<<<grid, 256, 0, s>>>(scratch, t.n_nodes, nw, kp, np, len_hi, len_lo, P, Bh, Bl);
+  return 4;
 }
 
 }  // namespace frc

@@ -23,6 +23,7 @@ struct DevTree {
   const int32_t* child_ptr = nullptr;  // [B+1]
   const int32_t* child_idx = nullptr;  // [B-1], ascending id within a parent = file order
   const int32_t* level_nodes = nullptr;// [B] nodes grouped by height (leaves first), ascending id
+  const int32_t* level_parent = nullptr;// [B] parent of level_nodes[k] (root: 0)
 };
 
 struct DevCsr {
@@ -76,8 +77,8 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 int64_t presence_fused_scratch_words(int32_t kp, int32_t nw);
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t kp, const double* lenq, const uint16_t* len_hi,
-                                const uint16_t* len_lo, uint32_t* scratch, double* r, uint16_t* P,
-                                uint16_t* Bh, uint16_t* Bl, cudaStream_t s);
+                                const uint16_t* len_lo, uint32_t* scratch, double* partial, double* r,
+                                uint16_t* P, uint16_t* Bh, uint16_t* Bl, cudaStream_t s);
 
 // ---- exact.cu ---------------------------------------------------------------
 // fp64 reference-order distances for pairs [first, first+count) of the triangle.
@@ -101,7 +102,7 @@ void tc_operands_destroy(TcOperands* o);
 int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, const Tile* tiles,
                          int32_t n_tiles, int64_t n_samples, int64_t first, double* out,
                          double flag_below, uint32_t* flagged, unsigned long long* n_flagged,
-                         int num_sms, cudaStream_t s);
+                         int num_sms, int ctas, cudaStream_t s);
 // fp64 recompute of the flagged pairs from the presence rows and true lengths.
 int launch_unweighted_fixup(const TcOperands* ops, int32_t n_nodes, int32_t kp, const double* length,
                             const uint32_t* flagged, const unsigned long long* n_flagged,

@@ -191,6 +191,7 @@ struct frc_job {
   unsigned long long* d_flag_counts = nullptr;  // one per band of this rank
   bool fused_embed = true;
   bool zero_copy = false;
+  int tc_ctas = 1;  // CTAs per tensor-core tile group (2 = cta_group::2 pairs)
   uint16_t *d_len_hi = nullptr, *d_len_lo = nullptr;
   double* d_lenq = nullptr;
   float* d_lenf = nullptr;
@@ -238,7 +239,9 @@ int64_t choose_band_rows(int64_t N, int64_t requested, int world, bool d2h = tru
   const int64_t tile_rows = (N + kTile - 1) / kTile;
   int64_t g;
   if (!d2h && world == 1) {
-    g = tile_rows;  // nothing to overlap with: as few launches as memory allows
+    // nothing to overlap with: few launches, but no more than 16 tile rows per band once the
+    // operands outgrow L2 (a band's i-tiles should stay L2-resident while its j-tiles stream)
+    g = tile_rows <= 64 ? tile_rows : 16;
   } else {
     // at least ~8 bands per rank (D2H overlap, load balance), at most 12 tile rows per band
     // (the more i-tiles run together, the more often a j-side operand tile is reused from L2)
@@ -296,8 +299,8 @@ int run_embedding(frc_job* j) {
   } else {
     if (j->fused_embed) {
       launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->kp, j->d_lenq,
-                                              j->d_len_hi, j->d_len_lo, j->d_bits, j->d_r, j->d_P, j->d_Bh,
-                                              j->d_Bl, s);
+                                              j->d_len_hi, j->d_len_lo, j->d_bits, j->d_scratch, j->d_r, j->d_P,
+                                              j->d_Bh, j->d_Bl, s);
     } else {
       launches += launch_embed_bits(j->dtree, j->level_ptr.data(), j->dcsr, j->d_bits, j->nw, s);
       launches += launch_presence_rowsum(j->d_bits, j->B, j->nw, j->d_lenq, j->d_r, j->d_scratch, s);
@@ -339,7 +342,7 @@ int enqueue_band(frc_job* j, size_t idx) {
     // per run; the fix-up kernel publishes the count through mapped pinned memory.
     unsigned long long* cnt = j->d_flag_counts + idx;
     launches += launch_unweighted_tc(j->tc, j->kp, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
-                                     b.first, sl.dev, kFlagBelow, sl.flagged, cnt, c->num_sms, s);
+                                     b.first, sl.dev, kFlagBelow, sl.flagged, cnt, c->num_sms, j->tc_ctas, s);
     JOB_CUDA(j, cudaEventRecord(sl.k1, s));
     launches += launch_unweighted_fixup(j->tc, j->B, j->kp, j->dtree.length, sl.flagged, cnt,
                                         sl.n_flagged_host, b.first, sl.dev, c->num_sms, s);
@@ -588,7 +591,13 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->info.n_nodes_padded = j->exact ? B : j->kp;
 
   // ---------------------------------------------------------------------- bands
-  const int64_t band_rows = choose_band_rows(N, opts->band_rows, world, !(opts->flags & FRC_FLAG_NO_D2H));
+  {
+    const char* e = getenv("FRC_TC_CTAS");
+    // CTA pairs (cta_group::2) by default; FRC_TC_CTAS=1 selects the single-CTA kernel
+    j->tc_ctas = (!(e && atoi(e) == 1) && !j->exact && !j->weighted) ? 2 : 1;
+  }
+  int64_t band_rows = choose_band_rows(N, opts->band_rows, world, !(opts->flags & FRC_FLAG_NO_D2H));
+  if (j->tc_ctas == 2) band_rows = round_up(band_rows, 2 * kTile);  // bands start on a tile-pair boundary
   for (int64_t r0 = 0; r0 < N; r0 += band_rows) {
     Band b;
     b.row0 = r0; b.row1 = std::min(N, r0 + band_rows);
@@ -614,8 +623,15 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       int32_t t0 = static_cast<int32_t>(b.row0 / kTile), t1 = static_cast<int32_t>((b.row1 - 1) / kTile);
       // column-major inside the band: CTAs running together share the few
       // i-tiles of the band and neighbouring j-tiles (L2 reuse of both operands)
-      for (int32_t tj = 0; tj <= t1; ++tj)
-        for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) j->tiles.push_back({ti, tj});
+      if (j->tc_ctas == 2) {
+        // pair tiles: (ti, tj) and (ti+1, tj) with ti even; needed when ti + 1 >= tj
+        for (int32_t tj = 0; tj <= t1; ++tj)
+          for (int32_t ti = std::max((tj - 1) & ~1, t0); ti <= t1; ti += 2)
+            if (ti >= 0 && ti + 1 >= tj) j->tiles.push_back({ti, tj});
+      } else {
+        for (int32_t tj = 0; tj <= t1; ++tj)
+          for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) j->tiles.push_back({ti, tj});
+      }
       b.n_tiles = static_cast<int32_t>(j->tiles.size()) - b.tile_off;
     }
 
@@ -644,9 +660,9 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       s_val = seg(need_val ? sizeof(double) * nnz : 0), s_parent = seg(sizeof(int32_t) * B),
       s_len = seg(sizeof(double) * B), s_cptr = seg(sizeof(int32_t) * (B + 1)),
       s_cidx = seg(sizeof(int32_t) * B), s_lvl = seg(sizeof(int32_t) * B),
-      s_hi = seg(sizeof(uint16_t) * B), s_lo = seg(sizeof(uint16_t) * B), s_lenq = seg(sizeof(double) * B),
+      s_hi = seg(sizeof(uint16_t) * B), s_lo = seg(sizeof(uint16_t) * B), s_lenq = seg(sizeof(double) * j->kp),
       s_lenf = seg(sizeof(float) * j->kp), s_tiles = seg(sizeof(Tile) * j->tiles.size()),
-      s_lptr = seg(sizeof(int32_t) * (H + 2));
+      s_lptr = seg(sizeof(int32_t) * (H + 2)), s_lpar = seg(sizeof(int32_t) * B);
   char* stage = pin_alloc<char>(j, total, &rc);
   if (!stage) return bail(rc);
   j->d_inputs = dev_alloc<char>(j, total, &rc);
@@ -723,6 +739,8 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     int32_t* lvl = reinterpret_cast<int32_t*>(stage + s_lvl.off);
     std::vector<int32_t> lfill(j->level_ptr.begin(), j->level_ptr.end() - 1);
     for (int32_t v = 0; v < B; ++v) lvl[lfill[height[v]]++] = v;
+    int32_t* lpar = reinterpret_cast<int32_t*>(stage + s_lpar.off);
+    for (int32_t k = 0; k < B; ++k) lpar[k] = lvl[k] ? tree->parent[lvl[k]] : 0;
     uint16_t* hi = reinterpret_cast<uint16_t*>(stage + s_hi.off);
     uint16_t* lo = reinterpret_cast<uint16_t*>(stage + s_lo.off);
     double* lq = reinterpret_cast<double*>(stage + s_lenq.off);
@@ -735,7 +753,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       lq[v] = static_cast<double>(bf16_to_float(hi[v])) + static_cast<double>(bf16_to_float(lo[v]));
       lf[v] = static_cast<float>(l);
     }
-    for (int32_t v = B; v < j->kp; ++v) lf[v] = 0.f;
+    for (int32_t v = B; v < j->kp; ++v) { lf[v] = 0.f; lq[v] = 0.0; }
     if (!j->tiles.empty()) memcpy(stage + s_tiles.off, j->tiles.data(), sizeof(Tile) * j->tiles.size());
     memcpy(stage + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
   }
@@ -767,6 +785,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->d_lenf = reinterpret_cast<float*>(d + s_lenf.off);
   j->d_tiles = reinterpret_cast<Tile*>(d + s_tiles.off);
   j->d_level_ptr = reinterpret_cast<int32_t*>(d + s_lptr.off);
+  j->dtree.level_parent = reinterpret_cast<int32_t*>(d + s_lpar.off);
 
   mark("events + H2D enqueue");
   // ------------------------------------------------------------ device buffers

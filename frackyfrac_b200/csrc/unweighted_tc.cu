@@ -225,6 +225,190 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   }
 }
 
+
+// ----------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster (one TPC) compute two
+// vertically adjacent 128 x 128 tiles (ti, tj) and (ti+1, tj) with ONE MMA
+// stream of shape M256 x N256 x K16 issued by the leader CTA:
+//   A (256 rows)  = each CTA's own P[i-tile] in its own shared memory,
+//   B (256 rows)  = [Bh; Bl] of the j-tile, split across the pair: the leader
+//                   holds Bh, the peer holds Bl (same offset in both CTAs),
+//   D             = each CTA's TMEM holds its 128 rows x [hi | lo] columns.
+// Per SM this halves the B-side shared-memory reads and the L2 -> SM operand
+// traffic (32 KB per 64-node block per SM instead of 48 KB), which is what bounds
+// the single-CTA kernel (shared memory: 96 + 96 B/clk demanded of 128 B/clk).
+// Barrier protocol: both producers' TMA bytes land on the LEADER's full barrier;
+// tcgen05.commit multicasts to both CTAs' empty / accumulator-full barriers; both
+// CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+constexpr int STAGES2 = 6;
+constexpr int STAGE2_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_BARS2 = 2 * STAGES2 + 4;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + NUM_BARS2 * 8 + 16 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapBh,
+                 const __grid_constant__ CUtensorMap mapBl, int32_t n_kblocks, int32_t chunk_kblocks,
+                 const double* __restrict__ r, const Tile* __restrict__ tiles, int32_t n_tiles,
+                 int64_t n_samples, int64_t first, double* __restrict__ out, double flag_below,
+                 uint32_t* __restrict__ flagged, unsigned long long* __restrict__ n_flagged) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw + pad;
+  const uint32_t bar_base = smem_base + STAGES2 * STAGE2_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES2 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES2 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES2 + 2 + b); };
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES2 * STAGE2_BYTES + NUM_BARS2 * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = ptx::cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapP);
+    ptx::prefetch_tensormap(cta == 0 ? &mapBh : &mapBl);
+    for (int s = 0; s < STAGES2; ++s) {
+      ptx::mbar_init(full_bar(s), 1);   // leader's producer arms it; both CTAs' TMA bytes complete it
+      ptx::mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar(b), 1);
+      ptx::mbar_init(tempty_bar(b), 2 * EPI_WARPS);  // epilogue warps of both CTAs
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<2>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+    ptx::tmem_relinquish<2>();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_chunks = (n_kblocks + chunk_kblocks - 1) / chunk_kblocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const void* mapB = cta == 0 ? static_cast<const void*>(&mapBh) : static_cast<const void*>(&mapBl);
+      for (int t = pair; t < n_tiles; t += n_pairs) {
+        const Tile tile = tiles[t];
+        const int row_a = (tile.ti + static_cast<int>(cta)) * BM, row_b = tile.tj * BN;
+        for (int kb = 0; kb < n_kblocks; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+          // bytes of BOTH CTAs complete the leader's barrier
+          if (cta == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
+          const uint32_t lead_bar = ptx::mapa_u32(full_bar(stage), 0);
+          ptx::tma_load_2d_2sm(sa, &mapP, lead_bar, kb * BK, row_a);
+          ptx::tma_load_2d_2sm(sa + A_BYTES, mapB, lead_bar, kb * BK, row_b);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // -------------------------------------------------- MMA issuer (leader only)
+    if (lane == 0 && cta == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, DN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t chunk = 0;
+      for (int t = pair; t < n_tiles; t += n_pairs) {
+        for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
+          const uint32_t buf = chunk & 1u;
+          ptx::mbar_wait(tempty_bar(buf), ((chunk >> 1) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * DN;
+          const int kb_end = min(n_kblocks, (ch + 1) * chunk_kblocks);
+          for (int kb = ch * chunk_kblocks; kb < kb_end; ++kb) {
+            ptx::mbar_wait(full_bar(stage), phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+            const uint64_t da = ptx::umma_desc_k_sw128(sa);
+            const uint64_t db = ptx::umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k)
+              ptx::umma_bf16<2>(d_tmem, da + 2u * k, db + 2u * k, idesc,
+                                (kb > ch * chunk_kblocks || k > 0) ? 1u : 0u);
+            ptx::umma_commit_2sm(empty_bar(stage), 3);  // frees the stage in both CTAs
+            if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+          }
+          ptx::umma_commit_2sm(tfull_bar(buf), 3);  // accumulators of both CTAs complete
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int half = (warp - EPI_WARP0) >> 2;
+    uint32_t chunk = 0;
+    for (int t = pair; t < n_tiles; t += n_pairs) {
+      const Tile tile = tiles[t];
+      float acc[64];
+#pragma unroll
+      for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+      for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
+        const uint32_t buf = chunk & 1u;
+        ptx::mbar_wait(tfull_bar(buf), (chunk >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * DN + half * 64;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t v[16], w[16];
+          ptx::tmem_ld_32x16(taddr + cc * 16, v);
+          ptx::tmem_ld_32x16(taddr + BN + cc * 16, w);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int x = 0; x < 16; ++x)
+            acc[cc * 16 + x] += __uint_as_float(v[x]) + __uint_as_float(w[x]);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(buf), 0);  // the leader's barrier
+      }
+      const int64_t i = static_cast<int64_t>(tile.ti + static_cast<int>(cta)) * BM + q * 32 + lane;
+      if (i < n_samples) {
+        const double ri = r[i];
+        const int64_t rowoff = i * (i - 1) / 2 - first;
+        const int64_t j0 = static_cast<int64_t>(tile.tj) * BN + half * 64;
+#pragma unroll
+        for (int n = 0; n < 64; ++n) {
+          const int64_t j = j0 + n;
+          if (j < i) {
+            const double R = ri + r[j];
+            const double s = static_cast<double>(acc[n]);
+            const double d = (R - 2.0 * s) / (R - s);
+            out[rowoff + j] = d;
+            if (d < flag_below) {
+              unsigned long long slot = atomicAdd(n_flagged, 1ULL);
+              flagged[slot] = static_cast<uint32_t>(rowoff + j);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // the peer may still read our shared memory / signal our barriers
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc<2>(tmem_base, TMEM_COLS);
+  }
+}
+
 // Exact recompute of flagged pairs from the bf16 presence rows: one warp per
 // pair, fp64, true branch lengths.  Identical samples give exactly 0.
 __global__ void __launch_bounds__(256)
@@ -310,6 +494,8 @@ bool tc_setup(std::string* err) {
   }
   g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
   e = cudaFuncSetAttribute(k_unweighted_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_unweighted_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
   if (e != cudaSuccess) {
     if (err) *err = std::string("cudaFuncSetAttribute(k_unweighted_tc): ") + cudaGetErrorString(e);
     g_encode = nullptr;
@@ -342,8 +528,16 @@ static int tc_chunk_kblocks() {
 int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, const Tile* tiles,
                          int32_t n_tiles, int64_t n_samples, int64_t first, double* out,
                          double flag_below, uint32_t* flagged, unsigned long long* n_flagged,
-                         int num_sms, cudaStream_t s) {
+                         int num_sms, int ctas, cudaStream_t s) {
   if (n_tiles <= 0) return 0;
+  if (ctas == 2) {  // `tiles` lists pair tiles (ti even): one cluster of two CTAs each
+    int pairs = num_sms / 2;
+    int grid = 2 * (n_tiles < pairs ? n_tiles : pairs);
+    k_unweighted_tc2<<<grid, THREADS, SMEM2_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, kp / BK,
+                                                        tc_chunk_kblocks(), r, tiles, n_tiles, n_samples,
+                                                        first, out, flag_below, flagged, n_flagged);
+    return 1;
+  }
   int grid = n_tiles < num_sms ? n_tiles : num_sms;
   k_unweighted_tc<<<grid, THREADS, SMEM_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, kp / BK,
                                                     tc_chunk_kblocks(), r, tiles, n_tiles, n_samples,
