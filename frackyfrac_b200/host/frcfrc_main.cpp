@@ -140,7 +140,7 @@ int main(int argc, char** argv) {
       if (frc_next(job, &d, &first, &n) != FRC_OK) { std::string m = frc_last_error(job); frc_destroy(job); die(m); }
       if (n == 0) break;
       text.clear();
-      frchost::append_lines(d, n, text);
+      frchost::format_lines_parallel(d, n, static_cast<int>(fl.nt), text);  // -p threads format, one writer
       if (fwrite(text.data(), 1, text.size(), w) != text.size()) {  // frcfrc.go:59-63
         std::string m = std::string("write: ") + strerror(errno);
         frc_destroy(job);

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 namespace frchost {
 
@@ -308,6 +309,25 @@ void append_lines(const double* d, int64_t n, std::string& out) {
   }
 }
 
+void format_lines_parallel(const double* d, int64_t n, int threads, std::string& out) {
+  if (threads < 1) threads = 1;
+  if (threads == 1 || n < 4096) { append_lines(d, n, out); return; }
+  threads = static_cast<int>(std::min<int64_t>(threads, n / 2048));
+  std::vector<std::string> parts(threads);
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t) {
+    const int64_t b = n * t / threads, e = n * (t + 1) / threads;
+    th.emplace_back([&, t, b, e] {
+      parts[t].reserve(static_cast<size_t>(e - b) * 20);
+      append_lines(d + b, e - b, parts[t]);
+    });
+  }
+  size_t total = out.size();
+  for (int t = 0; t < threads; ++t) { th[t].join(); total += parts[t].size(); }
+  out.reserve(total);
+  for (auto& p : parts) out.append(p);
+}
+
 }  // namespace frchost
 
 // -------------------------------------------------------------------- C ABI
@@ -353,5 +373,17 @@ const int32_t* frch_csr_col(const frch_csr* c) { return c->c.col.data(); }
 const double* frch_csr_val(const frch_csr* c) { return c->c.val.data(); }
 
 int frch_format_go(double v, char* buf) { return frchost::format_go(v, buf); }
+
+// Formats n values, one per line; returns a malloc'd buffer (free with frch_free) and its length.
+char* frch_format_lines(const double* d, int64_t n, int threads, size_t* len) {
+  std::string out;
+  frchost::format_lines_parallel(d, n, threads, out);
+  char* p = static_cast<char*>(malloc(out.size() + 1));
+  memcpy(p, out.data(), out.size());
+  p[out.size()] = 0;
+  *len = out.size();
+  return p;
+}
+void frch_free(void* p) { free(p); }
 
 }  // extern "C"

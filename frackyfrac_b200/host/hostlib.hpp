@@ -51,4 +51,9 @@ int format_go(double v, char* buf);
 // One distance per line, exactly as `fmt.Fprintln(w, f)`; appends to `out`.
 void append_lines(const double* d, int64_t n, std::string& out);
 
+// Same bytes, formatted by `threads` workers over contiguous slices and joined in order
+// (the reference formats on one goroutine, frcfrc.go:58-62; at 10^9 pairs/s that is the
+// end-to-end bottleneck).
+void format_lines_parallel(const double* d, int64_t n, int threads, std::string& out);
+
 }  // namespace frchost

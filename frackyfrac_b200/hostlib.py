@@ -65,6 +65,9 @@ def lib():
         L.frch_csr_val.argtypes = [C.c_void_p]
         L.frch_csr_val.restype = C.POINTER(C.c_double)
         L.frch_format_go.argtypes = [C.c_double, C.c_char_p]
+        L.frch_format_lines.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_size_t)]
+        L.frch_format_lines.restype = C.c_void_p
+        L.frch_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -141,3 +144,14 @@ def format_go(v: float) -> str:
     buf = C.create_string_buffer(48)
     lib().frch_format_go(float(v), buf)
     return buf.value.decode()
+
+
+def format_lines(values, threads: int = 1) -> bytes:
+    """One Go-%v formatted value per line (what frcfrc writes to stdout / -o)."""
+    a = np.ascontiguousarray(values, np.float64)
+    n = C.c_size_t()
+    p = lib().frch_format_lines(a.ctypes.data, len(a), threads, C.byref(n))
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        lib().frch_free(p)

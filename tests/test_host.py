@@ -98,3 +98,26 @@ def test_cli_flag_rules(built):
     tree = os.path.join(GOLDEN, "wtd.tree")
     r = subprocess.run([hostlib.CLI_PATH, "-t", tree, "-s"], input="nope:1\n", capture_output=True, text=True)
     assert r.returncode == 2 and 'species "nope" which is not in the tree' in r.stderr
+
+
+def test_parallel_writer_is_byte_identical(built):
+    """N1: the ordered parallel writer must emit exactly the single-threaded bytes."""
+    import time
+
+    from frackyfrac_b200 import hostlib
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(17)
+    v = rng.random(300_000)
+    v[::1000] = 0.0
+    v[1::1000] = 1.0
+    v[2::1000] = np.nan
+    v[3::1000] = rng.random(300) * 1e-7
+    one = hostlib.format_lines(v, 1)
+    assert one == hostlib.format_lines(v, 7) == hostlib.format_lines(v, 64)
+    lines = one.decode().split("\n")
+    assert lines[-1] == "" and len(lines) == len(v) + 1
+    for k in list(range(0, 4000, 7)) + [len(v) - 1]:
+        assert lines[k] == orc.format_go(float(v[k]))
+    t0 = time.perf_counter(); hostlib.format_lines(v, 1); t1 = time.perf_counter(); hostlib.format_lines(v, 8); t2 = time.perf_counter()
+    assert (t2 - t1) < (t1 - t0) * 1.5  # never pathologically slower
