@@ -204,6 +204,7 @@ def run_ours(args, world, rank, local_rank):
     total_pairs = samples * (samples - 1) // 2
     ctx = engine.Context(local_rank)
     peaks, peaks_kind = load_peaks()
+    uw_flags = engine.FLAG_UW_BF16 if args.uw_kernel == "bf16" else 0
 
     def barrier():
         if dist is not None:
@@ -219,7 +220,7 @@ def run_ours(args, world, rank, local_rank):
 
     # ---------------------------------------------- value: inputs resident in HBM
     job = engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
-                     rank=rank, world=world, flags=engine.FLAG_NO_D2H)
+                     rank=rank, world=world, flags=engine.FLAG_NO_D2H | uw_flags)
     sampler = ClockSampler(local_rank)
     sampler.start()
     job.drain()
@@ -249,7 +250,7 @@ def run_ours(args, world, rank, local_rank):
 
     def e2e_step():
         with engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
-                        rank=rank, world=world) as j:
+                        rank=rank, world=world, flags=uw_flags) as j:
             n = j.drain()
             i = j.info()
         return n, i
@@ -277,7 +278,7 @@ def run_ours(args, world, rank, local_rank):
     roofline, cpu = None, None
     if rank == 0 and not args.no_roofline:
         rj = engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
-                        band_rows=1 << 20, flags=engine.FLAG_NO_D2H)
+                        band_rows=1 << 20, flags=engine.FLAG_NO_D2H | uw_flags)
         rj.drain()
         ms = []
         for _ in range(max(3, args.steps)):
@@ -295,17 +296,26 @@ def run_ours(args, world, rank, local_rank):
                         "unit": "T lane-op/s", "frac": ach / peak, "traffic": None, "kernel_ms": k_ms,
                         "peak_source": "derived: 148 SM x 128 lanes x sm_max_mhz"}
         else:
-            peak = peaks["bf16_tflops"]
+            # algorithmic work = one multiply-add per (pair, node) = 2*B flops per pair.
+            # bf16 hi/lo kernel: executes 2 bf16 planes on the kind::f16 pipe -> peak = measured bf16 burst.
+            # u8 kernel: executes 2 u8 planes on the kind::i8 pipe, whose rate is 2x the bf16 one
+            # (no measured int8 figure in MEASURED_PEAKS.json: derived as 2 x bf16_tflops, stated).
+            i8 = ri.operand_kind == 2
+            peak = peaks["bf16_tflops"] * (2.0 if i8 else 1.0)
             ach = total_pairs * 2.0 * B / (k_ms / 1e3) / 1e12
             n_tiles = sum(t + 1 for t in range((samples + 127) // 128))
             executed = n_tiles * 128 * 128 * ri.n_nodes_padded * 2 * 2.0 / (k_ms / 1e3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "k_unweighted_tc", "achieved": ach, "peak": peak,
-                        "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "kernel_ms": k_ms,
+            roofline = {"bound": "tensor", "kernel": "k_unweighted_tc2<u8>" if i8 else "k_unweighted_tc2<bf16>",
+                        "achieved": ach, "peak": peak,
+                        "unit": "TOP/s" if i8 else "TFLOP/s", "frac": ach / peak, "traffic": None, "kernel_ms": k_ms,
                         "executed_tflops": executed, "executed_frac": executed / peak,
-                        "peak_source": f"{peaks_kind} bf16_tflops (burst; kernel timed alone, one launch over all tiles)",
-                        "note": "algorithmic flops = 2*B per pair; the kernel executes 2 bf16 planes (hi/lo) and "
-                                "full diagonal tiles, reported as executed_* (the CTA-pair kernel also runs one "
-                                "masked tile above each second diagonal tile, not counted)"}
+                        "achieved_vs_bf16_peak": ach / peaks["bf16_tflops"],
+                        "peak_source": (f"2 x {peaks_kind} bf16_tflops (kind::i8 issues at twice the kind::f16 rate; "
+                                        "no measured int8 peak available)" if i8 else
+                                        f"{peaks_kind} bf16_tflops") + " (burst; kernel timed alone, one launch over all tiles)",
+                        "note": "algorithmic ops = 2*B per pair; the kernel executes 2 operand planes and full "
+                                "diagonal tiles over the padded contraction length, reported as executed_* (the "
+                                "CTA-pair kernel also runs one masked tile above each second diagonal tile, not counted)"}
     if rank == 0:
         if not args.no_cpu:
             cpu = cpu_baseline(tree, csr, weighted, target_s=args.ref_seconds)
@@ -316,7 +326,8 @@ def run_ours(args, world, rank, local_rank):
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32 numerator tiles, f64 embedding/denominators/output" if weighted else
-                        "bf16 x bf16 -> f32 (tcgen05), f64 row sums/epilogue/output",
+                        ("bf16 x bf16 -> f32 (tcgen05 kind::f16), f64 row sums/epilogue/output" if info.operand_kind == 1 else
+                         "u8 x u8 -> s32 (tcgen05 kind::i8, exact), f64 chunk scaling/row sums/epilogue/output"),
                "data": "synthetic",
                "config": workload_config(args.config, mode, leaves, samples, density, world),
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -345,6 +356,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (configs whose output exceeds host RAM)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-alone timing leg")
     ap.add_argument("--min-warmup", type=int, default=3)
+    ap.add_argument("--uw-kernel", default="u8", choices=["u8", "bf16"],
+                    help="operand encoding of the unweighted tensor-core kernel (FRC_FLAG_UW_BF16)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

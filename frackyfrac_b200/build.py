@@ -52,7 +52,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(OUT, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("FRC_BUILD_DEFS", "").split(), "-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             log = os.path.join(OUT, src + ".ptxas.log")
             with open(log, "w") as f:

@@ -186,35 +186,29 @@ k_expand_operands(const uint32_t* __restrict__ bits, int32_t n_nodes, int32_t nw
 
 
 // ------------------------------------------------- fused presence embedding
-// One launch for the whole unweighted embedding stage.  Samples are
-// independent, so a CTA that owns one word column (32 samples) can run the
-// entire bottom-up pass for them with block-level barriers only: its column of
-// the presence matrix (one 32-bit word per node) lives in shared memory (or in
-// a private global scratch column when the tree is too large for that).
+// Samples are independent, so a CTA that owns one word column (32 samples) can run the
+// entire bottom-up pass for them with block-level barriers only: its column of the
+// presence matrix (one 32-bit word per node) lives in shared memory (or in a private
+// global scratch column when the tree is too large for that).
 //   phase 1  scatter the 32 CSR rows into leaf words (shared-memory atomics)
-//   phase 2  per tree level: word(v) = OR of the children's words
-//   phase 3  publish the column to bitsT[w][kp] for k_presence_rowsum_t (r[s] =
-//            sum_v lenq[v] * present(v,s), fp64, fixed order) and k_expand_operands_t, which
-//            writes the three bf16 operands at HBM speed with thousands of CTAs
-//            (doing that from these 160 CTAs reached only 2.3 TB/s).
+//   phase 2  per tree level: every node ORs its word into its parent
+//   phase 3  publish the column in operand-column order: bitsT[w][k] = word(order[k])
+// k_presence_rowsum_t and k_expand_operands_t then run with thousands of CTAs (writing the
+// operands from these few hundred CTAs reached only 2.3 TB/s).
 template <bool kSmem>
 __global__ void __launch_bounds__(512)
 k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                        int64_t n_samples, const int32_t* __restrict__ level_nodes,
                        const int32_t* __restrict__ level_parent, const int32_t* __restrict__ level_ptr,
-                       int32_t height,
-                       int32_t n_nodes, int32_t kp, const double* __restrict__ lenq,
-                       const uint16_t* __restrict__ len_hi, const uint16_t* __restrict__ len_lo,
-                       uint32_t* __restrict__ scratch, double* __restrict__ r, uint16_t* __restrict__ P,
-                       uint16_t* __restrict__ Bh, uint16_t* __restrict__ Bl) {
+                       int32_t height, int32_t n_nodes, int32_t kp, const int32_t* __restrict__ order,
+                       uint32_t* __restrict__ node_scratch, uint32_t* __restrict__ bitsT) {
   extern __shared__ __align__(16) uint32_t smem_words[];
   __shared__ int32_t lptr[128];
   const int w = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // column storage padded to a multiple of 8 words so phase 4 can read groups of 8
-  uint32_t* colw = kSmem ? smem_words : scratch + static_cast<int64_t>(w) * kp;
+  uint32_t* colw = kSmem ? smem_words : node_scratch + static_cast<int64_t>(w) * n_nodes;
 
-  for (int32_t v = tid; v < kp; v += 512) colw[v] = 0u;
+  for (int32_t v = tid; v < n_nodes; v += 512) colw[v] = 0u;
   if (tid < 128 && tid <= height + 1) lptr[tid] = level_ptr[tid];
   __syncthreads();
   // phase 1
@@ -236,16 +230,16 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
     }
     __syncthreads();
   }
-  // phase 3: publish the column (already in place when it lives in global memory)
-  if (kSmem) {
-    uint32_t* dst = scratch + static_cast<int64_t>(w) * kp;
-    for (int32_t g = tid; g * 4 < kp; g += 512)
-      *reinterpret_cast<uint4*>(dst + g * 4) = *reinterpret_cast<const uint4*>(colw + g * 4);
+  // phase 3
+  uint32_t* dst = bitsT + static_cast<int64_t>(w) * kp;
+  for (int32_t k = tid; k < kp; k += 512) {
+    const int32_t v = order[k];
+    dst[k] = v >= 0 ? colw[v] : 0u;
   }
 }
 
-// partial[c][s] = sum over the nodes of chunk c of lenq[v] * present(v, s): one warp per
-// (word column, node chunk), lane = sample; words and lengths are read as 16-byte broadcasts.
+// partial[c][s] = sum over the columns of chunk c of lenq[k] * present(k, s): one warp per
+// (word column, column chunk), lane = sample; words and lengths are read as 16-byte broadcasts.
 __global__ void __launch_bounds__(32)
 k_presence_rowsum_t(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
                     const double* __restrict__ lenq8, double* __restrict__ partial, int64_t ld) {
@@ -269,11 +263,11 @@ k_presence_rowsum_t(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
   partial[static_cast<int64_t>(blockIdx.y) * ld + w * 32 + lane] = a0 + a1;
 }
 
-// Presence columns bitsT[nw][kp] (word w holds samples 32w..32w+31 of one node) -> the three
-// K-major bf16 operands [np][kp].  Block = 64 nodes x 256 samples; the only HBM-heavy kernel of
-// the embedding stage: 3 * np * kp * 2 bytes written, each warp store covers 128 contiguous bytes.
+// Presence columns bitsT[nw][kp] (word w holds samples 32w..32w+31 of one operand column) -> the
+// three K-major bf16 operands [np][kp].  Block = 64 columns x 256 samples; the only HBM-heavy kernel
+// of the embedding stage: 3 * np * kp * 2 bytes written, each warp store covers 128 contiguous bytes.
 __global__ void __launch_bounds__(256)
-k_expand_operands_t(const uint32_t* __restrict__ bitsT, int32_t n_nodes, int32_t nw, int32_t kp,
+k_expand_operands_t(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
                     int64_t np, const uint16_t* __restrict__ len_hi, const uint16_t* __restrict__ len_lo,
                     uint16_t* __restrict__ P, uint16_t* __restrict__ Bh, uint16_t* __restrict__ Bl) {
   __shared__ uint32_t words[8][64];
@@ -287,22 +281,97 @@ k_expand_operands_t(const uint32_t* __restrict__ bitsT, int32_t n_nodes, int32_t
   }
   __syncthreads();
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int32_t va = v0 + 2 * lane, vb = va + 1;
+  const int32_t va = v0 + 2 * lane;
   const uint2 wab = *reinterpret_cast<const uint2*>(&words[wi][2 * lane]);
   const uint32_t wa = wab.x, wb = wab.y;
-  const uint32_t ha = va < n_nodes ? len_hi[va] : 0, hb = vb < n_nodes ? len_hi[vb] : 0;
-  const uint32_t la = va < n_nodes ? len_lo[va] : 0, lb = vb < n_nodes ? len_lo[vb] : 0;
+  const uint32_t hab = *reinterpret_cast<const uint32_t*>(len_hi + va);  // len arrays are padded to kp
+  const uint32_t lab = *reinterpret_cast<const uint32_t*>(len_lo + va);
   const int64_t s0 = (static_cast<int64_t>(w0) + wi) * 32;
 #pragma unroll 4
   for (int it = 0; it < 32; ++it) {
     const int64_t s = s0 + it;
     if (s >= np) break;
-    const uint32_t ma = 0u - ((wa >> it) & 1u), mb = 0u - ((wb >> it) & 1u);
+    const uint32_t m = (0xFFFFu & (0u - ((wa >> it) & 1u))) | (0xFFFF0000u & (0u - ((wb >> it) & 1u)));
     const int64_t o = s * kp + va;
-    *reinterpret_cast<uint32_t*>(P + o) = (0x3F80u & ma) | ((0x3F80u & mb) << 16);
-    *reinterpret_cast<uint32_t*>(Bh + o) = (ha & ma) | ((hb & mb) << 16);
-    *reinterpret_cast<uint32_t*>(Bl + o) = (la & ma) | ((lb & mb) << 16);
+    *reinterpret_cast<uint32_t*>(P + o) = 0x3F803F80u & m;
+    *reinterpret_cast<uint32_t*>(Bh + o) = hab & m;
+    *reinterpret_cast<uint32_t*>(Bl + o) = lab & m;
   }
+}
+
+// Same for the u8 operands: block = 128 columns x 256 samples, 4 columns (one 32-bit store per
+// operand) per thread and sample; 3 * np * kp bytes written.
+__global__ void __launch_bounds__(256)
+k_expand_operands_u8(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp, int64_t np,
+                     const uint8_t* __restrict__ qa, const uint8_t* __restrict__ qh,
+                     const uint8_t* __restrict__ ql, uint8_t* __restrict__ A, uint8_t* __restrict__ Bh,
+                     uint8_t* __restrict__ Bl) {
+  __shared__ __align__(16) uint32_t words[8][128];
+  const int32_t v0 = blockIdx.x * 128;
+  const int32_t w0 = blockIdx.y * 8;
+  for (int idx = threadIdx.x; idx < 1024; idx += 256) {
+    int word = idx >> 7, node = idx & 127;
+    uint32_t x = 0;
+    if (w0 + word < nw) x = bitsT[static_cast<int64_t>(w0 + word) * kp + v0 + node];
+    words[word][node] = x;
+  }
+  __syncthreads();
+  const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t va = v0 + 4 * lane;
+  const uint4 w4 = *reinterpret_cast<const uint4*>(&words[wi][4 * lane]);
+  const uint32_t a4 = *reinterpret_cast<const uint32_t*>(qa + va);
+  const uint32_t h4 = *reinterpret_cast<const uint32_t*>(qh + va);
+  const uint32_t l4 = *reinterpret_cast<const uint32_t*>(ql + va);
+  const int64_t s0 = (static_cast<int64_t>(w0) + wi) * 32;
+#pragma unroll 4
+  for (int it = 0; it < 32; ++it) {
+    const int64_t s = s0 + it;
+    if (s >= np) break;
+    const uint32_t bits = ((w4.x >> it) & 1u) | (((w4.y >> it) & 1u) << 8) | (((w4.z >> it) & 1u) << 16) |
+                          (((w4.w >> it) & 1u) << 24);
+    const uint32_t m = bits * 0xFFu;  // 0x01 -> 0xFF per byte
+    const int64_t o = s * kp + va;
+    *reinterpret_cast<uint32_t*>(A + o) = a4 & m;
+    *reinterpret_cast<uint32_t*>(Bh + o) = h4 & m;
+    *reinterpret_cast<uint32_t*>(Bl + o) = l4 & m;
+  }
+}
+
+// One thread per operand column: x = len * 2^-e in [0, 2^24); search the 8-bit factor a for
+// the 16-bit m = round(x / a) that brings a * m closest to x.
+__global__ void k_quantize_lengths(const double* __restrict__ len_col, const int32_t* __restrict__ col_exp,
+                                   int32_t kp, uint8_t* __restrict__ qa, uint8_t* __restrict__ qh,
+                                   uint8_t* __restrict__ ql, double* __restrict__ lenq,
+                                   double* __restrict__ flag_u) {
+  const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kp) return;
+  const double len = len_col[k];
+  const int e = col_exp[k];
+  const double x = ldexp(len, -e);
+  int best_a = 0, best_m = 0;
+  if (len > 0.0) {
+    double best = 1e300;
+    int a0 = static_cast<int>(ceil(x / 65535.0));
+    if (a0 < 1) a0 = 1;
+    for (int a = a0; a <= 255; ++a) {
+      double m = rint(x / static_cast<double>(a));
+      if (m > 65535.0) continue;
+      if (m < 1.0) m = 1.0;
+      const double err = fabs(static_cast<double>(a) * m - x);
+      if (err < best) { best = err; best_a = a; best_m = static_cast<int>(m); }
+    }
+    if (best_a == 0) { best_a = 255; best_m = 65535; }  // x beyond the representable range: saturate
+  }
+  qa[k] = static_cast<uint8_t>(best_a);
+  qh[k] = static_cast<uint8_t>(best_m >> 8);
+  ql[k] = static_cast<uint8_t>(best_m & 255);
+  const double q = ldexp(static_cast<double>(best_a) * static_cast<double>(best_m), e);
+  lenq[k] = q;
+  // columns kept to 4e-6 relative bound every pair's error by 4e-6 of its own sums; the absolute
+  // errors of the others (small lengths merged into a chunk of larger ones) are summed, and a
+  // pair is recomputed exactly when that sum could exceed 2e-6 of its unique length
+  const double err = fabs(q - len);
+  if (err > 4e-6 * len) atomicAdd(flag_u, 5e5 * err);
 }
 
 }  // namespace
@@ -406,13 +475,15 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 }
 
 
-int64_t presence_fused_scratch_words(int32_t kp, int32_t nw) { return static_cast<int64_t>(kp) * nw; }
+int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw) {
+  return static_cast<size_t>(n_nodes) * 4 <= 200 * 1024 ? 0 : static_cast<int64_t>(n_nodes) * nw;
+}
 
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
-                                int32_t nw, int32_t kp, const double* lenq, const uint16_t* len_hi,
-                                const uint16_t* len_lo, uint32_t* scratch, double* partial, double* r,
-                                uint16_t* P, uint16_t* Bh, uint16_t* Bl, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(kp) * 4;
+                                int32_t nw, int32_t kp, const int32_t* order, const double* lenq,
+                                uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
+                                cudaStream_t s) {
+  const size_t smem = (static_cast<size_t>(t.n_nodes) * 4 + 15) & ~size_t(15);
   if (smem <= 200 * 1024) {
     static bool attr = false;
     if (!attr) {
@@ -420,24 +491,46 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
       attr = true;
     }
     k_embed_presence_fused<true><<<nw, 512, smem, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
-                                                       t.level_parent, level_ptr_dev, t.height,
-                                                       t.n_nodes, kp, lenq, len_hi, len_lo, scratch, r, P, Bh, Bl);
+                                                       t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
+                                                       order, node_scratch, bitsT);
   } else {
     k_embed_presence_fused<false><<<nw, 512, 0, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
-                                                     t.level_parent, level_ptr_dev, t.height,
-                                                     t.n_nodes, kp, lenq, len_hi, len_lo, scratch, r, P, Bh, Bl);
+                                                     t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
+                                                     order, node_scratch, bitsT);
   }
   const int64_t np = static_cast<int64_t>(nw) * 32;
-  {
-    const int chunks = pick_chunks(t.n_nodes);
-    const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 8));
-    dim3 g(nw, chunks);
-    k_presence_rowsum_t<<<g, 32, 0, s>>>(scratch, kp, per, lenq, partial, np);
-    k_reduce_partials<<<static_cast<unsigned>((np + kThreads - 1) / kThreads), kThreads, 0, s>>>(partial, chunks, np, np, r);
+  const int chunks = pick_chunks(t.n_nodes);
+  const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 8));
+  dim3 g(nw, chunks);
+  k_presence_rowsum_t<<<g, 32, 0, s>>>(bitsT, kp, per, lenq, partial, np);
+  k_reduce_partials<<<static_cast<unsigned>((np + kThreads - 1) / kThreads), kThreads, 0, s>>>(partial, chunks, np, np, r);
+  return 3;
+}
+
+int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
+                             const void* q0, const void* q1, const void* q2, void* P, void* Bh, void* Bl,
+                             cudaStream_t s) {
+  if (i8) {
+    dim3 grid(kp / 128, static_cast<unsigned>((np + 255) / 256));
+    k_expand_operands_u8<<<grid, 256, 0, s>>>(bitsT, nw, kp, np, static_cast<const uint8_t*>(q0),
+                                              static_cast<const uint8_t*>(q1), static_cast<const uint8_t*>(q2),
+                                              static_cast<uint8_t*>(P), static_cast<uint8_t*>(Bh),
+                                              static_cast<uint8_t*>(Bl));
+  } else {
+    (void)q0;
+    dim3 grid(kp / 64, static_cast<unsigned>((np + 255) / 256));
+    k_expand_operands_t<<<grid, 256, 0, s>>>(bitsT, nw, kp, np, static_cast<const uint16_t*>(q1),
+                                             static_cast<const uint16_t*>(q2), static_cast<uint16_t*>(P),
+                                             static_cast<uint16_t*>(Bh), static_cast<uint16_t*>(Bl));
   }
-  dim3 grid(kp / 64, static_cast<unsigned>((np + 255) / 256));
-  k_expand_operands_t<<<grid, 256, 0, s>>>(scratch, t.n_nodes, nw, kp, np, len_hi, len_lo, P, Bh, Bl);
-  return 4;
+  return 1;
+}
+
+int launch_quantize_lengths(const double* len_col, const int32_t* col_exp, int32_t kp, uint8_t* qa,
+                            uint8_t* qh, uint8_t* ql, double* lenq, double* flag_u, cudaStream_t s) {
+  cudaMemsetAsync(flag_u, 0, sizeof(double), s);
+  k_quantize_lengths<<<(kp + 127) / 128, 128, 0, s>>>(len_col, col_exp, kp, qa, qh, ql, lenq, flag_u);
+  return 1;
 }
 
 }  // namespace frc

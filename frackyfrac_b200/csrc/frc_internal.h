@@ -70,15 +70,30 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
                            int64_t np, const uint16_t* len_hi, const uint16_t* len_lo,
                            uint16_t* P, uint16_t* Bh, uint16_t* Bl, cudaStream_t s);
 
-// The whole unweighted embedding stage in one launch (scatter, level passes, row
-// sums, operand expansion); one CTA per 32 samples.  `scratch` holds the
-// per-CTA presence column when it does not fit shared memory
-// (presence_fused_scratch_words(kp, nw) words, 0 when shared memory is used).
-int64_t presence_fused_scratch_words(int32_t kp, int32_t nw);
+// The unweighted embedding stage of the fast path: one CTA per 32 samples runs the whole
+// bottom-up presence pass in shared memory (scatter, one block barrier per tree level) and
+// publishes its word column in OPERAND COLUMN order: bitsT[w][k] = presence word of node
+// order[k] (0 where order[k] < 0); then the row sums r[s] = sum_k lenq[k] * present(k, s)
+// (fp64, fixed order) and the expansion into the three K-major operands [np][kp]:
+//   bf16: P = 0/1, Bh = P * len_hi, Bl = P * len_lo          (len_hi / len_lo per column)
+//   u8  : A = P * qa, Bh = P * qh, Bl = P * ql               (see k_quantize_lengths)
+// `node_scratch` holds the per-CTA node-indexed column when the tree is too large for shared
+// memory (presence_node_scratch_words(n_nodes, nw) words, 0 when shared memory is used).
+int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw);
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
-                                int32_t nw, int32_t kp, const double* lenq, const uint16_t* len_hi,
-                                const uint16_t* len_lo, uint32_t* scratch, double* partial, double* r,
-                                uint16_t* P, uint16_t* Bh, uint16_t* Bl, cudaStream_t s);
+                                int32_t nw, int32_t kp, const int32_t* order, const double* lenq,
+                                uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
+                                cudaStream_t s);
+int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
+                             const void* q0, const void* q1, const void* q2, void* P, void* Bh, void* Bl,
+                             cudaStream_t s);
+// u8 block floating point: for operand column k with true length len_col[k] >= 0 and chunk
+// exponent col_exp[k], find the 8-bit a and 16-bit m = 256*qh + ql minimising
+// |a * m * 2^e - len| ; lenq[k] = a * m * 2^e (exact in fp64).
+// flag_u[0] = 5e5 * sum of |lenq - len| over the columns whose relative quantisation error
+// exceeds 4e-6 (pairs with a unique length below that are recomputed exactly).
+int launch_quantize_lengths(const double* len_col, const int32_t* col_exp, int32_t kp, uint8_t* qa,
+                            uint8_t* qh, uint8_t* ql, double* lenq, double* flag_u, cudaStream_t s);
 
 // ---- exact.cu ---------------------------------------------------------------
 // fp64 reference-order distances for pairs [first, first+count) of the triangle.
@@ -92,22 +107,26 @@ int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* l
 void weighted_setup();  // cudaFuncSetAttribute calls, once per process
 
 // ---- unweighted_tc.cu -------------------------------------------------------
-struct TcOperands;  // opaque: tensor maps
-TcOperands* tc_operands_create(const uint16_t* P, const uint16_t* Bh, const uint16_t* Bl, int64_t np,
-                               int32_t kp, std::string* err);
+struct TcOperands;  // opaque: tensor maps + chunk table
+// Runs of 128-byte K blocks that accumulate uninterrupted in TMEM; device arrays.
+struct TcChunks { const int32_t* end = nullptr; const double* scale = nullptr; int32_t n = 0; };
+// flag_u: device scalar; pairs with unique length below it are recomputed exactly (null: none).
+TcOperands* tc_operands_create(const void* P, const void* Bh, const void* Bl, int64_t np, int32_t kp,
+                               bool i8, const TcChunks& chunks, const double* len_col, const double* flag_u,
+                               std::string* err);
 void tc_operands_destroy(TcOperands* o);
+int tc_chunk_kblocks();  // bf16: K blocks per fp32 accumulation run (FRC_TC_CHUNK_KBLOCKS)
 // Distances of the tiles in `tiles` into out[index - first]; the band offset of
 // every pair with d < flag_below is appended to flagged[] (count in *n_flagged;
 // capacity = pairs of the band, so it cannot overflow) for the fix-up pass.
-int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, const Tile* tiles,
-                         int32_t n_tiles, int64_t n_samples, int64_t first, double* out,
-                         double flag_below, uint32_t* flagged, unsigned long long* n_flagged,
-                         int num_sms, int ctas, cudaStream_t s);
+int launch_unweighted_tc(const TcOperands* ops, const double* r, const Tile* tiles, int32_t n_tiles,
+                         int64_t n_samples, int64_t first, double* out, double flag_below,
+                         uint32_t* flagged, unsigned long long* n_flagged, int num_sms, int ctas,
+                         cudaStream_t s);
 // fp64 recompute of the flagged pairs from the presence rows and true lengths.
-int launch_unweighted_fixup(const TcOperands* ops, int32_t n_nodes, int32_t kp, const double* length,
-                            const uint32_t* flagged, const unsigned long long* n_flagged,
-                            unsigned long long* count_host, int64_t first, double* out, int num_sms,
-                            cudaStream_t s);
+int launch_unweighted_fixup(const TcOperands* ops, const uint32_t* flagged,
+                            const unsigned long long* n_flagged, unsigned long long* count_host,
+                            int64_t first, double* out, int num_sms, cudaStream_t s);
 bool tc_setup(std::string* err);  // smem attribute + driver entry points, once per process
 
 }  // namespace frc

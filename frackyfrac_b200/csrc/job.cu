@@ -8,6 +8,7 @@
 // order by frc_next (the ordered iter.Seq of unifrac.go:209-228).
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -192,13 +193,17 @@ struct frc_job {
   bool fused_embed = true;
   bool zero_copy = false;
   int tc_ctas = 1;  // CTAs per tensor-core tile group (2 = cta_group::2 pairs)
-  uint16_t *d_len_hi = nullptr, *d_len_lo = nullptr;
-  double* d_lenq = nullptr;
+  bool i8 = false;  // fast unweighted: u8 block-floating-point operands (kind::i8) instead of bf16 hi/lo
+  // per operand column (fast unweighted): q0/q1/q2 = bf16 (unused, len_hi, len_lo) or u8 (a, m_hi, m_lo)
+  void *d_q0 = nullptr, *d_q1 = nullptr, *d_q2 = nullptr;
+  int32_t *d_order = nullptr, *d_col_exp = nullptr;
+  double *d_lenq = nullptr, *d_len_col = nullptr, *d_flag_u = nullptr;
+  TcChunks d_chunks;
   float* d_lenf = nullptr;
   double *d_E = nullptr, *d_total = nullptr, *d_W = nullptr, *d_r = nullptr, *d_scratch = nullptr;
   float* d_A = nullptr;
-  uint32_t* d_bits = nullptr;
-  uint16_t *d_P = nullptr, *d_Bh = nullptr, *d_Bl = nullptr;
+  uint32_t *d_bits = nullptr, *d_node_scratch = nullptr;
+  void *d_P = nullptr, *d_Bh = nullptr, *d_Bl = nullptr;
   TcOperands* tc = nullptr;
 
   Slot slots[kSlots];
@@ -298,17 +303,20 @@ int run_embedding(frc_job* j) {
     j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
   } else {
     if (j->fused_embed) {
-      launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->kp, j->d_lenq,
-                                              j->d_len_hi, j->d_len_lo, j->d_bits, j->d_scratch, j->d_r, j->d_P,
-                                              j->d_Bh, j->d_Bl, s);
+      launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->kp, j->d_order,
+                                              j->d_lenq, j->d_node_scratch, j->d_bits, j->d_scratch, j->d_r, s);
+      launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
+                                           j->d_P, j->d_Bh, j->d_Bl, s);
     } else {
       launches += launch_embed_bits(j->dtree, j->level_ptr.data(), j->dcsr, j->d_bits, j->nw, s);
       launches += launch_presence_rowsum(j->d_bits, j->B, j->nw, j->d_lenq, j->d_r, j->d_scratch, s);
-      launches += launch_expand_operands(j->d_bits, j->B, j->nw, j->kp, j->np, j->d_len_hi, j->d_len_lo,
-                                         j->d_P, j->d_Bh, j->d_Bl, s);
+      launches += launch_expand_operands(j->d_bits, j->B, j->nw, j->kp, j->np,
+                                         static_cast<const uint16_t*>(j->d_q1), static_cast<const uint16_t*>(j->d_q2),
+                                         static_cast<uint16_t*>(j->d_P), static_cast<uint16_t*>(j->d_Bh),
+                                         static_cast<uint16_t*>(j->d_Bl), s);
     }
     // bits written + read once per level pass, three bf16 operands written once (+ CSR cols)
-    j->info.embed_bytes = 2LL * j->B * j->nw * 4 + 3LL * j->np * j->kp * 2 + 4LL * j->nnz;
+    j->info.embed_bytes = 2LL * j->B * j->nw * 4 + 3LL * j->np * j->kp * (j->i8 ? 1 : 2) + 4LL * j->nnz;
   }
   JOB_CUDA(j, cudaGetLastError());
   JOB_CUDA(j, cudaEventRecord(j->ev_embed1, s));
@@ -341,11 +349,11 @@ int enqueue_band(frc_job* j, size_t idx) {
     // previous band's bulk D2H and stall this band (measured).  Counters are per band, zeroed once
     // per run; the fix-up kernel publishes the count through mapped pinned memory.
     unsigned long long* cnt = j->d_flag_counts + idx;
-    launches += launch_unweighted_tc(j->tc, j->kp, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
+    launches += launch_unweighted_tc(j->tc, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
                                      b.first, sl.dev, kFlagBelow, sl.flagged, cnt, c->num_sms, j->tc_ctas, s);
     JOB_CUDA(j, cudaEventRecord(sl.k1, s));
-    launches += launch_unweighted_fixup(j->tc, j->B, j->kp, j->dtree.length, sl.flagged, cnt,
-                                        sl.n_flagged_host, b.first, sl.dev, c->num_sms, s);
+    launches += launch_unweighted_fixup(j->tc, sl.flagged, cnt, sl.n_flagged_host, b.first, sl.dev,
+                                        c->num_sms, s);
   }
   JOB_CUDA(j, cudaGetLastError());
   if (j->exact || j->weighted) JOB_CUDA(j, cudaEventRecord(sl.k1, s));
@@ -596,8 +604,84 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     // CTA pairs (cta_group::2) by default; FRC_TC_CTAS=1 selects the single-CTA kernel
     j->tc_ctas = (!(e && atoi(e) == 1) && !j->exact && !j->weighted) ? 2 : 1;
   }
+  // ------------------------------------- operand columns of the fast unweighted path
+  // Column k of the K-major operands holds node col_order[k] (-1: padding).  bf16: identity
+  // order, uniform accumulation chunks.  u8: nodes grouped by binade pairs of their length so
+  // that one power-of-two scale per chunk leaves every length a 21..24-bit integer a * m
+  // (zero-length nodes contribute nothing and get no column).
+  std::vector<int32_t> col_order, col_exp, chunk_end;
+  std::vector<double> len_col, chunk_scale;
+  if (!j->exact && !j->weighted) {
+    { const char* e = getenv("FRC_EMBED_LEVELS"); j->fused_embed = !(e && atoi(e) == 1); }
+    const char* ek = getenv("FRC_UW_KERNEL");  // "bf16" forces the bf16 hi/lo kernel
+    j->i8 = j->tc_ctas == 2 && j->fused_embed && !neg_len && !(opts->flags & FRC_FLAG_UW_BF16) &&
+            !(ek && strcmp(ek, "bf16") == 0);
+    if (j->i8) {
+      constexpr int kGroups = 24, kBlockCols = 128, kMaxChunkBlocks = 128;
+      int e_max = INT32_MIN;
+      for (int32_t v = 0; v < B; ++v)
+        if (tree->length[v] > 0) e_max = std::max(e_max, std::ilogb(tree->length[v]));
+      int gb = 3;  // binades per group: x = len * 2^-e in [2^20, 2^23), >= 110 candidate factors a
+      if (const char* e = getenv("FRC_U8_GROUP_BINADES")) gb = std::max(1, std::min(16, atoi(e)));
+      auto group_of = [&](double l) { return std::min(kGroups - 1, (e_max - std::ilogb(l)) / gb); };
+      int32_t cnt[kGroups] = {0};
+      for (int32_t v = 0; v < B; ++v)
+        if (tree->length[v] > 0) cnt[group_of(tree->length[v])]++;
+      // Groups -> accumulation chunks.  Every chunk costs a TMEM drain (>= 2k cycles: 128 KB at
+      // 64 B/clk) that only hides behind a long enough MMA run, so a group opens a chunk of its own
+      // only when it is large; smaller groups below it join the current chunk at that chunk's
+      // (larger) scale.  Their lengths then keep fewer significant bits; k_quantize_lengths sums the
+      // absolute error of every column that misses 4e-6 relative, and pairs whose unique length is
+      // too small for that sum to be harmless are recomputed exactly (flag_u).
+      constexpr int32_t kMinChunkCols = 1024;
+      int chunk_of[kGroups], chunk_exp[kGroups], n_ch = 0;
+      int32_t ch_cols[kGroups] = {0};
+      for (int g = 0; g < kGroups; ++g) {
+        if (cnt[g] == 0) { chunk_of[g] = -1; continue; }
+        if (n_ch == 0 || cnt[g] >= kMinChunkCols) {
+          chunk_exp[n_ch] = e_max - gb * g - 22;  // top of the group: len < 2^(e_max-gb*g+1) -> x < 2^23
+          ++n_ch;
+        }
+        chunk_of[g] = n_ch - 1;
+        ch_cols[n_ch - 1] += cnt[g];
+      }
+      int32_t ch_off[kGroups + 1] = {0}, fill[kGroups];
+      for (int c = 0; c < n_ch; ++c) ch_off[c + 1] = ch_off[c] + static_cast<int32_t>(round_up(ch_cols[c], kBlockCols));
+      j->kp = std::max<int32_t>(ch_off[n_ch], kBlockCols);
+      col_order.assign(j->kp, -1); col_exp.assign(j->kp, 0); len_col.assign(j->kp, 0.0);
+      {  // columns of a chunk: its groups from large to small lengths, node id order inside a group
+        int32_t next = 0;
+        for (int c = 0, g = 0; c < n_ch; ++c) {
+          next = ch_off[c];
+          for (; g < kGroups && (chunk_of[g] == c || chunk_of[g] < 0); ++g)
+            if (chunk_of[g] == c) { fill[g] = next; next += cnt[g]; }
+        }
+      }
+      for (int32_t v = 0; v < B; ++v) {
+        const double l = tree->length[v];
+        if (!(l > 0)) continue;
+        const int32_t k = fill[group_of(l)]++;
+        col_order[k] = v; len_col[k] = l;
+      }
+      for (int c = 0; c < n_ch; ++c) {
+        for (int32_t k = ch_off[c]; k < ch_off[c + 1]; ++k) col_exp[k] = chunk_exp[c];
+        for (int32_t kb = ch_off[c] / kBlockCols; kb < ch_off[c + 1] / kBlockCols;) {
+          kb = std::min(ch_off[c + 1] / kBlockCols, kb + kMaxChunkBlocks);  // plane sums stay < 2^31
+          chunk_end.push_back(kb);
+          chunk_scale.push_back(std::ldexp(1.0, chunk_exp[c]));
+        }
+      }
+      if (chunk_end.empty()) { chunk_end.push_back(1); chunk_scale.push_back(1.0); }
+    } else {
+      col_order.assign(j->kp, -1); len_col.assign(j->kp, 0.0);
+      for (int32_t v = 0; v < B; ++v) { col_order[v] = v; len_col[v] = tree->length[v]; }
+      const int32_t nkb = j->kp / kKBlock, per = tc_chunk_kblocks();
+      for (int32_t kb = 0; kb < nkb;) { kb = std::min(nkb, kb + per); chunk_end.push_back(kb); chunk_scale.push_back(1.0); }
+    }
+    j->info.n_nodes_padded = j->kp;
+    j->info.operand_kind = j->i8 ? 2 : 1;
+  }
   int64_t band_rows = choose_band_rows(N, opts->band_rows, world, !(opts->flags & FRC_FLAG_NO_D2H));
-  if (j->tc_ctas == 2) band_rows = round_up(band_rows, 2 * kTile);  // bands start on a tile-pair boundary
   for (int64_t r0 = 0; r0 < N; r0 += band_rows) {
     Band b;
     b.row0 = r0; b.row1 = std::min(N, r0 + band_rows);
@@ -624,10 +708,9 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       // column-major inside the band: CTAs running together share the few
       // i-tiles of the band and neighbouring j-tiles (L2 reuse of both operands)
       if (j->tc_ctas == 2) {
-        // pair tiles: (ti, tj) and (ti+1, tj) with ti even; needed when ti + 1 >= tj
-        for (int32_t tj = 0; tj <= t1; ++tj)
-          for (int32_t ti = std::max((tj - 1) & ~1, t0); ti <= t1; ti += 2)
-            if (ti >= 0 && ti + 1 >= tj) j->tiles.push_back({ti, tj});
+        // pair tiles: (ti, tj) and (ti, tj+1) with tj even; needed when tj <= ti
+        for (int32_t tj = 0; tj <= t1; tj += 2)
+          for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) j->tiles.push_back({ti, tj});
       } else {
         for (int32_t tj = 0; tj <= t1; ++tj)
           for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) j->tiles.push_back({ti, tj});
@@ -660,9 +743,13 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       s_val = seg(need_val ? sizeof(double) * nnz : 0), s_parent = seg(sizeof(int32_t) * B),
       s_len = seg(sizeof(double) * B), s_cptr = seg(sizeof(int32_t) * (B + 1)),
       s_cidx = seg(sizeof(int32_t) * B), s_lvl = seg(sizeof(int32_t) * B),
-      s_hi = seg(sizeof(uint16_t) * B), s_lo = seg(sizeof(uint16_t) * B), s_lenq = seg(sizeof(double) * j->kp),
+      s_q0 = seg(j->kp), s_hi = seg(sizeof(uint16_t) * j->kp), s_lo = seg(sizeof(uint16_t) * j->kp),
+      s_lenq = seg(sizeof(double) * j->kp),
       s_lenf = seg(sizeof(float) * j->kp), s_tiles = seg(sizeof(Tile) * j->tiles.size()),
-      s_lptr = seg(sizeof(int32_t) * (H + 2)), s_lpar = seg(sizeof(int32_t) * B);
+      s_lptr = seg(sizeof(int32_t) * (H + 2)), s_lpar = seg(sizeof(int32_t) * B),
+      s_order = seg(sizeof(int32_t) * col_order.size()), s_cexp = seg(sizeof(int32_t) * col_exp.size()),
+      s_lcol = seg(sizeof(double) * len_col.size()), s_cend = seg(sizeof(int32_t) * chunk_end.size()),
+      s_cscale = seg(sizeof(double) * chunk_scale.size());
   char* stage = pin_alloc<char>(j, total, &rc);
   if (!stage) return bail(rc);
   j->d_inputs = dev_alloc<char>(j, total, &rc);
@@ -745,15 +832,22 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     uint16_t* lo = reinterpret_cast<uint16_t*>(stage + s_lo.off);
     double* lq = reinterpret_cast<double*>(stage + s_lenq.off);
     float* lf = reinterpret_cast<float*>(stage + s_lenf.off);
-    for (int32_t v = 0; v < B; ++v) {
-      double l = tree->length[v];
-      hi[v] = bf16_rn(static_cast<float>(l));
-      double res = l - static_cast<double>(bf16_to_float(hi[v]));
-      lo[v] = (l == l && !std::isinf(l)) ? bf16_rn(static_cast<float>(res)) : 0;
-      lq[v] = static_cast<double>(bf16_to_float(hi[v])) + static_cast<double>(bf16_to_float(lo[v]));
-      lf[v] = static_cast<float>(l);
+    if (!j->i8) {  // (u8: k_quantize_lengths fills q0/q1/q2 and lenq on the device)
+      for (int32_t v = 0; v < B; ++v) {
+        double l = tree->length[v];
+        hi[v] = bf16_rn(static_cast<float>(l));
+        double res = l - static_cast<double>(bf16_to_float(hi[v]));
+        lo[v] = (l == l && !std::isinf(l)) ? bf16_rn(static_cast<float>(res)) : 0;
+        lq[v] = static_cast<double>(bf16_to_float(hi[v])) + static_cast<double>(bf16_to_float(lo[v]));
+      }
+      for (int32_t v = B; v < j->kp; ++v) { hi[v] = 0; lo[v] = 0; lq[v] = 0.0; }
     }
-    for (int32_t v = B; v < j->kp; ++v) { lf[v] = 0.f; lq[v] = 0.0; }
+    for (int32_t v = 0; v < j->kp; ++v) lf[v] = v < B ? static_cast<float>(tree->length[v]) : 0.f;
+    if (!col_order.empty()) memcpy(stage + s_order.off, col_order.data(), s_order.bytes);
+    if (!col_exp.empty()) memcpy(stage + s_cexp.off, col_exp.data(), s_cexp.bytes);
+    if (!len_col.empty()) memcpy(stage + s_lcol.off, len_col.data(), s_lcol.bytes);
+    if (!chunk_end.empty()) memcpy(stage + s_cend.off, chunk_end.data(), s_cend.bytes);
+    if (!chunk_scale.empty()) memcpy(stage + s_cscale.off, chunk_scale.data(), s_cscale.bytes);
     if (!j->tiles.empty()) memcpy(stage + s_tiles.off, j->tiles.data(), sizeof(Tile) * j->tiles.size());
     memcpy(stage + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
   }
@@ -779,9 +873,16 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->dtree.child_ptr = reinterpret_cast<int32_t*>(d + s_cptr.off);
   j->dtree.child_idx = reinterpret_cast<int32_t*>(d + s_cidx.off);
   j->dtree.level_nodes = reinterpret_cast<int32_t*>(d + s_lvl.off);
-  j->d_len_hi = reinterpret_cast<uint16_t*>(d + s_hi.off);
-  j->d_len_lo = reinterpret_cast<uint16_t*>(d + s_lo.off);
+  j->d_q0 = d + s_q0.off;
+  j->d_q1 = d + s_hi.off;
+  j->d_q2 = d + s_lo.off;
   j->d_lenq = reinterpret_cast<double*>(d + s_lenq.off);
+  j->d_order = reinterpret_cast<int32_t*>(d + s_order.off);
+  j->d_col_exp = reinterpret_cast<int32_t*>(d + s_cexp.off);
+  j->d_len_col = reinterpret_cast<double*>(d + s_lcol.off);
+  j->d_chunks.end = reinterpret_cast<int32_t*>(d + s_cend.off);
+  j->d_chunks.scale = reinterpret_cast<double*>(d + s_cscale.off);
+  j->d_chunks.n = static_cast<int32_t>(chunk_end.size());
   j->d_lenf = reinterpret_cast<float*>(d + s_lenf.off);
   j->d_tiles = reinterpret_cast<Tile*>(d + s_tiles.off);
   j->d_level_ptr = reinterpret_cast<int32_t*>(d + s_lptr.off);
@@ -800,22 +901,31 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     }
   } else {
     {
-      const char* e = getenv("FRC_EMBED_LEVELS");  // 1 = the multi-launch level-synchronous path
-      j->fused_embed = !(e && atoi(e) == 1);
-      size_t words = j->fused_embed ? static_cast<size_t>(presence_fused_scratch_words(j->kp, j->nw))
-                                    : static_cast<size_t>(B) * j->nw;
+      // fused: published columns bitsT[nw][kp] (+ node-indexed scratch for trees beyond shared memory);
+      // FRC_EMBED_LEVELS=1: node-major bits[B][nw], one launch per tree level
+      size_t words = j->fused_embed ? static_cast<size_t>(j->kp) * j->nw : static_cast<size_t>(B) * j->nw;
       if (!(j->d_bits = dev_alloc<uint32_t>(j, std::max<size_t>(words, 64), &rc))) return bail(rc);
+      const size_t ns = j->fused_embed ? static_cast<size_t>(presence_node_scratch_words(B, j->nw)) : 0;
+      if (ns && !(j->d_node_scratch = dev_alloc<uint32_t>(j, ns, &rc))) return bail(rc);
     }
-    const size_t opsz = static_cast<size_t>(j->np) * j->kp;
-    if (!(j->d_P = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
-    if (!(j->d_Bh = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
-    if (!(j->d_Bl = dev_alloc<uint16_t>(j, opsz, &rc))) return bail(rc);
+    const size_t opsz = static_cast<size_t>(j->np) * j->kp * (j->i8 ? 1 : 2);
+    if (!(j->d_P = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
+    if (!(j->d_Bh = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
+    if (!(j->d_Bl = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
     if (!(j->d_r = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
     if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
     if (!(j->d_flag_counts = dev_alloc<unsigned long long>(j, j->mine.size() + 1, &rc))) return bail(rc);
     std::string terr;
-    j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, &terr);
+    if (j->i8 && !(j->d_flag_u = dev_alloc<double>(j, 1, &rc))) return bail(rc);
+    j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, j->i8, j->d_chunks, j->d_len_col,
+                               j->d_flag_u, &terr);
     if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
+    if (j->i8) {  // a function of the tree only: once per job, not per restart
+      j->info.kernel_launches += launch_quantize_lengths(
+          j->d_len_col, j->d_col_exp, j->kp, static_cast<uint8_t*>(j->d_q0), static_cast<uint8_t*>(j->d_q1),
+          static_cast<uint8_t*>(j->d_q2), j->d_lenq, j->d_flag_u, c->stream[0]);
+      CREATE_CUDA(cudaGetLastError());
+    }
   }
   { const char* e = getenv("FRC_ZERO_COPY"); j->zero_copy = e && atoi(e) == 1; }
   {

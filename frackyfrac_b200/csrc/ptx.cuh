@@ -138,6 +138,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, 8-bit integers -> int32 (K = 32 per instruction).
+template <int CG>
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                        uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // Arrive on `bar` once every tcgen05.mma issued so far by this thread is done.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -175,6 +193,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -196,6 +221,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4)                              // D format: F32
          | (1u << 7)                            // A format: BF16
          | (1u << 10)                           // B format: BF16
+         | (static_cast<uint32_t>(n >> 3) << 17)
+         | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// kind::i8 instruction descriptor: u8 x u8 -> s32, both operands K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_u8(int m, int n) {
+  return (2u << 4)                              // D format: S32
+         | (0u << 7)                            // A format: unsigned 8-bit
+         | (0u << 10)                           // B format: unsigned 8-bit
          | (static_cast<uint32_t>(n >> 3) << 17)
          | (static_cast<uint32_t>(m >> 4) << 24);
 }

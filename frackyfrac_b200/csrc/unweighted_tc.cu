@@ -42,6 +42,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "frc_internal.h"
 #include "ptx.cuh"
@@ -118,7 +119,7 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const Tile tile = tiles[t];
-        const int row_a = tile.ti * BM, row_b = tile.tj * BN;
+        const int row_a = tile.tj * BM, row_b = tile.ti * BN;  // lanes = column samples j (coalesced stores)
         for (int kb = 0; kb < n_kblocks; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
@@ -194,23 +195,23 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
       }
-      // fused ratio epilogue, fp64
-      const int64_t i = static_cast<int64_t>(tile.ti) * BM + q * 32 + lane;
-      if (i < n_samples) {
-        const double ri = r[i];
-        const int64_t rowoff = i * (i - 1) / 2 - first;
-        const int64_t j0 = static_cast<int64_t>(tile.tj) * BN + half * 64;
+      // fused ratio epilogue, fp64: lane = column sample j, registers = 64 row samples i
+      const int64_t j = static_cast<int64_t>(tile.tj) * BM + q * 32 + lane;
+      const int64_t i0 = static_cast<int64_t>(tile.ti) * BN + half * 64;
+      if (j < n_samples && j < i0 + 64) {
+        const double rj = r[j];
 #pragma unroll
         for (int n = 0; n < 64; ++n) {
-          const int64_t j = j0 + n;
-          if (j < i) {
-            const double R = ri + r[j];
+          const int64_t i = i0 + n;
+          if (i < n_samples && j < i) {
+            const double R = r[i] + rj;
             const double s = static_cast<double>(acc[n]);
             const double d = (R - 2.0 * s) / (R - s);
-            out[rowoff + j] = d;
+            const int64_t off = i * (i - 1) / 2 - first + j;
+            out[off] = d;
             if (d < flag_below) {
               unsigned long long slot = atomicAdd(n_flagged, 1ULL);
-              flagged[slot] = static_cast<uint32_t>(rowoff + j);
+              flagged[slot] = static_cast<uint32_t>(off);
             }
           }
         }
@@ -228,29 +229,84 @@ k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
 
 // ----------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): two CTAs of a cluster (one TPC) compute two
-// vertically adjacent 128 x 128 tiles (ti, tj) and (ti+1, tj) with ONE MMA
-// stream of shape M256 x N256 x K16 issued by the leader CTA:
-//   A (256 rows)  = each CTA's own P[i-tile] in its own shared memory,
-//   B (256 rows)  = [Bh; Bl] of the j-tile, split across the pair: the leader
+// horizontally adjacent 128 x 128 tiles (ti, tj) and (ti, tj+1) with ONE MMA
+// stream of shape M256 x N256 issued by the leader CTA.  The MMA's M side is the
+// COLUMN sample of the output (S is symmetric, so the roles are free) because a TMEM
+// lane is a thread of the epilogue and consecutive columns j are what is contiguous
+// in the flat lower triangle: stores come out coalesced without any transpose
+// (with rows on the lanes every store hit 32 different sectors and the epilogue,
+// not the tensor pipe, bounded the kernel).
+//   A (256 rows)  = each CTA's own P[j-tile] in its own shared memory,
+//   B (256 rows)  = [Bh; Bl] of the i-tile, split across the pair: the leader
 //                   holds Bh, the peer holds Bl (same offset in both CTAs),
-//   D             = each CTA's TMEM holds its 128 rows x [hi | lo] columns.
+//   D             = each CTA's TMEM: 128 lanes (its j samples) x [hi | lo] columns (i samples).
 // Per SM this halves the B-side shared-memory reads and the L2 -> SM operand
-// traffic (32 KB per 64-node block per SM instead of 48 KB), which is what bounds
+// traffic (32 KB per 128-byte K block per SM instead of 48 KB), which is what bounds
 // the single-CTA kernel (shared memory: 96 + 96 B/clk demanded of 128 B/clk).
 // Barrier protocol: both producers' TMA bytes land on the LEADER's full barrier;
 // tcgen05.commit multicasts to both CTAs' empty / accumulator-full barriers; both
 // CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+//
+// Two operand encodings share this kernel (template kI8):
+//   bf16 (north-star form)  P in {0,1}, Bh = P*len_hi, Bl = P*len_lo as bf16, kind::f16,
+//        K = 16 per MMA, fp32 accumulators; chunk sums added in fp32 registers.
+//   u8 block floating point  every branch length is quantised to a * m * 2^e with an
+//        8-bit factor a, a 16-bit factor m = 256*mh + ml and a per-chunk exponent e
+//        (nodes are grouped by binade pairs along K): A = P*a, Bh = P*mh, Bl = P*ml as
+//        unsigned bytes, kind::i8, K = 32 per MMA (twice the nodes per instruction and
+//        per operand byte), int32 accumulators -- the contraction is EXACT integer
+//        arithmetic; chunk sums are scaled by 2^e and added in fp64 registers.
+// A K block is 128 bytes of every operand row either way (64 bf16 / 128 u8 nodes);
+// chunks are runs of K blocks [chunk_end[c-1], chunk_end[c]) with scale chunk_scale[c].
 constexpr int STAGES2 = 6;
 constexpr int STAGE2_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_BARS2 = 2 * STAGES2 + 4;
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + NUM_BARS2 * 8 + 16 + 1024;
+constexpr int BKB = 128;  // bytes of K per block and operand row
+// 16 epilogue warps = 4 TMEM lane quarters x 4 groups of 32 columns per plane: with the u8
+// operands the mainloop of a tile takes ~82k cycles, and 8 warps holding 64 fp64 accumulators
+// each (no registers left for instruction-level parallelism) needed longer than that for the
+// chunk drains + the ratio epilogue (ncu: stall_math on dependent DADD/DFMA chains).
+// Timeline counters for FRC_TC_DEBUG & 8 (cycles, per CTA): [0] MMA thread waiting for a free
+// TMEM buffer, [1] MMA thread waiting for operands, [2] MMA thread total, [3] producer waiting
+// for a free stage, [4] epilogue warp 2 waiting for an accumulator, [5] its drains, [6] its
+// ratio epilogue + stores, [7] its total.
+// Built only with -DFRC_TC_TIMELINE (scripts/exp_timeline.py); FRC_TC_DEBUG then also accepts
+// 1 = do not load B, 2 = do not load A, 4 = no ratio epilogue (timing attribution; garbage results).
+#ifdef FRC_TC_TIMELINE
+__device__ unsigned long long g_tc_dbg[512 * 8];
+#define TL(x) x
+#define TL_ON(mask) ((dbg & (mask)) != 0)
+#else
+#define TL(x)
+#define TL_ON(mask) false
+#endif
+constexpr int EPI2_WARPS = 16;
+constexpr int EPI2_COLS = 128 / (EPI2_WARPS / 4);  // accumulator columns per thread and plane
+constexpr int THREADS2 = 32 * (EPI_WARP0 + EPI2_WARPS);
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+// U / V for the ratio epilogue without the ~30-instruction IEEE fp64 division: fp32 reciprocal
+// seed, two fp64 Newton steps (relative error ~1e-16).  0/0 -> NaN as the reference (A8).
+__device__ __forceinline__ double ratio_div(double U, double V) {
+  if (!(V > 1e-30 && V < 1e30)) return U / V;
+  const double x0 = static_cast<double>(__frcp_rn(static_cast<float>(V)));
+  const double e0 = fma(-V, x0, 1.0);
+  const double x1 = fma(x0, e0, x0);
+  const double e1 = fma(-V, x1, 1.0);
+  const double x2 = fma(x1, e1, x1);
+  return U * x2;
+}
+
+template <bool kI8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapBh,
-                 const __grid_constant__ CUtensorMap mapBl, int32_t n_kblocks, int32_t chunk_kblocks,
+                 const __grid_constant__ CUtensorMap mapBl, const int32_t* __restrict__ chunk_end,
+                 const double* __restrict__ chunk_scale, int32_t n_chunks,
                  const double* __restrict__ r, const Tile* __restrict__ tiles, int32_t n_tiles,
                  int64_t n_samples, int64_t first, double* __restrict__ out, double flag_below,
-                 uint32_t* __restrict__ flagged, unsigned long long* __restrict__ n_flagged) {
+                 const double* __restrict__ flag_u_ptr, uint32_t* __restrict__ flagged,
+                 unsigned long long* __restrict__ n_flagged, int dbg) {
+  (void)dbg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -279,7 +335,7 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(tfull_bar(b), 1);
-      ptx::mbar_init(tempty_bar(b), 2 * EPI_WARPS);  // epilogue warps of both CTAs
+      ptx::mbar_init(tempty_bar(b), 2 * EPI2_WARPS);  // epilogue warps of both CTAs
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -293,7 +349,7 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_chunks = (n_kblocks + chunk_kblocks - 1) / chunk_kblocks;
+  const int n_kblocks = chunk_end[n_chunks - 1];
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -301,104 +357,167 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const void* mapB = cta == 0 ? static_cast<const void*>(&mapBh) : static_cast<const void*>(&mapBl);
+      constexpr int kElems = kI8 ? BKB : BKB / 2;  // tensor-map elements per K block
+      TL(long long w_empty = 0;)
       for (int t = pair; t < n_tiles; t += n_pairs) {
         const Tile tile = tiles[t];
-        const int row_a = (tile.ti + static_cast<int>(cta)) * BM, row_b = tile.tj * BN;
+        const int row_a = (tile.tj + static_cast<int>(cta)) * BM, row_b = tile.ti * BN;
         for (int kb = 0; kb < n_kblocks; ++kb) {
+          TL(const long long c0 = clock64();)
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          TL(w_empty += clock64() - c0;)
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;
           // bytes of BOTH CTAs complete the leader's barrier
-          if (cta == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
+          if (cta == 0)
+            ptx::mbar_expect_tx(full_bar(stage), 2 * ((TL_ON(2) ? 0 : A_BYTES) + (TL_ON(1) ? 0 : B_BYTES)));
           const uint32_t lead_bar = ptx::mapa_u32(full_bar(stage), 0);
-          ptx::tma_load_2d_2sm(sa, &mapP, lead_bar, kb * BK, row_a);
-          ptx::tma_load_2d_2sm(sa + A_BYTES, mapB, lead_bar, kb * BK, row_b);
+          if (!TL_ON(2)) ptx::tma_load_2d_2sm(sa, &mapP, lead_bar, kb * kElems, row_a);
+          if (!TL_ON(1)) ptx::tma_load_2d_2sm(sa + A_BYTES, mapB, lead_bar, kb * kElems, row_b);
           if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
         }
       }
+      TL(g_tc_dbg[blockIdx.x * 8 + 3] = w_empty;)
     }
     __syncwarp();
   } else if (warp == 1) {
     // -------------------------------------------------- MMA issuer (leader only)
     if (lane == 0 && cta == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, DN);
+      constexpr uint32_t idesc = kI8 ? ptx::umma_idesc_u8(2 * BM, DN) : ptx::umma_idesc_bf16(2 * BM, DN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t chunk = 0;
+      TL(long long w_tempty = 0; long long w_full = 0; const long long c_start = clock64();)
       for (int t = pair; t < n_tiles; t += n_pairs) {
+        int kb = 0;
         for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
           const uint32_t buf = chunk & 1u;
+          TL(const long long c0 = clock64();)
           ptx::mbar_wait(tempty_bar(buf), ((chunk >> 1) & 1u) ^ 1u);
+          TL(w_tempty += clock64() - c0;)
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * DN;
-          const int kb_end = min(n_kblocks, (ch + 1) * chunk_kblocks);
-          for (int kb = ch * chunk_kblocks; kb < kb_end; ++kb) {
+          const int kb_begin = kb, kb_end = chunk_end[ch];
+          for (; kb < kb_end; ++kb) {
+            TL(const long long c1 = clock64();)
             ptx::mbar_wait(full_bar(stage), phase);
+            TL(w_full += clock64() - c1;)
             ptx::tc_fence_after();
             const uint32_t sa = smem_base + stage * STAGE2_BYTES;
             const uint64_t da = ptx::umma_desc_k_sw128(sa);
             const uint64_t db = ptx::umma_desc_k_sw128(sa + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UK; ++k)
-              ptx::umma_bf16<2>(d_tmem, da + 2u * k, db + 2u * k, idesc,
-                                (kb > ch * chunk_kblocks || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // one MMA consumes 32 B of K per row (16 bf16 / 32 u8): +2 in the (>>4) start-address field
+              const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
+              if constexpr (kI8) ptx::umma_i8<2>(d_tmem, da + 2u * k, db + 2u * k, idesc, accum);
+              else ptx::umma_bf16<2>(d_tmem, da + 2u * k, db + 2u * k, idesc, accum);
+            }
             ptx::umma_commit_2sm(empty_bar(stage), 3);  // frees the stage in both CTAs
             if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
           }
           ptx::umma_commit_2sm(tfull_bar(buf), 3);  // accumulators of both CTAs complete
         }
       }
+      TL(g_tc_dbg[blockIdx.x * 8 + 0] = w_tempty; g_tc_dbg[blockIdx.x * 8 + 1] = w_full;
+         g_tc_dbg[blockIdx.x * 8 + 2] = clock64() - c_start;)
     }
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;
-    const int half = (warp - EPI_WARP0) >> 2;
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int cg = (warp - EPI_WARP0) >> 2;      // which EPI2_COLS columns of each plane it owns
+    using Acc = typename std::conditional<kI8, double, float>::type;
+    // pairs whose unique length U is below this are recomputed exactly as well: the summed absolute
+    // error of the imprecisely quantised branch lengths could exceed 2e-6 of U (k_quantize_lengths)
+    const double flag_u = flag_u_ptr ? *flag_u_ptr : 0.0;
     uint32_t chunk = 0;
+    TL(long long w_tfull = 0; long long t_drain = 0; long long t_ratio = 0; const long long e_start = clock64();)
     for (int t = pair; t < n_tiles; t += n_pairs) {
       const Tile tile = tiles[t];
-      float acc[64];
+      Acc acc[EPI2_COLS];
 #pragma unroll
-      for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+      for (int n = 0; n < EPI2_COLS; ++n) acc[n] = 0;
       for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
         const uint32_t buf = chunk & 1u;
+        const double scale = kI8 ? chunk_scale[ch] : 1.0;
+        TL(const long long c0 = clock64();)
         ptx::mbar_wait(tfull_bar(buf), (chunk >> 1) & 1u);
+        TL(const long long c1 = clock64();)
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * DN + half * 64;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * DN + cg * EPI2_COLS;
+        if constexpr (kI8) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t v[16], w[16];
-          ptx::tmem_ld_32x16(taddr + cc * 16, v);
-          ptx::tmem_ld_32x16(taddr + BN + cc * 16, w);
-          ptx::tmem_ld_wait();
+          for (int cc = 0; cc < EPI2_COLS / 8; ++cc) {
+            uint32_t v[8], w[8];
+            ptx::tmem_ld_32x8(taddr + cc * 8, v);
+            ptx::tmem_ld_32x8(taddr + BN + cc * 8, w);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int x = 0; x < 16; ++x)
-            acc[cc * 16 + x] += __uint_as_float(v[x]) + __uint_as_float(w[x]);
+            for (int x = 0; x < 8; ++x) {
+              // exact: both plane sums are in [0, 2^31), so S = 256*hi + lo < 2^40 is built with one
+              // 32x32->64 integer multiply-add and turned into a double by the 2^52 trick
+              // (mantissa bits = S, then one exact fp64 subtract) instead of two I2F conversions
+              const unsigned long long S = static_cast<unsigned long long>(v[x]) * 256ull + w[x];
+              const double sum = __longlong_as_double(static_cast<long long>(S | 0x4330000000000000ull)) - 4503599627370496.0;
+              acc[cc * 8 + x] = fma(scale, sum, acc[cc * 8 + x]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < EPI2_COLS / 16; ++cc) {
+            uint32_t v[16], w[16];
+            ptx::tmem_ld_32x16(taddr + cc * 16, v);
+            ptx::tmem_ld_32x16(taddr + BN + cc * 16, w);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int x = 0; x < 16; ++x) acc[cc * 16 + x] += __uint_as_float(v[x]) + __uint_as_float(w[x]);
+          }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar(buf), 0);  // the leader's barrier
+        TL(w_tfull += c1 - c0; t_drain += clock64() - c1;)
       }
-      const int64_t i = static_cast<int64_t>(tile.ti + static_cast<int>(cta)) * BM + q * 32 + lane;
-      if (i < n_samples) {
-        const double ri = r[i];
-        const int64_t rowoff = i * (i - 1) / 2 - first;
-        const int64_t j0 = static_cast<int64_t>(tile.tj) * BN + half * 64;
+      TL(const long long c2 = clock64();)
+      // this thread's TMEM lane is a COLUMN sample j of the output; its registers run over
+      // EPI2_COLS ROW samples i.  For a fixed register the 32 lanes of the warp therefore write
+      // 32 consecutive doubles of one row of the flat triangle: fully coalesced 256-byte stores.
+      const int64_t j = static_cast<int64_t>(tile.tj + static_cast<int>(cta)) * BM + q * 32 + lane;
+      const int64_t i0 = static_cast<int64_t>(tile.ti) * BN + cg * EPI2_COLS;
+      static_assert(EPI2_COLS == 32, "r[i] is broadcast from lane n");
+      if (TL_ON(4)) {
+        if (acc[0] == static_cast<Acc>(-1.5)) out[0] = 0.0;
+      } else if (static_cast<int64_t>(tile.tj + static_cast<int>(cta)) * BM + q * 32 < i0 + EPI2_COLS) {  // warp-uniform
+        // r is padded to a multiple of the tile size: both loads are in range and coalesced
+        const double rj = j < n_samples ? r[j] : 0.0;
+        const double ri_lane = r[i0 + lane];
+        int64_t off = i0 * (i0 - 1) / 2 - first + j;  // flat index of (i0, j) relative to the band
 #pragma unroll
-        for (int n = 0; n < 64; ++n) {
-          const int64_t j = j0 + n;
-          if (j < i) {
-            const double R = ri + r[j];
+        for (int n = 0; n < EPI2_COLS; ++n) {
+          const int64_t i = i0 + n;
+          const double ri = __shfl_sync(0xffffffffu, ri_lane, n);
+          if (i < n_samples && j < i) {
+            const double R = ri + rj;
             const double s = static_cast<double>(acc[n]);
-            const double d = (R - 2.0 * s) / (R - s);
-            out[rowoff + j] = d;
-            if (d < flag_below) {
+            const double U = R - 2.0 * s;
+            const double d = ratio_div(U, R - s);
+            out[off] = d;
+            if (d < flag_below || U < flag_u) {
               unsigned long long slot = atomicAdd(n_flagged, 1ULL);
-              flagged[slot] = static_cast<uint32_t>(rowoff + j);
+              flagged[slot] = static_cast<uint32_t>(off);
             }
           }
+          off += i;  // row i+1 starts i entries later
         }
       }
+      TL(t_ratio += clock64() - c2;)
     }
+    TL(if (warp == EPI_WARP0 && lane == 0) {
+      g_tc_dbg[blockIdx.x * 8 + 4] = w_tfull;
+      g_tc_dbg[blockIdx.x * 8 + 5] = t_drain;
+      g_tc_dbg[blockIdx.x * 8 + 6] = t_ratio;
+      g_tc_dbg[blockIdx.x * 8 + 7] = clock64() - e_start;
+    })
   }
 
   ptx::tc_fence_before();
@@ -409,17 +528,21 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
   }
 }
 
-// Exact recompute of flagged pairs from the bf16 presence rows: one warp per
-// pair, fp64, true branch lengths.  Identical samples give exactly 0.
+// Exact recompute of flagged pairs from the presence rows of the A operand (bf16 P, or u8
+// P*a which is non-zero exactly where the node is present and has a non-zero length): one
+// warp per pair, fp64, TRUE branch lengths (len_col[k] = length of the node in operand column
+// k, 0 in padding columns).  Identical samples give exactly 0.
+template <bool kI8>
 __global__ void __launch_bounds__(256)
-k_unweighted_fixup(const uint16_t* __restrict__ P, int32_t n_nodes, int32_t kp,
-                   const double* __restrict__ length, const uint32_t* __restrict__ flagged,
-                   const unsigned long long* __restrict__ n_flagged,
+k_unweighted_fixup(const void* __restrict__ Pv, int32_t kp, const double* __restrict__ len_col,
+                   const uint32_t* __restrict__ flagged, const unsigned long long* __restrict__ n_flagged,
                    unsigned long long* __restrict__ count_host, int64_t first, double* __restrict__ out) {
+  constexpr int kPer = kI8 ? 16 : 8;  // operand columns per 16-byte load
   const unsigned long long total = *n_flagged;
   if (blockIdx.x == 0 && threadIdx.x == 0) *count_host = total;  // mapped pinned memory
   const int lane = threadIdx.x & 31;
   const unsigned long long warps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t row_bytes = static_cast<int64_t>(kp) * (kI8 ? 1 : 2);
   for (unsigned long long w = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
        w < total; w += warps) {
     const uint32_t off = flagged[w];
@@ -428,21 +551,25 @@ k_unweighted_fixup(const uint16_t* __restrict__ P, int32_t n_nodes, int32_t kp,
     while (i * (i - 1) / 2 > p) --i;
     while ((i + 1) * i / 2 <= p) ++i;
     const int64_t j = p - i * (i - 1) / 2;
-    const uint4* pi = reinterpret_cast<const uint4*>(P + i * kp);
-    const uint4* pj = reinterpret_cast<const uint4*>(P + j * kp);
+    const uint4* pi = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(Pv) + i * row_bytes);
+    const uint4* pj = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(Pv) + j * row_bytes);
     double uniq = 0.0, comm = 0.0;
-    for (int32_t c = lane; c * 8 < n_nodes; c += 32) {
+    for (int32_t c = lane; c * kPer < kp; c += 32) {
       const uint4 a = pi[c], b = pj[c];
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        const int32_t k = c * 8 + h;
-        if (k < n_nodes) {
-          const bool pa = ((aw[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu) != 0;
-          const bool pb = ((bw[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu) != 0;
-          if (pa && pb) comm += length[k];
-          else if (pa || pb) uniq += length[k];
+      for (int h = 0; h < kPer; ++h) {
+        const int32_t k = c * kPer + h;
+        bool pa, pb;
+        if constexpr (kI8) {
+          pa = ((aw[h >> 2] >> ((h & 3) * 8)) & 0xFFu) != 0;
+          pb = ((bw[h >> 2] >> ((h & 3) * 8)) & 0xFFu) != 0;
+        } else {
+          pa = ((aw[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu) != 0;
+          pb = ((bw[h >> 1] >> ((h & 1) * 16)) & 0xFFFFu) != 0;
         }
+        if (pa && pb) comm += len_col[k];
+        else if (pa || pb) uniq += len_col[k];
       }
     }
 #pragma unroll
@@ -460,15 +587,18 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_tmapEncodeTiled g_encode = nullptr;
 
-bool make_map(CUtensorMap* m, const void* base, int64_t rows, int32_t kp, int box_rows,
+// K-major operand [rows][kp]; a box is 128 bytes of K x box_rows rows.
+bool make_map(CUtensorMap* m, const void* base, int64_t rows, int32_t kp, int box_rows, bool i8,
               std::string* err) {
+  const int esz = i8 ? 1 : 2;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp) * 2};
-  cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BKB / esz), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult rc = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult rc = g_encode(m, i8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(rc));
     return false;
@@ -480,7 +610,12 @@ bool make_map(CUtensorMap* m, const void* base, int64_t rows, int32_t kp, int bo
 
 struct TcOperands {
   CUtensorMap mapP, mapBh, mapBl;
-  const uint16_t* P;
+  const void* P;
+  bool i8;
+  int32_t kp;
+  TcChunks chunks;
+  const double* len_col;
+  const double* flag_u;  // device scalar (u8) or null
 };
 
 bool tc_setup(std::string* err) {
@@ -495,7 +630,9 @@ bool tc_setup(std::string* err) {
   g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
   e = cudaFuncSetAttribute(k_unweighted_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_unweighted_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    e = cudaFuncSetAttribute(k_unweighted_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_unweighted_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
   if (e != cudaSuccess) {
     if (err) *err = std::string("cudaFuncSetAttribute(k_unweighted_tc): ") + cudaGetErrorString(e);
     g_encode = nullptr;
@@ -504,13 +641,19 @@ bool tc_setup(std::string* err) {
   return true;
 }
 
-TcOperands* tc_operands_create(const uint16_t* P, const uint16_t* Bh, const uint16_t* Bl, int64_t np,
-                               int32_t kp, std::string* err) {
+TcOperands* tc_operands_create(const void* P, const void* Bh, const void* Bl, int64_t np, int32_t kp,
+                               bool i8, const TcChunks& chunks, const double* len_col, const double* flag_u,
+                               std::string* err) {
   if (!tc_setup(err)) return nullptr;
   TcOperands* o = new TcOperands();
   o->P = P;
-  if (!make_map(&o->mapP, P, np, kp, BM, err) || !make_map(&o->mapBh, Bh, np, kp, BN, err) ||
-      !make_map(&o->mapBl, Bl, np, kp, BN, err)) {
+  o->i8 = i8;
+  o->kp = kp;
+  o->chunks = chunks;
+  o->len_col = len_col;
+  o->flag_u = flag_u;
+  if (!make_map(&o->mapP, P, np, kp, BM, i8, err) || !make_map(&o->mapBh, Bh, np, kp, BN, i8, err) ||
+      !make_map(&o->mapBl, Bl, np, kp, BN, i8, err)) {
     delete o;
     return nullptr;
   }
@@ -518,39 +661,63 @@ TcOperands* tc_operands_create(const uint16_t* P, const uint16_t* Bh, const uint
 }
 void tc_operands_destroy(TcOperands* o) { delete o; }
 
-static int tc_chunk_kblocks() {
-  // 64 blocks = 4096 nodes per uninterrupted fp32 TMEM accumulation run
+}  // namespace frc
+// Debug helper (not part of the C ABI): copies the FRC_TC_DEBUG=8 timeline counters.
+extern "C" int frc_debug_tc_counters(unsigned long long* out, int n) {
+#ifdef FRC_TC_TIMELINE
+  if (n > 512 * 8) n = 512 * 8;
+  return static_cast<int>(cudaMemcpyFromSymbol(out, frc::g_tc_dbg, sizeof(unsigned long long) * n));
+#else
+  (void)out; (void)n;
+  return -1;  // built without -DFRC_TC_TIMELINE
+#endif
+}
+namespace frc {
+
+int tc_chunk_kblocks() {
+  // bf16: 64 blocks = 4096 nodes per uninterrupted fp32 TMEM accumulation run
   const char* e = getenv("FRC_TC_CHUNK_KBLOCKS");
   int x = e ? atoi(e) : 64;
   return x < 1 ? 1 : x;
 }
 
-int launch_unweighted_tc(const TcOperands* ops, int32_t kp, const double* r, const Tile* tiles,
-                         int32_t n_tiles, int64_t n_samples, int64_t first, double* out,
-                         double flag_below, uint32_t* flagged, unsigned long long* n_flagged,
-                         int num_sms, int ctas, cudaStream_t s) {
+int launch_unweighted_tc(const TcOperands* ops, const double* r, const Tile* tiles, int32_t n_tiles,
+                         int64_t n_samples, int64_t first, double* out, double flag_below,
+                         uint32_t* flagged, unsigned long long* n_flagged, int num_sms, int ctas,
+                         cudaStream_t s) {
   if (n_tiles <= 0) return 0;
   if (ctas == 2) {  // `tiles` lists pair tiles (ti even): one cluster of two CTAs each
     int pairs = num_sms / 2;
     int grid = 2 * (n_tiles < pairs ? n_tiles : pairs);
-    k_unweighted_tc2<<<grid, THREADS, SMEM2_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, kp / BK,
-                                                        tc_chunk_kblocks(), r, tiles, n_tiles, n_samples,
-                                                        first, out, flag_below, flagged, n_flagged);
+    const TcChunks& c = ops->chunks;
+    const char* de = getenv("FRC_TC_DEBUG");
+    const int dbg = de ? atoi(de) : 0;
+    if (ops->i8)
+      k_unweighted_tc2<true><<<grid, THREADS2, SMEM2_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, c.end, c.scale,
+                                                                c.n, r, tiles, n_tiles, n_samples, first, out,
+                                                                flag_below, ops->flag_u, flagged, n_flagged, dbg);
+    else
+      k_unweighted_tc2<false><<<grid, THREADS2, SMEM2_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, c.end, c.scale,
+                                                                 c.n, r, tiles, n_tiles, n_samples, first, out,
+                                                                 flag_below, ops->flag_u, flagged, n_flagged, dbg);
     return 1;
   }
   int grid = n_tiles < num_sms ? n_tiles : num_sms;
-  k_unweighted_tc<<<grid, THREADS, SMEM_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, kp / BK,
+  k_unweighted_tc<<<grid, THREADS, SMEM_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, ops->kp / BK,
                                                     tc_chunk_kblocks(), r, tiles, n_tiles, n_samples,
                                                     first, out, flag_below, flagged, n_flagged);
   return 1;
 }
 
-int launch_unweighted_fixup(const TcOperands* ops, int32_t n_nodes, int32_t kp, const double* length,
-                            const uint32_t* flagged, const unsigned long long* n_flagged,
+int launch_unweighted_fixup(const TcOperands* ops, const uint32_t* flagged, const unsigned long long* n_flagged,
                             unsigned long long* count_host, int64_t first, double* out, int num_sms,
                             cudaStream_t s) {
-  k_unweighted_fixup<<<num_sms * 4, 256, 0, s>>>(ops->P, n_nodes, kp, length, flagged, n_flagged, count_host,
-                                                 first, out);
+  if (ops->i8)
+    k_unweighted_fixup<true><<<num_sms * 4, 256, 0, s>>>(ops->P, ops->kp, ops->len_col, flagged, n_flagged,
+                                                         count_host, first, out);
+  else
+    k_unweighted_fixup<false><<<num_sms * 4, 256, 0, s>>>(ops->P, ops->kp, ops->len_col, flagged, n_flagged,
+                                                          count_host, first, out);
   return 1;
 }
 

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "_build", "libfrcfrc_cuda.so")
 UNWEIGHTED, WEIGHTED = 0, 1
 PATH_AUTO, PATH_FAST, PATH_EXACT = -1, 0, 1
 FLAG_NO_D2H = 1
+FLAG_UW_BF16 = 2
 
 EXPORTS = ["frc_abi_version", "frc_ctx_create", "frc_ctx_destroy", "frc_create", "frc_next",
            "frc_restart", "frc_job_info", "frc_destroy", "frc_last_error", "frc_plan_bands"]
@@ -52,7 +53,8 @@ class _Info(C.Structure):
                 ("n_nodes_padded", C.c_int64), ("kernel_launches", C.c_int64), ("h2d_ms", C.c_double),
                 ("embed_ms", C.c_double), ("pairs_ms", C.c_double), ("fixup_ms", C.c_double),
                 ("run_ms", C.c_double), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64), ("embed_bytes", C.c_int64), ("flagged_pairs", C.c_int64)]
+                ("d2h_bytes", C.c_int64), ("embed_bytes", C.c_int64), ("flagged_pairs", C.c_int64),
+                ("operand_kind", C.c_int64)]
 
 
 @dataclass
@@ -74,6 +76,7 @@ class JobInfo:
     d2h_bytes: int
     embed_bytes: int
     flagged_pairs: int
+    operand_kind: int
 
 
 _lib = None

@@ -47,8 +47,9 @@ typedef enum { FRC_UNWEIGHTED = 0, FRC_WEIGHTED = 1 } frc_mode;
 /* Which pair kernel runs.
  *   AUTO : EXACT when n_pairs * n_nodes is small (bit-exact testdata .want files),
  *          otherwise FAST.
- *   FAST : unweighted -> tcgen05 bf16 hi/lo GEMM; weighted -> FP32 L1 tiles.
- *          Within 1e-5 relative of the reference.
+ *   FAST : unweighted -> tcgen05 GEMM (u8 block floating point with exact int32
+ *          accumulation by default, bf16 hi/lo planes with FRC_FLAG_UW_BF16);
+ *          weighted -> FP32 L1 tiles.  Within 1e-5 relative of the reference.
  *   EXACT: fp64, the reference's summation order (ascending node id, separate
  *          multiply and add): bit-identical to frcfrc/unifrac.go:144-205. */
 typedef enum { FRC_PATH_AUTO = -1, FRC_PATH_FAST = 0, FRC_PATH_EXACT = 1 } frc_path;
@@ -76,6 +77,10 @@ typedef struct {
 
 #define FRC_FLAG_NO_D2H 1u /* keep distances in HBM: frc_next returns DEVICE
                               pointers (kernel-only timing, GPU consumers)     */
+
+#define FRC_FLAG_UW_BF16 2u /* fast unweighted: run the bf16 hi/lo (kind::f16) tensor-core
+                              kernel instead of the default u8 block-floating-point
+                              (kind::i8, exact integer accumulation) one             */
 
 typedef struct {
   int32_t mode;       /* frc_mode                                               */
@@ -110,6 +115,8 @@ typedef struct {
   int64_t h2d_bytes, d2h_bytes;
   int64_t embed_bytes;     /* algorithmic HBM bytes of the embedding stage      */
   int64_t flagged_pairs;   /* fast unweighted: pairs recomputed exactly (d tiny) */
+  int64_t operand_kind;    /* fast unweighted: 1 = bf16 hi/lo planes, 2 = u8 block floating
+                              point; 0 otherwise                                    */
 } frc_info_t;
 
 int frc_abi_version(void);

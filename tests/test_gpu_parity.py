@@ -109,25 +109,84 @@ def test_empty_samples_give_nan(gpu_ctx):
 
 
 # ------------------------------------------------------------------- fast paths
+# the two operand encodings of the unweighted tensor-core kernel (include/frcfrc_cuda.h FRC_FLAG_UW_BF16)
+UW_KERNELS = [("u8", 0, 2), ("bf16", 2, 1)]  # (id, flags, info.operand_kind)
+uw_kernels = pytest.mark.parametrize("uw", UW_KERNELS, ids=[k[0] for k in UW_KERNELS])
+
+
 @pytest.mark.parametrize("weighted,normalize", [(False, 1), (True, 1), (True, 2)])
-def test_fast_path_within_tolerance(gpu_ctx, weighted, normalize):
+@uw_kernels
+def test_fast_path_within_tolerance(gpu_ctx, weighted, normalize, uw):
     """north_star: every distance within 1e-5 relative of the reference."""
     from frackyfrac_b200 import engine, synth
 
+    if weighted and uw[0] == "bf16":
+        pytest.skip("operand encoding only concerns unweighted")
     tree = synth.random_tree(1000, 21)
     csr = synth.random_table(tree, 300, 0.02, 22)
     want = oracle_flat(tree, csr, weighted, normalize)
-    got = gpu_flat(tree, csr, weighted, normalize == 1, path=engine.PATH_FAST, ctx=gpu_ctx)
+    got = gpu_flat(tree, csr, weighted, normalize == 1, path=engine.PATH_FAST, ctx=gpu_ctx, flags=uw[1])
     e = rel_err(got, want)
     assert e.max() < 1e-5, f"max rel err {e.max():.3e}"
 
 
-@pytest.mark.parametrize("shape,levels", [("caterpillar", 0), ("caterpillar", 1), ("balanced", 0), ("random", 1)])
+@uw_kernels
+@pytest.mark.parametrize("lengths", ["heavy_tail", "zeros_and_tiny", "constant", "one_huge"])
+def test_fast_unweighted_length_distributions(gpu_ctx, uw, lengths):
+    """Branch lengths spanning many binades, exact zeros, a single dominating branch: the u8 block
+    floating point must keep every length to ~2^-20 relative, the bf16 split to 2^-17."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(1500, 91)
+    rng = np.random.default_rng(92)
+    L = tree.length.copy()
+    if lengths == "heavy_tail":
+        L = np.exp(rng.normal(-3.0, 4.0, len(L)))          # ~ 2^-30 .. 2^20 relative spread
+    elif lengths == "zeros_and_tiny":
+        L[rng.random(len(L)) < 0.3] = 0.0
+        L[rng.random(len(L)) < 0.1] *= 1e-9
+    elif lengths == "constant":
+        L[:] = 0.37
+    elif lengths == "one_huge":
+        L[int(tree.leaf_ids[5])] = 1e6
+    L[0] = 0.0
+    tree = synth.Tree(tree.parent, L, tree.leaf_ids, tree.names)
+    csr = synth.random_table(tree, 260, 0.03, 93)
+    want = oracle_flat(tree, csr, False)
+    with engine.Job(tree.parent, tree.length, *csr, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx,
+                    flags=uw[1]) as job:
+        got = np.concatenate([a for _, a in job.chunks()])
+        assert job.info().operand_kind == uw[2]
+    e = rel_err(got, want)
+    # bf16 hi/lo planes with fp32 TMEM accumulation lose small addends next to huge ones: on the
+    # heavy-tailed tree that encoding reaches 2e-5 (measured on B200), which is why u8 block floating
+    # point with exact integer accumulation is the default; everywhere else both meet 1e-5.
+    tol = 5e-5 if (uw[0] == "bf16" and lengths == "heavy_tail") else 1e-5
+    assert e.max() < tol, f"{lengths}: max rel err {e.max():.3e}"
+
+
+def test_fast_unweighted_u8_is_tighter_than_bf16(gpu_ctx):
+    """The u8 path accumulates exactly (int32) and quantises lengths to ~2^-20: its worst error must
+    sit well below the 1e-5 budget and not above the bf16 path's."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(4000, 95)
+    csr = synth.random_table(tree, 384, 0.02, 96)
+    want = oracle_flat(tree, csr, False)
+    e8 = rel_err(gpu_flat(tree, csr, False, path=engine.PATH_FAST, ctx=gpu_ctx), want).max()
+    e16 = rel_err(gpu_flat(tree, csr, False, path=engine.PATH_FAST, ctx=gpu_ctx, flags=engine.FLAG_UW_BF16), want).max()
+    assert e8 < 2e-6 and e8 <= e16 * 1.5, (e8, e16)
+
+
+@pytest.mark.parametrize("shape,levels", [("caterpillar", 0), ("caterpillar", 1), ("balanced", 0), ("random", 1),
+                                          ("caterpillar", 2), ("random", 2)])
 def test_fast_unweighted_embedding_variants(gpu_ctx, monkeypatch, shape, levels):
     """Both embedding implementations (fused single launch / one launch per level), deep and flat trees (H9)."""
     from frackyfrac_b200 import engine, synth
 
-    monkeypatch.setenv("FRC_EMBED_LEVELS", str(levels))
+    monkeypatch.setenv("FRC_EMBED_LEVELS", str(min(levels, 1)))  # 2 = fused embedding feeding the bf16 kernel
+    if levels == 2:
+        monkeypatch.setenv("FRC_UW_KERNEL", "bf16")
     tree = synth.random_tree(700, 71, shape=shape)
     csr = synth.random_table(tree, 200, 0.03, 72)
     want = oracle_flat(tree, csr, False)
@@ -137,8 +196,8 @@ def test_fast_unweighted_embedding_variants(gpu_ctx, monkeypatch, shape, levels)
     assert rel_err(got, want).max() < 1e-5
 
 
-@pytest.mark.parametrize("weighted", [False, True])
-def test_fast_path_identical_and_near_identical_samples(gpu_ctx, weighted):
+@pytest.mark.parametrize("weighted,flags", [(False, 0), (False, 2), (True, 0)])
+def test_fast_path_identical_and_near_identical_samples(gpu_ctx, weighted, flags):
     """Identical samples must give exactly 0; near-identical ones stay within 1e-5 relative."""
     from frackyfrac_b200 import engine, synth
 
@@ -152,15 +211,19 @@ def test_fast_path_identical_and_near_identical_samples(gpu_ctx, weighted):
     others = np.setdiff1d(tree.leaf_ids, col[:m])
     col[2 * m] = others[0]
     want = oracle_flat(tree, (rp, col, val), weighted)
-    got = gpu_flat(tree, (rp, col, val), weighted, path=engine.PATH_FAST, ctx=gpu_ctx)
+    got = gpu_flat(tree, (rp, col, val), weighted, path=engine.PATH_FAST, ctx=gpu_ctx, flags=flags)
     assert want[0] == 0.0 and got[0] == 0.0
     assert rel_err(got, want).max() < 1e-5
 
 
-@pytest.mark.parametrize("weighted", [False, True])
-def test_fast_path_multi_band_and_sharded(gpu_ctx, weighted):
+@pytest.mark.parametrize("weighted,flags", [(False, 0), (False, 2), (True, 0)])
+def test_fast_path_multi_band_and_sharded(gpu_ctx, weighted, flags):
     """Band streaming order, and world=2 band sharding: union of ranks == single rank, same bytes."""
     from frackyfrac_b200 import engine, synth
+    import functools
+
+    engine = type("E", (), {"unifrac": staticmethod(functools.partial(engine.unifrac, flags=flags)),
+                            "PATH_FAST": engine.PATH_FAST})
 
     tree = synth.random_tree(500, 41)
     rp, col, val = synth.random_table(tree, 700, 0.02, 42)
