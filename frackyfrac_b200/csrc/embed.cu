@@ -221,14 +221,27 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
   }
   __syncthreads();
   // phase 2: every node ORs its (final) word into its parent, one tree level at a time from the
-  // leaves up.  level_nodes / level_parent are read coalesced; no dependent global loads.
+  // leaves up.  level_nodes / level_parent are read coalesced, and the first 512 entries of the
+  // NEXT level are fetched before this level's barrier: the deep levels of a tree hold few nodes,
+  // so without the prefetch every level paid a full global-load latency on top of its barrier.
+  auto lp = [&](int32_t h) { return h < 128 ? lptr[h] : level_ptr[h]; };
+  int32_t b = lp(0), e = lp(1);
+  int32_t pn = -1, pp = 0;
+  if (height > 0 && b + tid < e) { pn = level_nodes[b + tid]; pp = level_parent[b + tid]; }
   for (int32_t h = 0; h < height; ++h) {
-    const int32_t b = h < 127 ? lptr[h] : level_ptr[h], e = h < 127 ? lptr[h + 1] : level_ptr[h + 1];
-    for (int32_t idx = b + tid; idx < e; idx += 512) {
+    const int32_t nb = e, ne = h + 1 < height ? lp(h + 2) : e;
+    int32_t qn = -1, qp = 0;
+    if (nb + tid < ne) { qn = level_nodes[nb + tid]; qp = level_parent[nb + tid]; }
+    if (pn >= 0) {
+      const uint32_t x = colw[pn];
+      if (x) atomicOr(colw + pp, x);
+    }
+    for (int32_t idx = b + tid + 512; idx < e; idx += 512) {
       const uint32_t x = colw[level_nodes[idx]];
       if (x) atomicOr(colw + level_parent[idx], x);
     }
     __syncthreads();
+    b = nb; e = ne; pn = qn; pp = qp;
   }
   // phase 3
   uint32_t* dst = bitsT + static_cast<int64_t>(w) * kp;
@@ -261,6 +274,40 @@ k_presence_rowsum_t(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
     a1 += ((wb.w >> lane) & 1u) ? l3.y : 0.0;
   }
   partial[static_cast<int64_t>(blockIdx.y) * ld + w * 32 + lane] = a0 + a1;
+}
+
+// u8 block floating point: the same row sums in integers.  q[k] = a*m < 2^24 and every aligned
+// block of 128 columns has one power-of-two scale 2^col_exp, so a block sums exactly in 32 bits
+// (128 * 2^24 = 2^31) and costs one integer add per (sample, column) instead of an fp64 add
+// (fp64 instructions run at ~1/8 of the integer rate on B200); one fp64 multiply-add per block.
+__global__ void __launch_bounds__(32)
+k_presence_rowsum_u8(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
+                     const uint32_t* __restrict__ qam, const int32_t* __restrict__ col_exp,
+                     double* __restrict__ partial, int64_t ld) {
+  const int32_t w = blockIdx.x, lane = threadIdx.x;
+  const int32_t v0 = blockIdx.y * per, v1 = min(kp, v0 + per);  // per is a multiple of 128
+  const uint32_t* col = bitsT + static_cast<int64_t>(w) * kp;
+  const uint32_t m = 1u << lane;
+  double tot = 0.0;
+  for (int32_t blk = v0; blk < v1; blk += 128) {
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
+    for (int32_t v = blk; v < blk + 128; v += 8) {
+      const uint4 wa = *reinterpret_cast<const uint4*>(col + v), wb = *reinterpret_cast<const uint4*>(col + v + 4);
+      const uint4 qa = *reinterpret_cast<const uint4*>(qam + v), qb = *reinterpret_cast<const uint4*>(qam + v + 4);
+      if (wa.x & m) a0 += qa.x;
+      if (wa.y & m) a1 += qa.y;
+      if (wa.z & m) a2 += qa.z;
+      if (wa.w & m) a3 += qa.w;
+      if (wb.x & m) a0 += qb.x;
+      if (wb.y & m) a1 += qb.y;
+      if (wb.z & m) a2 += qb.z;
+      if (wb.w & m) a3 += qb.w;
+    }
+    const uint32_t sum = (a0 + a1) + (a2 + a3);  // < 2^31
+    tot = fma(ldexp(1.0, col_exp[blk]), static_cast<double>(sum), tot);
+  }
+  partial[static_cast<int64_t>(blockIdx.y) * ld + w * 32 + lane] = tot;
 }
 
 // Presence columns bitsT[nw][kp] (word w holds samples 32w..32w+31 of one operand column) -> the
@@ -341,8 +388,8 @@ k_expand_operands_u8(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
 // the 16-bit m = round(x / a) that brings a * m closest to x.
 __global__ void k_quantize_lengths(const double* __restrict__ len_col, const int32_t* __restrict__ col_exp,
                                    int32_t kp, uint8_t* __restrict__ qa, uint8_t* __restrict__ qh,
-                                   uint8_t* __restrict__ ql, double* __restrict__ lenq,
-                                   double* __restrict__ flag_u) {
+                                   uint8_t* __restrict__ ql, uint32_t* __restrict__ qam,
+                                   double* __restrict__ lenq, double* __restrict__ flag_u) {
   const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= kp) return;
   const double len = len_col[k];
@@ -365,6 +412,7 @@ __global__ void k_quantize_lengths(const double* __restrict__ len_col, const int
   qa[k] = static_cast<uint8_t>(best_a);
   qh[k] = static_cast<uint8_t>(best_m >> 8);
   ql[k] = static_cast<uint8_t>(best_m & 255);
+  qam[k] = static_cast<uint32_t>(best_a) * static_cast<uint32_t>(best_m);
   const double q = ldexp(static_cast<double>(best_a) * static_cast<double>(best_m), e);
   lenq[k] = q;
   // columns kept to 4e-6 relative bound every pair's error by 4e-6 of its own sums; the absolute
@@ -481,8 +529,8 @@ int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw) {
 
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t kp, const int32_t* order, const double* lenq,
-                                uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
-                                cudaStream_t s) {
+                                const uint32_t* qam, const int32_t* col_exp, uint32_t* node_scratch,
+                                uint32_t* bitsT, double* partial, double* r, cudaStream_t s) {
   const size_t smem = (static_cast<size_t>(t.n_nodes) * 4 + 15) & ~size_t(15);
   if (smem <= 200 * 1024) {
     static bool attr = false;
@@ -500,9 +548,14 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
   }
   const int64_t np = static_cast<int64_t>(nw) * 32;
   const int chunks = pick_chunks(t.n_nodes);
-  const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 8));
   dim3 g(nw, chunks);
-  k_presence_rowsum_t<<<g, 32, 0, s>>>(bitsT, kp, per, lenq, partial, np);
+  if (qam) {
+    const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 128));
+    k_presence_rowsum_u8<<<g, 32, 0, s>>>(bitsT, kp, per, qam, col_exp, partial, np);
+  } else {
+    const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 8));
+    k_presence_rowsum_t<<<g, 32, 0, s>>>(bitsT, kp, per, lenq, partial, np);
+  }
   k_reduce_partials<<<static_cast<unsigned>((np + kThreads - 1) / kThreads), kThreads, 0, s>>>(partial, chunks, np, np, r);
   return 3;
 }
@@ -527,9 +580,10 @@ int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int6
 }
 
 int launch_quantize_lengths(const double* len_col, const int32_t* col_exp, int32_t kp, uint8_t* qa,
-                            uint8_t* qh, uint8_t* ql, double* lenq, double* flag_u, cudaStream_t s) {
+                            uint8_t* qh, uint8_t* ql, uint32_t* qam, double* lenq, double* flag_u,
+                            cudaStream_t s) {
   cudaMemsetAsync(flag_u, 0, sizeof(double), s);
-  k_quantize_lengths<<<(kp + 127) / 128, 128, 0, s>>>(len_col, col_exp, kp, qa, qh, ql, lenq, flag_u);
+  k_quantize_lengths<<<(kp + 127) / 128, 128, 0, s>>>(len_col, col_exp, kp, qa, qh, ql, qam, lenq, flag_u);
   return 1;
 }
 

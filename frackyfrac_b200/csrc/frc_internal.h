@@ -80,10 +80,11 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 // `node_scratch` holds the per-CTA node-indexed column when the tree is too large for shared
 // memory (presence_node_scratch_words(n_nodes, nw) words, 0 when shared memory is used).
 int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw);
+// qam / col_exp non-null (u8): integer row sums from q[k] = a*m and the per-column exponents.
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t kp, const int32_t* order, const double* lenq,
-                                uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
-                                cudaStream_t s);
+                                const uint32_t* qam, const int32_t* col_exp, uint32_t* node_scratch,
+                                uint32_t* bitsT, double* partial, double* r, cudaStream_t s);
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
                              const void* q0, const void* q1, const void* q2, void* P, void* Bh, void* Bl,
                              cudaStream_t s);
@@ -93,7 +94,8 @@ int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int6
 // flag_u[0] = 5e5 * sum of |lenq - len| over the columns whose relative quantisation error
 // exceeds 4e-6 (pairs with a unique length below that are recomputed exactly).
 int launch_quantize_lengths(const double* len_col, const int32_t* col_exp, int32_t kp, uint8_t* qa,
-                            uint8_t* qh, uint8_t* ql, double* lenq, double* flag_u, cudaStream_t s);
+                            uint8_t* qh, uint8_t* ql, uint32_t* qam, double* lenq, double* flag_u,
+                            cudaStream_t s);
 
 // ---- exact.cu ---------------------------------------------------------------
 // fp64 reference-order distances for pairs [first, first+count) of the triangle.
@@ -109,7 +111,12 @@ void weighted_setup();  // cudaFuncSetAttribute calls, once per process
 // ---- unweighted_tc.cu -------------------------------------------------------
 struct TcOperands;  // opaque: tensor maps + chunk table
 // Runs of 128-byte K blocks that accumulate uninterrupted in TMEM; device arrays.
-struct TcChunks { const int32_t* end = nullptr; const double* scale = nullptr; int32_t n = 0; };
+struct TcChunks {
+  const int32_t* end = nullptr;
+  const double* scale = nullptr;
+  int32_t n = 0;
+  bool biased = false;  // u8: all scales within 2^8 -> single-instruction biased accumulation
+};
 // flag_u: device scalar; pairs with unique length below it are recomputed exactly (null: none).
 TcOperands* tc_operands_create(const void* P, const void* Bh, const void* Bl, int64_t np, int32_t kp,
                                bool i8, const TcChunks& chunks, const double* len_col, const double* flag_u,

@@ -197,6 +197,7 @@ struct frc_job {
   // per operand column (fast unweighted): q0/q1/q2 = bf16 (unused, len_hi, len_lo) or u8 (a, m_hi, m_lo)
   void *d_q0 = nullptr, *d_q1 = nullptr, *d_q2 = nullptr;
   int32_t *d_order = nullptr, *d_col_exp = nullptr;
+  uint32_t* d_qam = nullptr;  // u8: a * m per operand column
   double *d_lenq = nullptr, *d_len_col = nullptr, *d_flag_u = nullptr;
   TcChunks d_chunks;
   float* d_lenf = nullptr;
@@ -304,7 +305,8 @@ int run_embedding(frc_job* j) {
   } else {
     if (j->fused_embed) {
       launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->kp, j->d_order,
-                                              j->d_lenq, j->d_node_scratch, j->d_bits, j->d_scratch, j->d_r, s);
+                                              j->d_lenq, j->i8 ? j->d_qam : nullptr, j->d_col_exp,
+                                              j->d_node_scratch, j->d_bits, j->d_scratch, j->d_r, s);
       launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
                                            j->d_P, j->d_Bh, j->d_Bl, s);
     } else {
@@ -708,9 +710,18 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       // column-major inside the band: CTAs running together share the few
       // i-tiles of the band and neighbouring j-tiles (L2 reuse of both operands)
       if (j->tc_ctas == 2) {
-        // pair tiles: (ti, tj) and (ti, tj+1) with tj even; needed when tj <= ti
-        for (int32_t tj = 0; tj <= t1; tj += 2)
-          for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) j->tiles.push_back({ti, tj});
+        // pair tiles: (ti, tj) and (ti, tj+1) with tj even; needed when tj <= ti.  The clusters
+        // that run together (74 on a B200) take consecutive list entries, so the list walks
+        // compact super-tiles of ~9 tile rows x ~8 tile-pair columns: the wave then shares
+        // 9 + 8 operand panels instead of 2 + 37 and its working set fits the 126 MB L2.
+        const int32_t rows_blk = std::min<int32_t>(9, t1 - t0 + 1);
+        const int32_t cols_blk = std::max<int32_t>(1, 74 / rows_blk);  // in tile pairs
+        for (int32_t tb = t0; tb <= t1; tb += rows_blk) {
+          const int32_t te = std::min(t1, tb + rows_blk - 1);
+          for (int32_t pb = 0; 2 * pb <= te; pb += cols_blk)
+            for (int32_t tp = pb; tp < pb + cols_blk && 2 * tp <= te; ++tp)
+              for (int32_t ti = std::max(2 * tp, tb); ti <= te; ++ti) j->tiles.push_back({ti, 2 * tp});
+        }
       } else {
         for (int32_t tj = 0; tj <= t1; ++tj)
           for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) j->tiles.push_back({ti, tj});
@@ -883,6 +894,10 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->d_chunks.end = reinterpret_cast<int32_t*>(d + s_cend.off);
   j->d_chunks.scale = reinterpret_cast<double*>(d + s_cscale.off);
   j->d_chunks.n = static_cast<int32_t>(chunk_end.size());
+  if (j->i8 && !chunk_scale.empty()) {
+    const auto mm = std::minmax_element(chunk_scale.begin(), chunk_scale.end());
+    j->d_chunks.biased = *mm.second <= *mm.first * 256.0;
+  }
   j->d_lenf = reinterpret_cast<float*>(d + s_lenf.off);
   j->d_tiles = reinterpret_cast<Tile*>(d + s_tiles.off);
   j->d_level_ptr = reinterpret_cast<int32_t*>(d + s_lptr.off);
@@ -917,13 +932,14 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (!(j->d_flag_counts = dev_alloc<unsigned long long>(j, j->mine.size() + 1, &rc))) return bail(rc);
     std::string terr;
     if (j->i8 && !(j->d_flag_u = dev_alloc<double>(j, 1, &rc))) return bail(rc);
+    if (j->i8 && !(j->d_qam = dev_alloc<uint32_t>(j, j->kp, &rc))) return bail(rc);
     j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, j->i8, j->d_chunks, j->d_len_col,
                                j->d_flag_u, &terr);
     if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
     if (j->i8) {  // a function of the tree only: once per job, not per restart
       j->info.kernel_launches += launch_quantize_lengths(
           j->d_len_col, j->d_col_exp, j->kp, static_cast<uint8_t*>(j->d_q0), static_cast<uint8_t*>(j->d_q1),
-          static_cast<uint8_t*>(j->d_q2), j->d_lenq, j->d_flag_u, c->stream[0]);
+          static_cast<uint8_t*>(j->d_q2), j->d_qam, j->d_lenq, j->d_flag_u, c->stream[0]);
       CREATE_CUDA(cudaGetLastError());
     }
   }

@@ -285,23 +285,27 @@ constexpr int EPI2_WARPS = 16;
 constexpr int EPI2_COLS = 128 / (EPI2_WARPS / 4);  // accumulator columns per thread and plane
 constexpr int THREADS2 = 32 * (EPI_WARP0 + EPI2_WARPS);
 
-// U / V for the ratio epilogue without the ~30-instruction IEEE fp64 division: fp32 reciprocal
-// seed, two fp64 Newton steps (relative error ~1e-16).  0/0 -> NaN as the reference (A8).
-__device__ __forceinline__ double ratio_div(double U, double V) {
-  if (!(V > 1e-30 && V < 1e30)) return U / V;
-  const double x0 = static_cast<double>(__frcp_rn(static_cast<float>(V)));
-  const double e0 = fma(-V, x0, 1.0);
-  const double x1 = fma(x0, e0, x0);
-  const double e1 = fma(-V, x1, 1.0);
-  const double x2 = fma(x1, e1, x1);
-  return U * x2;
+// Exact float -> double widening with integer instructions only.  On B200 every fp64-pipe
+// instruction (DADD/DFMA/F2F) costs an SM ~4 cycles per warp (measured: the fp64 ratio epilogue
+// took 54k cycles per tile, more than half of the u8 mainloop), so the epilogue keeps fp64 for
+// the one cancellation that needs it (U = R - 2s) and does the rest in fp32 / integers.
+// f is 0, NaN (0/0, A8) or a normal number in [2^-3, 1] here; smaller values are overwritten by
+// the exact fix-up pass.
+__device__ __forceinline__ double widen_f32(float f) {
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t e = (u >> 23) & 0xFFu;
+  uint32_t hi = (u & 0x80000000u) | (((u & 0x7FFFFFFFu) >> 3) + 0x38000000u);
+  uint32_t lo = u << 29;
+  if (e == 0u) { hi = u & 0x80000000u; lo = 0u; }
+  if (e == 0xFFu) { hi = 0x7FF80000u; lo = 0u; }
+  return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
 }
 
 template <bool kI8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapBh,
                  const __grid_constant__ CUtensorMap mapBl, const int32_t* __restrict__ chunk_end,
-                 const double* __restrict__ chunk_scale, int32_t n_chunks,
+                 const double* __restrict__ chunk_scale, int32_t n_chunks, int32_t biased,
                  const double* __restrict__ r, const Tile* __restrict__ tiles, int32_t n_tiles,
                  int64_t n_samples, int64_t first, double* __restrict__ out, double flag_below,
                  const double* __restrict__ flag_u_ptr, uint32_t* __restrict__ flagged,
@@ -429,14 +433,18 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
     using Acc = typename std::conditional<kI8, double, float>::type;
     // pairs whose unique length U is below this are recomputed exactly as well: the summed absolute
     // error of the imprecisely quantised branch lengths could exceed 2e-6 of U (k_quantize_lengths)
-    const double flag_u = flag_u_ptr ? *flag_u_ptr : 0.0;
+    const float flag_u = flag_u_ptr ? static_cast<float>(*flag_u_ptr) : 0.f;
+    const float flag_d = static_cast<float>(flag_below);
+    double acc0 = 0.0;  // u8, biased accumulation: minus the 2^52-bias of every chunk
+    if constexpr (kI8)
+      if (biased) for (int ch = 0; ch < n_chunks; ++ch) acc0 -= 4503599627370496.0 * chunk_scale[ch];
     uint32_t chunk = 0;
     TL(long long w_tfull = 0; long long t_drain = 0; long long t_ratio = 0; const long long e_start = clock64();)
     for (int t = pair; t < n_tiles; t += n_pairs) {
       const Tile tile = tiles[t];
       Acc acc[EPI2_COLS];
 #pragma unroll
-      for (int n = 0; n < EPI2_COLS; ++n) acc[n] = 0;
+      for (int n = 0; n < EPI2_COLS; ++n) acc[n] = static_cast<Acc>(acc0);
       for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
         const uint32_t buf = chunk & 1u;
         const double scale = kI8 ? chunk_scale[ch] : 1.0;
@@ -446,22 +454,29 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * DN + cg * EPI2_COLS;
         if constexpr (kI8) {
+          // both plane sums are in [0, 2^31): S = 256*hi + lo < 2^40 comes from one 32x32->64 integer
+          // multiply-add; OR-ing it into the mantissa of 2^52 gives the double 2^52 + S without any
+          // conversion instruction.  biased: ONE fp64 instruction per element accumulates
+          // scale * (2^52 + S); the offsets 2^52 * scale were pre-subtracted (acc0), and the rounding
+          // (to multiples of the largest chunk scale) is ~2^-28 of a sum because the host only sets
+          // `biased` when all chunk scales lie within 2^8.  Otherwise 2^52 is subtracted first (exact).
+          auto drain = [&](auto kBiased) {
 #pragma unroll
-          for (int cc = 0; cc < EPI2_COLS / 8; ++cc) {
-            uint32_t v[8], w[8];
-            ptx::tmem_ld_32x8(taddr + cc * 8, v);
-            ptx::tmem_ld_32x8(taddr + BN + cc * 8, w);
-            ptx::tmem_ld_wait();
+            for (int cc = 0; cc < EPI2_COLS / 8; ++cc) {
+              uint32_t v[8], w[8];
+              ptx::tmem_ld_32x8(taddr + cc * 8, v);
+              ptx::tmem_ld_32x8(taddr + BN + cc * 8, w);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int x = 0; x < 8; ++x) {
-              // exact: both plane sums are in [0, 2^31), so S = 256*hi + lo < 2^40 is built with one
-              // 32x32->64 integer multiply-add and turned into a double by the 2^52 trick
-              // (mantissa bits = S, then one exact fp64 subtract) instead of two I2F conversions
-              const unsigned long long S = static_cast<unsigned long long>(v[x]) * 256ull + w[x];
-              const double sum = __longlong_as_double(static_cast<long long>(S | 0x4330000000000000ull)) - 4503599627370496.0;
-              acc[cc * 8 + x] = fma(scale, sum, acc[cc * 8 + x]);
+              for (int x = 0; x < 8; ++x) {
+                const unsigned long long S = static_cast<unsigned long long>(v[x]) * 256ull + w[x];
+                double D = __longlong_as_double(static_cast<long long>(S | 0x4330000000000000ull));
+                if (!decltype(kBiased)::value) D -= 4503599627370496.0;
+                acc[cc * 8 + x] = fma(scale, D, acc[cc * 8 + x]);
+              }
             }
-          }
+          };
+          if (biased) drain(std::true_type{}); else drain(std::false_type{});
         } else {
 #pragma unroll
           for (int cc = 0; cc < EPI2_COLS / 16; ++cc) {
@@ -497,12 +512,13 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
           const int64_t i = i0 + n;
           const double ri = __shfl_sync(0xffffffffu, ri_lane, n);
           if (i < n_samples && j < i) {
-            const double R = ri + rj;
+            // fp64 only where cancellation needs it: U = R - 2s (the reference's `result`)
             const double s = static_cast<double>(acc[n]);
-            const double U = R - 2.0 * s;
-            const double d = ratio_div(U, R - s);
-            out[off] = d;
-            if (d < flag_below || U < flag_u) {
+            const double U = fma(-2.0, s, ri + rj);
+            const float Uf = static_cast<float>(U), sf = static_cast<float>(s);
+            const float d = __fdiv_rn(Uf, Uf + sf);  // U / (U + common), unifrac.go:169
+            out[off] = widen_f32(d);
+            if (d < flag_d || Uf < flag_u) {
               unsigned long long slot = atomicAdd(n_flagged, 1ULL);
               flagged[slot] = static_cast<uint32_t>(off);
             }
@@ -694,11 +710,11 @@ int launch_unweighted_tc(const TcOperands* ops, const double* r, const Tile* til
     const int dbg = de ? atoi(de) : 0;
     if (ops->i8)
       k_unweighted_tc2<true><<<grid, THREADS2, SMEM2_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, c.end, c.scale,
-                                                                c.n, r, tiles, n_tiles, n_samples, first, out,
+                                                                c.n, c.biased ? 1 : 0, r, tiles, n_tiles, n_samples, first, out,
                                                                 flag_below, ops->flag_u, flagged, n_flagged, dbg);
     else
       k_unweighted_tc2<false><<<grid, THREADS2, SMEM2_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, c.end, c.scale,
-                                                                 c.n, r, tiles, n_tiles, n_samples, first, out,
+                                                                 c.n, 0, r, tiles, n_tiles, n_samples, first, out,
                                                                  flag_below, ops->flag_u, flagged, n_flagged, dbg);
     return 1;
   }

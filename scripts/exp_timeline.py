@@ -9,7 +9,7 @@ ctx = engine.Context(0)
 L = engine.lib()
 names = ["mma:wait_tmem", "mma:wait_operands", "mma:total", "prod:wait_stage", "epi:wait_acc", "epi:drain", "epi:ratio", "epi:total"]
 for flags, name in ((0, "u8"), (engine.FLAG_UW_BF16, "bf16")):
-    for dbg in (8, 12):
+    for dbg in (0, 4):
         os.environ["FRC_TC_DEBUG"] = str(dbg)
         j = engine.Job(tree.parent, tree.length, rp, col, val, weighted=False, path=engine.PATH_FAST, ctx=ctx,
                        band_rows=1 << 20, flags=engine.FLAG_NO_D2H | flags)
