@@ -179,13 +179,14 @@ def run_reference(args, world, rank):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(name, mode, leaves, samples, density, world):
+def workload_config(name, mode, leaves, samples, density, world, shard=False):
     return {"workload": f"{name}: {mode} UniFrac, synthetic {leaves}-leaf random-join tree ({2 * leaves - 1} nodes) x "
                         f"{samples} samples, leaf density {density}, lognormal counts",
             "leaves": leaves, "nodes": 2 * leaves - 1, "samples": samples, "pairs": samples * (samples - 1) // 2,
-            "parallelism": f"tile-band sharding x{world}" if world > 1 else "single GPU",
-            "l2": "operands (P, P*len_hi, P*len_lo: 3 x samples x nodes bf16) exceed the 126 MB L2; "
-                  "every step rewrites them, no L2 flush needed"}
+            "parallelism": (f"tile-band sharding x{world}, embedding " +
+                            ("sample-sharded + NCCL all-gather" if shard else "rebuilt per rank")) if world > 1 else "single GPU",
+            "l2": "operands (3 x samples x nodes, u8 or bf16 = 0.3 / 0.6 GB at cfg2) exceed the 126 MB L2 and "
+                  "every step rewrites them: no L2 flush needed"}
 
 
 def run_ours(args, world, rank, local_rank):
@@ -205,6 +206,13 @@ def run_ours(args, world, rank, local_rank):
     ctx = engine.Context(local_rank)
     peaks, peaks_kind = load_peaks()
     uw_flags = engine.FLAG_UW_BF16 if args.uw_kernel == "bf16" else 0
+    # sample-sharded embedding + NCCL all-gather of its compact form: pays from 4 GPUs on at this
+    # size (measured at N=2: the all-gather costs 35 us more than the half embedding it saves)
+    shard = world > 1 and not args.no_shard_embed and (world >= 4 or args.shard_embed)
+    if shard:
+        from frackyfrac_b200 import dist as fdist
+        fdist.init_comm(ctx, rank, world)
+        uw_flags |= engine.FLAG_SHARD_EMBED
 
     def barrier():
         if dist is not None:
@@ -329,7 +337,7 @@ def run_ours(args, world, rank, local_rank):
                         ("bf16 x bf16 -> f32 (tcgen05 kind::f16), f64 row sums/epilogue/output" if info.operand_kind == 1 else
                          "u8 x u8 -> s32 (tcgen05 kind::i8, exact), f64 chunk scaling/row sums/epilogue/output"),
                "data": "synthetic",
-               "config": workload_config(args.config, mode, leaves, samples, density, world),
+               "config": workload_config(args.config, mode, leaves, samples, density, world, shard and not weighted),
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                "roofline": roofline, "cpu_baseline": cpu,
                "stages_ms": {"h2d": ei.h2d_ms, "embed": info.embed_ms, "pairs_kernels_sum": info.pairs_ms,
@@ -356,6 +364,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (configs whose output exceeds host RAM)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-alone timing leg")
     ap.add_argument("--min-warmup", type=int, default=3)
+    ap.add_argument("--shard-embed", action="store_true", help="N=2: force the sharded embedding + all-gather")
+    ap.add_argument("--no-shard-embed", action="store_true",
+                    help="N>1: every rank rebuilds the whole embedding (no NCCL all-gather)")
     ap.add_argument("--uw-kernel", default="u8", choices=["u8", "bf16"],
                     help="operand encoding of the unweighted tensor-core kernel (FRC_FLAG_UW_BF16)")
     args = ap.parse_args()

@@ -20,7 +20,7 @@ OUT = os.path.join(HERE, "_build")
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 
-CUDA_SOURCES = ["job.cu", "embed.cu", "exact.cu", "weighted.cu", "unweighted_tc.cu"]
+CUDA_SOURCES = ["job.cu", "embed.cu", "exact.cu", "weighted.cu", "unweighted_tc.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -62,7 +62,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
             if r.returncode:
                 raise RuntimeError(f"nvcc failed on {src}")
     if force or _stale(lib, objs):
-        cmd = [_nvcc(), "-shared", "-o", lib, *objs, "-cudart", "shared"]
+        cmd = [_nvcc(), "-shared", "-o", lib, *objs, "-cudart", "shared", "-ldl"]
         subprocess.run(cmd, check=True)
     return lib
 

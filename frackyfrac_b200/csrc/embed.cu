@@ -201,12 +201,12 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
                        int64_t n_samples, const int32_t* __restrict__ level_nodes,
                        const int32_t* __restrict__ level_parent, const int32_t* __restrict__ level_ptr,
                        int32_t height, int32_t n_nodes, int32_t kp, const int32_t* __restrict__ order,
-                       uint32_t* __restrict__ node_scratch, uint32_t* __restrict__ bitsT) {
+                       uint32_t* __restrict__ node_scratch, uint32_t* __restrict__ bitsT, int32_t w0) {
   extern __shared__ __align__(16) uint32_t smem_words[];
   __shared__ int32_t lptr[128];
-  const int w = blockIdx.x;
+  const int w = blockIdx.x + w0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* colw = kSmem ? smem_words : node_scratch + static_cast<int64_t>(w) * n_nodes;
+  uint32_t* colw = kSmem ? smem_words : node_scratch + static_cast<int64_t>(blockIdx.x) * n_nodes;
 
   for (int32_t v = tid; v < n_nodes; v += 512) colw[v] = 0u;
   if (tid < 128 && tid <= height + 1) lptr[tid] = level_ptr[tid];
@@ -255,8 +255,8 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
 // (word column, column chunk), lane = sample; words and lengths are read as 16-byte broadcasts.
 __global__ void __launch_bounds__(32)
 k_presence_rowsum_t(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
-                    const double* __restrict__ lenq8, double* __restrict__ partial, int64_t ld) {
-  const int32_t w = blockIdx.x, lane = threadIdx.x;
+                    const double* __restrict__ lenq8, double* __restrict__ partial, int64_t ld, int32_t w0) {
+  const int32_t w = blockIdx.x + w0, lane = threadIdx.x;
   const int32_t v0 = blockIdx.y * per, v1 = min(kp, v0 + per);  // per is a multiple of 8
   const uint32_t* col = bitsT + static_cast<int64_t>(w) * kp;
   double a0 = 0.0, a1 = 0.0;
@@ -283,8 +283,8 @@ k_presence_rowsum_t(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
 __global__ void __launch_bounds__(32)
 k_presence_rowsum_u8(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
                      const uint32_t* __restrict__ qam, const int32_t* __restrict__ col_exp,
-                     double* __restrict__ partial, int64_t ld) {
-  const int32_t w = blockIdx.x, lane = threadIdx.x;
+                     double* __restrict__ partial, int64_t ld, int32_t w0) {
+  const int32_t w = blockIdx.x + w0, lane = threadIdx.x;
   const int32_t v0 = blockIdx.y * per, v1 = min(kp, v0 + per);  // per is a multiple of 128
   const uint32_t* col = bitsT + static_cast<int64_t>(w) * kp;
   const uint32_t m = 1u << lane;
@@ -523,14 +523,16 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 }
 
 
+// (nw = word columns this rank builds)
 int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw) {
   return static_cast<size_t>(n_nodes) * 4 <= 200 * 1024 ? 0 : static_cast<int64_t>(n_nodes) * nw;
 }
 
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
-                                int32_t nw, int32_t kp, const int32_t* order, const double* lenq,
-                                const uint32_t* qam, const int32_t* col_exp, uint32_t* node_scratch,
-                                uint32_t* bitsT, double* partial, double* r, cudaStream_t s) {
+                                int32_t nw, int32_t w0, int32_t w_count, int32_t kp, const int32_t* order,
+                                const double* lenq, const uint32_t* qam, const int32_t* col_exp,
+                                uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
+                                cudaStream_t s) {
   const size_t smem = (static_cast<size_t>(t.n_nodes) * 4 + 15) & ~size_t(15);
   if (smem <= 200 * 1024) {
     static bool attr = false;
@@ -538,25 +540,27 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
       cudaFuncSetAttribute(k_embed_presence_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr = true;
     }
-    k_embed_presence_fused<true><<<nw, 512, smem, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
-                                                       t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
-                                                       order, node_scratch, bitsT);
+    k_embed_presence_fused<true><<<w_count, 512, smem, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
+                                                            t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
+                                                            order, node_scratch, bitsT, w0);
   } else {
-    k_embed_presence_fused<false><<<nw, 512, 0, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
-                                                     t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
-                                                     order, node_scratch, bitsT);
+    k_embed_presence_fused<false><<<w_count, 512, 0, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
+                                                          t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
+                                                          order, node_scratch, bitsT, w0);
   }
   const int64_t np = static_cast<int64_t>(nw) * 32;
   const int chunks = pick_chunks(t.n_nodes);
-  dim3 g(nw, chunks);
+  dim3 g(w_count, chunks);
   if (qam) {
     const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 128));
-    k_presence_rowsum_u8<<<g, 32, 0, s>>>(bitsT, kp, per, qam, col_exp, partial, np);
+    k_presence_rowsum_u8<<<g, 32, 0, s>>>(bitsT, kp, per, qam, col_exp, partial, np, w0);
   } else {
     const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 8));
-    k_presence_rowsum_t<<<g, 32, 0, s>>>(bitsT, kp, per, lenq, partial, np);
+    k_presence_rowsum_t<<<g, 32, 0, s>>>(bitsT, kp, per, lenq, partial, np, w0);
   }
-  k_reduce_partials<<<static_cast<unsigned>((np + kThreads - 1) / kThreads), kThreads, 0, s>>>(partial, chunks, np, np, r);
+  const int64_t s0 = static_cast<int64_t>(w0) * 32, ns = static_cast<int64_t>(w_count) * 32;
+  k_reduce_partials<<<static_cast<unsigned>((ns + kThreads - 1) / kThreads), kThreads, 0, s>>>(partial + s0, chunks, np,
+                                                                                              ns, r + s0);
   return 3;
 }
 

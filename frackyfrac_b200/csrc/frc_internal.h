@@ -81,10 +81,12 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 // memory (presence_node_scratch_words(n_nodes, nw) words, 0 when shared memory is used).
 int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw);
 // qam / col_exp non-null (u8): integer row sums from q[k] = a*m and the per-column exponents.
+// Only the word columns [w0, w0 + w_count) (32 samples each) are built: the sample shard of this rank.
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
-                                int32_t nw, int32_t kp, const int32_t* order, const double* lenq,
-                                const uint32_t* qam, const int32_t* col_exp, uint32_t* node_scratch,
-                                uint32_t* bitsT, double* partial, double* r, cudaStream_t s);
+                                int32_t nw, int32_t w0, int32_t w_count, int32_t kp, const int32_t* order,
+                                const double* lenq, const uint32_t* qam, const int32_t* col_exp,
+                                uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
+                                cudaStream_t s);
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
                              const void* q0, const void* q1, const void* q2, void* P, void* Bh, void* Bl,
                              cudaStream_t s);
@@ -96,6 +98,18 @@ int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int6
 int launch_quantize_lengths(const double* len_col, const int32_t* col_exp, int32_t kp, uint8_t* qa,
                             uint8_t* qh, uint8_t* ql, uint32_t* qam, double* lenq, double* flag_u,
                             cudaStream_t s);
+
+// ---- comm.cu ----------------------------------------------------------------
+struct Comm;  // one NCCL communicator (dlopen-bound)
+bool comm_unique_id(char* id128, std::string* err);
+Comm* comm_create(const char* id128, int rank, int world, std::string* err);  // collective
+void comm_destroy(Comm* c);
+int comm_rank(const Comm* c);
+int comm_world(const Comm* c);
+// In-place all-gathers (rank r owns bytes [r*bytes_per_rank, (r+1)*bytes_per_rank) of each buffer),
+// issued as one NCCL group on stream s.
+bool comm_all_gather_inplace(Comm* c, void* const* bufs, const size_t* bytes_per_rank, int n, cudaStream_t s,
+                             std::string* err);
 
 // ---- exact.cu ---------------------------------------------------------------
 // fp64 reference-order distances for pairs [first, first+count) of the triangle.

@@ -153,6 +153,7 @@ struct frc_ctx {
   std::vector<std::vector<int64_t>> stamps;  // per-worker duplicate-detection scratch
   int64_t stamp_epoch = 0;
   bool in_use = false;
+  Comm* comm = nullptr;  // NCCL communicator over the ranks of a multi-GPU run (frc_ctx_comm_init)
 };
 
 struct Band { int64_t row0, row1, first, count; int32_t tile_off, n_tiles; };
@@ -192,6 +193,8 @@ struct frc_job {
   unsigned long long* d_flag_counts = nullptr;  // one per band of this rank
   bool fused_embed = true;
   bool zero_copy = false;
+  bool sharded = false;       // embedding built for this rank's sample shard, then all-gathered
+  int32_t shard_w0 = 0, shard_nw = 0;  // word columns (32 samples) of the shard
   int tc_ctas = 1;  // CTAs per tensor-core tile group (2 = cta_group::2 pairs)
   bool i8 = false;  // fast unweighted: u8 block-floating-point operands (kind::i8) instead of bf16 hi/lo
   // per operand column (fast unweighted): q0/q1/q2 = bf16 (unused, len_hi, len_lo) or u8 (a, m_hi, m_lo)
@@ -232,29 +235,62 @@ namespace {
 
 int fail(frc_job* j, int code, const std::string& msg) { j->err = msg; return code; }
 
-// Band b of the triangle costs ~b (its rows have ~b*band_rows columns), so
-// ranks take bands in boustrophedon order: 0..G-1, G-1..0, ... which pairs a
-// cheap band with an expensive one and balances to within one band.
-int band_owner(size_t b, int world) {
-  size_t m = b % (2 * static_cast<size_t>(world));
-  return static_cast<int>(m < static_cast<size_t>(world) ? m : 2 * world - 1 - m);
+// Which rank computes which band: bands are as equal as whole tile rows allow, and the rest of
+// the imbalance is removed by dealing them largest-first to the least loaded rank (deterministic,
+// the same on every rank and in frc_plan_bands).
+std::vector<int> band_owners(const std::vector<int64_t>& rows, int world) {
+  const size_t n = rows.size() > 0 ? rows.size() - 1 : 0;
+  std::vector<int> owner(n, 0);
+  if (world <= 1) return owner;
+  std::vector<size_t> order(n);
+  std::vector<int64_t> cnt(n);
+  for (size_t k = 0; k < n; ++k) {
+    order[k] = k;
+    cnt[k] = tri(rows[k + 1]) - (rows[k] >= 2 ? tri(rows[k]) : 0);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cnt[a] > cnt[b]; });
+  std::vector<int64_t> load(world, 0);
+  for (size_t k : order) {
+    int best = 0;
+    for (int r = 1; r < world; ++r)
+      if (load[r] < load[best]) best = r;
+    owner[k] = best;
+    load[best] += cnt[k];
+  }
+  return owner;
 }
 
-int64_t choose_band_rows(int64_t N, int64_t requested, int world, bool d2h = true) {
-  if (requested > 0) return round_up(requested, kTile);
-  const int64_t tile_rows = (N + kTile - 1) / kTile;
-  int64_t g;
-  if (!d2h && world == 1) {
-    // nothing to overlap with: few launches, but no more than 16 tile rows per band once the
-    // operands outgrow L2 (a band's i-tiles should stay L2-resident while its j-tiles stream)
-    g = tile_rows <= 64 ? tile_rows : 16;
-  } else {
-    // at least ~8 bands per rank (D2H overlap, load balance), at most 12 tile rows per band
-    // (the more i-tiles run together, the more often a j-side operand tile is reused from L2)
-    g = std::min<int64_t>(12, std::max<int64_t>(1, tile_rows / (8 * static_cast<int64_t>(world))));
+// Row boundaries of the bands of the triangle (multiples of the tile size, first 0, last N).
+//   requested > 0 : uniform bands of that many rows (rounded up to whole tiles);
+//   otherwise     : bands of (nearly) EQUAL PAIR COUNT, boundaries at N * sqrt(k / n) -- equal work per
+//                   launch, so the ranks are balanced and no band is a sliver that cannot fill the GPU.
+//                   Distances stay in HBM (no D2H to overlap): one band, or two per rank;
+//                   with D2H: about 8 per rank so that copies overlap the kernels.  More bands when one
+//                   would exceed 1.5 GB of distances.
+std::vector<int64_t> band_boundaries(int64_t N, int64_t requested, int world, bool d2h) {
+  std::vector<int64_t> rows;
+  rows.push_back(0);
+  if (N <= 0) return rows;
+  if (requested > 0) {
+    const int64_t step = round_up(requested, kTile);
+    for (int64_t r = step; r < N; r += step) rows.push_back(r);
+    rows.push_back(N);
+    return rows;
   }
-  while (g > 1 && g * kTile * N * 8 > (1536LL << 20)) --g;
-  return g * kTile;
+  const int64_t tile_rows = (N + kTile - 1) / kTile;
+  int64_t n = d2h ? 8LL * world : (world == 1 ? 1 : 2LL * world);
+  const double total_bytes = 8.0 * static_cast<double>(N) * static_cast<double>(N - 1) / 2.0;
+  const int64_t by_size = static_cast<int64_t>(std::ceil(total_bytes / (1536.0 * 1024 * 1024)));
+  if (by_size > n) n = round_up(by_size, 2LL * world);
+  n = std::max<int64_t>(1, std::min(n, std::max<int64_t>(world, tile_rows / 2)));
+  for (int64_t k = 1; k < n; ++k) {
+    int64_t r = static_cast<int64_t>(std::llround(static_cast<double>(N) * std::sqrt(static_cast<double>(k) / n) / kTile)) * kTile;
+    r = std::max(r, rows.back() + kTile);
+    if (r >= N) break;
+    rows.push_back(r);
+  }
+  rows.push_back(N);
+  return rows;
 }
 
 template <class T>
@@ -304,9 +340,19 @@ int run_embedding(frc_job* j) {
     j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
   } else {
     if (j->fused_embed) {
-      launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->kp, j->d_order,
-                                              j->d_lenq, j->i8 ? j->d_qam : nullptr, j->d_col_exp,
-                                              j->d_node_scratch, j->d_bits, j->d_scratch, j->d_r, s);
+      launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->shard_w0, j->shard_nw,
+                                              j->kp, j->d_order, j->d_lenq, j->i8 ? j->d_qam : nullptr,
+                                              j->d_col_exp, j->d_node_scratch, j->d_bits, j->d_scratch, j->d_r, s);
+      if (j->sharded) {
+        // the one exchange step of the path: presence bit columns + row sums of every rank's
+        // sample shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
+        void* bufs[2] = {j->d_bits, j->d_r};
+        const size_t bytes[2] = {static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t),
+                                 static_cast<size_t>(j->shard_nw) * 32 * sizeof(double)};
+        std::string cerr;
+        if (!comm_all_gather_inplace(c->comm, bufs, bytes, 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
+        j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
+      }
       launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
                                            j->d_P, j->d_Bh, j->d_Bl, s);
     } else {
@@ -470,7 +516,7 @@ int frc_ctx_create(int32_t device, frc_ctx_t** out) {
   c->pin.pinned = true;  c->pin.min_block = 8u << 20;
   {
     int hw = static_cast<int>(std::thread::hardware_concurrency());
-    int n = std::max(1, std::min(8, hw)) - 1;
+    int n = std::max(1, std::min(16, hw)) - 1;
     if (const char* e = getenv("FRC_HOST_THREADS")) n = std::max(1, atoi(e)) - 1;
     c->pool.reset(new Pool(n));
     c->stamps.resize(n + 1);
@@ -497,11 +543,36 @@ void frc_ctx_destroy(frc_ctx_t* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   c->pool.reset();
-  for (auto s : c->stream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  for (auto s : c->stream) if (s) cudaStreamSynchronize(s);
+  comm_destroy(c->comm);
+  c->comm = nullptr;
+  for (auto s : c->stream) if (s) cudaStreamDestroy(s);
   c->dev.release();
   c->pin.release();
   cudaGetLastError();
   delete c;
+}
+
+int frc_comm_unique_id(char* id) {
+  if (!id) { g_create_error = "frc_comm_unique_id: id is NULL"; return FRC_ERR_ARG; }
+  std::string err;
+  if (!comm_unique_id(id, &err)) { g_create_error = err; return FRC_ERR_UNSUPPORTED; }
+  return FRC_OK;
+}
+
+int frc_ctx_comm_init(frc_ctx_t* ctx, const char* id, int32_t rank, int32_t world) {
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world) {
+    g_create_error = "frc_ctx_comm_init: bad argument";
+    return FRC_ERR_ARG;
+  }
+  if (ctx->in_use) { g_create_error = "context has a live job"; return FRC_ERR_STATE; }
+  cudaSetDevice(ctx->device);
+  comm_destroy(ctx->comm);
+  ctx->comm = nullptr;
+  std::string err;
+  ctx->comm = comm_create(id, rank, world, &err);
+  if (!ctx->comm) { g_create_error = err; return FRC_ERR_CUDA; }
+  return FRC_OK;
 }
 
 int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, const frc_opts_t* opts,
@@ -585,7 +656,14 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
 
   // --------------------------------------------------------------- choose path
   j->N = N; j->B = B; j->nnz = nnz;
-  j->np = std::max<int64_t>(kTile, round_up(N, kTile));
+  j->sharded = (opts->flags & FRC_FLAG_SHARD_EMBED) != 0 && world > 1;
+  if (j->sharded) {
+    if (!ctx || !ctx->comm || comm_world(ctx->comm) != world || comm_rank(ctx->comm) != rank)
+      return bail(fail(j, FRC_ERR_STATE, "FRC_FLAG_SHARD_EMBED needs a context whose communicator "
+                                         "(frc_ctx_comm_init) matches opts->rank / opts->world"));
+  }
+  // sharded: every rank owns np / world samples, a whole number of tiles
+  j->np = std::max<int64_t>(kTile, round_up(N, j->sharded ? kTile * static_cast<int64_t>(world) : kTile));
   j->kp = static_cast<int32_t>(round_up(B, kKBlock));
   j->nw = static_cast<int32_t>(j->np / 32);
   const int64_t n_pairs = N >= 2 ? tri(N) : 0;
@@ -595,6 +673,9 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   if (!j->exact && bad_len)
     return bail(fail(j, FRC_ERR_UNSUPPORTED, "non-finite branch length: only the exact path handles it"));
   j->prescale = !neg_len;
+  if (j->sharded && (j->exact || j->weighted)) j->sharded = false;  // (these rebuild the embedding per rank)
+  j->shard_nw = j->sharded ? j->nw / world : j->nw;
+  j->shard_w0 = j->sharded ? rank * j->shard_nw : 0;
   j->info.path_taken = j->exact ? FRC_PATH_EXACT : FRC_PATH_FAST;
   j->info.tree_height = H;
   j->info.n_pairs_total = n_pairs;
@@ -615,17 +696,26 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   std::vector<double> len_col, chunk_scale;
   if (!j->exact && !j->weighted) {
     { const char* e = getenv("FRC_EMBED_LEVELS"); j->fused_embed = !(e && atoi(e) == 1); }
+    if (j->sharded && !j->fused_embed)
+      return bail(fail(j, FRC_ERR_UNSUPPORTED, "FRC_EMBED_LEVELS=1 cannot build a sample shard"));
     const char* ek = getenv("FRC_UW_KERNEL");  // "bf16" forces the bf16 hi/lo kernel
     j->i8 = j->tc_ctas == 2 && j->fused_embed && !neg_len && !(opts->flags & FRC_FLAG_UW_BF16) &&
             !(ek && strcmp(ek, "bf16") == 0);
     if (j->i8) {
       constexpr int kGroups = 24, kBlockCols = 128, kMaxChunkBlocks = 128;
+      // floor(log2(l)) of a positive finite double straight from its exponent field (denormals: -1023,
+      // they all land in the last group)
+      auto ilog = [](double l) {
+        uint64_t u;
+        memcpy(&u, &l, 8);
+        return static_cast<int>((u >> 52) & 0x7FF) - 1023;
+      };
       int e_max = INT32_MIN;
       for (int32_t v = 0; v < B; ++v)
-        if (tree->length[v] > 0) e_max = std::max(e_max, std::ilogb(tree->length[v]));
+        if (tree->length[v] > 0) e_max = std::max(e_max, ilog(tree->length[v]));
       int gb = 3;  // binades per group: x = len * 2^-e in [2^20, 2^23), >= 110 candidate factors a
       if (const char* e = getenv("FRC_U8_GROUP_BINADES")) gb = std::max(1, std::min(16, atoi(e)));
-      auto group_of = [&](double l) { return std::min(kGroups - 1, (e_max - std::ilogb(l)) / gb); };
+      auto group_of = [&](double l) { return std::min(kGroups - 1, (e_max - ilog(l)) / gb); };
       int32_t cnt[kGroups] = {0};
       for (int32_t v = 0; v < B; ++v)
         if (tree->length[v] > 0) cnt[group_of(tree->length[v])]++;
@@ -683,18 +773,19 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     j->info.n_nodes_padded = j->kp;
     j->info.operand_kind = j->i8 ? 2 : 1;
   }
-  int64_t band_rows = choose_band_rows(N, opts->band_rows, world, !(opts->flags & FRC_FLAG_NO_D2H));
-  for (int64_t r0 = 0; r0 < N; r0 += band_rows) {
+  const std::vector<int64_t> brows = band_boundaries(N, opts->band_rows, world, !(opts->flags & FRC_FLAG_NO_D2H));
+  for (size_t kb = 0; kb + 1 < brows.size(); ++kb) {
     Band b;
-    b.row0 = r0; b.row1 = std::min(N, r0 + band_rows);
+    b.row0 = brows[kb]; b.row1 = brows[kb + 1];
     b.first = b.row0 >= 2 ? tri(b.row0) : 0;
     b.count = tri(b.row1) - b.first;
     b.tile_off = 0; b.n_tiles = 0;
     if (b.count > 0) j->bands.push_back(b);
   }
   int64_t max_band = 1;
+  const std::vector<int> owners = band_owners(brows, world);
   for (size_t k = 0; k < j->bands.size(); ++k)
-    if (band_owner(k, world) == rank) {
+    if (owners[k] == rank) {
       j->mine.push_back(static_cast<int>(k));
       j->info.n_pairs_mine += j->bands[k].count;
       max_band = std::max(max_band, j->bands[k].count);
@@ -920,7 +1011,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       // FRC_EMBED_LEVELS=1: node-major bits[B][nw], one launch per tree level
       size_t words = j->fused_embed ? static_cast<size_t>(j->kp) * j->nw : static_cast<size_t>(B) * j->nw;
       if (!(j->d_bits = dev_alloc<uint32_t>(j, std::max<size_t>(words, 64), &rc))) return bail(rc);
-      const size_t ns = j->fused_embed ? static_cast<size_t>(presence_node_scratch_words(B, j->nw)) : 0;
+      const size_t ns = j->fused_embed ? static_cast<size_t>(presence_node_scratch_words(B, j->shard_nw)) : 0;
       if (ns && !(j->d_node_scratch = dev_alloc<uint32_t>(j, ns, &rc))) return bail(rc);
     }
     const size_t opsz = static_cast<size_t>(j->np) * j->kp * (j->i8 ? 1 : 2);
@@ -1060,23 +1151,22 @@ int frc_job_info(const frc_job_t* cj, frc_info_t* info) {
 
 void frc_destroy(frc_job_t* j) { destroy_job(j); }
 
-int64_t frc_plan_bands(int64_t n_samples, int64_t band_rows, int32_t rank, int32_t world,
+int64_t frc_plan_bands(int64_t n_samples, int64_t band_rows, int32_t rank, int32_t world, uint32_t flags,
                        int64_t* first_index, int64_t* count, int64_t cap) {
   if (world <= 0) { world = 1; rank = 0; }
   if (n_samples < 0 || band_rows < 0 || rank < 0 || rank >= world) return -FRC_ERR_ARG;
-  const int64_t rows = choose_band_rows(n_samples, band_rows, world);
+  const std::vector<int64_t> brows = band_boundaries(n_samples, band_rows, world, !(flags & FRC_FLAG_NO_D2H));
+  const std::vector<int> owners = band_owners(brows, world);
   int64_t n = 0;
-  size_t k = 0;
-  for (int64_t r0 = 0; r0 < n_samples; r0 += rows) {
-    const int64_t r1 = std::min(n_samples, r0 + rows);
+  for (size_t kb = 0; kb + 1 < brows.size(); ++kb) {
+    const int64_t r0 = brows[kb], r1 = brows[kb + 1];
     const int64_t first = r0 >= 2 ? tri(r0) : 0;
     const int64_t cnt = tri(r1) - first;
     if (cnt <= 0) continue;
-    if (band_owner(k, world) == rank) {
+    if (owners[kb] == rank) {
       if (n < cap && first_index && count) { first_index[n] = first; count[n] = cnt; }
       ++n;
     }
-    ++k;
   }
   return n;
 }

@@ -1,8 +1,9 @@
 """Multi-process plumbing around the C ABI: one process per GPU, torch.distributed.
 
-The pair stage shards by tile bands with no data-path collective (every rank
-builds the embedding, which is <1 % of a step).  What
-needs plumbing is host-side: the per-rank ordered streams are merged back into
+The embedding is built sample-sharded and exchanged with ONE NCCL all-gather of its compact
+form inside libfrcfrc_cuda (FRC_FLAG_SHARD_EMBED; the communicator is created here from an id
+that torch.distributed carries between the ranks).  The pair stage then shards by tile bands
+with no further exchange.  Host-side: the per-rank ordered streams are merged back into
 IterPairs order, and timings are reduced as the max over ranks.
 """
 from __future__ import annotations
@@ -16,6 +17,23 @@ def env_rank_world():
     import os
 
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_comm(ctx: "engine.Context", rank: int, world: int, device=None) -> None:
+    """Creates the engine's NCCL communicator on `ctx`: rank 0 draws the id, torch.distributed
+    (any backend) broadcasts its 128 bytes, every rank joins (collective)."""
+    import torch
+    import torch.distributed as dist
+
+    if world <= 1:
+        return
+    if dist.get_backend() == "nccl" and device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    t = torch.zeros(engine.COMM_ID_BYTES, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t = torch.tensor(list(engine.comm_unique_id()), dtype=torch.uint8, device=device)
+    dist.broadcast(t, src=0)
+    ctx.comm_init(bytes(t.cpu().tolist()), rank, world)
 
 
 def max_over_ranks(x: float, device=None) -> float:

@@ -21,9 +21,12 @@ UNWEIGHTED, WEIGHTED = 0, 1
 PATH_AUTO, PATH_FAST, PATH_EXACT = -1, 0, 1
 FLAG_NO_D2H = 1
 FLAG_UW_BF16 = 2
+FLAG_SHARD_EMBED = 4
+COMM_ID_BYTES = 128
 
 EXPORTS = ["frc_abi_version", "frc_ctx_create", "frc_ctx_destroy", "frc_create", "frc_next",
-           "frc_restart", "frc_job_info", "frc_destroy", "frc_last_error", "frc_plan_bands"]
+           "frc_restart", "frc_job_info", "frc_destroy", "frc_last_error", "frc_plan_bands",
+           "frc_comm_unique_id", "frc_ctx_comm_init"]
 
 
 class FrcError(RuntimeError):
@@ -54,7 +57,7 @@ class _Info(C.Structure):
                 ("embed_ms", C.c_double), ("pairs_ms", C.c_double), ("fixup_ms", C.c_double),
                 ("run_ms", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("embed_bytes", C.c_int64), ("flagged_pairs", C.c_int64),
-                ("operand_kind", C.c_int64)]
+                ("operand_kind", C.c_int64), ("gather_bytes", C.c_int64)]
 
 
 @dataclass
@@ -77,6 +80,7 @@ class JobInfo:
     embed_bytes: int
     flagged_pairs: int
     operand_kind: int
+    gather_bytes: int
 
 
 _lib = None
@@ -103,8 +107,11 @@ def lib():
         L.frc_destroy.restype = None
         L.frc_last_error.argtypes = [C.c_void_p]
         L.frc_last_error.restype = C.c_char_p
-        L.frc_plan_bands.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+        L.frc_plan_bands.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                     C.c_int64]
         L.frc_plan_bands.restype = C.c_int64
+        L.frc_comm_unique_id.argtypes = [C.c_char_p]
+        L.frc_ctx_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
         _lib = L
     return _lib
 
@@ -119,6 +126,12 @@ class Context:
             raise FrcError(rc, lib().frc_last_error(None).decode())
         self.h = h
 
+    def comm_init(self, comm_id: bytes, rank: int, world: int):
+        """Collective over the ranks: binds an NCCL communicator to this context."""
+        rc = lib().frc_ctx_comm_init(self.h, comm_id, rank, world)
+        if rc:
+            raise FrcError(rc, lib().frc_last_error(None).decode())
+
     def close(self):
         if self.h:
             lib().frc_ctx_destroy(self.h)
@@ -129,6 +142,15 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def comm_unique_id() -> bytes:
+    """The 128-byte NCCL id (call on one rank, hand the bytes to the others)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib().frc_comm_unique_id(buf)
+    if rc:
+        raise FrcError(rc, lib().frc_last_error(None).decode())
+    return buf.raw
 
 
 class Job:
@@ -213,14 +235,14 @@ class Job:
             pass
 
 
-def plan_bands(n_samples: int, rank: int = 0, world: int = 1, band_rows: int = 0):
+def plan_bands(n_samples: int, rank: int = 0, world: int = 1, band_rows: int = 0, flags: int = 0):
     """(first_index, count) of the bands `rank` yields, in stream order (host-only helper)."""
-    n = lib().frc_plan_bands(n_samples, band_rows, rank, world, None, None, 0)
+    n = lib().frc_plan_bands(n_samples, band_rows, rank, world, flags, None, None, 0)
     if n < 0:
         raise FrcError(-n, "bad band plan arguments")
     first = np.zeros(n, np.int64)
     count = np.zeros(n, np.int64)
-    lib().frc_plan_bands(n_samples, band_rows, rank, world, first.ctypes.data, count.ctypes.data, n)
+    lib().frc_plan_bands(n_samples, band_rows, rank, world, flags, first.ctypes.data, count.ctypes.data, n)
     return first, count
 
 

@@ -82,6 +82,14 @@ typedef struct {
                               kernel instead of the default u8 block-floating-point
                               (kind::i8, exact integer accumulation) one             */
 
+#define FRC_FLAG_SHARD_EMBED 4u /* world > 1: build the embedding for this rank's sample
+                                  shard only and exchange the compact form (presence bit
+                                  columns + row sums) with one NCCL all-gather; needs a
+                                  context with a communicator (frc_ctx_comm_init).  Every
+                                  rank of the communicator must create its job with the
+                                  same inputs (the call is collective).  Without the flag
+                                  each rank rebuilds the whole embedding.              */
+
 typedef struct {
   int32_t mode;       /* frc_mode                                               */
   int32_t normalize;  /* 1 = default; 0 = flag -l (frcfrc.go:25, unifrac.go:108) */
@@ -89,7 +97,8 @@ typedef struct {
   int32_t device;     /* CUDA device ordinal; -1 = current device               */
   int32_t rank;       /* tile-band sharding over `world` processes (one per GPU): */
   int32_t world;      /*   bands are dealt 0..G-1,G-1..0,...; 0/1 = all bands     */
-  int64_t band_rows;  /* rows of the lower triangle per output chunk; 0 = auto  */
+  int64_t band_rows;  /* rows of the lower triangle per output chunk; 0 = auto
+                         (bands of equal pair count, see frc_plan_bands)        */
   uint32_t flags;     /* FRC_FLAG_*                                             */
   uint32_t reserved;
 } frc_opts_t;
@@ -117,6 +126,7 @@ typedef struct {
   int64_t flagged_pairs;   /* fast unweighted: pairs recomputed exactly (d tiny) */
   int64_t operand_kind;    /* fast unweighted: 1 = bf16 hi/lo planes, 2 = u8 block floating
                               point; 0 otherwise                                    */
+  int64_t gather_bytes;    /* bytes this rank received in the embedding all-gather  */
 } frc_info_t;
 
 int frc_abi_version(void);
@@ -125,6 +135,13 @@ int frc_abi_version(void);
  * one.  Reusing a context across jobs reuses its device / pinned allocations. */
 int frc_ctx_create(int32_t device, frc_ctx_t **out);
 void frc_ctx_destroy(frc_ctx_t *ctx);
+
+/* Multi-GPU, one process per GPU.  frc_comm_unique_id produces the 128-byte NCCL id on one
+ * rank; the host distributes it (any channel) and every rank calls frc_ctx_comm_init
+ * (collective) on its context.  The communicator is destroyed with the context. */
+#define FRC_COMM_ID_BYTES 128
+int frc_comm_unique_id(char *id /* [FRC_COMM_ID_BYTES] */);
+int frc_ctx_comm_init(frc_ctx_t *ctx, const char *id, int32_t rank, int32_t world);
 
 /* Replaces the body of unifrac() (frcfrc/unifrac.go:97-124): validates, copies
  * and uploads the inputs, builds the branch embedding on the device and queues
@@ -146,14 +163,14 @@ int frc_restart(frc_job_t *job);
 
 int frc_job_info(const frc_job_t *job, frc_info_t *info);
 
-/* Pure host helper (no device needed): the band decomposition frc_create uses.
- * Writes, for the bands that `rank` of `world` yields (all bands when world
- * <= 1), the flat index of their first pair and their pair count, in stream
- * order; returns the number of such bands (also when it exceeds `cap`), or a
- * negative frc_status.  Lets a multi-process host merge the per-rank streams
- * back into IterPairs order. */
+/* Pure host helper (no device needed): the band decomposition frc_create uses for these
+ * options (band_rows, world and FRC_FLAG_NO_D2H in `flags` select it).  Writes, for the bands
+ * that `rank` of `world` yields (all bands when world <= 1), the flat index of their first pair
+ * and their pair count, in stream order; returns the number of such bands (also when it exceeds
+ * `cap`), or a negative frc_status.  Lets a multi-process host merge the per-rank streams back
+ * into IterPairs order. */
 int64_t frc_plan_bands(int64_t n_samples, int64_t band_rows, int32_t rank, int32_t world,
-                       int64_t *first_index, int64_t *count, int64_t cap);
+                       uint32_t flags, int64_t *first_index, int64_t *count, int64_t cap);
 
 /* Legal at any time, also mid-stream (the consumer's `break`, frcfrc.go:59-61). */
 void frc_destroy(frc_job_t *job);

@@ -73,17 +73,26 @@ def test_band_plan_covers_the_triangle(built):
     for n in (0, 1, 2, 127, 128, 129, 1000, 5000, 14142):
         total = n * (n - 1) // 2 if n >= 2 else 0
         for world in (1, 2, 3, 8):
-            seen = []
-            for r in range(world):
-                f, c = engine.plan_bands(n, r, world)
-                assert (np.diff(f) > 0).all()
-                seen += list(zip(f.tolist(), c.tolist()))
-            seen.sort()
-            pos = 0
-            for f, c in seen:
-                assert f == pos and c > 0
-                pos += c
-            assert pos == total
-    # boustrophedon dealing keeps per-rank pair counts within one band of each other
-    per = [engine.plan_bands(14142, r, 8)[1].sum() for r in range(8)]
-    assert max(per) - min(per) <= engine.plan_bands(14142, 0, 1)[1].max()
+            for flags in (0, engine.FLAG_NO_D2H):
+                seen = []
+                for r in range(world):
+                    f, c = engine.plan_bands(n, r, world, flags=flags)
+                    assert (np.diff(f) > 0).all()
+                    seen += list(zip(f.tolist(), c.tolist()))
+                seen.sort()
+                pos = 0
+                for f, c in seen:
+                    assert f == pos and c > 0
+                    pos += c
+                assert pos == total
+    # bands hold (nearly) equal pair counts, so the ranks are balanced: within 10 % of the mean
+    for flags in (0, engine.FLAG_NO_D2H):
+        per = np.array([engine.plan_bands(14142, r, 8, flags=flags)[1].sum() for r in range(8)], float)
+        assert per.max() / per.mean() < 1.10 and per.min() / per.mean() > 0.90, per
+    # distances stay in HBM: one launch on one GPU, two per rank otherwise; with D2H about 8 per rank
+    assert len(engine.plan_bands(5000, 0, 1, flags=engine.FLAG_NO_D2H)[0]) == 1
+    assert sum(len(engine.plan_bands(14142, r, 8, flags=engine.FLAG_NO_D2H)[0]) for r in range(8)) == 16
+    assert len(engine.plan_bands(5000, 0, 1)[0]) == 8
+    # explicit band_rows: uniform bands of whole tiles
+    f, c = engine.plan_bands(700, 0, 1, band_rows=128)
+    assert len(f) == 6 and c[0] == 128 * 127 // 2
