@@ -44,6 +44,17 @@ CONFIGS = {
 }
 
 
+def load_traffic(config: str, kernel: str, world: int):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of this config (1 GPU)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(f"{config}:{kernel}")
+    return e["bytes"] if e else None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -301,7 +312,8 @@ def run_ours(args, world, rank, local_rank):
             peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
             ach = total_pairs * 2.0 * B / (k_ms / 1e3) / 1e12
             roofline = {"bound": "fp32", "kernel": "k_weighted_tiles", "achieved": ach, "peak": peak,
-                        "unit": "T lane-op/s", "frac": ach / peak, "traffic": None, "kernel_ms": k_ms,
+                        "unit": "T lane-op/s", "frac": ach / peak,
+                        "traffic": load_traffic(args.config, "k_weighted_tiles", world), "kernel_ms": k_ms,
                         "peak_source": "derived: 148 SM x 128 lanes x sm_max_mhz"}
         else:
             # algorithmic work = one multiply-add per (pair, node) = 2*B flops per pair.
@@ -313,9 +325,11 @@ def run_ours(args, world, rank, local_rank):
             ach = total_pairs * 2.0 * B / (k_ms / 1e3) / 1e12
             n_tiles = sum(t + 1 for t in range((samples + 127) // 128))
             executed = n_tiles * 128 * 128 * ri.n_nodes_padded * 2 * 2.0 / (k_ms / 1e3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "k_unweighted_tc2<u8>" if i8 else "k_unweighted_tc2<bf16>",
+            kname = "k_unweighted_tc2<u8>" if i8 else "k_unweighted_tc2<bf16>"
+            roofline = {"bound": "tensor", "kernel": kname,
                         "achieved": ach, "peak": peak,
-                        "unit": "TOP/s" if i8 else "TFLOP/s", "frac": ach / peak, "traffic": None, "kernel_ms": k_ms,
+                        "unit": "TOP/s" if i8 else "TFLOP/s", "frac": ach / peak,
+                        "traffic": load_traffic(args.config, kname, world), "kernel_ms": k_ms,
                         "executed_tflops": executed, "executed_frac": executed / peak,
                         "achieved_vs_bf16_peak": ach / peaks["bf16_tflops"],
                         "peak_source": (f"2 x {peaks_kind} bf16_tflops (kind::i8 issues at twice the kind::f16 rate; "

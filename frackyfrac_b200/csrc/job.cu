@@ -138,7 +138,7 @@ class Pool {
 
 constexpr int kSlots = 8;                       // output ring: enough for the compute to run ahead of the D2H
 constexpr int kMinSlots = 3;
-constexpr int64_t kSlotBytesBudget = 4LL << 30;  // device (and pinned) bytes the ring may take beyond kMinSlots
+constexpr int64_t kSlotBytesBudget = 1LL << 30;  // bytes the output ring may take beyond kMinSlots (pinned allocation is slow: ~0.4 s per GB)
 constexpr double kFlagBelow = 0.125;            // fast unweighted: recompute d below this exactly
 constexpr int64_t kExactWorkLimit = 1LL << 28;  // AUTO: pairs * nodes at or below this -> exact
 
@@ -266,7 +266,7 @@ std::vector<int> band_owners(const std::vector<int64_t>& rows, int world) {
 //                   launch, so the ranks are balanced and no band is a sliver that cannot fill the GPU.
 //                   Distances stay in HBM (no D2H to overlap): one band, or two per rank;
 //                   with D2H: about 8 per rank so that copies overlap the kernels.  More bands when one
-//                   would exceed 1.5 GB of distances.
+//                   would exceed 96 MB (streamed) / 1.5 GB (kept in HBM) of distances.
 std::vector<int64_t> band_boundaries(int64_t N, int64_t requested, int world, bool d2h) {
   std::vector<int64_t> rows;
   rows.push_back(0);
@@ -280,7 +280,10 @@ std::vector<int64_t> band_boundaries(int64_t N, int64_t requested, int world, bo
   const int64_t tile_rows = (N + kTile - 1) / kTile;
   int64_t n = d2h ? 8LL * world : (world == 1 ? 1 : 2LL * world);
   const double total_bytes = 8.0 * static_cast<double>(N) * static_cast<double>(N - 1) / 2.0;
-  const int64_t by_size = static_cast<int64_t>(std::ceil(total_bytes / (1536.0 * 1024 * 1024)));
+  // streamed to the host: bands of <= 96 MB keep the pinned ring small (pinning memory costs ~0.4 s
+  // per GB, paid by the first job of a context) and are still several waves of tiles each
+  const double band_cap = d2h ? 96.0 * 1024 * 1024 : 1536.0 * 1024 * 1024;
+  const int64_t by_size = static_cast<int64_t>(std::ceil(total_bytes / band_cap));
   if (by_size > n) n = round_up(by_size, 2LL * world);
   n = std::max<int64_t>(1, std::min(n, std::max<int64_t>(world, tile_rows / 2)));
   for (int64_t k = 1; k < n; ++k) {

@@ -1,0 +1,59 @@
+"""Runs one BASELINE config at full size on one GPU through the C ABI (host buffers -> pinned host
+distances), checks the last rows of the triangle against the oracle, prints throughput."""
+import argparse, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from frackyfrac_b200 import engine, synth  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("config")
+ap.add_argument("--check-rows", type=int, default=16)
+ap.add_argument("--no-d2h", action="store_true")
+ap.add_argument("--flags", type=int, default=0)
+a = ap.parse_args()
+mode, leaves, samples, density, ts, bs = bench.CONFIGS[a.config]
+weighted = mode == "weighted"
+t0 = time.perf_counter()
+tree = synth.random_tree(leaves, ts)
+rp, col, val = synth.random_table(tree, samples, density, bs)
+print(f"{a.config}: {mode}, {leaves} leaves ({tree.n_nodes} nodes) x {samples} samples, nnz {len(col)}; generated in {time.perf_counter() - t0:.1f}s", flush=True)
+import torch
+ctx = engine.Context(0)
+n = samples
+total = n * (n - 1) // 2
+r0 = n - a.check_rows
+first_checked = r0 * (r0 - 1) // 2
+tail = np.zeros(total - first_checked)
+t0 = time.perf_counter()
+job = engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
+                 flags=a.flags | (engine.FLAG_NO_D2H if a.no_d2h else 0))
+t1 = time.perf_counter()
+seen = 0
+if a.no_d2h:
+    seen = job.drain()
+else:
+    for first, arr in job.chunks(copy=False):
+        seen += len(arr)
+        lo = max(first, first_checked)
+        if first + len(arr) > lo:
+            tail[lo - first_checked: first + len(arr) - first_checked] = arr[lo - first:]
+t2 = time.perf_counter()
+info = job.info()
+free, tot = torch.cuda.mem_get_info(0)
+job.close()
+assert seen == total, (seen, total)
+print(f"create {t1 - t0:.3f}s  stream {t2 - t1:.3f}s  device: h2d {info.h2d_ms:.1f} ms embed {info.embed_ms:.1f} ms pair kernels {info.pairs_ms:.1f} ms "
+      f"fixup {info.fixup_ms:.1f} ms run {info.run_ms:.1f} ms | bands {info.n_bands_total} flagged {info.flagged_pairs} kp {info.n_nodes_padded} "
+      f"| HBM in use {(tot - free) / 2**30:.1f} GiB", flush=True)
+print(f"pairs/s: device {total / (info.run_ms / 1e3):.3e}  pair-kernels-only {total / (info.pairs_ms / 1e3):.3e}  end-to-end {total / (t2 - t0):.3e}", flush=True)
+if not a.no_d2h:
+    ot, tab = orc.Tree.from_flat(tree.parent, tree.length), orc.Table.from_csr(rp, col, val)
+    t0 = time.perf_counter()
+    want, emb_s, pair_s = orc.unifrac_rows(tab, ot, weighted, 1, os.cpu_count(), r0, n)
+    err = np.abs(tail - want) / np.maximum(np.abs(want), 1e-12)
+    print(f"oracle rows [{r0},{n}): {len(want)} pairs in {pair_s:.2f}s (+{emb_s:.2f}s embedding) -> {len(want) / pair_s:.3e} pairs/s on {os.cpu_count()} cores; "
+          f"max rel err {err.max():.2e} (mean {err.mean():.1e})", flush=True)
+    assert err.max() < 1e-5
+ctx.close()
