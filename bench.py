@@ -217,9 +217,12 @@ def run_ours(args, world, rank, local_rank):
     ctx = engine.Context(local_rank)
     peaks, peaks_kind = load_peaks()
     uw_flags = engine.FLAG_UW_BF16 if args.uw_kernel == "bf16" else 0
-    # sample-sharded embedding + NCCL all-gather of its compact form: pays from 4 GPUs on at this
-    # size (measured at N=2: the all-gather costs 35 us more than the half embedding it saves)
-    shard = world > 1 and not args.no_shard_embed and (world >= 4 or args.shard_embed)
+    # sample-sharded embedding + NCCL all-gather of its compact form (FRC_FLAG_SHARD_EMBED): pays when
+    # the shardable part of the embedding (bit columns + row sums, ~O(samples x nodes)) outweighs the
+    # latency of an all-gather (measured ~140 us at 8 ranks).  At the cfg2-derived sizes of the scaling
+    # run it does not (N=8: 0.738 ms per step sharded vs 0.688 ms rebuilt per rank), so the default
+    # is size-based; --shard-embed / --no-shard-embed force either.
+    shard = world > 1 and not args.no_shard_embed and (args.shard_embed or samples * (2 * leaves - 1) >= 2_000_000_000)
     if shard:
         from frackyfrac_b200 import dist as fdist
         fdist.init_comm(ctx, rank, world)
@@ -378,7 +381,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (configs whose output exceeds host RAM)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-alone timing leg")
     ap.add_argument("--min-warmup", type=int, default=3)
-    ap.add_argument("--shard-embed", action="store_true", help="N=2: force the sharded embedding + all-gather")
+    ap.add_argument("--shard-embed", action="store_true", help="N>1: force the sharded embedding + all-gather")
     ap.add_argument("--no-shard-embed", action="store_true",
                     help="N>1: every rank rebuilds the whole embedding (no NCCL all-gather)")
     ap.add_argument("--uw-kernel", default="u8", choices=["u8", "bf16"],

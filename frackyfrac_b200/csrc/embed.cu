@@ -316,10 +316,13 @@ k_presence_rowsum_u8(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per
 __global__ void __launch_bounds__(256)
 k_expand_operands_t(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
                     int64_t np, const uint16_t* __restrict__ len_hi, const uint16_t* __restrict__ len_lo,
-                    uint16_t* __restrict__ P, uint16_t* __restrict__ Bh, uint16_t* __restrict__ Bl) {
+                    uint16_t* __restrict__ P, uint16_t* __restrict__ Bh, uint16_t* __restrict__ Bl,
+                    const uint8_t* __restrict__ need) {
   __shared__ uint32_t words[8][64];
   const int32_t v0 = blockIdx.x * 64;
   const int32_t w0 = blockIdx.y * 8;
+  const uint32_t nd = need ? need[blockIdx.y] : 3u;  // see k_expand_operands_u8
+  if (nd == 0u) return;
   for (int idx = threadIdx.x; idx < 512; idx += 256) {
     int word = idx >> 6, node = idx & 63;
     uint32_t x = 0;
@@ -340,9 +343,11 @@ k_expand_operands_t(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
     if (s >= np) break;
     const uint32_t m = (0xFFFFu & (0u - ((wa >> it) & 1u))) | (0xFFFF0000u & (0u - ((wb >> it) & 1u)));
     const int64_t o = s * kp + va;
-    *reinterpret_cast<uint32_t*>(P + o) = 0x3F803F80u & m;
-    *reinterpret_cast<uint32_t*>(Bh + o) = hab & m;
-    *reinterpret_cast<uint32_t*>(Bl + o) = lab & m;
+    if (nd & 1u) *reinterpret_cast<uint32_t*>(P + o) = 0x3F803F80u & m;
+    if (nd & 2u) {
+      *reinterpret_cast<uint32_t*>(Bh + o) = hab & m;
+      *reinterpret_cast<uint32_t*>(Bl + o) = lab & m;
+    }
   }
 }
 
@@ -352,10 +357,14 @@ __global__ void __launch_bounds__(256)
 k_expand_operands_u8(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp, int64_t np,
                      const uint8_t* __restrict__ qa, const uint8_t* __restrict__ qh,
                      const uint8_t* __restrict__ ql, uint8_t* __restrict__ A, uint8_t* __restrict__ Bh,
-                     uint8_t* __restrict__ Bl) {
+                     uint8_t* __restrict__ Bl, const uint8_t* __restrict__ need) {
   __shared__ __align__(16) uint32_t words[8][128];
   const int32_t v0 = blockIdx.x * 128;
   const int32_t w0 = blockIdx.y * 8;
+  // need[block of 256 samples]: bit 0 = these samples occur as columns (A), bit 1 = as rows (Bh, Bl)
+  // of a tile of this rank's bands; a rank of a multi-GPU run skips the operands it never reads
+  const uint32_t nd = need ? need[blockIdx.y] : 3u;
+  if (nd == 0u) return;
   for (int idx = threadIdx.x; idx < 1024; idx += 256) {
     int word = idx >> 7, node = idx & 127;
     uint32_t x = 0;
@@ -378,9 +387,11 @@ k_expand_operands_u8(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
                           (((w4.w >> it) & 1u) << 24);
     const uint32_t m = bits * 0xFFu;  // 0x01 -> 0xFF per byte
     const int64_t o = s * kp + va;
-    *reinterpret_cast<uint32_t*>(A + o) = a4 & m;
-    *reinterpret_cast<uint32_t*>(Bh + o) = h4 & m;
-    *reinterpret_cast<uint32_t*>(Bl + o) = l4 & m;
+    if (nd & 1u) *reinterpret_cast<uint32_t*>(A + o) = a4 & m;
+    if (nd & 2u) {
+      *reinterpret_cast<uint32_t*>(Bh + o) = h4 & m;
+      *reinterpret_cast<uint32_t*>(Bl + o) = l4 & m;
+    }
   }
 }
 
@@ -566,19 +577,19 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
 
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
                              const void* q0, const void* q1, const void* q2, void* P, void* Bh, void* Bl,
-                             cudaStream_t s) {
+                             const uint8_t* need, cudaStream_t s) {
   if (i8) {
     dim3 grid(kp / 128, static_cast<unsigned>((np + 255) / 256));
     k_expand_operands_u8<<<grid, 256, 0, s>>>(bitsT, nw, kp, np, static_cast<const uint8_t*>(q0),
                                               static_cast<const uint8_t*>(q1), static_cast<const uint8_t*>(q2),
                                               static_cast<uint8_t*>(P), static_cast<uint8_t*>(Bh),
-                                              static_cast<uint8_t*>(Bl));
+                                              static_cast<uint8_t*>(Bl), need);
   } else {
     (void)q0;
     dim3 grid(kp / 64, static_cast<unsigned>((np + 255) / 256));
     k_expand_operands_t<<<grid, 256, 0, s>>>(bitsT, nw, kp, np, static_cast<const uint16_t*>(q1),
                                              static_cast<const uint16_t*>(q2), static_cast<uint16_t*>(P),
-                                             static_cast<uint16_t*>(Bh), static_cast<uint16_t*>(Bl));
+                                             static_cast<uint16_t*>(Bh), static_cast<uint16_t*>(Bl), need);
   }
   return 1;
 }

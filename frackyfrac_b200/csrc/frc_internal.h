@@ -87,9 +87,11 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
                                 const double* lenq, const uint32_t* qam, const int32_t* col_exp,
                                 uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
                                 cudaStream_t s);
+// need[np / 256] (device, may be null = everything): bit 0 = write the A rows of that block of 256
+// samples, bit 1 = write its Bh / Bl rows.
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
                              const void* q0, const void* q1, const void* q2, void* P, void* Bh, void* Bl,
-                             cudaStream_t s);
+                             const uint8_t* need, cudaStream_t s);
 // u8 block floating point: for operand column k with true length len_col[k] >= 0 and chunk
 // exponent col_exp[k], find the 8-bit a and 16-bit m = 256*qh + ql minimising
 // |a * m * 2^e - len| ; lenq[k] = a * m * 2^e (exact in fp64).

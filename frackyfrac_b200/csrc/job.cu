@@ -201,6 +201,7 @@ struct frc_job {
   void *d_q0 = nullptr, *d_q1 = nullptr, *d_q2 = nullptr;
   int32_t *d_order = nullptr, *d_col_exp = nullptr;
   uint32_t* d_qam = nullptr;  // u8: a * m per operand column
+  uint8_t* d_need = nullptr;  // per block of 256 samples: which operands this rank's tiles read (world > 1)
   double *d_lenq = nullptr, *d_len_col = nullptr, *d_flag_u = nullptr;
   TcChunks d_chunks;
   float* d_lenf = nullptr;
@@ -357,7 +358,7 @@ int run_embedding(frc_job* j) {
         j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
       }
       launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
-                                           j->d_P, j->d_Bh, j->d_Bl, s);
+                                           j->d_P, j->d_Bh, j->d_Bl, j->d_need, s);
     } else {
       launches += launch_embed_bits(j->dtree, j->level_ptr.data(), j->dcsr, j->d_bits, j->nw, s);
       launches += launch_presence_rowsum(j->d_bits, j->B, j->nw, j->d_lenq, j->d_r, j->d_scratch, s);
@@ -823,6 +824,18 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       b.n_tiles = static_cast<int32_t>(j->tiles.size()) - b.tile_off;
     }
 
+  // which operand rows this rank's tiles read (fast unweighted, world > 1): a tile (ti, tj) reads the
+  // Bh / Bl rows of its row samples and the A rows of its column samples (both tiles of a pair)
+  std::vector<uint8_t> need_blocks;
+  if (!j->exact && !j->weighted && world > 1 && j->fused_embed) {
+    need_blocks.assign(static_cast<size_t>((j->np + 255) / 256), 0);
+    const int32_t pairw = j->tc_ctas == 2 ? 2 : 1;
+    for (const Tile& t : j->tiles) {
+      need_blocks[t.ti / 2] |= 2;
+      for (int32_t c = 0; c < pairw; ++c)
+        if ((static_cast<int64_t>(t.tj) + c) * kTile < j->np) need_blocks[(t.tj + c) / 2] |= 1;
+    }
+  }
   mark("row_ptr check + bands/tiles");
   // -------------------------------------------------------------------- context
   int rc = FRC_OK;
@@ -854,7 +867,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       s_lptr = seg(sizeof(int32_t) * (H + 2)), s_lpar = seg(sizeof(int32_t) * B),
       s_order = seg(sizeof(int32_t) * col_order.size()), s_cexp = seg(sizeof(int32_t) * col_exp.size()),
       s_lcol = seg(sizeof(double) * len_col.size()), s_cend = seg(sizeof(int32_t) * chunk_end.size()),
-      s_cscale = seg(sizeof(double) * chunk_scale.size());
+      s_cscale = seg(sizeof(double) * chunk_scale.size()), s_need = seg(need_blocks.size());
   char* stage = pin_alloc<char>(j, total, &rc);
   if (!stage) return bail(rc);
   j->d_inputs = dev_alloc<char>(j, total, &rc);
@@ -864,59 +877,8 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     int64_t* rp = reinterpret_cast<int64_t*>(stage + s_rowptr.off);
     if (N > 0) memcpy(rp, abnd->row_ptr, sizeof(int64_t) * (N + 1)); else rp[0] = 0;
     mark("staging alloc + row_ptr copy");
-    // validate + copy the CSR entries in one pass, samples split over host threads
-    {
-      int32_t* dcol = reinterpret_cast<int32_t*>(stage + s_col.off);
-      double* dval = need_val ? reinterpret_cast<double*>(stage + s_val.off) : nullptr;
-      const int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->pool->size(), nnz / 32768)));
-      std::vector<std::string> errs(T);
-      // duplicate detection: stamp[leaf] = epoch-tagged sample id; the arrays persist in the
-      // context, so nothing is cleared between jobs
-      const int64_t tag = c->stamp_epoch;
-      c->stamp_epoch += N + 1;
-      std::function<void(int)> work = [&](int t) {
-        auto row_at = [&](int64_t target) {
-          return static_cast<int64_t>(std::lower_bound(abnd->row_ptr, abnd->row_ptr + N, target) - abnd->row_ptr);
-        };
-        const int64_t s0 = t == 0 ? 0 : row_at(nnz * t / T), s1 = t == T - 1 ? N : row_at(nnz * (t + 1) / T);
-        std::vector<int64_t>& stamp = c->stamps[t];
-        if (static_cast<int32_t>(stamp.size()) < B) stamp.assign(B, -1);
-        for (int64_t s = s0; s < s1; ++s) {
-          const int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
-          const int64_t mark_s = tag + s;
-          for (int64_t k = b; k < e; ++k) {
-            const int32_t cc = abnd->col[k];
-            const double v = abnd->val[k];
-            const char* what = nullptr;
-            if (cc < 0 || cc >= B) what = "node id out of range";
-            else if (child_cnt[cc] != 0) what = "node is not a leaf";
-            else if (!(v > 0) || std::isinf(v)) what = "bad value";
-            else if (stamp[cc] == mark_s) what = "leaf listed twice";
-            if (what) {
-              errs[t] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
-                        std::to_string(cc) + "): " + what;
-              return;
-            }
-            stamp[cc] = mark_s;
-#if defined(__x86_64__)
-            // streaming stores: the staging buffer is read next by the DMA engine, not by a core
-            _mm_stream_si32(dcol + k, cc);
-            if (dval) _mm_stream_si64(reinterpret_cast<long long*>(dval + k), static_cast<long long>(__builtin_bit_cast(int64_t, v)));
-#else
-            dcol[k] = cc;
-            if (dval) dval[k] = v;
-#endif
-          }
-        }
-#if defined(__x86_64__)
-        _mm_sfence();
-#endif
-      };
-      c->pool->run(T, work);
-      for (auto& e : errs)
-        if (!e.empty()) return bail(fail(j, FRC_ERR_ARG, e));
-    }
-    mark("validate+copy CSR entries");
+    // everything derived from the tree alone; runs on the calling thread while the pool validates the table
+    auto prep_tree = [&]() {
     memcpy(stage + s_parent.off, tree->parent, sizeof(int32_t) * B);
     memcpy(stage + s_len.off, tree->length, sizeof(double) * B);
     int32_t* cptr = reinterpret_cast<int32_t*>(stage + s_cptr.off);
@@ -953,8 +915,71 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (!len_col.empty()) memcpy(stage + s_lcol.off, len_col.data(), s_lcol.bytes);
     if (!chunk_end.empty()) memcpy(stage + s_cend.off, chunk_end.data(), s_cend.bytes);
     if (!chunk_scale.empty()) memcpy(stage + s_cscale.off, chunk_scale.data(), s_cscale.bytes);
+    if (!need_blocks.empty()) memcpy(stage + s_need.off, need_blocks.data(), s_need.bytes);
     if (!j->tiles.empty()) memcpy(stage + s_tiles.off, j->tiles.data(), sizeof(Tile) * j->tiles.size());
     memcpy(stage + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
+    };
+    // validate + copy the CSR entries in one pass, samples split over host threads
+    {
+      int32_t* dcol = reinterpret_cast<int32_t*>(stage + s_col.off);
+      double* dval = need_val ? reinterpret_cast<double*>(stage + s_val.off) : nullptr;
+      const int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->pool->size(), nnz / 32768)));
+      // with enough workers the caller (t == 0) prepares the tree arrays instead of taking a CSR share
+      const bool split = T >= 4;
+      const int TS = split ? T - 1 : T;  // CSR shares
+      std::vector<std::string> errs(T);
+      // duplicate detection: stamp[leaf] = epoch-tagged sample id; the arrays persist in the
+      // context, so nothing is cleared between jobs
+      const int64_t tag = c->stamp_epoch;
+      c->stamp_epoch += N + 1;
+      std::function<void(int)> work = [&](int t) {
+        if (split) {
+          if (t == 0) { prep_tree(); return; }
+          --t;
+        }
+        auto row_at = [&](int64_t target) {
+          return static_cast<int64_t>(std::lower_bound(abnd->row_ptr, abnd->row_ptr + N, target) - abnd->row_ptr);
+        };
+        const int64_t s0 = t == 0 ? 0 : row_at(nnz * t / TS), s1 = t == TS - 1 ? N : row_at(nnz * (t + 1) / TS);
+        std::vector<int64_t>& stamp = c->stamps[t];
+        if (static_cast<int32_t>(stamp.size()) < B) stamp.assign(B, -1);
+        for (int64_t s = s0; s < s1; ++s) {
+          const int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
+          const int64_t mark_s = tag + s;
+          for (int64_t k = b; k < e; ++k) {
+            const int32_t cc = abnd->col[k];
+            const double v = abnd->val[k];
+            const char* what = nullptr;
+            if (cc < 0 || cc >= B) what = "node id out of range";
+            else if (child_cnt[cc] != 0) what = "node is not a leaf";
+            else if (!(v > 0) || std::isinf(v)) what = "bad value";
+            else if (stamp[cc] == mark_s) what = "leaf listed twice";
+            if (what) {
+              errs[t] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
+                        std::to_string(cc) + "): " + what;
+              return;
+            }
+            stamp[cc] = mark_s;
+#if defined(__x86_64__)
+            // streaming stores: the staging buffer is read next by the DMA engine, not by a core
+            _mm_stream_si32(dcol + k, cc);
+            if (dval) _mm_stream_si64(reinterpret_cast<long long*>(dval + k), static_cast<long long>(__builtin_bit_cast(int64_t, v)));
+#else
+            dcol[k] = cc;
+            if (dval) dval[k] = v;
+#endif
+          }
+        }
+#if defined(__x86_64__)
+        _mm_sfence();
+#endif
+      };
+      c->pool->run(T, work);
+      if (!split) prep_tree();
+      for (auto& e : errs)
+        if (!e.empty()) return bail(fail(j, FRC_ERR_ARG, e));
+    }
+    mark("validate+copy CSR entries (+ tree arrays on the calling thread)");
   }
   mark("tree arrays, hi/lo, tiles");
   CREATE_CUDA(cudaEventCreate(&j->ev_h2d0));
@@ -988,6 +1013,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->d_chunks.end = reinterpret_cast<int32_t*>(d + s_cend.off);
   j->d_chunks.scale = reinterpret_cast<double*>(d + s_cscale.off);
   j->d_chunks.n = static_cast<int32_t>(chunk_end.size());
+  j->d_need = need_blocks.empty() ? nullptr : reinterpret_cast<uint8_t*>(d + s_need.off);
   if (j->i8 && !chunk_scale.empty()) {
     const auto mm = std::minmax_element(chunk_scale.begin(), chunk_scale.end());
     j->d_chunks.biased = *mm.second <= *mm.first * 256.0;
