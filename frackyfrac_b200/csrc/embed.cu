@@ -24,14 +24,15 @@ constexpr int kThreads = 256;
 
 // ---------------------------------------------------------------- fp64 path
 // One warp per sample: scatter its CSR row into the leaf rows.
+// Samples [s_base, s_end) go to columns [0, s_end - s_base) of E (a slab of the sample range).
 __global__ void k_scatter_f64(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
-                              const double* __restrict__ val, int64_t n_samples, double* E,
+                              const double* __restrict__ val, int64_t s_base, int64_t s_end, double* E,
                               int64_t ld) {
-  int64_t s = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int64_t s = s_base + ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
   int lane = threadIdx.x & 31;
-  if (s >= n_samples) return;
+  if (s >= s_end) return;
   int64_t b = row_ptr[s], e = row_ptr[s + 1];
-  for (int64_t k = b + lane; k < e; k += 32) E[static_cast<int64_t>(col[k]) * ld + s] = val[k];
+  for (int64_t k = b + lane; k < e; k += 32) E[static_cast<int64_t>(col[k]) * ld + (s - s_base)] = val[k];
 }
 
 // One tree level: E[v] = ((0 + E[c1]) + E[c2]) + ... in child order.
@@ -81,8 +82,31 @@ __global__ void k_normalize_f64(double* E, int32_t n_nodes, int64_t ld, int64_t 
   }
 }
 
+// Fast-path totals: partial[c][s] = sum of E[v][s] over the nodes of chunk c (any order will do off
+// the exact path; the sequential ascending-id loop of k_totals_f64 is one dependent fp64 chain per
+// sample and was latency-bound).
+__global__ void k_totals_partial_f64(const double* __restrict__ E, int32_t n_nodes, int64_t ld,
+                                     double* __restrict__ partial) {
+  int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= ld) return;
+  int32_t per = (n_nodes + gridDim.y - 1) / gridDim.y;
+  int32_t v0 = blockIdx.y * per, v1 = min(n_nodes, v0 + per);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int32_t v = v0;
+  for (; v + 4 <= v1; v += 4) {
+    a0 += E[static_cast<int64_t>(v) * ld + s];
+    a1 += E[static_cast<int64_t>(v + 1) * ld + s];
+    a2 += E[static_cast<int64_t>(v + 2) * ld + s];
+    a3 += E[static_cast<int64_t>(v + 3) * ld + s];
+  }
+  for (; v < v1; ++v) a0 += E[static_cast<int64_t>(v) * ld + s];
+  partial[static_cast<int64_t>(blockIdx.y) * ld + s] = (a0 + a1) + (a2 + a3);
+}
+
 // Weighted operand + per-chunk partial denominators.
-// grid.x covers samples, grid.y = node chunks; partial[chunk][s].
+// grid.x covers samples, grid.y = node chunks; partial[chunk][s].  The proportion is x * (1/T) (one
+// fp64 multiply; the exact path divides): fp64-pipe instructions are the scarce resource on B200
+// and a division is ~30 of them.
 __global__ void k_weighted_operand(const double* __restrict__ E, const double* __restrict__ length,
                                    int32_t n_nodes, int64_t ld, const double* __restrict__ total,
                                    int prescale, float* __restrict__ A, double* __restrict__ partial) {
@@ -91,15 +115,44 @@ __global__ void k_weighted_operand(const double* __restrict__ E, const double* _
   int32_t per = (n_nodes + gridDim.y - 1) / gridDim.y;
   int32_t v0 = blockIdx.y * per, v1 = min(n_nodes, v0 + per);
   const double t = total ? total[s] : 1.0;
+  const double inv = t > 0.0 ? 1.0 / t : 0.0;  // empty sample: every x is 0
   double w = 0.0;
   for (int32_t v = v0; v < v1; ++v) {
-    double x = E[static_cast<int64_t>(v) * ld + s];
-    double a = (x != 0.0 && total) ? x / t : x;
-    double la = length[v] * a;
+    const double x = E[static_cast<int64_t>(v) * ld + s];
+    const double a = total ? x * inv : x;
+    const double la = length[v] * a;
     w += la;
     A[static_cast<int64_t>(v) * ld + s] = static_cast<float>(prescale ? la : a);
   }
   partial[static_cast<int64_t>(blockIdx.y) * ld + s] = w;
+}
+
+// Same, writing the tile-panel layout of the fast weighted path: Ap[tile][kp][128] (tile = 128
+// consecutive samples), E being a slab of S = ld samples starting at sample s_base (a multiple of 128).
+// Rows [n_nodes, kp) of the panels are zeroed by the last chunk.
+__global__ void k_weighted_operand_panels(const double* __restrict__ E, const double* __restrict__ length,
+                                          int32_t n_nodes, int32_t kp, int64_t ld, int64_t s_base,
+                                          const double* __restrict__ total, int prescale,
+                                          float* __restrict__ Ap, double* __restrict__ partial) {
+  int64_t ls = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (ls >= ld) return;
+  int32_t per = (n_nodes + gridDim.y - 1) / gridDim.y;
+  int32_t v0 = blockIdx.y * per, v1 = min(n_nodes, v0 + per);
+  const int64_t s = s_base + ls;
+  float* dst = Ap + ((s >> 7) * kp) * 128 + (s & 127);
+  const double t = total ? total[ls] : 1.0;
+  const double inv = t > 0.0 ? 1.0 / t : 0.0;
+  double w = 0.0;
+  for (int32_t v = v0; v < v1; ++v) {
+    const double x = E[static_cast<int64_t>(v) * ld + ls];
+    const double a = total ? x * inv : x;
+    const double la = length[v] * a;
+    w += la;
+    dst[static_cast<int64_t>(v) * 128] = static_cast<float>(prescale ? la : a);
+  }
+  if (blockIdx.y == gridDim.y - 1)
+    for (int32_t v = n_nodes; v < kp; ++v) dst[static_cast<int64_t>(v) * 128] = 0.f;
+  partial[static_cast<int64_t>(blockIdx.y) * ld + ls] = w;
 }
 
 __global__ void k_reduce_partials(const double* __restrict__ partial, int n_chunks, int64_t ld,
@@ -437,13 +490,14 @@ __global__ void k_quantize_lengths(const double* __restrict__ len_col, const int
 
 // ------------------------------------------------------------------ launchers
 int launch_embed_f64(const DevTree& t, const int32_t* level_ptr, const DevCsr& a, double* E,
-                     int64_t ld, cudaStream_t s) {
+                     int64_t ld, int64_t s_base, cudaStream_t s) {
   int launches = 0;
   cudaMemsetAsync(E, 0, sizeof(double) * ld * t.n_nodes, s);
-  if (a.n_samples > 0 && a.nnz > 0) {
-    int64_t threads = a.n_samples * 32;
+  const int64_t s_end = s_base + ld < a.n_samples ? s_base + ld : a.n_samples;
+  if (s_end > s_base && a.nnz > 0) {
+    int64_t threads = (s_end - s_base) * 32;
     k_scatter_f64<<<static_cast<unsigned>((threads + kThreads - 1) / kThreads), kThreads, 0, s>>>(
-        a.row_ptr, a.col, a.val, a.n_samples, E, ld);
+        a.row_ptr, a.col, a.val, s_base, s_end, E, ld);
     ++launches;
   }
   for (int32_t h = 1; h <= t.height; ++h) {
@@ -454,6 +508,21 @@ int launch_embed_f64(const DevTree& t, const int32_t* level_ptr, const DevCsr& a
     ++launches;
   }
   return launches;
+}
+
+static int pick_chunks(int32_t n_nodes) {
+  int c = n_nodes / 256;
+  return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+
+int launch_totals_fast_f64(const double* E, int32_t n_nodes, int64_t ld, double* total, double* scratch,
+                           cudaStream_t s) {
+  const int chunks = pick_chunks(n_nodes);
+  dim3 grid(static_cast<unsigned>((ld + kThreads - 1) / kThreads), chunks);
+  k_totals_partial_f64<<<grid, kThreads, 0, s>>>(E, n_nodes, ld, scratch);
+  k_reduce_partials<<<static_cast<unsigned>((ld + kThreads - 1) / kThreads), kThreads, 0, s>>>(scratch, chunks, ld, ld,
+                                                                                             total);
+  return 2;
 }
 
 int launch_totals_f64(const double* E, int32_t n_nodes, int64_t ld, int64_t n_samples, double* total,
@@ -473,10 +542,6 @@ int launch_normalize_f64(double* E, int32_t n_nodes, int64_t ld, int64_t n_sampl
   return 1;
 }
 
-static int pick_chunks(int32_t n_nodes) {
-  int c = n_nodes / 256;
-  return c < 1 ? 1 : (c > 64 ? 64 : c);
-}
 
 int launch_weighted_operand(const double* E, const double* length, int32_t n_nodes, int32_t kp,
                             int64_t ld, int64_t n_samples, const double* total, bool prescale,
@@ -490,6 +555,17 @@ int launch_weighted_operand(const double* E, const double* length, int32_t n_nod
   k_reduce_partials<<<static_cast<unsigned>((ld + kThreads - 1) / kThreads), kThreads, 0, s>>>(
       scratch, chunks, ld, ld, W);
   (void)n_samples;
+  return 2;
+}
+int launch_weighted_operand_panels(const double* E, const double* length, int32_t n_nodes, int32_t kp,
+                                   int64_t ld, int64_t s_base, const double* total, bool prescale, float* Ap,
+                                   double* W, double* scratch, cudaStream_t s) {
+  int chunks = pick_chunks(n_nodes);
+  dim3 grid(static_cast<unsigned>((ld + kThreads - 1) / kThreads), chunks);
+  k_weighted_operand_panels<<<grid, kThreads, 0, s>>>(E, length, n_nodes, kp, ld, s_base, total, prescale ? 1 : 0,
+                                                      Ap, scratch);
+  k_reduce_partials<<<static_cast<unsigned>((ld + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+      scratch, chunks, ld, ld, W + s_base);
   return 2;
 }
 int weighted_scratch_chunks(int32_t n_nodes) { return pick_chunks(n_nodes); }

@@ -41,11 +41,15 @@ struct Tile { int32_t ti, tj; };
 // fp64 branch embedding, node-major E[B][ld] (unifrac.go:32-53): leaf rows
 // scattered from the CSR, then one pass per tree level, children summed in
 // child order starting from 0.0.  Returns launches.
+// E holds the ld samples starting at sample s_base (the whole table: s_base = 0, ld = np).
 int launch_embed_f64(const DevTree& t, const int32_t* level_ptr_host, const DevCsr& a, double* E,
-                     int64_t ld, cudaStream_t s);
+                     int64_t ld, int64_t s_base, cudaStream_t s);
 // total[s] = sum over ALL nodes in ascending id order (unifrac.go:60-63).
 int launch_totals_f64(const double* E, int32_t n_nodes, int64_t ld, int64_t n_samples,
                       double* total, cudaStream_t s);
+// Same totals for the fast path (chunked partial sums, any order; scratch as for launch_weighted_operand).
+int launch_totals_fast_f64(const double* E, int32_t n_nodes, int64_t ld, double* total, double* scratch,
+                           cudaStream_t s);
 // E[v][s] /= total[s] for non-zero entries (unifrac.go:64-66).
 int launch_normalize_f64(double* E, int32_t n_nodes, int64_t ld, int64_t n_samples,
                          const double* total, cudaStream_t s);
@@ -55,6 +59,13 @@ int launch_normalize_f64(double* E, int32_t n_nodes, int64_t ld, int64_t n_sampl
 int launch_weighted_operand(const double* E, const double* length, int32_t n_nodes, int32_t kp,
                             int64_t ld, int64_t n_samples, const double* total, bool prescale,
                             float* A, double* W, double* scratch, cudaStream_t s);
+// Fast weighted path: the same operand in tile-panel layout Ap[np/128][kp][128] (a pair tile reads
+// 32-node x 128-sample slabs that are contiguous 16 KB, and sample shards of a multi-GPU run are
+// contiguous byte ranges), from a slab E[B][ld] of the samples [s_base, s_base + ld); total is the
+// slab's (ld entries), W the global array.
+int launch_weighted_operand_panels(const double* E, const double* length, int32_t n_nodes, int32_t kp,
+                                   int64_t ld, int64_t s_base, const double* total, bool prescale, float* Ap,
+                                   double* W, double* scratch, cudaStream_t s);
 // Rows of scratch (each ld doubles) the two partial-sum reductions need.
 int weighted_scratch_chunks(int32_t n_nodes);
 
@@ -119,6 +130,7 @@ int launch_exact_pairs(const double* E, const double* length, int32_t n_nodes, i
                        bool weighted, int64_t first, int64_t count, double* out, cudaStream_t s);
 
 // ---- weighted.cu ------------------------------------------------------------
+// A is the tile-panel operand Ap[np/128][kp][128].
 int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
                           const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
                           int64_t first, double* out, cudaStream_t s);

@@ -193,6 +193,7 @@ struct frc_job {
   unsigned long long* d_flag_counts = nullptr;  // one per band of this rank
   bool fused_embed = true;
   bool zero_copy = false;
+  int64_t ws_slab = 0;        // fast weighted: samples per fp64 embedding slab
   bool sharded = false;       // embedding built for this rank's sample shard, then all-gathered
   int32_t shard_w0 = 0, shard_nw = 0;  // word columns (32 samples) of the shard
   int tc_ctas = 1;  // CTAs per tensor-core tile group (2 = cta_group::2 pairs)
@@ -327,18 +328,35 @@ int run_embedding(frc_job* j) {
   if (j->d_flag_counts)
     JOB_CUDA(j, cudaMemsetAsync(j->d_flag_counts, 0, sizeof(unsigned long long) * (j->mine.size() + 1), s));
   JOB_CUDA(j, cudaEventRecord(j->ev_embed0, s));
-  if (j->exact || j->weighted) {
-    launches += launch_embed_f64(j->dtree, j->level_ptr.data(), j->dcsr, j->d_E, j->np, s);
+  if (j->exact) {
+    launches += launch_embed_f64(j->dtree, j->level_ptr.data(), j->dcsr, j->d_E, j->np, 0, s);
+    if (j->opts.normalize != 0) {
+      launches += launch_totals_f64(j->d_E, j->B, j->np, j->N, j->d_total, s);
+      launches += launch_normalize_f64(j->d_E, j->B, j->np, j->N, j->d_total, s);
+    }
+    j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
+  } else if (j->weighted) {
+    // fast weighted: the fp64 embedding is built one slab of samples at a time (E[B][slab] stays
+    // <= 2 GB whatever the sample count) and leaves as the fp32 tile-panel operand + denominators;
+    // a rank of a sharded run only builds the slabs of its own sample shard
     const bool norm = j->opts.normalize != 0;
-    if (norm) launches += launch_totals_f64(j->d_E, j->B, j->np, j->N, j->d_total, s);
-    if (j->exact) {
-      if (norm) launches += launch_normalize_f64(j->d_E, j->B, j->np, j->N, j->d_total, s);
-    } else {
-      if (norm && j->np > j->N)  // padding samples: total = 1 avoids touching garbage
-        JOB_CUDA(j, cudaMemsetAsync(j->d_total + j->N, 0, sizeof(double) * (j->np - j->N), s));
-      launches += launch_weighted_operand(j->d_E, j->dtree.length, j->B, j->kp, j->np, j->N,
-                                          norm ? j->d_total : nullptr, j->prescale, j->d_A, j->d_W,
-                                          j->d_scratch, s);
+    const int64_t per_rank = j->np / (j->sharded ? j->opts.world : 1);
+    const int64_t s_begin = j->sharded ? j->opts.rank * per_rank : 0, s_stop = s_begin + per_rank;
+    for (int64_t sb = s_begin; sb < s_stop; sb += j->ws_slab) {
+      const int64_t ld = std::min<int64_t>(j->ws_slab, s_stop - sb);
+      launches += launch_embed_f64(j->dtree, j->level_ptr.data(), j->dcsr, j->d_E, ld, sb, s);
+      if (norm) launches += launch_totals_fast_f64(j->d_E, j->B, ld, j->d_total, j->d_scratch, s);
+      launches += launch_weighted_operand_panels(j->d_E, j->dtree.length, j->B, j->kp, ld, sb,
+                                                 norm ? j->d_total : nullptr, j->prescale, j->d_A, j->d_W,
+                                                 j->d_scratch, s);
+    }
+    if (j->sharded) {
+      void* bufs[2] = {j->d_A, j->d_W};
+      const size_t bytes[2] = {static_cast<size_t>(per_rank) * j->kp * sizeof(float),
+                               static_cast<size_t>(per_rank) * sizeof(double)};
+      std::string cerr;
+      if (!comm_all_gather_inplace(c->comm, bufs, bytes, 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
+      j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
     }
     // write each element once, read it once when folded into its parent (+ CSR)
     j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
@@ -677,7 +695,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   if (!j->exact && bad_len)
     return bail(fail(j, FRC_ERR_UNSUPPORTED, "non-finite branch length: only the exact path handles it"));
   j->prescale = !neg_len;
-  if (j->sharded && (j->exact || j->weighted)) j->sharded = false;  // (these rebuild the embedding per rank)
+  if (j->sharded && j->exact) j->sharded = false;  // (the exact path rebuilds the embedding per rank)
   j->shard_nw = j->sharded ? j->nw / world : j->nw;
   j->shard_w0 = j->sharded ? rank * j->shard_nw : 0;
   j->info.path_taken = j->exact ? FRC_PATH_EXACT : FRC_PATH_FAST;
@@ -1027,7 +1045,13 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   // ------------------------------------------------------------ device buffers
   const int chunks = weighted_scratch_chunks(B);
   if (j->exact || j->weighted) {
-    if (!(j->d_E = dev_alloc<double>(j, static_cast<size_t>(B) * j->np, &rc))) return bail(rc);
+    // exact: the whole fp64 embedding; fast weighted: one slab of samples at a time, <= 2 GB
+    const int64_t per_rank = j->np / (j->sharded ? world : 1);
+    j->ws_slab = j->exact ? j->np
+                          : std::min<int64_t>(per_rank, std::max<int64_t>(kTile, (2LL << 30) / (8LL * B) / kTile * kTile));
+    if (const char* e = getenv("FRC_WS_SLAB"))  // tests: force several slabs on a small problem
+      if (!j->exact && atoi(e) > 0) j->ws_slab = std::min<int64_t>(per_rank, round_up(atoi(e), kTile));
+    if (!(j->d_E = dev_alloc<double>(j, static_cast<size_t>(B) * j->ws_slab, &rc))) return bail(rc);
     if (!(j->d_total = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
     if (!j->exact) {
       if (!(j->d_A = dev_alloc<float>(j, static_cast<size_t>(j->kp) * j->np, &rc))) return bail(rc);

@@ -6,7 +6,7 @@
 //
 // The denominator is separable (W_i + W_j, computed once per sample in fp64 by
 // the embedding stage), so the pair kernel only accumulates the numerator: an
-// L1 distance between two columns of the node-major operand A[kp][ld].  With
+// L1 distance between two sample columns of the operand, stored as tile panels Ap[np/128][kp][128].  With
 // non-negative branch lengths the operand is pre-scaled (A = len * a), so the
 // inner loop is exactly two FP32 instructions per (pair, node): FADD d = a - b,
 // FADD acc = acc + |d| (|.| is a free source modifier).  Negative lengths use
@@ -60,14 +60,13 @@ k_weighted_tiles(const float* __restrict__ A, int64_t ld, int32_t kp, const floa
   auto load_slab = [&](int slab, int stage) {
     float* sa = smem + stage * STAGE_FLOATS;
     float* sb = sa + SLAB_FLOATS;
-    const float* ga = A + static_cast<int64_t>(slab) * KT * ld + i0;
-    const float* gb = A + static_cast<int64_t>(slab) * KT * ld + j0;
-    // 32 rows x 128 floats per side = 1024 16-byte chunks per side
+    // tile-panel layout Ap[tile][kp][128]: a slab of 32 nodes x 128 samples is 16 contiguous KB
+    const float* ga = A + (static_cast<int64_t>(tile.ti) * kp + static_cast<int64_t>(slab) * KT) * kTile;
+    const float* gb = A + (static_cast<int64_t>(tile.tj) * kp + static_cast<int64_t>(slab) * KT) * kTile;
 #pragma unroll
     for (int c = tid; c < KT * (kTile / 4); c += 256) {
-      int row = c >> 5, q = c & 31;
-      cp_async16(sa + row * kTile + q * 4, ga + static_cast<int64_t>(row) * ld + q * 4);
-      cp_async16(sb + row * kTile + q * 4, gb + static_cast<int64_t>(row) * ld + q * 4);
+      cp_async16(sa + c * 4, ga + c * 4);
+      cp_async16(sb + c * 4, gb + c * 4);
     }
     if (!kPrescaled && tid < KT) cp_async4(sb + SLAB_FLOATS + tid, lenf + slab * KT + tid);
   };

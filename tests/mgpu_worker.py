@@ -27,9 +27,9 @@ def main():
     rp, col, val = synth.random_table(tree, 1100, 0.03, 302)
     n = 1100
     ok = True
-    for uw_flags in (0, engine.FLAG_UW_BF16):
+    for weighted, uw_flags in ((False, 0), (False, engine.FLAG_UW_BF16), (True, 0)):
         chunks = []
-        with engine.Job(tree.parent, tree.length, rp, col, val, weighted=False, path=engine.PATH_FAST, ctx=ctx,
+        with engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
                         rank=rank, world=world, band_rows=128, flags=uw_flags | engine.FLAG_SHARD_EMBED) as job:
             for first, a in job.chunks():
                 chunks.append((first, a))
@@ -37,13 +37,14 @@ def main():
         assert info.gather_bytes > 0, "the embedding was not all-gathered"
         full = fdist.gather_distances(chunks, n)
         if rank == 0:
-            alone = engine.unifrac(tree.parent, tree.length, rp, col, val, False, path=engine.PATH_FAST, ctx=ctx,
+            alone = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, path=engine.PATH_FAST, ctx=ctx,
                                    band_rows=128, flags=uw_flags)
             same = np.array_equal(full, alone, equal_nan=True)
             from oracle import oracle as orc
-            want = orc.unifrac(orc.Table.from_csr(rp, col, val), orc.Tree.from_flat(tree.parent, tree.length), False, 1, 8)
+            want = orc.unifrac(orc.Table.from_csr(rp, col, val), orc.Tree.from_flat(tree.parent, tree.length), weighted, 1, 8)
             err = np.max(np.abs(full - want) / np.maximum(np.abs(want), 1e-12))
-            print(f"flags={uw_flags} world={world} identical={same} max_rel_err={err:.2e} gather_bytes={info.gather_bytes}", flush=True)
+            print(f"weighted={weighted} flags={uw_flags} world={world} identical={same} max_rel_err={err:.2e} "
+                  f"gather_bytes={info.gather_bytes}", flush=True)
             ok = ok and same and err < 1e-5
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)

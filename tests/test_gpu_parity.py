@@ -178,6 +178,21 @@ def test_fast_unweighted_u8_is_tighter_than_bf16(gpu_ctx):
     assert e8 < 2e-6 and e8 <= e16 * 1.5, (e8, e16)
 
 
+@pytest.mark.parametrize("slab", [128, 256])
+def test_fast_weighted_embedding_in_slabs(gpu_ctx, monkeypatch, slab):
+    """The fp64 embedding of the fast weighted path is built slab by slab of samples (bounded memory):
+    the slab width must not change a single byte."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(900, 81)
+    csr = synth.random_table(tree, 700, 0.03, 82, integer_counts=False)
+    whole = gpu_flat(tree, csr, True, path=engine.PATH_FAST, ctx=gpu_ctx)
+    monkeypatch.setenv("FRC_WS_SLAB", str(slab))
+    slabs = gpu_flat(tree, csr, True, path=engine.PATH_FAST, ctx=gpu_ctx)
+    assert np.array_equal(whole, slabs)
+    assert rel_err(slabs, oracle_flat(tree, csr, True)).max() < 1e-5
+
+
 @pytest.mark.parametrize("shape,levels", [("caterpillar", 0), ("caterpillar", 1), ("balanced", 0), ("random", 1),
                                           ("caterpillar", 2), ("random", 2)])
 def test_fast_unweighted_embedding_variants(gpu_ctx, monkeypatch, shape, levels):
