@@ -120,11 +120,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def make_workload(name: str, world: int):
+def make_workload(name: str, world: int, fixed: bool = False):
     from frackyfrac_b200 import synth
 
     mode, leaves, samples, density, ts, bs = CONFIGS[name]
-    if world > 1:  # weak scaling: pairs per GPU constant
+    if world > 1 and not fixed:  # weak scaling: pairs per GPU constant
         samples = int(round(samples * math.sqrt(world)))
     tree = synth.random_tree(leaves, ts)
     rp, col, val = synth.random_table(tree, samples, density, bs)
@@ -162,7 +162,7 @@ def cpu_baseline(tree, csr, weighted, target_s=12.0, threads=None):
 def run_reference(args, world, rank):
     if rank != 0:
         return
-    mode, tree, csr, samples, leaves, density = make_workload(args.config, world)
+    mode, tree, csr, samples, leaves, density = make_workload(args.config, world, args.fixed_size)
     weighted = mode == "weighted"
     vals, last = [], None
     t_all0 = time.perf_counter()
@@ -210,7 +210,7 @@ def run_ours(args, world, rank, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    mode, tree, csr, samples, leaves, density = make_workload(args.config, world)
+    mode, tree, csr, samples, leaves, density = make_workload(args.config, world, args.fixed_size)
     weighted = mode == "weighted"
     rp, col, val = csr
     total_pairs = samples * (samples - 1) // 2
@@ -349,7 +349,7 @@ def run_ours(args, world, rank, local_rank):
     if rank == 0:
         out = {"metric": f"UniFrac sample-pairs/sec ({mode})", "value": value, "unit": "sample-pairs/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "higher_is_better": True, "scaling": "strong" if args.fixed_size else "weak", "vs_baseline": None,
                "dtype": "f32 numerator tiles, f64 embedding/denominators/output" if weighted else
                         ("bf16 x bf16 -> f32 (tcgen05 kind::f16), f64 row sums/epilogue/output" if info.operand_kind == 1 else
                          "u8 x u8 -> s32 (tcgen05 kind::i8, exact), f64 chunk scaling/row sums/epilogue/output"),
@@ -381,6 +381,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (configs whose output exceeds host RAM)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-alone timing leg")
     ap.add_argument("--min-warmup", type=int, default=3)
+    ap.add_argument("--fixed-size", action="store_true",
+                    help="N>1: keep the config's sample count (strong scaling) instead of growing it with sqrt(N)")
     ap.add_argument("--shard-embed", action="store_true", help="N>1: force the sharded embedding + all-gather")
     ap.add_argument("--no-shard-embed", action="store_true",
                     help="N>1: every rank rebuilds the whole embedding (no NCCL all-gather)")

@@ -461,15 +461,20 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
           // (to multiples of the largest chunk scale) is ~2^-28 of a sum because the host only sets
           // `biased` when all chunk scales lie within 2^8.  Otherwise 2^52 is subtracted first (exact).
           auto drain = [&](auto kBiased) {
+            // two register sets: the tcgen05.ld of batch c+1 is in flight while batch c is folded in
+            uint32_t v[2][8], w[2][8];
+            ptx::tmem_ld_32x8(taddr, v[0]);
+            ptx::tmem_ld_32x8(taddr + BN, w[0]);
 #pragma unroll
             for (int cc = 0; cc < EPI2_COLS / 8; ++cc) {
-              uint32_t v[8], w[8];
-              ptx::tmem_ld_32x8(taddr + cc * 8, v);
-              ptx::tmem_ld_32x8(taddr + BN + cc * 8, w);
               ptx::tmem_ld_wait();
+              if (cc + 1 < EPI2_COLS / 8) {
+                ptx::tmem_ld_32x8(taddr + (cc + 1) * 8, v[(cc + 1) & 1]);
+                ptx::tmem_ld_32x8(taddr + BN + (cc + 1) * 8, w[(cc + 1) & 1]);
+              }
 #pragma unroll
               for (int x = 0; x < 8; ++x) {
-                const unsigned long long S = static_cast<unsigned long long>(v[x]) * 256ull + w[x];
+                const unsigned long long S = static_cast<unsigned long long>(v[cc & 1][x]) * 256ull + w[cc & 1][x];
                 double D = __longlong_as_double(static_cast<long long>(S | 0x4330000000000000ull));
                 if (!decltype(kBiased)::value) D -= 4503599627370496.0;
                 acc[cc * 8 + x] = fma(scale, D, acc[cc * 8 + x]);
@@ -507,23 +512,33 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
         const double rj = j < n_samples ? r[j] : 0.0;
         const double ri_lane = r[i0 + lane];
         int64_t off = i0 * (i0 - 1) / 2 - first + j;  // flat index of (i0, j) relative to the band
+        // batches of 8 row samples: first the arithmetic of all 8 (independent chains the scheduler can
+        // interleave: one element is ~25 dependent instructions, and issuing them element by element
+        // behind each store left the 16 warps latency-bound at 47k cycles per tile), then the stores
 #pragma unroll
-        for (int n = 0; n < EPI2_COLS; ++n) {
-          const int64_t i = i0 + n;
-          const double ri = __shfl_sync(0xffffffffu, ri_lane, n);
-          if (i < n_samples && j < i) {
+        for (int n0 = 0; n0 < EPI2_COLS; n0 += 8) {
+          float dv[8], uv[8];
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const double ri = __shfl_sync(0xffffffffu, ri_lane, n0 + x);
             // fp64 only where cancellation needs it: U = R - 2s (the reference's `result`)
-            const double s = static_cast<double>(acc[n]);
+            const double s = static_cast<double>(acc[n0 + x]);
             const double U = fma(-2.0, s, ri + rj);
-            const float Uf = static_cast<float>(U), sf = static_cast<float>(s);
-            const float d = __fdiv_rn(Uf, Uf + sf);  // U / (U + common), unifrac.go:169
-            out[off] = widen_f32(d);
-            if (d < flag_d || Uf < flag_u) {
-              unsigned long long slot = atomicAdd(n_flagged, 1ULL);
-              flagged[slot] = static_cast<uint32_t>(off);
-            }
+            uv[x] = static_cast<float>(U);
+            dv[x] = __fdividef(uv[x], uv[x] + static_cast<float>(s));  // U / (U + common), unifrac.go:169
           }
-          off += i;  // row i+1 starts i entries later
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const int64_t i = i0 + n0 + x;
+            if (i < n_samples && j < i) {
+              out[off] = widen_f32(dv[x]);
+              if (dv[x] < flag_d || uv[x] < flag_u) {
+                unsigned long long slot = atomicAdd(n_flagged, 1ULL);
+                flagged[slot] = static_cast<uint32_t>(off);
+              }
+            }
+            off += i;  // row i+1 starts i entries later
+          }
         }
       }
       TL(t_ratio += clock64() - c2;)
