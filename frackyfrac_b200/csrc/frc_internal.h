@@ -131,9 +131,17 @@ int launch_exact_pairs(const double* E, const double* length, int32_t n_nodes, i
 
 // ---- weighted.cu ------------------------------------------------------------
 // A is the tile-panel operand Ap[np/128][kp][128].
+// Pairs with d < flag_below are appended to flagged[] for the fix-up pass (as the unweighted kernel).
 int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
                           const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
-                          int64_t first, double* out, cudaStream_t s);
+                          int64_t first, double* out, double flag_below, uint32_t* flagged,
+                          unsigned long long* n_flagged, cudaStream_t s);
+// fp64 / fixed-point recompute of the flagged pairs from the CSR rows (total: per-sample normaliser,
+// null for -l); ws = ws_ctas zeroed int64 arrays of n_nodes entries, left zeroed.
+int launch_weighted_fixup(const DevCsr& a, const DevTree& t, const double* total, const double* W,
+                          const uint32_t* flagged, const unsigned long long* n_flagged,
+                          unsigned long long* count_host, int64_t first, long long* ws, int ws_ctas, double* out,
+                          cudaStream_t s);
 void weighted_setup();  // cudaFuncSetAttribute calls, once per process
 
 // ---- unweighted_tc.cu -------------------------------------------------------

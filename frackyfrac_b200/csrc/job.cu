@@ -140,6 +140,7 @@ constexpr int kSlots = 8;                       // output ring: enough for the c
 constexpr int kMinSlots = 3;
 constexpr int64_t kSlotBytesBudget = 1LL << 30;  // bytes the output ring may take beyond kMinSlots (pinned allocation is slow: ~0.4 s per GB)
 constexpr double kFlagBelow = 0.125;            // fast unweighted: recompute d below this exactly
+constexpr double kFlagBelowW = 0.03125;         // fast weighted: fp32 error is ~6e-8 / d -> 2e-6 at this d
 constexpr int64_t kExactWorkLimit = 1LL << 28;  // AUTO: pairs * nodes at or below this -> exact
 
 }  // namespace
@@ -202,6 +203,7 @@ struct frc_job {
   void *d_q0 = nullptr, *d_q1 = nullptr, *d_q2 = nullptr;
   int32_t *d_order = nullptr, *d_col_exp = nullptr;
   uint32_t* d_qam = nullptr;  // u8: a * m per operand column
+  long long* d_fix_ws = nullptr;  // fast weighted fix-up: one zeroed int64[B] per SM
   uint8_t* d_need = nullptr;  // per block of 256 samples: which operands this rank's tiles read (world > 1)
   double *d_lenq = nullptr, *d_len_col = nullptr, *d_flag_u = nullptr;
   TcChunks d_chunks;
@@ -345,18 +347,19 @@ int run_embedding(frc_job* j) {
     for (int64_t sb = s_begin; sb < s_stop; sb += j->ws_slab) {
       const int64_t ld = std::min<int64_t>(j->ws_slab, s_stop - sb);
       launches += launch_embed_f64(j->dtree, j->level_ptr.data(), j->dcsr, j->d_E, ld, sb, s);
-      if (norm) launches += launch_totals_fast_f64(j->d_E, j->B, ld, j->d_total, j->d_scratch, s);
+      if (norm) launches += launch_totals_fast_f64(j->d_E, j->B, ld, j->d_total + sb, j->d_scratch, s);
       launches += launch_weighted_operand_panels(j->d_E, j->dtree.length, j->B, j->kp, ld, sb,
-                                                 norm ? j->d_total : nullptr, j->prescale, j->d_A, j->d_W,
+                                                 norm ? j->d_total + sb : nullptr, j->prescale, j->d_A, j->d_W,
                                                  j->d_scratch, s);
     }
     if (j->sharded) {
-      void* bufs[2] = {j->d_A, j->d_W};
-      const size_t bytes[2] = {static_cast<size_t>(per_rank) * j->kp * sizeof(float),
+      void* bufs[3] = {j->d_A, j->d_W, j->d_total};
+      const size_t bytes[3] = {static_cast<size_t>(per_rank) * j->kp * sizeof(float),
+                               static_cast<size_t>(per_rank) * sizeof(double),
                                static_cast<size_t>(per_rank) * sizeof(double)};
       std::string cerr;
-      if (!comm_all_gather_inplace(c->comm, bufs, bytes, 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
-      j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
+      if (!comm_all_gather_inplace(c->comm, bufs, bytes, norm ? 3 : 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
+      j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (norm ? bytes[2] : 0)) * (j->opts.world - 1);
     }
     // write each element once, read it once when folded into its parent (+ CSR)
     j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
@@ -412,8 +415,13 @@ int enqueue_band(frc_job* j, size_t idx) {
     launches += launch_exact_pairs(j->d_E, j->dtree.length, j->B, j->np, j->weighted, b.first, b.count,
                                    sl.dev, s);
   } else if (j->weighted) {
+    unsigned long long* cnt = j->d_flag_counts + idx;
     launches += launch_weighted_tiles(j->d_A, j->np, j->kp, j->d_lenf, j->prescale, j->d_W,
-                                      j->d_tiles + b.tile_off, b.n_tiles, j->N, b.first, sl.dev, s);
+                                      j->d_tiles + b.tile_off, b.n_tiles, j->N, b.first, sl.dev, kFlagBelowW,
+                                      sl.flagged, cnt, s);
+    JOB_CUDA(j, cudaEventRecord(sl.k1, s));
+    launches += launch_weighted_fixup(j->dcsr, j->dtree, j->opts.normalize ? j->d_total : nullptr, j->d_W,
+                                      sl.flagged, cnt, sl.n_flagged_host, b.first, j->d_fix_ws, c->num_sms, sl.dev, s);
   } else {
     // no copy-engine work between the kernels: a memset or an 8-byte D2H would queue behind the
     // previous band's bulk D2H and stall this band (measured).  Counters are per band, zeroed once
@@ -426,7 +434,7 @@ int enqueue_band(frc_job* j, size_t idx) {
                                         c->num_sms, s);
   }
   JOB_CUDA(j, cudaGetLastError());
-  if (j->exact || j->weighted) JOB_CUDA(j, cudaEventRecord(sl.k1, s));
+  if (j->exact) JOB_CUDA(j, cudaEventRecord(sl.k1, s));
   JOB_CUDA(j, cudaEventRecord(sl.k2, s));
   // bulk D2H runs on its own stream so the compute streams never hold copy-engine work
   // (a kernel queued behind a copy in the same stream cannot overlap that copy)
@@ -1057,6 +1065,10 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       if (!(j->d_A = dev_alloc<float>(j, static_cast<size_t>(j->kp) * j->np, &rc))) return bail(rc);
       if (!(j->d_W = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
       if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
+      if (!(j->d_flag_counts = dev_alloc<unsigned long long>(j, j->mine.size() + 1, &rc))) return bail(rc);
+      const size_t ws_words = static_cast<size_t>(c->num_sms) * B;
+      if (!(j->d_fix_ws = dev_alloc<long long>(j, ws_words, &rc))) return bail(rc);
+      CREATE_CUDA(cudaMemsetAsync(j->d_fix_ws, 0, sizeof(long long) * ws_words, c->stream[0]));
     }
   } else {
     {
@@ -1098,7 +1110,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (!(opts->flags & FRC_FLAG_NO_D2H) && !(sl.host = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
     if (j->zero_copy && sl.host) sl.dev = sl.host;  // kernels store straight into pinned host memory (UVA)
     else if (!(sl.dev = dev_alloc<double>(j, max_band, &rc))) return bail(rc);
-    if (!j->exact && !j->weighted) {
+    if (!j->exact) {
       if (!(sl.flagged = dev_alloc<uint32_t>(j, max_band, &rc))) return bail(rc);
       if (!(sl.n_flagged_host = pin_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
       *sl.n_flagged_host = 0;

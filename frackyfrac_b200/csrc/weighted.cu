@@ -48,7 +48,8 @@ template <bool kPrescaled>
 __global__ void __launch_bounds__(256, 1)
 k_weighted_tiles(const float* __restrict__ A, int64_t ld, int32_t kp, const float* __restrict__ lenf,
                  const double* __restrict__ W, const Tile* __restrict__ tiles, int64_t n_samples,
-                 int64_t first, double* __restrict__ out) {
+                 int64_t first, double* __restrict__ out, double flag_below, uint32_t* __restrict__ flagged,
+                 unsigned long long* __restrict__ n_flagged) {
   extern __shared__ __align__(16) float smem[];
   const Tile tile = tiles[blockIdx.x];
   const int64_t i0 = static_cast<int64_t>(tile.ti) * kTile;
@@ -131,12 +132,107 @@ k_weighted_tiles(const float* __restrict__ A, int64_t ld, int32_t kp, const floa
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       const int64_t j = j0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
-      if (j < i) orow[j] = static_cast<double>(tot[a][b] + acc[a][b]) / (wi + W[j]);
+      if (j < i) {
+        const double d = static_cast<double>(tot[a][b] + acc[a][b]) / (wi + W[j]);
+        orow[j] = d;
+        // fp32 operands carry 6e-8 relative error each, so the L1 numerator is off by up to
+        // 6e-8 * (W_i + W_j) = 6e-8 / d relative: small distances are recomputed (k_weighted_fixup)
+        if (d < flag_below) {
+          unsigned long long slot = atomicAdd(n_flagged, 1ULL);
+          flagged[slot] = static_cast<uint32_t>(orow + j - out);
+        }
+      }
     }
   }
 }
 
+// Recompute of the flagged pairs from the CSR rows themselves, one CTA per pair at a time:
+//   diff[v] = a_i(v) - a_j(v) for every node on a leaf-to-root path of either sample, accumulated as
+//   62-bit fixed point with integer atomics (order-independent: deterministic, and identical samples
+//   cancel to exactly 0), then numerator = sum_v len_v * |diff[v]| in fp64 over the touched nodes (the
+//   second walk takes each node's value with an atomic exchange, which also restores the zeros).
+// ws is one zeroed int64 array of n_nodes entries per CTA.
+__global__ void __launch_bounds__(256)
+k_weighted_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                 const double* __restrict__ val, const int32_t* __restrict__ parent,
+                 const double* __restrict__ length, int32_t n_nodes, const double* __restrict__ total,
+                 const double* __restrict__ W, const uint32_t* __restrict__ flagged,
+                 const unsigned long long* __restrict__ n_flagged, unsigned long long* __restrict__ count_host,
+                 int64_t first, long long* __restrict__ ws, double* __restrict__ out) {
+  __shared__ double red[8];
+  const unsigned long long n = *n_flagged;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count_host = n;  // mapped pinned memory
+  long long* diff = ws + static_cast<int64_t>(blockIdx.x) * n_nodes;
+  constexpr double kFix = 1152921504606846976.0;  // 2^60: proportions are <= 1, a node sums <= 1
+  for (unsigned long long w = blockIdx.x; w < n; w += gridDim.x) {
+    const uint32_t off = flagged[w];
+    const int64_t p = first + off;
+    int64_t i = static_cast<int64_t>((1.0 + sqrt(1.0 + 8.0 * static_cast<double>(p))) * 0.5);
+    while (i * (i - 1) / 2 > p) --i;
+    while ((i + 1) * i / 2 <= p) ++i;
+    const int64_t j = p - i * (i - 1) / 2;
+    const int64_t smp[2] = {i, j};
+    // without normalisation (-l) raw values are summed: scale them into the fixed-point range
+    double inv[2];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const double t = total ? total[smp[side]] : 0.0;
+      inv[side] = total ? (t > 0.0 ? 1.0 / t : 0.0) : 0.0;
+    }
+    double unscale = 1.0 / kFix;
+    if (!total) {  // common power-of-two scale from the two raw sums (exact)
+      double big = 0.0;
+      for (int side = 0; side < 2; ++side)
+        for (int64_t k = row_ptr[smp[side]]; k < row_ptr[smp[side] + 1]; ++k) big += val[k];
+      int e;
+      frexp(big > 0.0 ? big : 1.0, &e);
+      inv[0] = inv[1] = ldexp(1.0, -e);
+      unscale = ldexp(1.0, e) / kFix;
+    }
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const int64_t b = row_ptr[smp[side]], e = row_ptr[smp[side] + 1];
+      for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x) {
+        const long long x = __double2ll_rn(val[k] * inv[side] * kFix);
+        const long long add = side == 0 ? x : -x;
+        for (int32_t v = col[k]; v >= 0; v = parent[v])
+          atomicAdd(reinterpret_cast<unsigned long long*>(diff + v), static_cast<unsigned long long>(add));
+      }
+    }
+    __syncthreads();
+    double num = 0.0;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const int64_t b = row_ptr[smp[side]], e = row_ptr[smp[side] + 1];
+      for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x)
+        for (int32_t v = col[k]; v >= 0; v = parent[v]) {
+          const long long x = static_cast<long long>(atomicExch(reinterpret_cast<unsigned long long*>(diff + v), 0ULL));
+          if (x != 0) num += length[v] * (fabs(static_cast<double>(x)) * unscale);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) num += __shfl_xor_sync(0xffffffffu, num, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = num;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int k = 0; k < 8; ++k) tot += red[k];
+      out[off] = tot / (W[i] + W[j]);
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
+
+int launch_weighted_fixup(const DevCsr& a, const DevTree& t, const double* total, const double* W,
+                          const uint32_t* flagged, const unsigned long long* n_flagged,
+                          unsigned long long* count_host, int64_t first, long long* ws, int ws_ctas, double* out,
+                          cudaStream_t s) {
+  k_weighted_fixup<<<ws_ctas, 256, 0, s>>>(a.row_ptr, a.col, a.val, t.parent, t.length, t.n_nodes, total, W, flagged,
+                                           n_flagged, count_host, first, ws, out);
+  return 1;
+}
 
 void weighted_setup() {
   cudaFuncSetAttribute(k_weighted_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -145,12 +241,15 @@ void weighted_setup() {
 
 int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
                           const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
-                          int64_t first, double* out, cudaStream_t s) {
+                          int64_t first, double* out, double flag_below, uint32_t* flagged,
+                          unsigned long long* n_flagged, cudaStream_t s) {
   if (n_tiles <= 0) return 0;
   if (prescaled)
-    k_weighted_tiles<true><<<n_tiles, 256, SMEM_BYTES, s>>>(A, ld, kp, lenf, W, tiles, n_samples, first, out);
+    k_weighted_tiles<true><<<n_tiles, 256, SMEM_BYTES, s>>>(A, ld, kp, lenf, W, tiles, n_samples, first, out,
+                                                            flag_below, flagged, n_flagged);
   else
-    k_weighted_tiles<false><<<n_tiles, 256, SMEM_BYTES, s>>>(A, ld, kp, lenf, W, tiles, n_samples, first, out);
+    k_weighted_tiles<false><<<n_tiles, 256, SMEM_BYTES, s>>>(A, ld, kp, lenf, W, tiles, n_samples, first, out,
+                                                             flag_below, flagged, n_flagged);
   return 1;
 }
 

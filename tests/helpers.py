@@ -18,11 +18,14 @@ def gpu_flat(tree: synth.Tree, csr, weighted, normalize=True, **kw):
 
 
 def rel_err(got, want):
-    """Per-distance relative error with a 1e-12 absolute floor; NaN must match NaN."""
+    """Per-distance relative error; NaN must match NaN.  Distances below 1e-7 are measured against
+    1e-7, i.e. with the 1e-5 tolerance of the tests an ABSOLUTE error of 1e-12 is accepted there
+    ("absolute 1e-12 floor for exact zeros"): identical proportions come out as 1e-16
+    rounding noise in the reference and as exactly 0 here, or the other way round."""
     got = np.asarray(got)
     want = np.asarray(want)
     assert got.shape == want.shape
     nan_g, nan_w = np.isnan(got), np.isnan(want)
     assert (nan_g == nan_w).all(), "NaN pattern differs"
     ok = ~nan_w
-    return np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-12) if ok.any() else np.zeros(0)
+    return np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-7) if ok.any() else np.zeros(0)

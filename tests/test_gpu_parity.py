@@ -178,6 +178,32 @@ def test_fast_unweighted_u8_is_tighter_than_bf16(gpu_ctx):
     assert e8 < 2e-6 and e8 <= e16 * 1.5, (e8, e16)
 
 
+@pytest.mark.parametrize("normalize", [1, 2])
+def test_fast_weighted_small_distances(gpu_ctx, normalize):
+    """Samples that differ by a relative 1e-2 .. 1e-7 in a few abundances: the fp32 L1 tiles lose
+    6e-8 / d relative there, so pairs with d < 1/32 must come out of the fixed-point fix-up pass
+    (normalize=2: flag -l as documented, raw counts)."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(1200, 85)
+    rp, col, val = synth.random_table(tree, 160, 0.04, 86, integer_counts=False)
+    m = rp[1]
+    rng = np.random.default_rng(87)
+    for k, eps in enumerate((1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7), start=1):
+        col[k * m:(k + 1) * m] = col[:m]
+        val[k * m:(k + 1) * m] = val[:m] * (1.0 + eps * rng.random(m) * (rng.random(m) < 0.2))
+    want = oracle_flat(tree, (rp, col, val), True, normalize)
+    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=True, normalize=normalize == 1,
+                    path=engine.PATH_FAST, ctx=gpu_ctx) as job:
+        got = np.concatenate([a for _, a in job.chunks()])
+        flagged = job.info().flagged_pairs
+    assert (want[:21] < 1 / 32).all() and want[:21].min() < 1e-6   # the seven near-copies, pairwise
+    assert flagged >= 21
+    e = rel_err(got, want)
+    assert e.max() < 1e-5, f"max rel err {e.max():.3e}"
+    assert np.abs(got[:21] - want[:21]).max() <= 1e-9 * want[:21].max() + 1e-15
+
+
 @pytest.mark.parametrize("slab", [128, 256])
 def test_fast_weighted_embedding_in_slabs(gpu_ctx, monkeypatch, slab):
     """The fp64 embedding of the fast weighted path is built slab by slab of samples (bounded memory):
