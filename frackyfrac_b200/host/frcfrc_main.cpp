@@ -114,9 +114,9 @@ int main(int argc, char** argv) {
     frchost::FlatTree tree = frchost::parse_newick(tt.data(), tt.size());
     fputs("Loading abundances\n", stderr);
     std::string it = slurp(fl.fin);
-    frchost::Table tab = frchost::parse_table(it.data(), it.size(), fl.sparse);
+    frchost::Table tab = frchost::parse_table(it.data(), it.size(), fl.sparse, static_cast<int>(fl.nt));  // -p workers (frcfrc.go:42-50)
     fputs("Validating\n", stderr);
-    frchost::Csr csr = frchost::resolve(tab, tree);
+    frchost::Csr csr = frchost::resolve(tab, tree, static_cast<int>(fl.nt));
 
     FILE* w = fl.fout.empty() ? stdout : fopen(fl.fout.c_str(), "wb");
     if (!w) die("open " + fl.fout + ": " + strerror(errno));

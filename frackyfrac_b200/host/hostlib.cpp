@@ -5,7 +5,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <memory>
 #include <stdexcept>
+#include <string_view>
 #include <thread>
 
 namespace frchost {
@@ -87,93 +90,139 @@ FlatTree parse_newick(const char* s, size_t len) {
 }
 
 // ------------------------------------------------------------------- tables
+// Map-free, parallel restatement of parser.ParseAbundance / ParseSparseAbundance
+// (parser/parser.go:21-140): rows are independent, so the text is cut at line boundaries into one
+// chunk per worker (the reference hands rows to `ngoroutines` workers through ppln.Serial the same
+// way, parser.go:24,87), every worker parses its rows straight into CSR fragments without a
+// per-sample map, a per-token string or a regexp, and the fragments are joined in file order.
+// Every accept / reject rule and the text of the first error (lowest row) are kept.
 namespace {
 // Go regexp \s = [\t\n\f\r ]; parser.go:17 tokenises with \S+.
-bool go_space(unsigned char c) { return c == '\t' || c == '\n' || c == '\f' || c == '\r' || c == ' '; }
+struct SpaceLut {
+  bool t[256] = {};
+  constexpr SpaceLut() { t['\t'] = t['\n'] = t['\f'] = t['\r'] = t[' '] = true; }
+};
+constexpr SpaceLut kSpace;
+inline bool go_space(unsigned char c) { return kSpace.t[c]; }
 
+// strconv.ParseFloat(s, 64).  Fast path: std::from_chars (correctly rounded, no allocation, no
+// locale); anything it does not consume entirely (hex floats, "+1", "infinity", ...) goes through
+// the strtod path the first version used for every token.
 bool parse_float(const char* s, size_t n, double* out) {
   if (n == 0) return false;
+  if (n == 1 && s[0] >= '0' && s[0] <= '9') { *out = s[0] - '0'; return true; }  // dense tables are mostly "0"
+  {
+    double v;
+    auto r = std::from_chars(s, s + n, v);  // general format; rejects a leading '+'
+    if (r.ec == std::errc() && r.ptr == s + n && !(s[0] == 'i' || s[0] == 'I' || s[0] == 'n' || s[0] == 'N') &&
+        !(n > 1 && (s[1] == 'i' || s[1] == 'I' || s[1] == 'n' || s[1] == 'N'))) {
+      *out = v;
+      return true;
+    }
+    if (r.ec == std::errc::result_out_of_range && r.ptr == s + n) {
+      // Go: 1e999 is an error (value out of range), 1e-999 parses to 0
+      bool neg_exp = false;
+      for (size_t q = 0; q + 1 < n; ++q)
+        if ((s[q] == 'e' || s[q] == 'E') && s[q + 1] == '-') neg_exp = true;
+      if (!neg_exp) return false;
+    }
+  }
   unsigned char c0 = static_cast<unsigned char>(s[0]);
   if (!(std::isdigit(c0) || c0 == '+' || c0 == '-' || c0 == '.' || c0 == 'i' || c0 == 'I' || c0 == 'n' || c0 == 'N'))
     return false;
-  std::string tok(s, n);
+  char small[64];
+  std::string big;
+  const char* z;
+  if (n < sizeof(small)) { memcpy(small, s, n); small[n] = 0; z = small; }
+  else { big.assign(s, n); z = big.c_str(); }
   char* end = nullptr;
   errno = 0;
-  double v = strtod(tok.c_str(), &end);
-  if (end == tok.c_str() || *end) return false;
+  double v = strtod(z, &end);
+  if (end == z || *end) return false;
   if (errno == ERANGE && std::isinf(v)) return false;  // Go: value out of range
   *out = v;
   return true;
 }
 
+// name -> id, open addressing (FNV-1a, linear probing); ids in order of first appearance.
 struct Interner {
-  std::unordered_map<std::string, int32_t> ids;
+  struct Slot { uint64_t h; int32_t id; };
+  std::vector<Slot> slots = std::vector<Slot>(1024, Slot{0, -1});
   std::vector<std::string>* names;
+  static uint64_t hash(const char* s, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= static_cast<unsigned char>(s[i]); h *= 1099511628211ull; }
+    return h | 1;
+  }
+  void grow() {
+    std::vector<Slot> old(slots.size() * 2, Slot{0, -1});
+    old.swap(slots);
+    for (const Slot& o : old)
+      if (o.id >= 0) {
+        size_t k = o.h & (slots.size() - 1);
+        while (slots[k].id >= 0) k = (k + 1) & (slots.size() - 1);
+        slots[k] = o;
+      }
+  }
   int32_t get(const char* s, size_t n) {
-    std::string k(s, n);
-    auto it = ids.find(k);
-    if (it != ids.end()) return it->second;
-    int32_t id = static_cast<int32_t>(names->size());
-    names->push_back(k);
-    ids.emplace(std::move(k), id);
+    const uint64_t h = hash(s, n);
+    size_t k = h & (slots.size() - 1);
+    while (slots[k].id >= 0) {
+      if (slots[k].h == h) {
+        const std::string& nm = (*names)[slots[k].id];
+        if (nm.size() == n && memcmp(nm.data(), s, n) == 0) return slots[k].id;
+      }
+      k = (k + 1) & (slots.size() - 1);
+    }
+    const int32_t id = static_cast<int32_t>(names->size());
+    names->emplace_back(s, n);
+    slots[k] = Slot{h, id};
+    if (names->size() * 2 > slots.size()) grow();
     return id;
   }
 };
 
 constexpr size_t kMaxRow = size_t(1) << 25;  // sc.Buffer(nil, 1<<25), parser.go:145
-}  // namespace
 
-Table parse_table(const char* text, size_t len, bool sparse) {
-  Table t;
+struct Fragment {                      // what one worker produced for its run of rows
+  std::vector<std::string> species;    // sparse: names in order of first appearance in this chunk
+  std::vector<int64_t> row_len;
+  std::vector<int32_t> sp;
+  std::vector<double> val;
+  int64_t err_row = -1;                // 1-based row number of the first failing row (-1: none)
+  std::string err;
+};
+
+// Parses the rows of text[begin, end) (begin at a line start); row numbers start at first_row + 1.
+void parse_rows(const char* text, size_t begin, size_t end, bool sparse, const std::vector<int32_t>& hdr,
+                int64_t first_row, Fragment* f) {
   Interner in;
-  in.names = &t.species;
-  std::vector<int32_t> hdr;
-  bool have_hdr = false;
-  std::vector<int64_t> stamp, pos;  // per species: sample that last set it, and where
-  size_t p = 0;
-  int64_t rowno = 0;
-  auto err = [&](int64_t k, const std::string& what) {
-    return std::runtime_error("row #" + std::to_string(rowno) + ": value #" + std::to_string(k) + ": " + what);
+  in.names = &f->species;
+  std::vector<int64_t> stamp, pos;  // per species: local sample that last set it, and where
+  if (!sparse) { stamp.assign(hdr.empty() ? 0 : *std::max_element(hdr.begin(), hdr.end()) + 1, 0); pos = stamp; }
+  size_t p = begin;
+  int64_t rowno = first_row, cur = 0;
+  auto fail = [&](const std::string& msg) { f->err_row = rowno; f->err = msg; };
+  auto verr = [&](int64_t k, const std::string& what) {
+    fail("row #" + std::to_string(rowno) + ": value #" + std::to_string(k) + ": " + what);
   };
-  while (p < len) {
+  while (p < end) {
     size_t e = p;
-    while (e < len && text[e] != '\n') ++e;
+    while (e < end && text[e] != '\n') ++e;
     size_t le = e;
     if (le > p && text[le - 1] == '\r') --le;  // bufio.ScanLines drops one trailing \r
-    if (le - p >= kMaxRow) throw std::runtime_error("bufio.Scanner: token too long");
     ++rowno;
+    if (le - p >= kMaxRow) { fail("bufio.Scanner: token too long"); return; }
     const char* row = text + p;
     const size_t rl = le - p;
     p = e + 1;
-    if (!sparse && !have_hdr) {
-      size_t i = 0;
-      while (i < rl) {
-        while (i < rl && go_space(static_cast<unsigned char>(row[i]))) ++i;
-        size_t st = i;
-        while (i < rl && !go_space(static_cast<unsigned char>(row[i]))) ++i;
-        if (i > st) hdr.push_back(in.get(row + st, i - st));
-      }
-      if (hdr.empty()) throw std::runtime_error("row #1 has 0 values");
-      have_hdr = true;
-      continue;
-    }
-    const int64_t cur = t.n_samples() + 1;
-    const size_t row_begin = t.sp.size();
+    ++cur;
+    const size_t row_begin = f->sp.size();
+    // dense: parseRow checks the token count before any value (parser.go:61-64); here the row is
+    // tokenised once, a value error is held back until the count is known to be right
+    std::string held;
     int64_t k = 0;
     size_t i = 0;
-    if (!sparse) {  // parseRow checks the count before any value (parser.go:61-64)
-      int64_t cnt = 0;
-      size_t q = 0;
-      while (q < rl) {
-        while (q < rl && go_space(static_cast<unsigned char>(row[q]))) ++q;
-        size_t st = q;
-        while (q < rl && !go_space(static_cast<unsigned char>(row[q]))) ++q;
-        if (q > st) ++cnt;
-      }
-      if (cnt != static_cast<int64_t>(hdr.size()))
-        throw std::runtime_error("row #" + std::to_string(rowno) + ": has " + std::to_string(cnt) +
-                                 " values, expected " + std::to_string(hdr.size()));
-    }
     while (i < rl) {
       while (i < rl && go_space(static_cast<unsigned char>(row[i]))) ++i;
       size_t st = i;
@@ -186,69 +235,205 @@ Table parse_table(const char* text, size_t len, bool sparse) {
       int32_t sp;
       if (sparse) {
         size_t last = std::string::npos;  // split on the LAST colon (parser.go:129-140)
-        for (size_t q = 0; q < tl; ++q) if (tok[q] == ':') last = q;
-        if (last == std::string::npos) throw err(k, "no colon in \"" + std::string(tok, tl) + "\"");
-        if (last == 0) throw err(k, "empty species name");
-        if (!parse_float(tok + last + 1, tl - last - 1, &v))
-          throw err(k, "strconv.ParseFloat: parsing \"" + std::string(tok + last + 1, tl - last - 1) + "\": invalid syntax");
-        if (std::isnan(v) || std::isinf(v) || v < 0) throw err(k, "bad value: " + std::to_string(v));
-        if (v == 0) throw err(k, "zeros are not allowed in sparse format");
+        for (size_t q = tl; q-- > 0;) if (tok[q] == ':') { last = q; break; }
+        if (last == std::string::npos) { verr(k, "no colon in \"" + std::string(tok, tl) + "\""); return; }
+        if (last == 0) { verr(k, "empty species name"); return; }
+        if (!parse_float(tok + last + 1, tl - last - 1, &v)) {
+          verr(k, "strconv.ParseFloat: parsing \"" + std::string(tok + last + 1, tl - last - 1) + "\": invalid syntax");
+          return;
+        }
+        if (std::isnan(v) || std::isinf(v) || v < 0) { verr(k, "bad value: " + std::to_string(v)); return; }
+        if (v == 0) { verr(k, "zeros are not allowed in sparse format"); return; }
         sp = in.get(tok, last);
+        if (static_cast<size_t>(sp) >= stamp.size()) { stamp.resize(f->species.size() * 2 + 16, 0); pos.resize(stamp.size(), 0); }
       } else {
-        if (!parse_float(tok, tl, &v))
-          throw err(k, "strconv.ParseFloat: parsing \"" + std::string(tok, tl) + "\": invalid syntax");
-        if (std::isnan(v) || std::isinf(v) || v < 0) throw err(k, "bad value: " + std::to_string(v));
+        if (tl == 1 && tok[0] == '0') continue;  // zeros are dropped (parser.go:75-77)
+        if (!held.empty() || k > static_cast<int64_t>(hdr.size())) continue;  // only counting from here on
+        if (!parse_float(tok, tl, &v)) {
+          held = "row #" + std::to_string(rowno) + ": value #" + std::to_string(k) +
+                 ": strconv.ParseFloat: parsing \"" + std::string(tok, tl) + "\": invalid syntax";
+          continue;
+        }
+        if (std::isnan(v) || std::isinf(v) || v < 0) {
+          held = "row #" + std::to_string(rowno) + ": value #" + std::to_string(k) + ": bad value: " + std::to_string(v);
+          continue;
+        }
         if (v == 0) continue;
         sp = hdr[k - 1];
       }
-      if (static_cast<size_t>(sp) >= stamp.size()) { stamp.resize(t.species.size(), 0); pos.resize(t.species.size(), 0); }
       if (stamp[sp] == cur) {
-        t.val[pos[sp]] = v;  // m[name] = f : last assignment wins (parser.go:78,124)
+        f->val[pos[sp]] = v;  // m[name] = f : last assignment wins (parser.go:78,124)
       } else {
         stamp[sp] = cur;
-        pos[sp] = static_cast<int64_t>(t.sp.size());
-        t.sp.push_back(sp);
-        t.val.push_back(v);
+        pos[sp] = static_cast<int64_t>(f->sp.size());
+        f->sp.push_back(sp);
+        f->val.push_back(v);
       }
     }
-    (void)row_begin;
-    t.row_ptr.push_back(static_cast<int64_t>(t.sp.size()));
+    if (!sparse) {
+      if (k != static_cast<int64_t>(hdr.size())) {
+        fail("row #" + std::to_string(rowno) + ": has " + std::to_string(k) + " values, expected " +
+             std::to_string(hdr.size()));
+        return;
+      }
+      if (!held.empty()) { fail(held); return; }
+    }
+    f->row_len.push_back(static_cast<int64_t>(f->sp.size() - row_begin));
   }
+}
+
+template <class F>
+void parallel_for(int n, F&& fn) {
+  if (n <= 1) { fn(0); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < n; ++t) th.emplace_back([&fn, t] { fn(t); });
+  fn(0);
+  for (auto& x : th) x.join();
+}
+}  // namespace
+
+Table parse_table(const char* text, size_t len, bool sparse, int threads) {
+  Table t;
+  std::vector<int32_t> hdr;
+  size_t body = 0;
+  int64_t first_row = 0;
+  if (!sparse) {  // the first row names the species (parser.go:33-38)
+    Interner in;
+    in.names = &t.species;
+    size_t e = 0;
+    while (e < len && text[e] != '\n') ++e;
+    size_t le = e;
+    if (le > 0 && text[le - 1] == '\r') --le;
+    if (le >= kMaxRow) throw std::runtime_error("bufio.Scanner: token too long");
+    size_t i = 0;
+    while (i < le) {
+      while (i < le && go_space(static_cast<unsigned char>(text[i]))) ++i;
+      size_t st = i;
+      while (i < le && !go_space(static_cast<unsigned char>(text[i]))) ++i;
+      if (i > st) hdr.push_back(in.get(text + st, i - st));
+    }
+    if (len == 0) return t;
+    if (hdr.empty()) throw std::runtime_error("row #1 has 0 values");
+    body = std::min(len, e + 1);
+    first_row = 1;
+  }
+  // chunks of whole rows, about equal in bytes
+  int T = std::max(1, threads);
+  T = static_cast<int>(std::min<size_t>(T, (len - body) / (1 << 16) + 1));
+  std::vector<size_t> cut(T + 1, len);
+  cut[0] = body;
+  for (int k = 1; k < T; ++k) {
+    size_t c = body + (len - body) * k / T;
+    c = std::max(c, cut[k - 1]);
+    while (c < len && c > body && text[c - 1] != '\n') ++c;
+    cut[k] = c;
+  }
+  // global row numbers: rows before each chunk
+  std::vector<int64_t> rows_before(T + 1, first_row);
+  {
+    std::vector<int64_t> cnt(T, 0);
+    parallel_for(T, [&](int k) {
+      int64_t c = 0;
+      const char* p = text + cut[k];
+      const char* e = text + cut[k + 1];
+      while (p < e) {
+        const void* q = memchr(p, '\n', e - p);
+        ++c;
+        if (!q) break;
+        p = static_cast<const char*>(q) + 1;
+      }
+      cnt[k] = c;
+    });
+    for (int k = 0; k < T; ++k) rows_before[k + 1] = rows_before[k] + cnt[k];
+  }
+  std::vector<Fragment> frag(T);
+  parallel_for(T, [&](int k) { parse_rows(text, cut[k], cut[k + 1], sparse, hdr, rows_before[k], &frag[k]); });
+  for (int k = 0; k < T; ++k)
+    if (frag[k].err_row >= 0) throw std::runtime_error(frag[k].err);  // chunks are in file order: lowest row first
+  // join: species ids of a sparse table are renumbered in order of first appearance in the file
+  std::vector<std::vector<int32_t>> remap(T);
+  if (sparse) {
+    Interner in;
+    in.names = &t.species;
+    for (int k = 0; k < T; ++k) {
+      remap[k].resize(frag[k].species.size());
+      for (size_t s = 0; s < frag[k].species.size(); ++s)
+        remap[k][s] = in.get(frag[k].species[s].data(), frag[k].species[s].size());
+    }
+  }
+  std::vector<int64_t> nnz_before(T + 1, 0), nrow_before(T + 1, 0);
+  for (int k = 0; k < T; ++k) {
+    nnz_before[k + 1] = nnz_before[k] + static_cast<int64_t>(frag[k].sp.size());
+    nrow_before[k + 1] = nrow_before[k] + static_cast<int64_t>(frag[k].row_len.size());
+  }
+  t.sp.resize(nnz_before[T]);
+  t.val.resize(nnz_before[T]);
+  t.row_ptr.assign(nrow_before[T] + 1, 0);
+  parallel_for(T, [&](int k) {
+    const Fragment& f = frag[k];
+    int32_t* dsp = t.sp.data() + nnz_before[k];
+    if (sparse) for (size_t q = 0; q < f.sp.size(); ++q) dsp[q] = remap[k][f.sp[q]];
+    else if (!f.sp.empty()) memcpy(dsp, f.sp.data(), f.sp.size() * sizeof(int32_t));
+    if (!f.val.empty()) memcpy(t.val.data() + nnz_before[k], f.val.data(), f.val.size() * sizeof(double));
+    int64_t at = nnz_before[k];
+    for (size_t r = 0; r < f.row_len.size(); ++r) {
+      at += f.row_len[r];
+      t.row_ptr[nrow_before[k] + r + 1] = at;
+    }
+  });
   return t;
 }
 
 // ------------------------------------------------------------------ resolve
-Csr resolve(const Table& t, const FlatTree& tree) {
+Csr resolve(const Table& t, const FlatTree& tree, int threads) {
   const int32_t B = static_cast<int32_t>(tree.parent.size());
   // treeNames(): any node name validates (unifrac.go:70-76); only leaves carry
   // abundance (unifrac.go:38-43).
-  std::unordered_map<std::string, std::vector<int32_t>> leaves_of;
-  leaves_of.reserve(B * 2);
+  std::unordered_map<std::string_view, std::vector<int32_t>> leaves_of;
+  leaves_of.reserve(static_cast<size_t>(B) * 2);
   for (int32_t v = 0; v < B; ++v) {
-    auto& l = leaves_of[tree.name[v]];
+    auto& l = leaves_of[std::string_view(tree.name[v])];
     if (tree.n_children[v] == 0) l.push_back(v);
   }
   std::vector<const std::vector<int32_t>*> sp_leaves(t.species.size(), nullptr);
-  std::vector<char> known(t.species.size(), 0);
   for (size_t s = 0; s < t.species.size(); ++s) {
-    auto it = leaves_of.find(t.species[s]);
-    if (it != leaves_of.end()) { known[s] = 1; sp_leaves[s] = &it->second; }
+    auto it = leaves_of.find(std::string_view(t.species[s]));
+    if (it != leaves_of.end()) sp_leaves[s] = &it->second;
   }
+  const int64_t N = t.n_samples();
   Csr c;
-  c.row_ptr.push_back(0);
-  for (int64_t r = 0; r < t.n_samples(); ++r) {
-    for (int64_t k = t.row_ptr[r]; k < t.row_ptr[r + 1]; ++k) {
-      const int32_t sp = t.sp[k];
-      if (!known[sp]) {
-        char vb[40];
-        format_go(t.val[k], vb);
-        throw std::runtime_error("sample #" + std::to_string(r + 1) + " has value " + vb + " for species \"" +
-                                 t.species[sp] + "\" which is not in the tree");
+  c.row_ptr.assign(N + 1, 0);
+  // pass 1: validate + count (first error by sample order), pass 2: fill
+  int T = std::max(1, std::min<int>(threads, static_cast<int>(N / 64 + 1)));
+  std::vector<int64_t> bad_row(T, -1), bad_k(T, -1);
+  parallel_for(T, [&](int k) {
+    for (int64_t r = N * k / T; r < N * (k + 1) / T; ++r) {
+      int64_t n = 0;
+      for (int64_t e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) {
+        const auto* l = sp_leaves[t.sp[e]];
+        if (!l) { if (bad_row[k] < 0) { bad_row[k] = r; bad_k[k] = e; } continue; }
+        n += static_cast<int64_t>(l->size());
       }
-      for (int32_t leaf : *sp_leaves[sp]) { c.col.push_back(leaf); c.val.push_back(t.val[k]); }
+      c.row_ptr[r + 1] = n;
     }
-    c.row_ptr.push_back(static_cast<int64_t>(c.col.size()));
-  }
+  });
+  for (int k = 0; k < T; ++k)
+    if (bad_row[k] >= 0) {
+      char vb[40];
+      format_go(t.val[bad_k[k]], vb);
+      throw std::runtime_error("sample #" + std::to_string(bad_row[k] + 1) + " has value " + vb + " for species \"" +
+                               t.species[t.sp[bad_k[k]]] + "\" which is not in the tree");
+    }
+  for (int64_t r = 0; r < N; ++r) c.row_ptr[r + 1] += c.row_ptr[r];
+  c.col.resize(c.row_ptr[N]);
+  c.val.resize(c.row_ptr[N]);
+  parallel_for(T, [&](int k) {
+    for (int64_t r = N * k / T; r < N * (k + 1) / T; ++r) {
+      int64_t at = c.row_ptr[r];
+      for (int64_t e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e)
+        for (int32_t leaf : *sp_leaves[t.sp[e]]) { c.col[at] = leaf; c.val[at] = t.val[e]; ++at; }
+    }
+  });
   return c;
 }
 
@@ -351,6 +536,14 @@ const int32_t* frch_tree_parent(const frch_tree* t) { return t->t.parent.data();
 const double* frch_tree_length(const frch_tree* t) { return t->t.length.data(); }
 const char* frch_tree_name(const frch_tree* t, int32_t v) { return t->t.name[v].c_str(); }
 
+frch_table* frch_table_parse_mt(const char* text, size_t len, int sparse, int threads) {
+  try { return new frch_table{frchost::parse_table(text, len, sparse != 0, threads)}; }
+  catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
+frch_csr* frch_resolve_mt(const frch_table* tab, const frch_tree* tree, int threads) {
+  try { return new frch_csr{frchost::resolve(tab->t, tree->t, threads)}; }
+  catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
 frch_table* frch_table_parse(const char* text, size_t len, int sparse) {
   try { return new frch_table{frchost::parse_table(text, len, sparse != 0)}; }
   catch (const std::exception& e) { g_err = e.what(); return nullptr; }

@@ -32,7 +32,8 @@ struct Table {
   std::vector<double> val;
   int64_t n_samples() const { return static_cast<int64_t>(row_ptr.size()) - 1; }
 };
-Table parse_table(const char* text, size_t len, bool sparse);
+// `threads` workers parse runs of whole rows in parallel (the reference's ngoroutines, parser.go:21,85).
+Table parse_table(const char* text, size_t len, bool sparse, int threads = 1);
 
 // validateSpecies + name -> leaf resolution.  Output is the frc_csr_t payload:
 // every leaf carrying the name gets the value (unifrac.go:38-43), names that
@@ -43,7 +44,7 @@ struct Csr {
   std::vector<int32_t> col;
   std::vector<double> val;
 };
-Csr resolve(const Table& t, const FlatTree& tree);
+Csr resolve(const Table& t, const FlatTree& tree, int threads = 1);
 
 // Go's fmt %v for float64, no newline.  Returns the length written (<= 32).
 int format_go(double v, char* buf);

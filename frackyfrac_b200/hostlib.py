@@ -55,6 +55,10 @@ def lib():
         L.frch_table_species_name.restype = C.c_char_p
         L.frch_resolve.restype = C.c_void_p
         L.frch_resolve.argtypes = [C.c_void_p, C.c_void_p]
+        L.frch_table_parse_mt.restype = C.c_void_p
+        L.frch_table_parse_mt.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        L.frch_resolve_mt.restype = C.c_void_p
+        L.frch_resolve_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.frch_csr_free.argtypes = [C.c_void_p]
         L.frch_csr_nnz.argtypes = [C.c_void_p]
         L.frch_csr_nnz.restype = C.c_int64
@@ -102,9 +106,10 @@ class Tree:
 class Table:
     """Per-sample species maps (parser.ParseAbundance / ParseSparseAbundance)."""
 
-    def __init__(self, text: str | bytes, sparse: bool):
+    def __init__(self, text: str | bytes, sparse: bool, threads: int = 1):
         b = text.encode() if isinstance(text, str) else text
-        self.h = lib().frch_table_parse(b, len(b), int(sparse))
+        self.threads = threads
+        self.h = lib().frch_table_parse_mt(b, len(b), int(sparse), threads)
         if not self.h:
             raise HostError(lib().frch_last_error().decode())
 
@@ -124,7 +129,7 @@ class Table:
     def resolve(self, tree: Tree):
         """validateSpecies + name -> leaf ids: (row_ptr, col, val) for the C ABI."""
         L = lib()
-        c = L.frch_resolve(self.h, tree.h)
+        c = L.frch_resolve_mt(self.h, tree.h, self.threads)
         if not c:
             raise HostError(L.frch_last_error().decode())
         try:

@@ -121,3 +121,43 @@ def test_parallel_writer_is_byte_identical(built):
         assert lines[k] == orc.format_go(float(v[k]))
     t0 = time.perf_counter(); hostlib.format_lines(v, 1); t1 = time.perf_counter(); hostlib.format_lines(v, 8); t2 = time.perf_counter()
     assert (t2 - t1) < (t1 - t0) * 1.5  # never pathologically slower
+
+
+def test_parallel_table_parser_matches_single_thread_and_oracle(built):
+    """N2: rows parsed by several workers (parser.go's ngoroutines) must give the same CSR, the same
+    species order and the same first error as one worker, and the same maps as the oracle's parser."""
+    from frackyfrac_b200 import hostlib, synth
+    from oracle import oracle as orc
+
+    tree = synth.random_tree(400, 5)
+    rp, col, val = synth.random_table(tree, 900, 0.05, 6, integer_counts=False)
+    ht = hostlib.Tree(synth.to_newick(tree))
+    for sparse, text in ((False, synth.to_dense_text(tree, rp, col, val)), (True, synth.to_sparse_text(tree, rp, col, val))):
+        assert len(text) > 5 * 65536  # enough for several chunks
+        one = hostlib.Table(text, sparse, 1)
+        many = hostlib.Table(text, sparse, 7)
+        assert one.maps() == many.maps() == orc.Table.parse(text, sparse).maps()
+        a, b = one.resolve(ht), many.resolve(ht)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        assert np.array_equal(a[0], rp)
+        # the first error in FILE order wins, whichever worker meets it
+        lines = text.split("\n")
+        bad_late, bad_early = len(lines) - 3, len(lines) // 2
+        for where, tok in ((bad_late, "1e999" if not sparse else "L1:1e999"), (bad_early, "-3" if not sparse else "L2:-3")):
+            row = lines[where].split("\t")
+            row[3 if not sparse else 0] = tok
+            lines[where] = "\t".join(row)
+        broken = "\n".join(lines)
+        msgs = []
+        for th in (1, 7):
+            with pytest.raises(hostlib.HostError) as ei:
+                hostlib.Table(broken, sparse, th)
+            msgs.append(str(ei.value))
+        assert msgs[0] == msgs[1] and f"row #{bad_early + 1}:" in msgs[0], msgs
+    # dense: a wrong token count is reported before a bad value of the same row (parser.go:61-64)
+    with pytest.raises(hostlib.HostError) as ei:
+        hostlib.Table("a b c\n1 x\n", False, 1)
+    assert "has 2 values, expected 3" in str(ei.value)
+    with pytest.raises(hostlib.HostError) as ei:
+        hostlib.Table("a b c\n1 x 2\n", False, 1)
+    assert "value #2" in str(ei.value) and "invalid syntax" in str(ei.value)
