@@ -108,15 +108,28 @@ int main(int argc, char** argv) {
   if (fl.nnorm && !fl.wgt) die("-l can only be used with weighted unifrac");
 
   auto t0 = std::chrono::steady_clock::now();
+  const bool timing = getenv("FRC_CLI_TIMING") != nullptr;  // stage times on stderr (not part of the reference's output)
+  auto tl = t0;
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[timing] %-22s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - tl).count());
+    tl = now;
+  };
+  double fmt_ms = 0, write_ms = 0, next_ms = 0;
   try {
     fputs("Reading tree\n", stderr);
     std::string tt = slurp(fl.ftree);
     frchost::FlatTree tree = frchost::parse_newick(tt.data(), tt.size());
+    lap("read + parse tree");
     fputs("Loading abundances\n", stderr);
     std::string it = slurp(fl.fin);
+    lap("read table file");
     frchost::Table tab = frchost::parse_table(it.data(), it.size(), fl.sparse, static_cast<int>(fl.nt));  // -p workers (frcfrc.go:42-50)
+    lap("parse table");
     fputs("Validating\n", stderr);
     frchost::Csr csr = frchost::resolve(tab, tree, static_cast<int>(fl.nt));
+    lap("validate + resolve");
 
     FILE* w = fl.fout.empty() ? stdout : fopen(fl.fout.c_str(), "wb");
     if (!w) die("open " + fl.fout + ": " + strerror(errno));
@@ -133,22 +146,34 @@ int main(int argc, char** argv) {
     fo.world = 1;
     frc_job_t* job = nullptr;
     if (frc_create(nullptr, &ft, &fc, &fo, &job) != FRC_OK) die(frc_last_error(nullptr));
+    lap("frc_create (+ CUDA init)");
     fputs("Calculating distances\n", stderr);
     std::string text;
     for (;;) {
       const double* d; int64_t first, n;
+      auto a0 = std::chrono::steady_clock::now();
       if (frc_next(job, &d, &first, &n) != FRC_OK) { std::string m = frc_last_error(job); frc_destroy(job); die(m); }
       if (n == 0) break;
+      auto a1 = std::chrono::steady_clock::now();
       text.clear();
       frchost::format_lines_parallel(d, n, static_cast<int>(fl.nt), text);  // -p threads format, one writer
-      if (fwrite(text.data(), 1, text.size(), w) != text.size()) {  // frcfrc.go:59-63
+      auto a2 = std::chrono::steady_clock::now();
+      const bool wrote = fwrite(text.data(), 1, text.size(), w) == text.size();
+      auto a3 = std::chrono::steady_clock::now();
+      next_ms += std::chrono::duration<double, std::milli>(a1 - a0).count();
+      fmt_ms += std::chrono::duration<double, std::milli>(a2 - a1).count();
+      write_ms += std::chrono::duration<double, std::milli>(a3 - a2).count();
+      if (!wrote) {  // frcfrc.go:59-63
         std::string m = std::string("write: ") + strerror(errno);
         frc_destroy(job);
         die(m);
       }
     }
+    if (timing) fprintf(stderr, "[timing] frc_next waits %.1f ms, formatting %.1f ms, fwrite %.1f ms\n", next_ms, fmt_ms, write_ms);
+    tl = std::chrono::steady_clock::now();
     frc_destroy(job);
     if (!fl.fout.empty()) fclose(w); else fflush(w);
+    lap("destroy + close");
   } catch (const std::exception& e) {
     die(e.what());
   }
