@@ -617,9 +617,8 @@ int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw) {
 
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t w0, int32_t w_count, int32_t kp, const int32_t* order,
-                                const double* lenq, const uint32_t* qam, const int32_t* col_exp,
-                                uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
-                                cudaStream_t s) {
+                                uint32_t* node_scratch, uint32_t* bitsT, cudaStream_t s) {
+  (void)nw;
   const size_t smem = (static_cast<size_t>(t.n_nodes) * 4 + 15) & ~size_t(15);
   if (smem <= 200 * 1024) {
     static bool attr = false;
@@ -635,8 +634,14 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
                                                           t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
                                                           order, node_scratch, bitsT, w0);
   }
+  return 1;
+}
+
+int launch_presence_rowsum_t(const uint32_t* bitsT, int32_t n_nodes, int32_t nw, int32_t w0, int32_t w_count,
+                             int32_t kp, const double* lenq, const uint32_t* qam, const int32_t* col_exp,
+                             double* partial, double* r, cudaStream_t s) {
   const int64_t np = static_cast<int64_t>(nw) * 32;
-  const int chunks = pick_chunks(t.n_nodes);
+  const int chunks = pick_chunks(n_nodes);
   dim3 g(w_count, chunks);
   if (qam) {
     const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 128));
@@ -648,7 +653,7 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
   const int64_t s0 = static_cast<int64_t>(w0) * 32, ns = static_cast<int64_t>(w_count) * 32;
   k_reduce_partials<<<static_cast<unsigned>((ns + kThreads - 1) / kThreads), kThreads, 0, s>>>(partial + s0, chunks, np,
                                                                                               ns, r + s0);
-  return 3;
+  return 2;
 }
 
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,

@@ -95,9 +95,12 @@ int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw);
 // Only the word columns [w0, w0 + w_count) (32 samples each) are built: the sample shard of this rank.
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t w0, int32_t w_count, int32_t kp, const int32_t* order,
-                                const double* lenq, const uint32_t* qam, const int32_t* col_exp,
-                                uint32_t* node_scratch, uint32_t* bitsT, double* partial, double* r,
-                                cudaStream_t s);
+                                uint32_t* node_scratch, uint32_t* bitsT, cudaStream_t s);
+// r[s] for the same word columns from bitsT (qam / col_exp non-null: integer row sums of the u8 path).
+// Independent of the operand expansion, so the job runs the two on different streams.
+int launch_presence_rowsum_t(const uint32_t* bitsT, int32_t n_nodes, int32_t nw, int32_t w0, int32_t w_count,
+                             int32_t kp, const double* lenq, const uint32_t* qam, const int32_t* col_exp,
+                             double* partial, double* r, cudaStream_t s);
 // need[np / 256] (device, may be null = everything): bit 0 = write the A rows of that block of 256
 // samples, bit 1 = write its Bh / Bl rows.
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,

@@ -219,7 +219,7 @@ struct frc_job {
   size_t next_enqueue = 0, next_deliver = 0;
   int held_slot = -1;  // slot whose buffer the caller currently reads
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_embed0 = nullptr, ev_embed1 = nullptr;
-  cudaEvent_t ev_run1 = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_run1 = nullptr, ev_join = nullptr, ev_bits = nullptr, ev_rsum = nullptr;
   bool run_timed = false;
   bool embed_timed = false;
   std::chrono::steady_clock::time_point t_host0;
@@ -366,8 +366,16 @@ int run_embedding(frc_job* j) {
   } else {
     if (j->fused_embed) {
       launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->shard_w0, j->shard_nw,
-                                              j->kp, j->d_order, j->d_lenq, j->i8 ? j->d_qam : nullptr,
-                                              j->d_col_exp, j->d_node_scratch, j->d_bits, j->d_scratch, j->d_r, s);
+                                              j->kp, j->d_order, j->d_node_scratch, j->d_bits, s);
+      // the row sums (integer-ALU-bound) and the operand expansion (HBM-bound) both only read the bit
+      // columns: they run side by side on the two compute streams unless an all-gather sits between
+      cudaStream_t rs = j->sharded ? s : c->stream[1];
+      if (!j->sharded) {
+        JOB_CUDA(j, cudaEventRecord(j->ev_bits, s));
+        JOB_CUDA(j, cudaStreamWaitEvent(rs, j->ev_bits, 0));
+      }
+      launches += launch_presence_rowsum_t(j->d_bits, j->B, j->nw, j->shard_w0, j->shard_nw, j->kp, j->d_lenq,
+                                           j->i8 ? j->d_qam : nullptr, j->d_col_exp, j->d_scratch, j->d_r, rs);
       if (j->sharded) {
         // the one exchange step of the path: presence bit columns + row sums of every rank's
         // sample shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
@@ -380,6 +388,10 @@ int run_embedding(frc_job* j) {
       }
       launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
                                            j->d_P, j->d_Bh, j->d_Bl, j->d_need, s);
+      if (!j->sharded) {
+        JOB_CUDA(j, cudaEventRecord(j->ev_rsum, rs));
+        JOB_CUDA(j, cudaStreamWaitEvent(s, j->ev_rsum, 0));
+      }
     } else {
       launches += launch_embed_bits(j->dtree, j->level_ptr.data(), j->dcsr, j->d_bits, j->nw, s);
       launches += launch_presence_rowsum(j->d_bits, j->B, j->nw, j->d_lenq, j->d_r, j->d_scratch, s);
@@ -495,6 +507,8 @@ void destroy_job(frc_job* j) {
   if (j->ev_embed1) cudaEventDestroy(j->ev_embed1);
   if (j->ev_run1) cudaEventDestroy(j->ev_run1);
   if (j->ev_join) cudaEventDestroy(j->ev_join);
+  if (j->ev_bits) cudaEventDestroy(j->ev_bits);
+  if (j->ev_rsum) cudaEventDestroy(j->ev_rsum);
   tc_operands_destroy(j->tc);
   if (j->ctx) {
     j->ctx->dev.reset();
@@ -767,17 +781,26 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
         chunk_of[g] = n_ch - 1;
         ch_cols[n_ch - 1] += cnt[g];
       }
-      int32_t ch_off[kGroups + 1] = {0}, fill[kGroups];
-      for (int c = 0; c < n_ch; ++c) ch_off[c + 1] = ch_off[c] + static_cast<int32_t>(round_up(ch_cols[c], kBlockCols));
+      // Chunks are laid out along K from the largest to the smallest (the order is free): the MMA
+      // run of a large chunk then covers the ratio epilogue of the previous tile plus the drain of
+      // the small chunk before it, and the two TMEM buffers are never both waiting for the epilogue
+      // warps (with the small chunk first the third chunk of a tile needed its buffer ~57k cycles
+      // after the previous tile ended, exactly when the ratio epilogue released it).
+      int ch_order[kGroups];
+      for (int c = 0; c < n_ch; ++c) ch_order[c] = c;
+      std::stable_sort(ch_order, ch_order + n_ch, [&](int a, int b) { return ch_cols[a] > ch_cols[b]; });
+      int32_t ch_off[kGroups + 1] = {0}, ch_at[kGroups], fill[kGroups];
+      for (int k = 0; k < n_ch; ++k) {
+        ch_at[ch_order[k]] = ch_off[k];
+        ch_off[k + 1] = ch_off[k] + static_cast<int32_t>(round_up(ch_cols[ch_order[k]], kBlockCols));
+      }
       j->kp = std::max<int32_t>(ch_off[n_ch], kBlockCols);
       col_order.assign(j->kp, -1); col_exp.assign(j->kp, 0); len_col.assign(j->kp, 0.0);
       {  // columns of a chunk: its groups from large to small lengths, node id order inside a group
-        int32_t next = 0;
-        for (int c = 0, g = 0; c < n_ch; ++c) {
-          next = ch_off[c];
-          for (; g < kGroups && (chunk_of[g] == c || chunk_of[g] < 0); ++g)
-            if (chunk_of[g] == c) { fill[g] = next; next += cnt[g]; }
-        }
+        int32_t next[kGroups];
+        for (int c = 0; c < n_ch; ++c) next[c] = ch_at[c];
+        for (int g = 0; g < kGroups; ++g)
+          if (chunk_of[g] >= 0) { fill[g] = next[chunk_of[g]]; next[chunk_of[g]] += cnt[g]; }
       }
       for (int32_t v = 0; v < B; ++v) {
         const double l = tree->length[v];
@@ -785,10 +808,11 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
         const int32_t k = fill[group_of(l)]++;
         col_order[k] = v; len_col[k] = l;
       }
-      for (int c = 0; c < n_ch; ++c) {
-        for (int32_t k = ch_off[c]; k < ch_off[c + 1]; ++k) col_exp[k] = chunk_exp[c];
-        for (int32_t kb = ch_off[c] / kBlockCols; kb < ch_off[c + 1] / kBlockCols;) {
-          kb = std::min(ch_off[c + 1] / kBlockCols, kb + kMaxChunkBlocks);  // plane sums stay < 2^31
+      for (int k = 0; k < n_ch; ++k) {
+        const int c = ch_order[k];
+        for (int32_t q = ch_off[k]; q < ch_off[k + 1]; ++q) col_exp[q] = chunk_exp[c];
+        for (int32_t kb = ch_off[k] / kBlockCols; kb < ch_off[k + 1] / kBlockCols;) {
+          kb = std::min(ch_off[k + 1] / kBlockCols, kb + kMaxChunkBlocks);  // plane sums stay < 2^31
           chunk_end.push_back(kb);
           chunk_scale.push_back(std::ldexp(1.0, chunk_exp[c]));
         }
@@ -1014,6 +1038,8 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   CREATE_CUDA(cudaEventCreate(&j->ev_embed1));
   CREATE_CUDA(cudaEventCreate(&j->ev_run1));
   CREATE_CUDA(cudaEventCreateWithFlags(&j->ev_join, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&j->ev_bits, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&j->ev_rsum, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventRecord(j->ev_h2d0, c->stream[0]));
   CREATE_CUDA(cudaMemcpyAsync(j->d_inputs, stage, total, cudaMemcpyHostToDevice, c->stream[0]));
   CREATE_CUDA(cudaEventRecord(j->ev_h2d1, c->stream[0]));
