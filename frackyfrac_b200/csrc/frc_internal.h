@@ -98,9 +98,11 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
                                 uint32_t* node_scratch, uint32_t* bitsT, cudaStream_t s);
 // r[s] for the same word columns from bitsT (qam / col_exp non-null: integer row sums of the u8 path).
 // Independent of the operand expansion, so the job runs the two on different streams.
+// r_int != null: also the exact integer row sums in units of 2^e_min (partial_int: scratch like partial).
 int launch_presence_rowsum_t(const uint32_t* bitsT, int32_t n_nodes, int32_t nw, int32_t w0, int32_t w_count,
                              int32_t kp, const double* lenq, const uint32_t* qam, const int32_t* col_exp,
-                             double* partial, double* r, cudaStream_t s);
+                             double* partial, double* r, int32_t e_min, long long* partial_int, long long* r_int,
+                             cudaStream_t s);
 // need[np / 256] (device, may be null = everything): bit 0 = write the A rows of that block of 256
 // samples, bit 1 = write its Bh / Bl rows.
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
@@ -153,13 +155,16 @@ struct TcOperands;  // opaque: tensor maps + chunk table
 struct TcChunks {
   const int32_t* end = nullptr;
   const double* scale = nullptr;
+  const int32_t* shift = nullptr;  // u8 integer mode: log2(scale / smallest scale) per chunk
   int32_t n = 0;
-  bool biased = false;  // u8: all scales within 2^8 -> single-instruction biased accumulation
+  bool biased = false;  // u8 fp64 mode: all scales within 2^8 -> single-instruction biased accumulation
 };
 // flag_u: device scalar; pairs with unique length below it are recomputed exactly (null: none).
 TcOperands* tc_operands_create(const void* P, const void* Bh, const void* Bl, int64_t np, int32_t kp,
                                bool i8, const TcChunks& chunks, const double* len_col, const double* flag_u,
                                std::string* err);
+// u8 integer mode (chunk scales within 2^16): row sums as integers in units of `unit` = the smallest scale.
+void tc_operands_set_int(TcOperands* o, const long long* r_int, double unit);
 void tc_operands_destroy(TcOperands* o);
 int tc_chunk_kblocks();  // bf16: K blocks per fp32 accumulation run (FRC_TC_CHUNK_KBLOCKS)
 // Distances of the tiles in `tiles` into out[index - first]; the band offset of

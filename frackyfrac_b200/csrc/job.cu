@@ -203,6 +203,9 @@ struct frc_job {
   void *d_q0 = nullptr, *d_q1 = nullptr, *d_q2 = nullptr;
   int32_t *d_order = nullptr, *d_col_exp = nullptr;
   uint32_t* d_qam = nullptr;  // u8: a * m per operand column
+  bool intacc = false;        // u8: chunk scales within 2^16 -> integer accumulation / integer row sums
+  int32_t e_min = 0;          // smallest chunk exponent (integer unit = 2^e_min)
+  long long *d_r_int = nullptr, *d_scratch_int = nullptr;
   long long* d_fix_ws = nullptr;  // fast weighted fix-up: one zeroed int64[B] per SM
   uint8_t* d_need = nullptr;  // per block of 256 samples: which operands this rank's tiles read (world > 1)
   double *d_lenq = nullptr, *d_len_col = nullptr, *d_flag_u = nullptr;
@@ -375,16 +378,18 @@ int run_embedding(frc_job* j) {
         JOB_CUDA(j, cudaStreamWaitEvent(rs, j->ev_bits, 0));
       }
       launches += launch_presence_rowsum_t(j->d_bits, j->B, j->nw, j->shard_w0, j->shard_nw, j->kp, j->d_lenq,
-                                           j->i8 ? j->d_qam : nullptr, j->d_col_exp, j->d_scratch, j->d_r, rs);
+                                           j->i8 ? j->d_qam : nullptr, j->d_col_exp, j->d_scratch, j->d_r, j->e_min,
+                                           j->d_scratch_int, j->intacc ? j->d_r_int : nullptr, rs);
       if (j->sharded) {
         // the one exchange step of the path: presence bit columns + row sums of every rank's
         // sample shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
-        void* bufs[2] = {j->d_bits, j->d_r};
-        const size_t bytes[2] = {static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t),
-                                 static_cast<size_t>(j->shard_nw) * 32 * sizeof(double)};
+        void* bufs[3] = {j->d_bits, j->d_r, j->d_r_int};
+        const size_t bytes[3] = {static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t),
+                                 static_cast<size_t>(j->shard_nw) * 32 * sizeof(double),
+                                 static_cast<size_t>(j->shard_nw) * 32 * sizeof(long long)};
         std::string cerr;
-        if (!comm_all_gather_inplace(c->comm, bufs, bytes, 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
-        j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
+        if (!comm_all_gather_inplace(c->comm, bufs, bytes, j->intacc ? 3 : 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
+        j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (j->intacc ? bytes[2] : 0)) * (j->opts.world - 1);
       }
       launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
                                            j->d_P, j->d_Bh, j->d_Bl, j->d_need, s);
@@ -736,7 +741,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   // order, uniform accumulation chunks.  u8: nodes grouped by binade pairs of their length so
   // that one power-of-two scale per chunk leaves every length a 21..24-bit integer a * m
   // (zero-length nodes contribute nothing and get no column).
-  std::vector<int32_t> col_order, col_exp, chunk_end;
+  std::vector<int32_t> col_order, col_exp, chunk_end, chunk_shift;
   std::vector<double> len_col, chunk_scale;
   if (!j->exact && !j->weighted) {
     { const char* e = getenv("FRC_EMBED_LEVELS"); j->fused_embed = !(e && atoi(e) == 1); }
@@ -818,6 +823,14 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
         }
       }
       if (chunk_end.empty()) { chunk_end.push_back(1); chunk_scale.push_back(1.0); }
+      {  // integer mode when all chunk scales lie within 2^16 (sums then stay below 2^60)
+        int lo = INT32_MAX, hi = INT32_MIN;
+        for (double sc : chunk_scale) { const int e = std::ilogb(sc); lo = std::min(lo, e); hi = std::max(hi, e); }
+        const char* ev = getenv("FRC_U8_ACC");  // "f64" forces the fp64 accumulation path (tests)
+        j->intacc = hi - lo <= 16 && !(ev && strcmp(ev, "f64") == 0);
+        j->e_min = lo;
+        for (double sc : chunk_scale) chunk_shift.push_back(std::ilogb(sc) - lo);
+      }
     } else {
       col_order.assign(j->kp, -1); len_col.assign(j->kp, 0.0);
       for (int32_t v = 0; v < B; ++v) { col_order[v] = v; len_col[v] = tree->length[v]; }
@@ -917,7 +930,8 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       s_lptr = seg(sizeof(int32_t) * (H + 2)), s_lpar = seg(sizeof(int32_t) * B),
       s_order = seg(sizeof(int32_t) * col_order.size()), s_cexp = seg(sizeof(int32_t) * col_exp.size()),
       s_lcol = seg(sizeof(double) * len_col.size()), s_cend = seg(sizeof(int32_t) * chunk_end.size()),
-      s_cscale = seg(sizeof(double) * chunk_scale.size()), s_need = seg(need_blocks.size());
+      s_cscale = seg(sizeof(double) * chunk_scale.size()), s_need = seg(need_blocks.size()),
+      s_cshift = seg(sizeof(int32_t) * chunk_shift.size());
   char* stage = pin_alloc<char>(j, total, &rc);
   if (!stage) return bail(rc);
   j->d_inputs = dev_alloc<char>(j, total, &rc);
@@ -966,6 +980,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (!chunk_end.empty()) memcpy(stage + s_cend.off, chunk_end.data(), s_cend.bytes);
     if (!chunk_scale.empty()) memcpy(stage + s_cscale.off, chunk_scale.data(), s_cscale.bytes);
     if (!need_blocks.empty()) memcpy(stage + s_need.off, need_blocks.data(), s_need.bytes);
+    if (!chunk_shift.empty()) memcpy(stage + s_cshift.off, chunk_shift.data(), s_cshift.bytes);
     if (!j->tiles.empty()) memcpy(stage + s_tiles.off, j->tiles.data(), sizeof(Tile) * j->tiles.size());
     memcpy(stage + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
     };
@@ -1065,6 +1080,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->d_chunks.end = reinterpret_cast<int32_t*>(d + s_cend.off);
   j->d_chunks.scale = reinterpret_cast<double*>(d + s_cscale.off);
   j->d_chunks.n = static_cast<int32_t>(chunk_end.size());
+  j->d_chunks.shift = chunk_shift.empty() ? nullptr : reinterpret_cast<int32_t*>(d + s_cshift.off);
   j->d_need = need_blocks.empty() ? nullptr : reinterpret_cast<uint8_t*>(d + s_need.off);
   if (j->i8 && !chunk_scale.empty()) {
     const auto mm = std::minmax_element(chunk_scale.begin(), chunk_scale.end());
@@ -1115,9 +1131,14 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     std::string terr;
     if (j->i8 && !(j->d_flag_u = dev_alloc<double>(j, 1, &rc))) return bail(rc);
     if (j->i8 && !(j->d_qam = dev_alloc<uint32_t>(j, j->kp, &rc))) return bail(rc);
+    if (j->intacc) {
+      if (!(j->d_r_int = dev_alloc<long long>(j, j->np, &rc))) return bail(rc);
+      if (!(j->d_scratch_int = dev_alloc<long long>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
+    }
     j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, j->i8, j->d_chunks, j->d_len_col,
                                j->d_flag_u, &terr);
     if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
+    if (j->intacc) tc_operands_set_int(j->tc, j->d_r_int, std::ldexp(1.0, j->e_min));
     if (j->i8) {  // a function of the tree only: once per job, not per restart
       j->info.kernel_launches += launch_quantize_lengths(
           j->d_len_col, j->d_col_exp, j->kp, static_cast<uint8_t*>(j->d_q0), static_cast<uint8_t*>(j->d_q1),

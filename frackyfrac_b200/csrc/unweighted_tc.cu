@@ -301,16 +301,23 @@ __device__ __forceinline__ double widen_f32(float f) {
   return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
 }
 
-template <bool kI8>
+// kMode: 0 = bf16 planes (fp32 accumulators), 1 = u8 planes with fp64 chunk accumulation (chunk scales
+// spanning more than 2^16), 2 = u8 planes with 64-bit INTEGER accumulation and an integer / fp32 ratio
+// epilogue: no fp64 instruction at all (every DADD/DFMA stalls its warp for tens of cycles on B200:
+// ncu showed half of the epilogue warps' samples in stall_math on them at 4.5 % fp64-pipe utilisation).
+template <int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapBh,
                  const __grid_constant__ CUtensorMap mapBl, const int32_t* __restrict__ chunk_end,
-                 const double* __restrict__ chunk_scale, int32_t n_chunks, int32_t biased,
-                 const double* __restrict__ r, const Tile* __restrict__ tiles, int32_t n_tiles,
+                 const double* __restrict__ chunk_scale, const int32_t* __restrict__ chunk_shift,
+                 int32_t n_chunks, int32_t biased, const double* __restrict__ r,
+                 const long long* __restrict__ r_int, double unit, const Tile* __restrict__ tiles, int32_t n_tiles,
                  int64_t n_samples, int64_t first, double* __restrict__ out, double flag_below,
                  const double* __restrict__ flag_u_ptr, uint32_t* __restrict__ flagged,
                  unsigned long long* __restrict__ n_flagged, int dbg) {
   (void)dbg;
+  constexpr bool kI8 = kMode != 0;
+  constexpr bool kInt = kMode == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -430,13 +437,16 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
     const int cg = (warp - EPI_WARP0) >> 2;      // which EPI2_COLS columns of each plane it owns
-    using Acc = typename std::conditional<kI8, double, float>::type;
+    using Acc = typename std::conditional<kInt, unsigned long long,
+                                          typename std::conditional<kI8, double, float>::type>::type;
     // pairs whose unique length U is below this are recomputed exactly as well: the summed absolute
     // error of the imprecisely quantised branch lengths could exceed 2e-6 of U (k_quantize_lengths)
     const float flag_u = flag_u_ptr ? static_cast<float>(*flag_u_ptr) : 0.f;
     const float flag_d = static_cast<float>(flag_below);
-    double acc0 = 0.0;  // u8, biased accumulation: minus the 2^52-bias of every chunk
-    if constexpr (kI8)
+    // integer mode: lengths, row sums and accumulators are integers in units of `unit` = the smallest chunk scale
+    const long long flag_u_int = (kInt && flag_u_ptr) ? static_cast<long long>(*flag_u_ptr / unit) : 0;
+    double acc0 = 0.0;  // u8 fp64 mode, biased accumulation: minus the 2^52-bias of every chunk
+    if constexpr (kI8 && !kInt)
       if (biased) for (int ch = 0; ch < n_chunks; ++ch) acc0 -= 4503599627370496.0 * chunk_scale[ch];
     uint32_t chunk = 0;
     TL(long long w_tfull = 0; long long t_drain = 0; long long t_ratio = 0; const long long e_start = clock64();)
@@ -447,13 +457,33 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
       for (int n = 0; n < EPI2_COLS; ++n) acc[n] = static_cast<Acc>(acc0);
       for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
         const uint32_t buf = chunk & 1u;
-        const double scale = kI8 ? chunk_scale[ch] : 1.0;
+        const double scale = (kI8 && !kInt) ? chunk_scale[ch] : 1.0;
+        const uint32_t shift = kInt ? static_cast<uint32_t>(chunk_shift[ch]) : 0u;
         TL(const long long c0 = clock64();)
         ptx::mbar_wait(tfull_bar(buf), (chunk >> 1) & 1u);
         TL(const long long c1 = clock64();)
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * DN + cg * EPI2_COLS;
-        if constexpr (kI8) {
+        if constexpr (kInt) {
+          // exact 64-bit accumulation in units of the smallest chunk scale: two 32x32+64 integer
+          // multiply-adds per element, (256*hi + lo) << shift with shift <= 16 (host-checked range)
+          const uint32_t m0 = 1u << shift, m1 = 256u << shift;
+          uint32_t v[2][8], w[2][8];
+          ptx::tmem_ld_32x8(taddr, v[0]);
+          ptx::tmem_ld_32x8(taddr + BN, w[0]);
+#pragma unroll
+          for (int cc = 0; cc < EPI2_COLS / 8; ++cc) {
+            ptx::tmem_ld_wait();
+            if (cc + 1 < EPI2_COLS / 8) {
+              ptx::tmem_ld_32x8(taddr + (cc + 1) * 8, v[(cc + 1) & 1]);
+              ptx::tmem_ld_32x8(taddr + BN + (cc + 1) * 8, w[(cc + 1) & 1]);
+            }
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+              acc[cc * 8 + x] += static_cast<unsigned long long>(v[cc & 1][x]) * m1 +
+                                 static_cast<unsigned long long>(w[cc & 1][x]) * m0;
+          }
+        } else if constexpr (kI8) {
           // both plane sums are in [0, 2^31): S = 256*hi + lo < 2^40 comes from one 32x32->64 integer
           // multiply-add; OR-ing it into the mantissa of 2^52 gives the double 2^52 + S without any
           // conversion instruction.  biased: ONE fp64 instruction per element accumulates
@@ -508,36 +538,71 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
       if (TL_ON(4)) {
         if (acc[0] == static_cast<Acc>(-1.5)) out[0] = 0.0;
       } else if (static_cast<int64_t>(tile.tj + static_cast<int>(cta)) * BM + q * 32 < i0 + EPI2_COLS) {  // warp-uniform
-        // r is padded to a multiple of the tile size: both loads are in range and coalesced
-        const double rj = j < n_samples ? r[j] : 0.0;
-        const double ri_lane = r[i0 + lane];
         int64_t off = i0 * (i0 - 1) / 2 - first + j;  // flat index of (i0, j) relative to the band
-        // batches of 8 row samples: first the arithmetic of all 8 (independent chains the scheduler can
-        // interleave: one element is ~25 dependent instructions, and issuing them element by element
-        // behind each store left the 16 warps latency-bound at 47k cycles per tile), then the stores
+        // r is padded to a multiple of the tile size: the loads are in range and coalesced.
+        // Batches of 8 row samples: first the arithmetic of all 8 (independent chains the scheduler can
+        // interleave), then the stores and the (rare) fix-up flags.
+        if constexpr (kInt) {
+          const long long rj = j < n_samples ? r_int[j] : 0;
+          const long long ri_lane = r_int[i0 + lane];
 #pragma unroll
-        for (int n0 = 0; n0 < EPI2_COLS; n0 += 8) {
-          float dv[8], uv[8];
+          for (int n0 = 0; n0 < EPI2_COLS; n0 += 8) {
+            float dv[8];
+            bool fu[8];
 #pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            const double ri = __shfl_sync(0xffffffffu, ri_lane, n0 + x);
-            // fp64 only where cancellation needs it: U = R - 2s (the reference's `result`)
-            const double s = static_cast<double>(acc[n0 + x]);
-            const double U = fma(-2.0, s, ri + rj);
-            uv[x] = static_cast<float>(U);
-            dv[x] = __fdividef(uv[x], uv[x] + static_cast<float>(s));  // U / (U + common), unifrac.go:169
-          }
-#pragma unroll
-          for (int x = 0; x < 8; ++x) {
-            const int64_t i = i0 + n0 + x;
-            if (i < n_samples && j < i) {
-              out[off] = widen_f32(dv[x]);
-              if (dv[x] < flag_d || uv[x] < flag_u) {
-                unsigned long long slot = atomicAdd(n_flagged, 1ULL);
-                flagged[slot] = static_cast<uint32_t>(off);
-              }
+            for (int x = 0; x < 8; ++x) {
+              const long long ri = __shfl_sync(0xffffffffu, ri_lane, n0 + x);
+              const long long sh = static_cast<long long>(acc[n0 + x]);
+              // exact: U = (r_i - s) + (r_j - s) >= 0 (the reference's `result`), V = U + common
+              const unsigned long long U = static_cast<unsigned long long>(ri + rj - 2 * sh);
+              const unsigned long long V = U + static_cast<unsigned long long>(sh);
+              const float Uf = fmaf(__uint2float_rn(static_cast<uint32_t>(U >> 32)), 4294967296.f,
+                                    __uint2float_rn(static_cast<uint32_t>(U)));
+              const float Vf = fmaf(__uint2float_rn(static_cast<uint32_t>(V >> 32)), 4294967296.f,
+                                    __uint2float_rn(static_cast<uint32_t>(V)));
+              dv[x] = __fdividef(Uf, Vf);  // unifrac.go:169; 0/0 -> NaN (A8)
+              fu[x] = static_cast<long long>(U) < flag_u_int;
             }
-            off += i;  // row i+1 starts i entries later
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              const int64_t i = i0 + n0 + x;
+              if (i < n_samples && j < i) {
+                out[off] = widen_f32(dv[x]);
+                if (dv[x] < flag_d || fu[x]) {
+                  unsigned long long slot = atomicAdd(n_flagged, 1ULL);
+                  flagged[slot] = static_cast<uint32_t>(off);
+                }
+              }
+              off += i;  // row i+1 starts i entries later
+            }
+          }
+        } else {
+          const double rj = j < n_samples ? r[j] : 0.0;
+          const double ri_lane = r[i0 + lane];
+#pragma unroll
+          for (int n0 = 0; n0 < EPI2_COLS; n0 += 8) {
+            float dv[8], uv[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              const double ri = __shfl_sync(0xffffffffu, ri_lane, n0 + x);
+              // fp64 only where cancellation needs it: U = R - 2s (the reference's `result`)
+              const double sd = static_cast<double>(acc[n0 + x]);
+              const double U = fma(-2.0, sd, ri + rj);
+              uv[x] = static_cast<float>(U);
+              dv[x] = __fdividef(uv[x], uv[x] + static_cast<float>(sd));  // U / (U + common), unifrac.go:169
+            }
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              const int64_t i = i0 + n0 + x;
+              if (i < n_samples && j < i) {
+                out[off] = widen_f32(dv[x]);
+                if (dv[x] < flag_d || uv[x] < flag_u) {
+                  unsigned long long slot = atomicAdd(n_flagged, 1ULL);
+                  flagged[slot] = static_cast<uint32_t>(off);
+                }
+              }
+              off += i;  // row i+1 starts i entries later
+            }
           }
         }
       }
@@ -647,6 +712,8 @@ struct TcOperands {
   TcChunks chunks;
   const double* len_col;
   const double* flag_u;  // device scalar (u8) or null
+  const long long* r_int = nullptr;  // u8 integer mode: row sums in units of `unit`
+  double unit = 1.0;
 };
 
 bool tc_setup(std::string* err) {
@@ -661,9 +728,11 @@ bool tc_setup(std::string* err) {
   g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
   e = cudaFuncSetAttribute(k_unweighted_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_unweighted_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    e = cudaFuncSetAttribute(k_unweighted_tc2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_unweighted_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    e = cudaFuncSetAttribute(k_unweighted_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_unweighted_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
   if (e != cudaSuccess) {
     if (err) *err = std::string("cudaFuncSetAttribute(k_unweighted_tc): ") + cudaGetErrorString(e);
     g_encode = nullptr;
@@ -690,6 +759,7 @@ TcOperands* tc_operands_create(const void* P, const void* Bh, const void* Bl, in
   }
   return o;
 }
+void tc_operands_set_int(TcOperands* o, const long long* r_int, double unit) { o->r_int = r_int; o->unit = unit; }
 void tc_operands_destroy(TcOperands* o) { delete o; }
 
 }  // namespace frc
@@ -723,14 +793,12 @@ int launch_unweighted_tc(const TcOperands* ops, const double* r, const Tile* til
     const TcChunks& c = ops->chunks;
     const char* de = getenv("FRC_TC_DEBUG");
     const int dbg = de ? atoi(de) : 0;
-    if (ops->i8)
-      k_unweighted_tc2<true><<<grid, THREADS2, SMEM2_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, c.end, c.scale,
-                                                                c.n, c.biased ? 1 : 0, r, tiles, n_tiles, n_samples, first, out,
-                                                                flag_below, ops->flag_u, flagged, n_flagged, dbg);
-    else
-      k_unweighted_tc2<false><<<grid, THREADS2, SMEM2_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, c.end, c.scale,
-                                                                 c.n, 0, r, tiles, n_tiles, n_samples, first, out,
-                                                                 flag_below, ops->flag_u, flagged, n_flagged, dbg);
+#define FRC_TC2_ARGS ops->mapP, ops->mapBh, ops->mapBl, c.end, c.scale, c.shift, c.n, c.biased ? 1 : 0, r, ops->r_int, \
+                     ops->unit, tiles, n_tiles, n_samples, first, out, flag_below, ops->flag_u, flagged, n_flagged, dbg
+    if (ops->i8 && ops->r_int) k_unweighted_tc2<2><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
+    else if (ops->i8) k_unweighted_tc2<1><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
+    else k_unweighted_tc2<0><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
+#undef FRC_TC2_ARGS
     return 1;
   }
   int grid = n_tiles < num_sms ? n_tiles : num_sms;

@@ -220,7 +220,7 @@ def test_fast_weighted_embedding_in_slabs(gpu_ctx, monkeypatch, slab):
 
 
 @pytest.mark.parametrize("shape,levels", [("caterpillar", 0), ("caterpillar", 1), ("balanced", 0), ("random", 1),
-                                          ("caterpillar", 2), ("random", 2)])
+                                          ("caterpillar", 2), ("random", 2), ("random", 3)])
 def test_fast_unweighted_embedding_variants(gpu_ctx, monkeypatch, shape, levels):
     """Both embedding implementations (fused single launch / one launch per level), deep and flat trees (H9)."""
     from frackyfrac_b200 import engine, synth
@@ -228,6 +228,9 @@ def test_fast_unweighted_embedding_variants(gpu_ctx, monkeypatch, shape, levels)
     monkeypatch.setenv("FRC_EMBED_LEVELS", str(min(levels, 1)))  # 2 = fused embedding feeding the bf16 kernel
     if levels == 2:
         monkeypatch.setenv("FRC_UW_KERNEL", "bf16")
+    if levels == 3:  # u8 operands with the fp64 chunk accumulation (used when chunk scales span > 2^16)
+        monkeypatch.setenv("FRC_EMBED_LEVELS", "0")
+        monkeypatch.setenv("FRC_U8_ACC", "f64")
     tree = synth.random_tree(700, 71, shape=shape)
     csr = synth.random_table(tree, 200, 0.03, 72)
     want = oracle_flat(tree, csr, False)
