@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(32)
 k_presence_rowsum_u8(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per,
                      const uint32_t* __restrict__ qam, const int32_t* __restrict__ col_exp,
                      double* __restrict__ partial, int64_t ld, int32_t w0, int32_t e_min,
-                     long long* __restrict__ partial_int) {
+                     long long* __restrict__ r_int) {
   const int32_t w = blockIdx.x + w0, lane = threadIdx.x;
   const int32_t v0 = blockIdx.y * per, v1 = min(kp, v0 + per);  // per is a multiple of 128
   const uint32_t* col = bitsT + static_cast<int64_t>(w) * kp;
@@ -361,20 +361,13 @@ k_presence_rowsum_u8(const uint32_t* __restrict__ bitsT, int32_t kp, int32_t per
     }
     const uint32_t sum = (a0 + a1) + (a2 + a3);  // < 2^31
     const int32_t e = col_exp[blk];
-    tot = fma(ldexp(1.0, e), static_cast<double>(sum), tot);
-    if (partial_int) tot_int += static_cast<unsigned long long>(sum) << (e - e_min);
+    if (r_int) tot_int += static_cast<unsigned long long>(sum) << (e - e_min);
+    else tot = fma(ldexp(1.0, e), static_cast<double>(sum), tot);
   }
-  partial[static_cast<int64_t>(blockIdx.y) * ld + w * 32 + lane] = tot;
-  if (partial_int) partial_int[static_cast<int64_t>(blockIdx.y) * ld + w * 32 + lane] = static_cast<long long>(tot_int);
-}
-
-__global__ void k_reduce_partials_i64(const long long* __restrict__ partial, int n_chunks, int64_t ld, int64_t n,
-                                      long long* __restrict__ out) {
-  int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  long long acc = 0;
-  for (int c = 0; c < n_chunks; ++c) acc += partial[static_cast<int64_t>(c) * ld + s];
-  out[s] = acc;
+  // integer mode: straight into r_int with a 64-bit integer atomic (order-independent, so still
+  // deterministic) -- no partial buffer, no reduce launch, no fp64
+  if (r_int) atomicAdd(reinterpret_cast<unsigned long long*>(r_int) + w * 32 + lane, tot_int);
+  else partial[static_cast<int64_t>(blockIdx.y) * ld + w * 32 + lane] = tot;
 }
 
 // Presence columns bitsT[nw][kp] (word w holds samples 32w..32w+31 of one operand column) -> the
@@ -653,27 +646,22 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
 
 int launch_presence_rowsum_t(const uint32_t* bitsT, int32_t n_nodes, int32_t nw, int32_t w0, int32_t w_count,
                              int32_t kp, const double* lenq, const uint32_t* qam, const int32_t* col_exp,
-                             double* partial, double* r, int32_t e_min, long long* partial_int, long long* r_int,
-                             cudaStream_t s) {
+                             double* partial, double* r, int32_t e_min, long long* r_int, cudaStream_t s) {
   const int64_t np = static_cast<int64_t>(nw) * 32;
   const int chunks = pick_chunks(n_nodes);
   dim3 g(w_count, chunks);
+  const int64_t s0 = static_cast<int64_t>(w0) * 32, ns = static_cast<int64_t>(w_count) * 32;
   if (qam) {
     const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 128));
-    k_presence_rowsum_u8<<<g, 32, 0, s>>>(bitsT, kp, per, qam, col_exp, partial, np, w0, e_min,
-                                          r_int ? partial_int : nullptr);
+    if (r_int) cudaMemsetAsync(r_int + s0, 0, sizeof(long long) * ns, s);
+    k_presence_rowsum_u8<<<g, 32, 0, s>>>(bitsT, kp, per, qam, col_exp, partial, np, w0, e_min, r_int);
+    if (r_int) return 1;
   } else {
     const int32_t per = static_cast<int32_t>(round_up((kp + chunks - 1) / chunks, 8));
     k_presence_rowsum_t<<<g, 32, 0, s>>>(bitsT, kp, per, lenq, partial, np, w0);
   }
-  const int64_t s0 = static_cast<int64_t>(w0) * 32, ns = static_cast<int64_t>(w_count) * 32;
   k_reduce_partials<<<static_cast<unsigned>((ns + kThreads - 1) / kThreads), kThreads, 0, s>>>(partial + s0, chunks, np,
                                                                                               ns, r + s0);
-  if (qam && r_int) {
-    k_reduce_partials_i64<<<static_cast<unsigned>((ns + kThreads - 1) / kThreads), kThreads, 0, s>>>(
-        partial_int + s0, chunks, np, ns, r_int + s0);
-    return 3;
-  }
   return 2;
 }
 

@@ -98,11 +98,10 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
                                 uint32_t* node_scratch, uint32_t* bitsT, cudaStream_t s);
 // r[s] for the same word columns from bitsT (qam / col_exp non-null: integer row sums of the u8 path).
 // Independent of the operand expansion, so the job runs the two on different streams.
-// r_int != null: also the exact integer row sums in units of 2^e_min (partial_int: scratch like partial).
+// r_int != null (u8 integer mode): INSTEAD of r, the exact integer row sums in units of 2^e_min.
 int launch_presence_rowsum_t(const uint32_t* bitsT, int32_t n_nodes, int32_t nw, int32_t w0, int32_t w_count,
                              int32_t kp, const double* lenq, const uint32_t* qam, const int32_t* col_exp,
-                             double* partial, double* r, int32_t e_min, long long* partial_int, long long* r_int,
-                             cudaStream_t s);
+                             double* partial, double* r, int32_t e_min, long long* r_int, cudaStream_t s);
 // need[np / 256] (device, may be null = everything): bit 0 = write the A rows of that block of 256
 // samples, bit 1 = write its Bh / Bl rows.
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,

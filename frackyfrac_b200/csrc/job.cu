@@ -205,7 +205,7 @@ struct frc_job {
   uint32_t* d_qam = nullptr;  // u8: a * m per operand column
   bool intacc = false;        // u8: chunk scales within 2^16 -> integer accumulation / integer row sums
   int32_t e_min = 0;          // smallest chunk exponent (integer unit = 2^e_min)
-  long long *d_r_int = nullptr, *d_scratch_int = nullptr;
+  long long* d_r_int = nullptr;
   long long* d_fix_ws = nullptr;  // fast weighted fix-up: one zeroed int64[B] per SM
   uint8_t* d_need = nullptr;  // per block of 256 samples: which operands this rank's tiles read (world > 1)
   double *d_lenq = nullptr, *d_len_col = nullptr, *d_flag_u = nullptr;
@@ -379,17 +379,16 @@ int run_embedding(frc_job* j) {
       }
       launches += launch_presence_rowsum_t(j->d_bits, j->B, j->nw, j->shard_w0, j->shard_nw, j->kp, j->d_lenq,
                                            j->i8 ? j->d_qam : nullptr, j->d_col_exp, j->d_scratch, j->d_r, j->e_min,
-                                           j->d_scratch_int, j->intacc ? j->d_r_int : nullptr, rs);
+                                           j->intacc ? j->d_r_int : nullptr, rs);
       if (j->sharded) {
         // the one exchange step of the path: presence bit columns + row sums of every rank's
         // sample shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
-        void* bufs[3] = {j->d_bits, j->d_r, j->d_r_int};
-        const size_t bytes[3] = {static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t),
-                                 static_cast<size_t>(j->shard_nw) * 32 * sizeof(double),
-                                 static_cast<size_t>(j->shard_nw) * 32 * sizeof(long long)};
+        void* bufs[2] = {j->d_bits, j->intacc ? static_cast<void*>(j->d_r_int) : static_cast<void*>(j->d_r)};
+        const size_t bytes[2] = {static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t),
+                                 static_cast<size_t>(j->shard_nw) * 32 * sizeof(double)};
         std::string cerr;
-        if (!comm_all_gather_inplace(c->comm, bufs, bytes, j->intacc ? 3 : 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
-        j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (j->intacc ? bytes[2] : 0)) * (j->opts.world - 1);
+        if (!comm_all_gather_inplace(c->comm, bufs, bytes, 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
+        j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
       }
       launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
                                            j->d_P, j->d_Bh, j->d_Bl, j->d_need, s);
@@ -1133,7 +1132,6 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (j->i8 && !(j->d_qam = dev_alloc<uint32_t>(j, j->kp, &rc))) return bail(rc);
     if (j->intacc) {
       if (!(j->d_r_int = dev_alloc<long long>(j, j->np, &rc))) return bail(rc);
-      if (!(j->d_scratch_int = dev_alloc<long long>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
     }
     j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, j->i8, j->d_chunks, j->d_len_col,
                                j->d_flag_u, &terr);
