@@ -486,11 +486,13 @@ __global__ void k_quantize_lengths(const double* __restrict__ len_col, const int
   qam[k] = static_cast<uint32_t>(best_a) * static_cast<uint32_t>(best_m);
   const double q = ldexp(static_cast<double>(best_a) * static_cast<double>(best_m), e);
   lenq[k] = q;
-  // columns kept to 4e-6 relative bound every pair's error by 4e-6 of its own sums; the absolute
-  // errors of the others (small lengths merged into a chunk of larger ones) are summed, and a
-  // pair is recomputed exactly when that sum could exceed 2e-6 of its unique length
+  // Error budget of a distance d = U / V (U, V exact integer sums of quantised lengths): columns kept
+  // to 2e-6 relative bound the error of U and of V by 2e-6 each; the absolute errors of the other
+  // columns (small lengths merged into a chunk of larger ones, or an unlucky search) are summed
+  // into A, and a pair with U < 1e6 * A (A could exceed 1e-6 of U, hence of V) is recomputed
+  // exactly: |rel err d| <= 2 * (2e-6 + 1e-6) = 6e-6 for every pair that is not.
   const double err = fabs(q - len);
-  if (err > 4e-6 * len) atomicAdd(flag_u, 5e5 * err);
+  if (err > 2e-6 * len) atomicAdd(flag_u, 1e6 * err);
 }
 
 }  // namespace

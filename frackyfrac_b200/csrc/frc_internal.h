@@ -110,8 +110,8 @@ int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int6
 // u8 block floating point: for operand column k with true length len_col[k] >= 0 and chunk
 // exponent col_exp[k], find the 8-bit a and 16-bit m = 256*qh + ql minimising
 // |a * m * 2^e - len| ; lenq[k] = a * m * 2^e (exact in fp64).
-// flag_u[0] = 5e5 * sum of |lenq - len| over the columns whose relative quantisation error
-// exceeds 4e-6 (pairs with a unique length below that are recomputed exactly).
+// flag_u[0] = 1e6 * sum of |lenq - len| over the columns whose relative quantisation error
+// exceeds 2e-6 (pairs with a unique length below that are recomputed exactly).
 int launch_quantize_lengths(const double* len_col, const int32_t* col_exp, int32_t kp, uint8_t* qa,
                             uint8_t* qh, uint8_t* ql, uint32_t* qam, double* lenq, double* flag_u,
                             cudaStream_t s);

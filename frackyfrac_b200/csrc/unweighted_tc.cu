@@ -568,7 +568,10 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
               const int64_t i = i0 + n0 + x;
               if (i < n_samples && j < i) {
                 out[off] = widen_f32(dv[x]);
-                if (dv[x] < flag_d || fu[x]) {
+                // U and V are exact integer sums of the quantised lengths: no cancellation error, so a
+                // small d needs no recompute here (identical samples give U = 0 exactly); only the
+                // absolute-error rule of the merged small-length columns applies
+                if (fu[x]) {
                   unsigned long long slot = atomicAdd(n_flagged, 1ULL);
                   flagged[slot] = static_cast<uint32_t>(off);
                 }
