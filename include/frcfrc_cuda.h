@@ -67,7 +67,8 @@ typedef struct {
  * after name resolution.  col = id of a LEAF node carrying that species name
  * (a name carried by several leaves is expanded to all of them, a name that
  * only matches internal nodes is dropped: unifrac.go:38-43).  val > 0, finite.
- * A leaf may appear at most once per row; order within a row is free. */
+ * A leaf may appear at most once per row (checked when values are used: weighted and
+ * exact jobs; for presence a repeat is harmless); order within a row is free. */
 typedef struct {
   int64_t n_samples;
   const int64_t *row_ptr; /* [n_samples + 1], row_ptr[0] = 0                    */

@@ -318,6 +318,14 @@ def test_bad_arguments_are_errors(gpu_ctx):
     bad_parent = tree.parent.copy(); bad_parent[3] = 7
     with pytest.raises(engine.FrcError):
         engine.unifrac(bad_parent, tree.length, rp, col, val, False, ctx=gpu_ctx)
+    # parent < child everywhere but not a pre-order numbering: node 3 hangs under 1 after 2 closed that subtree
+    with pytest.raises(engine.FrcError, match="pre-order"):
+        engine.unifrac(np.array([-1, 0, 0, 1], np.int32), np.ones(4), np.array([0, 1, 2], np.int64),
+                       np.array([2, 3], np.int32), np.ones(2), False, ctx=gpu_ctx)
+    # a leaf listed twice in a row: an error where values are used
+    dup_col = col.copy(); dup_col[1] = dup_col[0]
+    with pytest.raises(engine.FrcError, match="twice"):
+        engine.unifrac(tree.parent, tree.length, rp, dup_col, val, True, ctx=gpu_ctx)
     with pytest.raises(engine.FrcError):  # -l only with -w (frcfrc.go:84-86)
         engine.unifrac(tree.parent, tree.length, rp, col, val, False, normalize=False, ctx=gpu_ctx)
     ok = engine.unifrac(tree.parent, tree.length, rp, col, val, False, ctx=gpu_ctx)
