@@ -269,7 +269,14 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
     const int64_t s = static_cast<int64_t>(w) * 32 + sl;
     if (s < n_samples) {
       const int64_t b = row_ptr[s], e = row_ptr[s + 1];
-      for (int64_t k = b + lane; k < e; k += 32) atomicOr(colw + col[k], 1u << sl);
+      for (int64_t k = b + lane; k < e; k += 128) {  // four loads in flight per lane
+        int32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = k + 32 * u < e ? col[k + 32 * u] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c[u] >= 0) atomicOr(colw + c[u], 1u << sl);
+      }
     }
   }
   __syncthreads();
@@ -289,15 +296,29 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
       const uint32_t x = colw[pn];
       if (x) atomicOr(colw + pp, x);
     }
-    for (int32_t idx = b + tid + 512; idx < e; idx += 512) {
-      const uint32_t x = colw[level_nodes[idx]];
-      if (x) atomicOr(colw + level_parent[idx], x);
+    // the wide levels near the leaves: four independent index loads in flight per thread (one load
+    // at a time made this loop the bulk of the kernel: ~40 dependent L2 round trips per thread)
+    for (int32_t idx = b + tid + 512; idx < e; idx += 2048) {
+      int32_t n[4], p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int32_t k = idx + u * 512;
+        n[u] = k < e ? level_nodes[k] : -1;
+        p[u] = k < e ? level_parent[k] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (n[u] >= 0) {
+          const uint32_t x = colw[n[u]];
+          if (x) atomicOr(colw + p[u], x);
+        }
     }
     __syncthreads();
     b = nb; e = ne; pn = qn; pp = qp;
   }
   // phase 3
   uint32_t* dst = bitsT + static_cast<int64_t>(w) * kp;
+#pragma unroll 4
   for (int32_t k = tid; k < kp; k += 512) {
     const int32_t v = order[k];
     dst[k] = v >= 0 ? colw[v] : 0u;
