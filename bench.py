@@ -40,6 +40,8 @@ CONFIGS = {
     "cfg3u": ("unweighted", 50_000, 20_000, 0.02, 1003, 2003),
     "cfg4": ("unweighted", 100_000, 100_000, 0.02, 1004, 2004),
     "cfg4s": ("unweighted", 100_000, 30_000, 0.02, 1004, 2004),
+    # 150 GB of u8 operands: more than one GPU holds -> the pair kernel expands its tiles from the bit rows
+    "cfg4x": ("unweighted", 100_000, 250_000, 0.02, 1004, 2004),
     "tiny": ("unweighted", 1_000, 512, 0.02, 1009, 2009),
 }
 

@@ -254,7 +254,8 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
                        int64_t n_samples, const int32_t* __restrict__ level_nodes,
                        const int32_t* __restrict__ level_parent, const int32_t* __restrict__ level_ptr,
                        int32_t height, int32_t n_nodes, int32_t kp, const int32_t* __restrict__ order,
-                       uint32_t* __restrict__ node_scratch, uint32_t* __restrict__ bitsT, int32_t w0) {
+                       uint32_t* __restrict__ node_scratch, uint32_t* __restrict__ bitsT, int32_t w0,
+                       uint32_t* __restrict__ bitsS) {
   extern __shared__ __align__(16) uint32_t smem_words[];
   __shared__ int32_t lptr[128];
   const int w = blockIdx.x + w0;
@@ -322,6 +323,29 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
   for (int32_t k = tid; k < kp; k += 512) {
     const int32_t v = order[k];
     dst[k] = v >= 0 ? colw[v] : 0u;
+  }
+  // phase 3b (bits-fed pair kernel): the same bits sample-major, bitsS[s][kp / 32] (bit k % 32 of word
+  // k / 32 = operand column k).  A warp transposes 128 columns x 32 samples with ballots; lane b then
+  // holds the four words of sample b and stores them as one 16-byte piece of its row.
+  if (bitsS != nullptr) {
+    const int32_t words = kp >> 5;
+    for (int32_t g = warp; g * 128 < kp; g += 16) {
+      uint32_t wout[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int32_t v = order[g * 128 + u * 32 + lane];
+        const uint32_t wv = v >= 0 ? colw[v] : 0u;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, (wv >> b) & 1u);
+          if (lane == b) mine = bal;
+        }
+        wout[u] = mine;
+      }
+      const int64_t srow = static_cast<int64_t>(w) * 32 + lane;
+      *reinterpret_cast<uint4*>(bitsS + srow * words + g * 4) = make_uint4(wout[0], wout[1], wout[2], wout[3]);
+    }
   }
 }
 
@@ -647,7 +671,7 @@ int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw) {
 
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t w0, int32_t w_count, int32_t kp, const int32_t* order,
-                                uint32_t* node_scratch, uint32_t* bitsT, cudaStream_t s) {
+                                uint32_t* node_scratch, uint32_t* bitsT, uint32_t* bitsS, cudaStream_t s) {
   (void)nw;
   const size_t smem = (static_cast<size_t>(t.n_nodes) * 4 + 15) & ~size_t(15);
   if (smem <= 200 * 1024) {
@@ -658,11 +682,11 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
     }
     k_embed_presence_fused<true><<<w_count, 512, smem, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
                                                             t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
-                                                            order, node_scratch, bitsT, w0);
+                                                            order, node_scratch, bitsT, w0, bitsS);
   } else {
     k_embed_presence_fused<false><<<w_count, 512, 0, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
                                                           t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
-                                                          order, node_scratch, bitsT, w0);
+                                                          order, node_scratch, bitsT, w0, bitsS);
   }
   return 1;
 }

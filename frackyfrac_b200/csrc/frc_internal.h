@@ -93,9 +93,10 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw);
 // qam / col_exp non-null (u8): integer row sums from q[k] = a*m and the per-column exponents.
 // Only the word columns [w0, w0 + w_count) (32 samples each) are built: the sample shard of this rank.
+// bitsS != null: also the sample-major form bitsS[np][kp / 32] that the bits-fed pair kernel reads.
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t w0, int32_t w_count, int32_t kp, const int32_t* order,
-                                uint32_t* node_scratch, uint32_t* bitsT, cudaStream_t s);
+                                uint32_t* node_scratch, uint32_t* bitsT, uint32_t* bitsS, cudaStream_t s);
 // r[s] for the same word columns from bitsT (qam / col_exp non-null: integer row sums of the u8 path).
 // Independent of the operand expansion, so the job runs the two on different streams.
 // r_int != null (u8 integer mode): INSTEAD of r, the exact integer row sums in units of 2^e_min.
@@ -178,5 +179,21 @@ int launch_unweighted_fixup(const TcOperands* ops, const uint32_t* flagged,
                             const unsigned long long* n_flagged, unsigned long long* count_host,
                             int64_t first, double* out, int num_sms, cudaStream_t s);
 bool tc_setup(std::string* err);  // smem attribute + driver entry points, once per process
+
+// ---- unweighted_bits.cu -----------------------------------------------------
+// The same pair tiles with the u8 operand tiles expanded inside the kernel from the bit rows
+// bitsS[np][kp / 32] (integer mode only): no operand arrays in HBM.
+struct BitsOperands;
+BitsOperands* bits_operands_create(const uint32_t* bitsS, int64_t np, int32_t kp, const uint8_t* qa,
+                                   const uint8_t* qh, const uint8_t* ql, const TcChunks& chunks,
+                                   const double* len_col, const double* flag_u, const long long* r_int,
+                                   double unit, std::string* err);
+void bits_operands_destroy(BitsOperands* o);
+int launch_unweighted_bits(const BitsOperands* ops, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
+                           int64_t first, double* out, uint32_t* flagged, unsigned long long* n_flagged,
+                           int num_sms, cudaStream_t s);
+int launch_unweighted_fixup_bits(const BitsOperands* ops, const uint32_t* flagged, const unsigned long long* n_flagged,
+                                 unsigned long long* count_host, int64_t first, double* out, int num_sms,
+                                 cudaStream_t s);
 
 }  // namespace frc

@@ -204,6 +204,9 @@ struct frc_job {
   int32_t *d_order = nullptr, *d_col_exp = nullptr;
   uint32_t* d_qam = nullptr;  // u8: a * m per operand column
   bool intacc = false;        // u8: chunk scales within 2^16 -> integer accumulation / integer row sums
+  bool bits_feed = false;     // operand tiles expanded inside the pair kernel from bit rows (no operands in HBM)
+  uint32_t* d_bitsS = nullptr;
+  BitsOperands* bo = nullptr;
   int32_t e_min = 0;          // smallest chunk exponent (integer unit = 2^e_min)
   long long* d_r_int = nullptr;
   long long* d_fix_ws = nullptr;  // fast weighted fix-up: one zeroed int64[B] per SM
@@ -369,7 +372,7 @@ int run_embedding(frc_job* j) {
   } else {
     if (j->fused_embed) {
       launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->shard_w0, j->shard_nw,
-                                              j->kp, j->d_order, j->d_node_scratch, j->d_bits, s);
+                                              j->kp, j->d_order, j->d_node_scratch, j->d_bits, j->d_bitsS, s);
       // the row sums (integer-ALU-bound) and the operand expansion (HBM-bound) both only read the bit
       // columns: they run side by side on the two compute streams unless an all-gather sits between
       cudaStream_t rs = j->sharded ? s : c->stream[1];
@@ -383,15 +386,18 @@ int run_embedding(frc_job* j) {
       if (j->sharded) {
         // the one exchange step of the path: presence bit columns + row sums of every rank's
         // sample shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
-        void* bufs[2] = {j->d_bits, j->intacc ? static_cast<void*>(j->d_r_int) : static_cast<void*>(j->d_r)};
+        // (bits-fed kernel: the sample-major bit rows are what is exchanged, same size)
+        void* bufs[2] = {j->bits_feed ? j->d_bitsS : j->d_bits,
+                         j->intacc ? static_cast<void*>(j->d_r_int) : static_cast<void*>(j->d_r)};
         const size_t bytes[2] = {static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t),
                                  static_cast<size_t>(j->shard_nw) * 32 * sizeof(double)};
         std::string cerr;
         if (!comm_all_gather_inplace(c->comm, bufs, bytes, 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
         j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
       }
-      launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
-                                           j->d_P, j->d_Bh, j->d_Bl, j->d_need, s);
+      if (!j->bits_feed)
+        launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
+                                             j->d_P, j->d_Bh, j->d_Bl, j->d_need, s);
       if (!j->sharded) {
         JOB_CUDA(j, cudaEventRecord(j->ev_rsum, rs));
         JOB_CUDA(j, cudaStreamWaitEvent(s, j->ev_rsum, 0));
@@ -443,11 +449,19 @@ int enqueue_band(frc_job* j, size_t idx) {
     // previous band's bulk D2H and stall this band (measured).  Counters are per band, zeroed once
     // per run; the fix-up kernel publishes the count through mapped pinned memory.
     unsigned long long* cnt = j->d_flag_counts + idx;
-    launches += launch_unweighted_tc(j->tc, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
-                                     b.first, sl.dev, kFlagBelow, sl.flagged, cnt, c->num_sms, j->tc_ctas, s);
-    JOB_CUDA(j, cudaEventRecord(sl.k1, s));
-    launches += launch_unweighted_fixup(j->tc, sl.flagged, cnt, sl.n_flagged_host, b.first, sl.dev,
-                                        c->num_sms, s);
+    if (j->bits_feed) {
+      launches += launch_unweighted_bits(j->bo, j->d_tiles + b.tile_off, b.n_tiles, j->N, b.first, sl.dev,
+                                         sl.flagged, cnt, c->num_sms, s);
+      JOB_CUDA(j, cudaEventRecord(sl.k1, s));
+      launches += launch_unweighted_fixup_bits(j->bo, sl.flagged, cnt, sl.n_flagged_host, b.first, sl.dev,
+                                               c->num_sms, s);
+    } else {
+      launches += launch_unweighted_tc(j->tc, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
+                                       b.first, sl.dev, kFlagBelow, sl.flagged, cnt, c->num_sms, j->tc_ctas, s);
+      JOB_CUDA(j, cudaEventRecord(sl.k1, s));
+      launches += launch_unweighted_fixup(j->tc, sl.flagged, cnt, sl.n_flagged_host, b.first, sl.dev,
+                                          c->num_sms, s);
+    }
   }
   JOB_CUDA(j, cudaGetLastError());
   if (j->exact) JOB_CUDA(j, cudaEventRecord(sl.k1, s));
@@ -514,6 +528,7 @@ void destroy_job(frc_job* j) {
   if (j->ev_bits) cudaEventDestroy(j->ev_bits);
   if (j->ev_rsum) cudaEventDestroy(j->ev_rsum);
   tc_operands_destroy(j->tc);
+  bits_operands_destroy(j->bo);
   if (j->ctx) {
     j->ctx->dev.reset();
     j->ctx->pin.reset();
@@ -834,6 +849,8 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
         j->intacc = hi - lo <= 16 && !(ev && strcmp(ev, "f64") == 0);
         j->e_min = lo;
         for (double sc : chunk_scale) chunk_shift.push_back(std::ilogb(sc) - lo);
+        const char* ef = getenv("FRC_UW_FEED");  // "bits": expand the operand tiles inside the pair kernel
+        j->bits_feed = j->intacc && (((opts->flags & FRC_FLAG_UW_BITS) != 0) || (ef && strcmp(ef, "bits") == 0));
       }
     } else {
       col_order.assign(j->kp, -1); len_col.assign(j->kp, 0.0);
@@ -842,7 +859,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       for (int32_t kb = 0; kb < nkb;) { kb = std::min(nkb, kb + per); chunk_end.push_back(kb); chunk_scale.push_back(1.0); }
     }
     j->info.n_nodes_padded = j->kp;
-    j->info.operand_kind = j->i8 ? 2 : 1;
+    j->info.operand_kind = j->i8 ? (j->bits_feed ? 3 : 2) : 1;
   }
   const std::vector<int64_t> brows = band_boundaries(N, opts->band_rows, world, !(opts->flags & FRC_FLAG_NO_D2H));
   for (size_t kb = 0; kb + 1 < brows.size(); ++kb) {
@@ -1127,10 +1144,22 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       const size_t ns = j->fused_embed ? static_cast<size_t>(presence_node_scratch_words(B, j->shard_nw)) : 0;
       if (ns && !(j->d_node_scratch = dev_alloc<uint32_t>(j, ns, &rc))) return bail(rc);
     }
-    const size_t opsz = static_cast<size_t>(j->np) * j->kp * (j->i8 ? 1 : 2);
+    if (j->intacc && !j->bits_feed) {
+      // capacity: when the three u8 operand arrays would not fit the free HBM (with room for the
+      // output ring), the pair kernel expands its tiles from the bit rows instead (8x less memory,
+      // about half the speed: DESIGN.md)
+      size_t free_b = 0, total_b = 0;
+      CREATE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      const double need = 3.0 * static_cast<double>(j->np) * j->kp;
+      if (need > 0.80 * static_cast<double>(free_b)) j->bits_feed = true;
+      j->info.operand_kind = j->bits_feed ? 3 : 2;
+    }
+    const size_t opsz = j->bits_feed ? 256 : static_cast<size_t>(j->np) * j->kp * (j->i8 ? 1 : 2);
     if (!(j->d_P = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
     if (!(j->d_Bh = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
     if (!(j->d_Bl = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
+    if (j->bits_feed && !(j->d_bitsS = dev_alloc<uint32_t>(j, static_cast<size_t>(j->np) * (j->kp / 32), &rc)))
+      return bail(rc);
     if (!(j->d_r = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
     if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
     if (!(j->d_flag_counts = dev_alloc<unsigned long long>(j, j->mine.size() + 1, &rc))) return bail(rc);
@@ -1140,10 +1169,17 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (j->intacc) {
       if (!(j->d_r_int = dev_alloc<long long>(j, j->np, &rc))) return bail(rc);
     }
-    j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, j->i8, j->d_chunks, j->d_len_col,
-                               j->d_flag_u, &terr);
-    if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
-    if (j->intacc) tc_operands_set_int(j->tc, j->d_r_int, std::ldexp(1.0, j->e_min));
+    if (!j->bits_feed) {
+      j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, j->i8, j->d_chunks, j->d_len_col,
+                                 j->d_flag_u, &terr);
+      if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
+    } else {
+      j->bo = bits_operands_create(j->d_bitsS, j->np, j->kp, static_cast<const uint8_t*>(j->d_q0),
+                                   static_cast<const uint8_t*>(j->d_q1), static_cast<const uint8_t*>(j->d_q2),
+                                   j->d_chunks, j->d_len_col, j->d_flag_u, j->d_r_int, std::ldexp(1.0, j->e_min), &terr);
+      if (!j->bo) return bail(fail(j, FRC_ERR_CUDA, terr));
+    }
+    if (j->intacc && j->tc) tc_operands_set_int(j->tc, j->d_r_int, std::ldexp(1.0, j->e_min));
     if (j->i8) {  // a function of the tree only: once per job, not per restart
       j->info.kernel_launches += launch_quantize_lengths(
           j->d_len_col, j->d_col_exp, j->kp, static_cast<uint8_t*>(j->d_q0), static_cast<uint8_t*>(j->d_q1),

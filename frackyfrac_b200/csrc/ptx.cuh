@@ -46,6 +46,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
 }
+// Same without release semantics: the data it announces stays in the announcing CTA's own shared
+// memory (already made visible to the async proxy by the writers' fence.proxy.async and ordered
+// before this thread by a CTA-scope barrier), only the count travels.  A release.cluster arrive costs
+// the issuing thread ~1 us; one per K block serialised the bits-fed pair kernel.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
 // shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `cta`.
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
   uint32_t r;
@@ -86,6 +97,20 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* map, u
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// 1D bulk copy global -> shared (size a multiple of 16), completion bytes on `bar` (own CTA).
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// Register reallocation between warp groups (all warps of a warpgroup execute it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ----------------------------------------------------------------- tcgen05
 template <int CG>

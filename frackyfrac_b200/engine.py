@@ -22,6 +22,7 @@ PATH_AUTO, PATH_FAST, PATH_EXACT = -1, 0, 1
 FLAG_NO_D2H = 1
 FLAG_UW_BF16 = 2
 FLAG_SHARD_EMBED = 4
+FLAG_UW_BITS = 8
 COMM_ID_BYTES = 128
 
 EXPORTS = ["frc_abi_version", "frc_ctx_create", "frc_ctx_destroy", "frc_create", "frc_next",

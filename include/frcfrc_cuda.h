@@ -91,6 +91,10 @@ typedef struct {
                                   same inputs (the call is collective).  Without the flag
                                   each rank rebuilds the whole embedding.              */
 
+#define FRC_FLAG_UW_BITS 8u /* fast unweighted, u8 integer mode: expand the operand tiles inside
+                              the pair kernel from the presence bits instead of materialising
+                              them in HBM (3 bytes per (sample, node) saved; info.operand_kind 3) */
+
 typedef struct {
   int32_t mode;       /* frc_mode                                               */
   int32_t normalize;  /* 1 = default; 0 = flag -l (frcfrc.go:25, unifrac.go:108) */
@@ -126,7 +130,7 @@ typedef struct {
   int64_t embed_bytes;     /* algorithmic HBM bytes of the embedding stage      */
   int64_t flagged_pairs;   /* fast unweighted: pairs recomputed exactly (d tiny) */
   int64_t operand_kind;    /* fast unweighted: 1 = bf16 hi/lo planes, 2 = u8 block floating
-                              point; 0 otherwise                                    */
+                              point, 3 = u8 expanded in-kernel from bits; 0 otherwise */
   int64_t gather_bytes;    /* bytes this rank received in the embedding all-gather  */
 } frc_info_t;
 

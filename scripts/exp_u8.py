@@ -31,5 +31,6 @@ def run(label, env, flags=0):
         os.environ.pop(k, None)
 
 run("bf16", {}, engine.FLAG_UW_BF16)
+run("u8 bits-fed (in-kernel expand)", {}, engine.FLAG_UW_BITS)
 for gb in (1, 2, 3, 4, 6, 8, 16):
     run(f"u8 group_binades={gb}", {"FRC_U8_GROUP_BINADES": str(gb)})
