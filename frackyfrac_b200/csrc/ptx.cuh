@@ -74,6 +74,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       ::"r"(bar), "r"(parity) : "memory");
 }
 
+// Same, sleeping between polls: for warps that wait long (a whole accumulation chunk) next to warps
+// that need the issue slots (the producers of the bits-fed pair kernel).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
+
 // --------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

@@ -60,6 +60,13 @@ __device__ __forceinline__ uint32_t mask4(uint32_t nib) {
   return m;
 }
 
+#ifdef FRC_TC_TIMELINE
+__device__ unsigned long long g_bits_dbg[512 * 8];
+#define TL(x) x
+#else
+#define TL(x)
+#endif
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* __restrict__ qa,
                    const uint8_t* __restrict__ qh, const uint8_t* __restrict__ ql,
@@ -67,8 +74,7 @@ k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* _
                    int32_t n_chunks, const long long* __restrict__ r_int, double unit,
                    const Tile* __restrict__ tiles, int32_t n_tiles, int64_t n_samples, int64_t first,
                    double* __restrict__ out, const double* __restrict__ flag_u_ptr,
-                   uint32_t* __restrict__ flagged, unsigned long long* __restrict__ n_flagged, int dbg) {
-  // dbg (FRC_BITS_DEBUG, timing experiments; wrong results): 1 = no proxy fence, 2 = no mask arithmetic
+                   uint32_t* __restrict__ flagged, unsigned long long* __restrict__ n_flagged) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -132,7 +138,9 @@ k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* _
         const Tile tile = tiles[t];
         const int row_a = (tile.tj + static_cast<int>(cta)) * BM, row_b = tile.ti * BN;
         for (int kb = 0; kb < n_kblocks; ++kb) {
+          TL(const long long c0 = clock64();)
           ptx::mbar_wait(bempty_bar(stage), phase ^ 1u);
+          TL(g_bits_dbg[blockIdx.x * 8 + 0] += clock64() - c0;)
           const uint32_t sb = bits_base + stage * BSTAGE_BYTES;
           ptx::mbar_expect_tx(bfull_bar(stage), BSTAGE_BYTES);
           ptx::tma_load_2d(sb, &mapBits, bfull_bar(stage), kb * 16, row_a);
@@ -156,12 +164,16 @@ k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* _
         int kb = 0;
         for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
           const uint32_t buf = chunk & 1u;
+          TL(const long long c0 = clock64();)
           ptx::mbar_wait(tempty_bar(buf), ((chunk >> 1) & 1u) ^ 1u);
+          TL(g_bits_dbg[blockIdx.x * 8 + 1] += clock64() - c0;)
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * DN;
           const int kb_begin = kb, kb_end = chunk_end[ch];
           for (; kb < kb_end; ++kb) {
+            TL(const long long c1 = clock64();)
             ptx::mbar_wait(ofull_bar(stage), phase);
+            TL(g_bits_dbg[blockIdx.x * 8 + 2] += clock64() - c1;)
             ptx::tc_fence_after();
             const uint32_t sa = smem_base + stage * OSTAGE_BYTES;
             const uint64_t da = ptx::umma_desc_k_sw128(sa);
@@ -204,8 +216,11 @@ k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* _
     uint32_t ophase = 0, bphase = 0;
     for (int t = pair; t < n_tiles; t += n_pairs) {
       for (int kb = 0; kb < n_kblocks; ++kb) {
+        TL(const long long c0 = clock64();)
         ptx::mbar_wait(bfull_bar(bstage), bphase);
+        TL(const long long c1 = clock64();)
         ptx::mbar_wait(oempty_bar(ostage), ophase ^ 1u);
+        TL(const long long c2 = clock64();)
         const uint8_t* sb = smem + OSTAGES * OSTAGE_BYTES + bstage * BSTAGE_BYTES;
         uint8_t* so = smem + ostage * OSTAGE_BYTES;
         const uint4 qA = *reinterpret_cast<const uint4*>(sb + 2 * BITS_TILE + c * 16);
@@ -221,24 +236,25 @@ k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* _
             const uint32_t b16 = *reinterpret_cast<const uint16_t*>(bits + r * 16 + c * 2);
             const uint32_t lo8 = b16 & 0xFFu, hi8 = b16 >> 8;
             uint4 v;
-            if (dbg & 2) {
-              v = q; v.x ^= b16;
-            } else {
-              v.x = q.x & mask4(lo8 & 0xFu);
-              v.y = q.y & mask4(lo8 >> 4);
-              v.z = q.z & mask4(hi8 & 0xFu);
-              v.w = q.w & mask4(hi8 >> 4);
-            }
+            v.x = q.x & mask4(lo8 & 0xFu);
+            v.y = q.y & mask4(lo8 >> 4);
+            v.z = q.z & mask4(hi8 & 0xFu);
+            v.w = q.w & mask4(hi8 >> 4);
             // SWIZZLE_128B K-major: row r at (r / 8) * 1024 + (r % 8) * 128, 16-byte chunk c at c ^ (r % 8)
             *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
           }
         }
-        if (!(dbg & 1)) ptx::fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+        ptx::fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
         __syncwarp();
         if (lane == 0) {
           ptx::mbar_arrive(cta == 0 ? ofull_bar(ostage) : pfull_bar(ostage));
           ptx::mbar_arrive(bempty_bar(bstage));
         }
+        TL(if (pt == 0) {
+          g_bits_dbg[blockIdx.x * 8 + 3] += c1 - c0;             // waiting for bits
+          g_bits_dbg[blockIdx.x * 8 + 4] += c2 - c1;             // waiting for a free operand stage
+          g_bits_dbg[blockIdx.x * 8 + 5] += clock64() - c2;      // expanding + fence + arrive
+        })
         if (++ostage == OSTAGES) { ostage = 0; ophase ^= 1u; }
         if (++bstage == BSTAGES) { bstage = 0; bphase ^= 1u; }
       }
@@ -371,6 +387,19 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 }  // namespace
+}  // namespace frc
+extern "C" int frc_debug_bits_counters(unsigned long long* out, int n, int clear) {
+#ifdef FRC_TC_TIMELINE
+  if (n > 512 * 8) n = 512 * 8;
+  int rc = static_cast<int>(cudaMemcpyFromSymbol(out, frc::g_bits_dbg, sizeof(unsigned long long) * n));
+  if (clear) { static unsigned long long z[512 * 8] = {0}; cudaMemcpyToSymbol(frc::g_bits_dbg, z, sizeof(z)); }
+  return rc;
+#else
+  (void)out; (void)n; (void)clear;
+  return -1;
+#endif
+}
+namespace frc {
 
 struct BitsOperands {
   CUtensorMap mapBits;
@@ -431,10 +460,9 @@ int launch_unweighted_bits(const BitsOperands* ops, const Tile* tiles, int32_t n
   const int pairs = num_sms / 2;
   const int grid = 2 * (n_tiles < pairs ? n_tiles : pairs);
   const TcChunks& c = ops->chunks;
-  const char* de = getenv("FRC_BITS_DEBUG");
   k_unweighted_bits2<<<grid, THREADS, SMEM_BYTES, s>>>(ops->mapBits, ops->qa, ops->qh, ops->ql, c.end, c.shift, c.n,
                                                        ops->r_int, ops->unit, tiles, n_tiles, n_samples, first, out,
-                                                       ops->flag_u, flagged, n_flagged, de ? atoi(de) : 0);
+                                                       ops->flag_u, flagged, n_flagged);
   return 1;
 }
 
