@@ -40,6 +40,7 @@ CONFIGS = {
     "cfg3u": ("unweighted", 50_000, 20_000, 0.02, 1003, 2003),
     "cfg4": ("unweighted", 100_000, 100_000, 0.02, 1004, 2004),
     "cfg4s": ("unweighted", 100_000, 30_000, 0.02, 1004, 2004),
+    "cfg4w": ("weighted", 100_000, 100_000, 0.02, 1004, 2004),
     # 150 GB of u8 operands: more than one GPU holds -> the pair kernel expands its tiles from the bit rows
     "cfg4x": ("unweighted", 100_000, 250_000, 0.02, 1004, 2004),
     "tiny": ("unweighted", 1_000, 512, 0.02, 1009, 2009),
@@ -356,7 +357,7 @@ def run_ours(args, world, rank, local_rank):
                         ("bf16 x bf16 -> f32 (tcgen05 kind::f16), f64 row sums/epilogue/output" if info.operand_kind == 1 else
                          "u8 x u8 -> s32 (tcgen05 kind::i8, exact), f64 chunk scaling/row sums/epilogue/output"),
                "data": "synthetic",
-               "config": workload_config(args.config, mode, leaves, samples, density, world, shard and not weighted),
+               "config": workload_config(args.config, mode, leaves, samples, density, world, shard),
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                "roofline": roofline, "cpu_baseline": cpu,
                "stages_ms": {"h2d": ei.h2d_ms, "embed": info.embed_ms, "pairs_kernels_sum": info.pairs_ms,

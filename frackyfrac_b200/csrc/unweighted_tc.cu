@@ -8,16 +8,23 @@
 //     unique(i,j) = r_i + r_j - 2 shared           (the reference's `result`)
 //     d(i,j)      = unique / (unique + shared) = (R - 2s) / (R - s),  R = r_i + r_j
 // so the pairwise part is the dense contraction S = P diag(len) P^T: a GEMM.
-// P is exact in bf16; len is split len ~= hi + lo (two bf16 planes, relative
-// error <= 2^-18), the products P*hi and P*lo are exact in the fp32 accumulator,
-// and r is computed in fp64 from the SAME quantised lengths so that the
-// subtraction R - 2s cancels consistently.  Pairs whose distance comes out
-// small (where the subtraction loses relative accuracy) are flagged and
-// recomputed in fp64 from the presence rows by k_unweighted_fixup.
 //
-// Kernel structure (one CTA per SM, persistent over a tile list):
-//   warp 0     TMA producer: per 64-node block loads A = P[i-tile] and, stacked
-//              right behind each other, Bh = (P*hi)[j-tile] and Bl = (P*lo)[j-tile]
+// Kernels in this file ("Pair stage, unweighted"):
+//   k_unweighted_tc2<2>  default.  CTA pairs (cta_group::2), u8 block-floating-point operands
+//                        (len ~= a * m * 2^e), tcgen05 kind::i8 M256 x N256 x K32, exact int32
+//                        accumulation in TMEM, 64-bit integer chunk accumulation and an integer / fp32
+//                        ratio epilogue (no fp64 instruction).
+//   k_unweighted_tc2<1>  the same operands with fp64 chunk accumulation, for trees whose chunk
+//                        scales span more than 2^16.
+//   k_unweighted_tc2<0>  bf16 operands (P exact, len = hi + lo planes), kind::f16 K16, fp32
+//                        accumulators restarted every K-chunk (FRC_FLAG_UW_BF16; negative lengths).
+//   k_unweighted_tc      the first kernel of the round: one CTA per tile, bf16, M128 x N256
+//                        (FRC_TC_CTAS=1; kept as a cross-check), described below.
+//   k_unweighted_fixup   exact fp64 recompute of the pairs the epilogues flag.
+//
+// Single-CTA bf16 kernel (one CTA per SM, persistent over a tile list):
+//   warp 0     TMA producer: per 64-node block loads A = P[j-tile] and, stacked
+//              right behind each other, Bh = (P*hi)[i-tile] and Bl = (P*lo)[i-tile]
 //              (128-byte swizzle) into a 4-stage ring, mbarrier complete_tx.
 //   warp 1     allocates TMEM and issues tcgen05.mma M128 N256 K16 (bf16 -> fp32):
 //              the stacked [Bh; Bl] is ONE 256-row B operand, so A is read from
@@ -27,14 +34,16 @@
 //              the accumulator buffer.
 //   warps 2-9  epilogue (8 warps = 4 TMEM lane quarters x 2 column halves):
 //              tcgen05.ld the partial sums of each K-chunk and add them into fp32
-//              registers, then the fused ratio epilogue in fp64 and direct stores
-//              into the flat lower-triangle band buffer.
-// Why two accumulator halves and K-chunks: the tensor core's fp32 accumulate
+//              registers, then the fused ratio epilogue in fp64 and stores into the
+//              flat lower-triangle band buffer (TMEM lane = column sample: coalesced).
+// bf16: why two accumulator halves and K-chunks: the tensor core's fp32 accumulate
 // loses the addend bits below the accumulator's ulp (measured: a bias, not
 // noise).  hi-plane addends are 8-bit significands, so they add EXACTLY while the
 // running sum stays within 2^16 of them; keeping the 2^-9-smaller lo plane out of
 // that sum and restarting it every K-chunk keeps it so.  The chunk sums are then
-// added in registers with round-to-nearest.
+// added in registers with round-to-nearest.  r is computed in fp64 from the SAME
+// quantised lengths so that R - 2s cancels consistently, and pairs with a small
+// distance (where the subtraction loses relative accuracy) go to k_unweighted_fixup.
 // Two TMEM buffers (2 x 256 columns = all of TMEM) let the MMAs of chunk c+1
 // overlap the drain of chunk c, and the next tile's mainloop this tile's epilogue.
 #include <cuda.h>
