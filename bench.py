@@ -355,7 +355,7 @@ def run_ours(args, world, rank, local_rank):
                "higher_is_better": True, "scaling": "strong" if args.fixed_size else "weak", "vs_baseline": None,
                "dtype": "f32 numerator tiles, f64 embedding/denominators/output" if weighted else
                         ("bf16 x bf16 -> f32 (tcgen05 kind::f16), f64 row sums/epilogue/output" if info.operand_kind == 1 else
-                         "u8 x u8 -> s32 (tcgen05 kind::i8, exact), f64 chunk scaling/row sums/epilogue/output"),
+                         "u8 x u8 -> s32 (tcgen05 kind::i8, exact), s64 chunk / row sums, f32 ratio, f64 output"),
                "data": "synthetic",
                "config": workload_config(args.config, mode, leaves, samples, density, world, shard),
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
