@@ -161,3 +161,28 @@ def test_parallel_table_parser_matches_single_thread_and_oracle(built):
     with pytest.raises(hostlib.HostError) as ei:
         hostlib.Table("a b c\n1 x 2\n", False, 1)
     assert "value #2" in str(ei.value) and "invalid syntax" in str(ei.value)
+
+
+def test_float_token_forms_match_the_oracle_parser(built):
+    """strconv.ParseFloat forms the fast path (std::from_chars) does not take itself: sign, hex floats,
+    inf / nan spellings, underscores, out-of-range exponents.  Accept / reject must equal the oracle's."""
+    from frackyfrac_b200 import hostlib
+    from oracle import oracle as orc
+
+    tokens = ["7", "0", "+5", "-0", ".5", "5.", "1e3", "1E-3", "0x1p-2", "1_000", "1e999", "1e-999", "inf", "Inf",
+              "+Infinity", "nan", "NaN", "-1", "abc", "1.5e", "--1", "0x", "1e+400", "4.9e-324", "1.7976931348623157e308"]
+    for tok in tokens:
+        outcomes = []
+        for parse in (lambda t: hostlib.Table(t, True, 1).maps(), lambda t: orc.Table.parse(t, True).maps()):
+            try:
+                outcomes.append(parse(f"a:{tok}\n"))
+            except Exception:
+                outcomes.append("error")
+        assert outcomes[0] == outcomes[1], (tok, outcomes)
+        outcomes = []
+        for parse in (lambda t: hostlib.Table(t, False, 1).maps(), lambda t: orc.Table.parse(t, False).maps()):
+            try:
+                outcomes.append(parse(f"a b\n1 {tok}\n"))
+            except Exception:
+                outcomes.append("error")
+        assert outcomes[0] == outcomes[1], (tok, outcomes)
