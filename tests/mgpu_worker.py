@@ -27,7 +27,7 @@ def main():
     rp, col, val = synth.random_table(tree, 1100, 0.03, 302)
     n = 1100
     ok = True
-    for weighted, uw_flags in ((False, 0), (False, engine.FLAG_UW_BF16), (True, 0)):
+    for weighted, uw_flags in ((False, 0), (False, engine.FLAG_UW_BF16), (False, engine.FLAG_UW_BITS), (True, 0)):
         chunks = []
         with engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
                         rank=rank, world=world, band_rows=128, flags=uw_flags | engine.FLAG_SHARD_EMBED) as job:
