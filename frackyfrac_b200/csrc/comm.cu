@@ -23,6 +23,7 @@ typedef void* NcclComm;
 typedef int (*fn_get_id)(NcclId*);
 typedef int (*fn_init_rank)(NcclComm*, int, NcclId, int);
 typedef int (*fn_all_gather)(const void*, void*, size_t, int, NcclComm, cudaStream_t);
+typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
 typedef int (*fn_destroy)(NcclComm);
 typedef int (*fn_group)(void);
 typedef const char* (*fn_errstr)(int);
@@ -32,6 +33,7 @@ struct Api {
   fn_get_id get_id = nullptr;
   fn_init_rank init_rank = nullptr;
   fn_all_gather all_gather = nullptr;
+  fn_all_reduce all_reduce = nullptr;
   fn_destroy destroy = nullptr;
   fn_group group_start = nullptr, group_end = nullptr;
   fn_errstr errstr = nullptr;
@@ -52,11 +54,12 @@ Api& api() {
     a.get_id = reinterpret_cast<fn_get_id>(dlsym(a.handle, "ncclGetUniqueId"));
     a.init_rank = reinterpret_cast<fn_init_rank>(dlsym(a.handle, "ncclCommInitRank"));
     a.all_gather = reinterpret_cast<fn_all_gather>(dlsym(a.handle, "ncclAllGather"));
+    a.all_reduce = reinterpret_cast<fn_all_reduce>(dlsym(a.handle, "ncclAllReduce"));
     a.destroy = reinterpret_cast<fn_destroy>(dlsym(a.handle, "ncclCommDestroy"));
     a.group_start = reinterpret_cast<fn_group>(dlsym(a.handle, "ncclGroupStart"));
     a.group_end = reinterpret_cast<fn_group>(dlsym(a.handle, "ncclGroupEnd"));
     a.errstr = reinterpret_cast<fn_errstr>(dlsym(a.handle, "ncclGetErrorString"));
-    if (!a.get_id || !a.init_rank || !a.all_gather || !a.destroy || !a.group_start || !a.group_end)
+    if (!a.get_id || !a.init_rank || !a.all_gather || !a.all_reduce || !a.destroy || !a.group_start || !a.group_end)
       a.error = "libnccl lacks a required symbol";
   });
   return a;
@@ -74,7 +77,9 @@ constexpr int kNcclUint8 = 1;
 struct Comm {
   NcclComm comm = nullptr;
   int rank = 0, world = 1;
+  char* scratch = nullptr;  // device: small host<->host exchanges and the barrier
 };
+constexpr size_t kScratchBytes = 64 * 1024;
 
 bool comm_unique_id(char* id128, std::string* err) {
   Api& a = api();
@@ -95,12 +100,20 @@ Comm* comm_create(const char* id128, int rank, int world, std::string* err) {
   c->rank = rank; c->world = world;
   int rc = a.init_rank(&c->comm, world, id, rank);
   if (rc) { *err = nccl_error("ncclCommInitRank", rc); delete c; return nullptr; }
+  if (cudaMalloc(reinterpret_cast<void**>(&c->scratch), kScratchBytes) != cudaSuccess) {
+    cudaGetLastError();
+    *err = "cudaMalloc of the communicator scratch failed";
+    a.destroy(c->comm);
+    delete c;
+    return nullptr;
+  }
   return c;
 }
 
 void comm_destroy(Comm* c) {
   if (!c) return;
   if (c->comm) api().destroy(c->comm);
+  if (c->scratch) cudaFree(c->scratch);
   delete c;
 }
 
@@ -118,6 +131,31 @@ bool comm_all_gather_inplace(Comm* c, void* const* bufs, const size_t* bytes_per
   }
   int rc2 = a.group_end();
   if (rc || rc2) { *err = nccl_error("ncclAllGather", rc ? rc : rc2); return false; }
+  return true;
+}
+
+// Host-side all-gather of a few bytes per rank (IPC handles): through the device scratch, blocking.
+bool comm_all_gather_host(Comm* c, const void* mine, size_t bytes, void* all, cudaStream_t s, std::string* err) {
+  Api& a = api();
+  if (bytes * c->world > kScratchBytes) { *err = "comm_all_gather_host: message too large"; return false; }
+  if (cudaMemcpyAsync(c->scratch + static_cast<size_t>(c->rank) * bytes, mine, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+    *err = "comm_all_gather_host: H2D failed"; cudaGetLastError(); return false;
+  }
+  int rc = a.all_gather(c->scratch + static_cast<size_t>(c->rank) * bytes, c->scratch, bytes, kNcclUint8, c->comm, s);
+  if (rc) { *err = nccl_error("ncclAllGather", rc); return false; }
+  if (cudaMemcpyAsync(all, c->scratch, bytes * c->world, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess) {
+    *err = "comm_all_gather_host: D2H failed"; cudaGetLastError(); return false;
+  }
+  return true;
+}
+
+// Stream-ordered barrier over the ranks (a 4-byte all-reduce).
+bool comm_barrier(Comm* c, cudaStream_t s, std::string* err) {
+  Api& a = api();
+  constexpr int kNcclInt32 = 2, kNcclSum = 0;
+  int rc = a.all_reduce(c->scratch + kScratchBytes - 256, c->scratch + kScratchBytes - 128, 1, kNcclInt32, kNcclSum, c->comm, s);
+  if (rc) { *err = nccl_error("ncclAllReduce", rc); return false; }
   return true;
 }
 

@@ -255,7 +255,7 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
                        const int32_t* __restrict__ level_parent, const int32_t* __restrict__ level_ptr,
                        int32_t height, int32_t n_nodes, int32_t kp, const int32_t* __restrict__ order,
                        uint32_t* __restrict__ node_scratch, uint32_t* __restrict__ bitsT, int32_t w0,
-                       uint32_t* __restrict__ bitsS) {
+                       uint32_t* __restrict__ bitsS, const PeerPtrs peers) {
   extern __shared__ __align__(16) uint32_t smem_words[];
   __shared__ int32_t lptr[128];
   const int w = blockIdx.x + w0;
@@ -319,10 +319,24 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
   }
   // phase 3
   uint32_t* dst = bitsT + static_cast<int64_t>(w) * kp;
+  if (peers.n > 0) {
+    // fused all-gather: this CTA's column goes to the same place in every rank's bitsT, the remote
+    // ones as plain stores over NVLink (visible to the peers once this kernel has completed; the
+    // ranks meet at the small NCCL all-gather of the row sums before anyone reads bitsT)
+    const int64_t at = static_cast<int64_t>(w) * kp;
+    for (int32_t k = tid; k < kp; k += 512) {
+      const int32_t v = order[k];
+      const uint32_t x = v >= 0 ? colw[v] : 0u;
+#pragma unroll
+      for (int pr = 0; pr < 8; ++pr)
+        if (pr < peers.n) peers.p[pr][at + k] = x;
+    }
+  } else {
 #pragma unroll 4
-  for (int32_t k = tid; k < kp; k += 512) {
-    const int32_t v = order[k];
-    dst[k] = v >= 0 ? colw[v] : 0u;
+    for (int32_t k = tid; k < kp; k += 512) {
+      const int32_t v = order[k];
+      dst[k] = v >= 0 ? colw[v] : 0u;
+    }
   }
   // phase 3b (bits-fed pair kernel): the same bits sample-major, bitsS[s][kp / 32] (bit k % 32 of word
   // k / 32 = operand column k).  A warp transposes 128 columns x 32 samples with ballots; lane b then
@@ -671,7 +685,8 @@ int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw) {
 
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t w0, int32_t w_count, int32_t kp, const int32_t* order,
-                                uint32_t* node_scratch, uint32_t* bitsT, uint32_t* bitsS, cudaStream_t s) {
+                                uint32_t* node_scratch, uint32_t* bitsT, uint32_t* bitsS, const PeerPtrs& peers,
+                                cudaStream_t s) {
   (void)nw;
   const size_t smem = (static_cast<size_t>(t.n_nodes) * 4 + 15) & ~size_t(15);
   if (smem <= 200 * 1024) {
@@ -682,11 +697,11 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
     }
     k_embed_presence_fused<true><<<w_count, 512, smem, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
                                                             t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
-                                                            order, node_scratch, bitsT, w0, bitsS);
+                                                            order, node_scratch, bitsT, w0, bitsS, peers);
   } else {
     k_embed_presence_fused<false><<<w_count, 512, 0, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
                                                           t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
-                                                          order, node_scratch, bitsT, w0, bitsS);
+                                                          order, node_scratch, bitsT, w0, bitsS, peers);
   }
   return 1;
 }

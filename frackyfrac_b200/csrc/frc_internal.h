@@ -34,6 +34,13 @@ struct DevCsr {
   const double* val = nullptr;  // may be null for the presence-only path
 };
 
+// The same buffer in every rank's HBM (CUDA IPC mappings over NVLink); p[self] is the local one.
+struct PeerPtrs {
+  uint32_t* p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n = 0;     // ranks (0: no peers, local stores only)
+  int self = 0;
+};
+
 // One tile of the lower triangle: rows [128*ti, +128) x cols [128*tj, +128), tj <= ti.
 struct Tile { int32_t ti, tj; };
 
@@ -94,9 +101,12 @@ int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw);
 // qam / col_exp non-null (u8): integer row sums from q[k] = a*m and the per-column exponents.
 // Only the word columns [w0, w0 + w_count) (32 samples each) are built: the sample shard of this rank.
 // bitsS != null: also the sample-major form bitsS[np][kp / 32] that the bits-fed pair kernel reads.
+// peers.n > 0: the kernel stores its bit columns into bitsT of EVERY rank (peer memory over NVLink): the
+// all-gather of the sharded embedding is fused into the kernel that produces it.
 int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, const DevCsr& a,
                                 int32_t nw, int32_t w0, int32_t w_count, int32_t kp, const int32_t* order,
-                                uint32_t* node_scratch, uint32_t* bitsT, uint32_t* bitsS, cudaStream_t s);
+                                uint32_t* node_scratch, uint32_t* bitsT, uint32_t* bitsS, const PeerPtrs& peers,
+                                cudaStream_t s);
 // r[s] for the same word columns from bitsT (qam / col_exp non-null: integer row sums of the u8 path).
 // Independent of the operand expansion, so the job runs the two on different streams.
 // r_int != null (u8 integer mode): INSTEAD of r, the exact integer row sums in units of 2^e_min.
@@ -128,6 +138,9 @@ int comm_world(const Comm* c);
 // issued as one NCCL group on stream s.
 bool comm_all_gather_inplace(Comm* c, void* const* bufs, const size_t* bytes_per_rank, int n, cudaStream_t s,
                              std::string* err);
+
+bool comm_all_gather_host(Comm* c, const void* mine, size_t bytes, void* all, cudaStream_t s, std::string* err);
+bool comm_barrier(Comm* c, cudaStream_t s, std::string* err);
 
 // ---- exact.cu ---------------------------------------------------------------
 // fp64 reference-order distances for pairs [first, first+count) of the triangle.

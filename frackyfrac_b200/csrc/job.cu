@@ -155,6 +155,10 @@ struct frc_ctx {
   int64_t stamp_epoch = 0;
   bool in_use = false;
   Comm* comm = nullptr;  // NCCL communicator over the ranks of a multi-GPU run (frc_ctx_comm_init)
+  // "symmetric heap": buffers every rank allocates identically, so block index + offset name the same
+  // buffer on every rank; each block is mapped from the peers with CUDA IPC (peer stores over NVLink)
+  Arena sym;
+  std::vector<std::vector<char*>> sym_peer;  // [block][rank] mapped base (own rank: the local base)
 };
 
 struct Band { int64_t row0, row1, first, count; int32_t tile_off, n_tiles; };
@@ -195,6 +199,10 @@ struct frc_job {
   bool fused_embed = true;
   bool zero_copy = false;
   int64_t ws_slab = 0;        // fast weighted: samples per fp64 embedding slab
+  bool peer_push = false;     // sharded unweighted: the bits kernel stores into every rank's bitsT (no NCCL for the bits)
+  uint32_t* d_bits2[2] = {nullptr, nullptr};  // double-buffered by run parity (a rank may be one step ahead)
+  PeerPtrs peers[2];
+  int64_t run_count = 0;
   bool sharded = false;       // embedding built for this rank's sample shard, then all-gathered
   int32_t shard_w0 = 0, shard_nw = 0;  // word columns (32 samples) of the shard
   int tc_ctas = 1;  // CTAs per tensor-core tile group (2 = cta_group::2 pairs)
@@ -327,6 +335,31 @@ T* pin_alloc(frc_job* j, size_t n, int* rc) {
   return static_cast<T*>(p);
 }
 
+// Maps the blocks of the symmetric heap that the peers have not seen yet (collective: every rank
+// allocates the same sequence, so every rank gains the same blocks at the same time).
+int sym_sync(frc_job* j) {
+  frc_ctx* c = j->ctx;
+  const int world = comm_world(c->comm), rank = comm_rank(c->comm);
+  while (c->sym_peer.size() < c->sym.blocks.size()) {
+    const size_t b = c->sym_peer.size();
+    cudaIpcMemHandle_t mine;
+    JOB_CUDA(j, cudaIpcGetMemHandle(&mine, c->sym.blocks[b].p));
+    std::vector<cudaIpcMemHandle_t> all(world);
+    std::string cerr;
+    if (!comm_all_gather_host(c->comm, &mine, sizeof(mine), all.data(), c->stream[0], &cerr))
+      return fail(j, FRC_ERR_CUDA, cerr);
+    std::vector<char*> bases(world, nullptr);
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) { bases[r] = c->sym.blocks[b].p; continue; }
+      void* p = nullptr;
+      JOB_CUDA(j, cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+      bases[r] = static_cast<char*>(p);
+    }
+    c->sym_peer.push_back(bases);
+  }
+  return FRC_OK;
+}
+
 // Queue the embedding stage on stream 0.
 int run_embedding(frc_job* j) {
   frc_ctx* c = j->ctx;
@@ -371,8 +404,19 @@ int run_embedding(frc_job* j) {
     j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
   } else {
     if (j->fused_embed) {
+      const int cur = static_cast<int>(j->run_count & 1);
+      if (j->peer_push) {
+        j->d_bits = j->d_bits2[cur];
+        if (j->run_count == 0) {  // nobody may still be reading these buffers for an earlier job
+          std::string cerr;
+          if (!comm_barrier(c->comm, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
+        }
+      }
+      ++j->run_count;
+      static const PeerPtrs no_peers;
       launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->shard_w0, j->shard_nw,
-                                              j->kp, j->d_order, j->d_node_scratch, j->d_bits, j->d_bitsS, s);
+                                              j->kp, j->d_order, j->d_node_scratch, j->d_bits, j->d_bitsS,
+                                              j->peer_push ? j->peers[cur] : no_peers, s);
       // the row sums (integer-ALU-bound) and the operand expansion (HBM-bound) both only read the bit
       // columns: they run side by side on the two compute streams unless an all-gather sits between
       cudaStream_t rs = j->sharded ? s : c->stream[1];
@@ -387,12 +431,14 @@ int run_embedding(frc_job* j) {
         // the one exchange step of the path: presence bit columns + row sums of every rank's
         // sample shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
         // (bits-fed kernel: the sample-major bit rows are what is exchanged, same size)
-        void* bufs[2] = {j->bits_feed ? j->d_bitsS : j->d_bits,
-                         j->intacc ? static_cast<void*>(j->d_r_int) : static_cast<void*>(j->d_r)};
-        const size_t bytes[2] = {static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t),
-                                 static_cast<size_t>(j->shard_nw) * 32 * sizeof(double)};
+        void* bufs[2] = {j->intacc ? static_cast<void*>(j->d_r_int) : static_cast<void*>(j->d_r),
+                         j->bits_feed ? j->d_bitsS : j->d_bits};
+        const size_t bytes[2] = {static_cast<size_t>(j->shard_nw) * 32 * sizeof(double),
+                                 static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t)};
+        // peer_push: the bit columns already sit in every rank's bitsT (stored there by the embedding
+        // kernel itself); the small all-gather of the row sums is also the point where the ranks meet
         std::string cerr;
-        if (!comm_all_gather_inplace(c->comm, bufs, bytes, 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
+        if (!comm_all_gather_inplace(c->comm, bufs, bytes, j->peer_push ? 1 : 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
         j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
       }
       if (!j->bits_feed)
@@ -532,6 +578,7 @@ void destroy_job(frc_job* j) {
   if (j->ctx) {
     j->ctx->dev.reset();
     j->ctx->pin.reset();
+    j->ctx->sym.reset();
     j->ctx->in_use = false;
     if (j->own_ctx) frc_ctx_destroy(j->ctx);
   }
@@ -576,6 +623,7 @@ int frc_ctx_create(int32_t device, frc_ctx_t** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->dev.pinned = false; c->dev.min_block = 64u << 20;
+  c->sym.pinned = false; c->sym.min_block = 32u << 20;
   c->pin.pinned = true;  c->pin.min_block = 8u << 20;
   {
     int hw = static_cast<int>(std::thread::hardware_concurrency());
@@ -607,6 +655,11 @@ void frc_ctx_destroy(frc_ctx_t* c) {
   cudaSetDevice(c->device);
   c->pool.reset();
   for (auto s : c->stream) if (s) cudaStreamSynchronize(s);
+  for (size_t b = 0; b < c->sym_peer.size(); ++b)
+    for (size_t r = 0; r < c->sym_peer[b].size(); ++r)
+      if (c->sym_peer[b][r] && c->sym_peer[b][r] != c->sym.blocks[b].p) cudaIpcCloseMemHandle(c->sym_peer[b][r]);
+  c->sym_peer.clear();
+  c->sym.release();
   comm_destroy(c->comm);
   c->comm = nullptr;
   for (auto s : c->stream) if (s) cudaStreamDestroy(s);
@@ -1140,7 +1193,29 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       // fused: published columns bitsT[nw][kp] (+ node-indexed scratch for trees beyond shared memory);
       // FRC_EMBED_LEVELS=1: node-major bits[B][nw], one launch per tree level
       size_t words = j->fused_embed ? static_cast<size_t>(j->kp) * j->nw : static_cast<size_t>(B) * j->nw;
-      if (!(j->d_bits = dev_alloc<uint32_t>(j, std::max<size_t>(words, 64), &rc))) return bail(rc);
+      const char* ep = getenv("FRC_PEER_PUSH");  // "0": exchange the bit columns with NCCL instead
+      j->peer_push = j->sharded && j->fused_embed && !j->bits_feed && world <= 8 && !(ep && atoi(ep) == 0);
+      if (j->peer_push) {
+        // two buffers from the symmetric heap (same block + offset on every rank), mapped from the peers
+        for (int k = 0; k < 2; ++k) {
+          cudaError_t e = cudaSuccess;
+          j->d_bits2[k] = static_cast<uint32_t*>(c->sym.alloc(words * sizeof(uint32_t), &e));
+          if (!j->d_bits2[k]) return bail(fail(j, FRC_ERR_OOM, std::string("symmetric heap: ") + cudaGetErrorString(e)));
+        }
+        if ((rc = sym_sync(j)) != FRC_OK) return bail(rc);
+        for (int k = 0; k < 2; ++k) {
+          size_t blk = 0;
+          for (; blk < c->sym.blocks.size(); ++blk) {
+            char* base = c->sym.blocks[blk].p;
+            if (reinterpret_cast<char*>(j->d_bits2[k]) >= base &&
+                reinterpret_cast<char*>(j->d_bits2[k]) < base + c->sym.blocks[blk].cap) break;
+          }
+          const size_t off = reinterpret_cast<char*>(j->d_bits2[k]) - c->sym.blocks[blk].p;
+          j->peers[k].n = world; j->peers[k].self = rank;
+          for (int r = 0; r < world; ++r) j->peers[k].p[r] = reinterpret_cast<uint32_t*>(c->sym_peer[blk][r] + off);
+        }
+        j->d_bits = j->d_bits2[0];
+      } else if (!(j->d_bits = dev_alloc<uint32_t>(j, std::max<size_t>(words, 64), &rc))) return bail(rc);
       const size_t ns = j->fused_embed ? static_cast<size_t>(presence_node_scratch_words(B, j->shard_nw)) : 0;
       if (ns && !(j->d_node_scratch = dev_alloc<uint32_t>(j, ns, &rc))) return bail(rc);
     }
