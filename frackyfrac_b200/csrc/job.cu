@@ -1223,10 +1223,12 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       // capacity: when the three u8 operand arrays would not fit the free HBM (with room for the
       // output ring), the pair kernel expands its tiles from the bit rows instead (8x less memory,
       // about half the speed: DESIGN.md)
-      size_t free_b = 0, total_b = 0;
-      CREATE_CUDA(cudaMemGetInfo(&free_b, &total_b));
       const double need = 3.0 * static_cast<double>(j->np) * j->kp;
-      if (need > 0.80 * static_cast<double>(free_b)) j->bits_feed = true;
+      if (need > 32.0 * (1 << 30)) {  // (cudaMemGetInfo costs milliseconds: only asked when it can matter)
+        size_t free_b = 0, total_b = 0;
+        CREATE_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (need > 0.80 * static_cast<double>(free_b)) j->bits_feed = true;
+      }
       j->info.operand_kind = j->bits_feed ? 3 : 2;
     }
     const size_t opsz = j->bits_feed ? 256 : static_cast<size_t>(j->np) * j->kp * (j->i8 ? 1 : 2);
