@@ -76,11 +76,13 @@ def build_host(force: bool = False) -> tuple[str, str]:
     common = [cxx, "-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread",
               "-I", os.path.join(ROOT, "include")]
     if force or _stale(lib, srcs):
-        subprocess.run([*common, "-shared", "-o", lib, os.path.join(HOST, "hostlib.cpp")], check=True)
+        subprocess.run([*common, "-shared", "-o", lib, os.path.join(HOST, "hostlib.cpp"),
+                        os.path.join(HOST, "fileio.cpp"), "-lz", "-ldl"], check=True)
     cuda_lib = os.path.join(OUT, "libfrcfrc_cuda.so")
     if force or _stale(exe, srcs + ([cuda_lib] if os.path.exists(cuda_lib) else [])):
         subprocess.run([*common, "-o", exe, os.path.join(HOST, "frcfrc_main.cpp"),
-                        os.path.join(HOST, "hostlib.cpp"), "-L", OUT, "-lfrcfrc_cuda",
+                        os.path.join(HOST, "hostlib.cpp"), os.path.join(HOST, "fileio.cpp"),
+                        "-L", OUT, "-lfrcfrc_cuda", "-lz", "-ldl",
                         "-Wl,-rpath,$ORIGIN"], check=True)
     return lib, exe
 

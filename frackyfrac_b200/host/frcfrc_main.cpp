@@ -37,17 +37,6 @@ const char* kDefaults =
 }
 void usage() { fputs(kUsage, stderr); fputs(kDefaults, stderr); }
 
-std::string slurp(const std::string& path) {
-  FILE* f = path.empty() ? stdin : fopen(path.c_str(), "rb");
-  if (!f) die("open " + path + ": " + strerror(errno));
-  std::string out;
-  char buf[1 << 16];
-  size_t r;
-  while ((r = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, r);
-  if (!path.empty()) fclose(f);
-  return out;
-}
-
 struct Flags {
   std::string fin, fout, ftree;
   bool wgt = false, sparse = false, nnorm = false;
@@ -119,11 +108,11 @@ int main(int argc, char** argv) {
   double fmt_ms = 0, write_ms = 0, next_ms = 0;
   try {
     fputs("Reading tree\n", stderr);
-    std::string tt = slurp(fl.ftree);
+    std::string tt = frchost::read_file(fl.ftree);
     frchost::FlatTree tree = frchost::parse_newick(tt.data(), tt.size());
     lap("read + parse tree");
     fputs("Loading abundances\n", stderr);
-    std::string it = slurp(fl.fin);
+    std::string it = frchost::read_file(fl.fin);
     lap("read table file");
     frchost::Table tab = frchost::parse_table(it.data(), it.size(), fl.sparse, static_cast<int>(fl.nt));  // -p workers (frcfrc.go:42-50)
     lap("parse table");
@@ -131,8 +120,7 @@ int main(int argc, char** argv) {
     frchost::Csr csr = frchost::resolve(tab, tree, static_cast<int>(fl.nt));
     lap("validate + resolve");
 
-    FILE* w = fl.fout.empty() ? stdout : fopen(fl.fout.c_str(), "wb");
-    if (!w) die("open " + fl.fout + ": " + strerror(errno));
+    frchost::Writer w(fl.fout, static_cast<int>(fl.nt));  // aio.Create (frcfrc.go:100-106): ".gz" / ".zst" by suffix
 
     fputs("Converting abundances\n", stderr);
     frc_tree_t ft{static_cast<int32_t>(tree.parent.size()), tree.parent.data(), tree.length.data()};
@@ -158,21 +146,21 @@ int main(int argc, char** argv) {
       text.clear();
       frchost::format_lines_parallel(d, n, static_cast<int>(fl.nt), text);  // -p threads format, one writer
       auto a2 = std::chrono::steady_clock::now();
-      const bool wrote = fwrite(text.data(), 1, text.size(), w) == text.size();
+      std::string werr;
+      try { w.write(text.data(), text.size()); } catch (const std::exception& e) { werr = e.what(); }
       auto a3 = std::chrono::steady_clock::now();
       next_ms += std::chrono::duration<double, std::milli>(a1 - a0).count();
       fmt_ms += std::chrono::duration<double, std::milli>(a2 - a1).count();
       write_ms += std::chrono::duration<double, std::milli>(a3 - a2).count();
-      if (!wrote) {  // frcfrc.go:59-63
-        std::string m = std::string("write: ") + strerror(errno);
+      if (!werr.empty()) {  // frcfrc.go:59-63
         frc_destroy(job);
-        die(m);
+        die(werr);
       }
     }
     if (timing) fprintf(stderr, "[timing] frc_next waits %.1f ms, formatting %.1f ms, fwrite %.1f ms\n", next_ms, fmt_ms, write_ms);
     tl = std::chrono::steady_clock::now();
     frc_destroy(job);
-    if (!fl.fout.empty()) fclose(w); else fflush(w);
+    w.close();
     lap("destroy + close");
   } catch (const std::exception& e) {
     die(e.what());

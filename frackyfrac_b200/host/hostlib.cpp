@@ -525,6 +525,7 @@ struct frch_csr { frchost::Csr c; };
 
 static thread_local std::string g_err;
 const char* frch_last_error() { return g_err.c_str(); }
+void frch_set_error(const char* m) { g_err = m; }
 
 frch_tree* frch_tree_parse(const char* text, size_t len) {
   try { return new frch_tree{frchost::parse_newick(text, len)}; }

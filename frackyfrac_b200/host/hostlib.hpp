@@ -57,4 +57,23 @@ void append_lines(const double* d, int64_t n, std::string& out);
 // end-to-end bottleneck).
 void format_lines_parallel(const double* d, int64_t n, int threads, std::string& out);
 
+// aio.Open stand-in (frcfrc.go:93,109): the whole file, decoded by suffix (".gz", ".zst"); "" = stdin.
+std::string read_file(const std::string& path);
+
+// aio.Create stand-in (frcfrc.go:100-106): codec by suffix; compressed output is produced by `threads`
+// workers as independent members / frames written in order.  "" = stdout.  Throws on I/O errors.
+class Writer {
+ public:
+  Writer(const std::string& path, int threads);
+  ~Writer();
+  Writer(const Writer&) = delete;
+  Writer& operator=(const Writer&) = delete;
+  void write(const char* data, size_t n);
+  void close();
+
+ private:
+  struct Impl;
+  Impl* p_;
+};
+
 }  // namespace frchost

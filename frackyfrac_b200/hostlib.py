@@ -72,6 +72,9 @@ def lib():
         L.frch_format_lines.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_size_t)]
         L.frch_format_lines.restype = C.c_void_p
         L.frch_free.argtypes = [C.c_void_p]
+        L.frch_read_file.argtypes = [C.c_char_p, C.POINTER(C.c_size_t)]
+        L.frch_read_file.restype = C.c_void_p
+        L.frch_write_file.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -160,3 +163,23 @@ def format_lines(values, threads: int = 1) -> bytes:
         return C.string_at(p, n.value)
     finally:
         lib().frch_free(p)
+
+
+def read_file(path: str) -> bytes:
+    """aio.Open stand-in: the whole file, decoded by suffix (.gz, .zst)."""
+    n = C.c_size_t()
+    p = lib().frch_read_file(os.fsencode(path), C.byref(n))
+    if not p:
+        raise HostError(lib().frch_last_error().decode())
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        lib().frch_free(p)
+
+
+def write_file(path: str, chunks: list[bytes], threads: int = 1) -> None:
+    """aio.Create stand-in: writes the chunks in order, encoded by suffix (.gz, .zst) on `threads` workers."""
+    arr = (C.c_char_p * len(chunks))(*chunks)
+    sizes = (C.c_size_t * len(chunks))(*[len(c) for c in chunks])
+    if lib().frch_write_file(os.fsencode(path), arr, sizes, len(chunks), threads):
+        raise HostError(lib().frch_last_error().decode())

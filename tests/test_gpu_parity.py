@@ -61,6 +61,35 @@ def test_cli_binary_golden(built, tmp_path, fixture, sparse, weighted):
     assert out.read_text() == _read(fixture + ".want")
 
 
+def test_cli_binary_compressed_files(built, tmp_path):
+    """aio.Open / aio.Create pick the codec from the suffix (frcfrc.go:93,100-109): gzip'd tree and table in,
+    gzip'd and zstd'd distances out; the decoded output equals the golden .want, also with a multi-block output."""
+    import gzip
+
+    from frackyfrac_b200 import hostlib, synth
+
+    for name in ("wtd.tree", "wtd.sparse"):
+        (tmp_path / (name + ".gz")).write_bytes(gzip.compress(open(os.path.join(GOLDEN, name), "rb").read()))
+    for suffix, decode in ((".gz", lambda p: gzip.decompress(p.read_bytes())), (".zst", lambda p: hostlib.read_file(str(p)))):
+        out = tmp_path / ("got" + suffix)
+        r = subprocess.run([hostlib.CLI_PATH, "-w", "-s", "-i", str(tmp_path / "wtd.sparse.gz"),
+                            "-t", str(tmp_path / "wtd.tree.gz"), "-o", str(out), "-p", "3"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert decode(out).decode() == _read("wtd.want")
+    # 1500 samples -> 1.1 M lines (~20 MB of text): several compressed blocks from 4 workers
+    tree = synth.random_tree(400, 7)
+    rp, col, val = synth.random_table(tree, 1500, 0.05, 8)
+    (tmp_path / "big.tree").write_text(synth.to_newick(tree))
+    (tmp_path / "big.sparse.gz").write_bytes(gzip.compress(synth.to_sparse_text(tree, rp, col, val).encode()))
+    outs = []
+    for name in ("big.out", "big.out.gz"):
+        r = subprocess.run([hostlib.CLI_PATH, "-s", "-i", str(tmp_path / "big.sparse.gz"), "-t", str(tmp_path / "big.tree"),
+                            "-o", str(tmp_path / name), "-p", "4"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append((tmp_path / name).read_bytes())
+    assert len(outs[0]) > 8_000_000 and gzip.decompress(outs[1]) == outs[0]
+
+
 # ------------------------------------------------------------------ exact path
 @pytest.mark.parametrize("weighted,normalize", [(False, 1), (True, 1), (True, 2)])
 @pytest.mark.parametrize("shape", ["random", "caterpillar", "balanced"])

@@ -123,6 +123,58 @@ def test_parallel_writer_is_byte_identical(built):
     assert (t2 - t1) < (t1 - t0) * 1.5  # never pathologically slower
 
 
+def test_compressed_files_round_trip_by_suffix(built, tmp_path):
+    """aio.Open / aio.Create (frcfrc.go:93,100-106): the suffix picks the codec; what counts is the decoded bytes.
+    Output is a run of independent gzip members / zstd frames written in order by several workers."""
+    import gzip
+    import shutil
+
+    from frackyfrac_b200 import hostlib
+
+    rng = np.random.default_rng(5)
+    text = hostlib.format_lines(rng.random(1_200_000), 4)  # ~23 MB: several 4 MB blocks
+    chunks = [text[:7], b"", text[7:9_000_001], text[9_000_001:]]
+    plain = tmp_path / "d.txt"
+    hostlib.write_file(str(plain), chunks, 3)
+    assert plain.read_bytes() == text and hostlib.read_file(str(plain)) == text
+    for threads in (1, 5):
+        gz = tmp_path / f"d{threads}.txt.gz"
+        hostlib.write_file(str(gz), chunks, threads)
+        raw = gz.read_bytes()
+        assert raw[:2] == b"\x1f\x8b" and len(raw) < len(text) * 0.6
+        assert gzip.decompress(raw) == text          # an independent decoder reads every member
+        assert hostlib.read_file(str(gz)) == text
+    # input side: single-member and multi-member files from another encoder, and an empty payload
+    other = tmp_path / "in.tsv.gz"
+    other.write_bytes(gzip.compress(b"a\tb\n1\t2\n") + gzip.compress(b"3\t4\n", 9))
+    assert hostlib.read_file(str(other)) == b"a\tb\n1\t2\n3\t4\n"
+    empty = tmp_path / "e.gz"
+    hostlib.write_file(str(empty), [], 2)
+    assert gzip.decompress(empty.read_bytes()) == b"" and hostlib.read_file(str(empty)) == b""
+    # damaged input is an error, never silently short data
+    cut = tmp_path / "cut.gz"
+    cut.write_bytes(gz.read_bytes()[:-9])
+    with pytest.raises(hostlib.HostError, match="gzip"):
+        hostlib.read_file(str(cut))
+    junk = tmp_path / "junk.gz"
+    junk.write_bytes(b"plain text, wrong suffix\n")
+    with pytest.raises(hostlib.HostError, match="gzip"):
+        hostlib.read_file(str(junk))
+    with pytest.raises(hostlib.HostError, match="open .*missing.gz"):
+        hostlib.read_file(str(tmp_path / "missing.gz"))
+    # zstandard frames (libzstd is loaded at run time; the zstd CLI, when present, is the independent decoder)
+    zst = tmp_path / "d.txt.zst"
+    hostlib.write_file(str(zst), chunks, 4)
+    assert zst.read_bytes()[:4] == b"\x28\xb5\x2f\xfd" and hostlib.read_file(str(zst)) == text
+    if shutil.which("zstd"):
+        r = subprocess.run(["zstd", "-dc", str(zst)], capture_output=True)
+        assert r.returncode == 0 and r.stdout == text
+    bad = tmp_path / "bad.zst"
+    bad.write_bytes(zst.read_bytes()[:-5])
+    with pytest.raises(hostlib.HostError, match="zstd"):
+        hostlib.read_file(str(bad))
+
+
 def test_parallel_table_parser_matches_single_thread_and_oracle(built):
     """N2: rows parsed by several workers (parser.go's ngoroutines) must give the same CSR, the same
     species order and the same first error as one worker, and the same maps as the oracle's parser."""
