@@ -147,6 +147,13 @@ bool comm_barrier(Comm* c, cudaStream_t s, std::string* err);
 int launch_exact_pairs(const double* E, const double* length, int32_t n_nodes, int64_t ld,
                        bool weighted, int64_t first, int64_t count, double* out, cudaStream_t s);
 
+// ---- wire.cu ----------------------------------------------------------------
+// fp32 on PCIe for the fast paths: device narrows a finished band, the host widens it again.
+// *n_bad_mapped (mapped pinned memory) is incremented when a value does not survive fp32.
+int launch_narrow_band(const double* in, float* out, int64_t n, unsigned long long* n_bad_mapped, int num_sms,
+                       cudaStream_t s);
+void widen_band(const float* src, double* dst, int64_t n, bool stream_stores);  // host
+
 // ---- weighted.cu ------------------------------------------------------------
 // A is the tile-panel operand Ap[np/128][kp][128].
 // Pairs with d < flag_below are appended to flagged[] for the fix-up pass (as the unweighted kernel).

@@ -7,6 +7,7 @@
 // its own pinned D2H copy, and are handed to the caller strictly in flat-index
 // order by frc_next (the ordered iter.Seq of unifrac.go:209-228).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <climits>
 #include <cmath>
@@ -89,7 +90,7 @@ class Pool {
     for (int t = 0; t < n; ++t) workers_.emplace_back([this, t] { loop(t + 1); });
   }
   ~Pool() {
-    { std::lock_guard<std::mutex> g(m_); stop_ = true; ++epoch_; }
+    { std::lock_guard<std::mutex> g(m_); stop_ = true; epoch_.fetch_add(1, std::memory_order_release); }
     cv_.notify_all();
     for (auto& w : workers_) w.join();
   }
@@ -97,33 +98,67 @@ class Pool {
   // Runs fn(t) for t in [0, T) on T <= size() threads (t = 0 on the caller).
   void run(int T, const std::function<void(int)>& fn) {
     if (T <= 1) { fn(0); return; }
-    {
-      std::lock_guard<std::mutex> g(m_);
-      fn_ = &fn; active_ = T; pending_ = T - 1; ++epoch_;
-    }
-    cv_.notify_all();
+    post(&fn, /*shift=*/0, /*active=*/T, /*pending=*/T - 1);
     fn(0);
+    wait();
+  }
+  // Starts fn(t) for t in [0, T) on the worker threads alone and returns; wait() joins them.
+  // T <= size() - 1; a pool without workers runs the shares inline.
+  void start(int T, const std::function<void(int)>& fn) {
+    if (workers_.empty()) { for (int t = 0; t < T; ++t) fn(t); return; }
+    post(&fn, /*shift=*/1, /*active=*/T + 1, /*pending=*/T);
+  }
+  void wait() {
+    // the shares are tens of microseconds long: poll before paying a futex round trip
+    spin_while([this] { return pending_.load(std::memory_order_acquire) != 0; }, 300);
     std::unique_lock<std::mutex> g(m_);
-    done_.wait(g, [this] { return pending_ == 0; });
+    done_.wait(g, [this] { return pending_.load(std::memory_order_acquire) == 0; });
     fn_ = nullptr;
   }
 
  private:
+  static void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  template <class Pred>
+  static void spin_while(Pred busy, int max_us) {
+    const auto t0 = std::chrono::steady_clock::now();
+    while (busy()) {
+      for (int k = 0; k < 32 && busy(); ++k) cpu_relax();
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(max_us)) return;
+    }
+  }
+  void post(const std::function<void(int)>* fn, int shift, int active, int pending) {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      fn_ = fn; shift_ = shift; active_ = active;
+      pending_.store(pending, std::memory_order_release);
+      epoch_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+  }
   void loop(int id) {
     uint64_t seen = 0;
     for (;;) {
       const std::function<void(int)>* fn = nullptr;
+      int arg = 0;
+      // a job's calls arrive ~0.1 ms apart (one per output band): stay hot that long before parking
+      spin_while([&] { return epoch_.load(std::memory_order_acquire) == seen; }, 200);
       {
         std::unique_lock<std::mutex> g(m_);
-        cv_.wait(g, [&] { return epoch_ != seen; });
-        seen = epoch_;
+        cv_.wait(g, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+        seen = epoch_.load(std::memory_order_acquire);
         if (stop_) return;
-        if (id < active_) fn = fn_;
+        if (id < active_) { fn = fn_; arg = id - shift_; }
       }
       if (fn) {
-        (*fn)(id);
-        std::lock_guard<std::mutex> g(m_);
-        if (--pending_ == 0) done_.notify_one();
+        (*fn)(arg);
+        if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+          std::lock_guard<std::mutex> g(m_);
+          done_.notify_one();
+        }
       }
     }
   }
@@ -131,8 +166,9 @@ class Pool {
   std::mutex m_;
   std::condition_variable cv_, done_;
   const std::function<void(int)>* fn_ = nullptr;
-  int active_ = 0, pending_ = 0;
-  uint64_t epoch_ = 0;
+  int active_ = 0, shift_ = 0;
+  std::atomic<int> pending_{0};
+  std::atomic<uint64_t> epoch_{0};
   bool stop_ = false;
 };
 
@@ -166,9 +202,12 @@ struct Band { int64_t row0, row1, first, count; int32_t tile_off, n_tiles; };
 struct Slot {
   double* dev = nullptr;
   double* host = nullptr;
+  float* dev32 = nullptr;   // fp32 wire (wire.cu): narrowed copy of the band and its pinned landing buffer
+  float* host32 = nullptr;
+  unsigned long long* n_bad_host = nullptr;  // values of this band fp32 cannot carry (mapped pinned)
   uint32_t* flagged = nullptr;
   unsigned long long* n_flagged_host = nullptr;
-  cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr, done = nullptr;
+  cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr, k3 = nullptr, done = nullptr;
   int band = -1;  // index into mine[]
 };
 
@@ -198,6 +237,8 @@ struct frc_job {
   unsigned long long* d_flag_counts = nullptr;  // one per band of this rank
   bool fused_embed = true;
   bool zero_copy = false;
+  bool wire32 = false;  // bands cross PCIe as fp32 and are widened on the host (wire.cu)
+  double* wide = nullptr;  // wire32: the one band-sized double buffer frc_next hands out
   int64_t ws_slab = 0;        // fast weighted: samples per fp64 embedding slab
   bool peer_push = false;     // sharded unweighted: the bits kernel stores into every rank's bitsT (no NCCL for the bits)
   uint32_t* d_bits2[2] = {nullptr, nullptr};  // double-buffered by run parity (a rank may be one step ahead)
@@ -297,6 +338,7 @@ std::vector<int64_t> band_boundaries(int64_t N, int64_t requested, int world, bo
   }
   const int64_t tile_rows = (N + kTile - 1) / kTile;
   int64_t n = d2h ? 8LL * world : (world == 1 ? 1 : 2LL * world);
+  if (const char* e = getenv("FRC_BANDS")) { if (d2h && atoi(e) > 0) n = static_cast<int64_t>(atoi(e)) * world; }
   const double total_bytes = 8.0 * static_cast<double>(N) * static_cast<double>(N - 1) / 2.0;
   // streamed to the host: bands of <= 96 MB keep the pinned ring small (pinning memory costs ~0.4 s
   // per GB, paid by the first job of a context) and are still several waves of tiles each
@@ -515,7 +557,17 @@ int enqueue_band(frc_job* j, size_t idx) {
   // bulk D2H runs on its own stream so the compute streams never hold copy-engine work
   // (a kernel queued behind a copy in the same stream cannot overlap that copy)
   cudaStream_t cs = c->stream[2];
-  if (!(j->opts.flags & FRC_FLAG_NO_D2H) && sl.dev != sl.host) {
+  if (j->wire32) {
+    // the band crosses PCIe as fp32 (wire.cu); frc_next widens it into sl.host
+    *sl.n_bad_host = 0;
+    launches += launch_narrow_band(sl.dev, sl.dev32, b.count, sl.n_bad_host, c->num_sms, s);
+    JOB_CUDA(j, cudaGetLastError());
+    JOB_CUDA(j, cudaEventRecord(sl.k3, s));
+    JOB_CUDA(j, cudaStreamWaitEvent(cs, sl.k3, 0));
+    JOB_CUDA(j, cudaMemcpyAsync(sl.host32, sl.dev32, sizeof(float) * b.count, cudaMemcpyDeviceToHost, cs));
+    j->info.d2h_bytes += static_cast<int64_t>(sizeof(float)) * b.count;
+    JOB_CUDA(j, cudaEventRecord(sl.done, cs));
+  } else if (!(j->opts.flags & FRC_FLAG_NO_D2H) && sl.dev != sl.host) {
     JOB_CUDA(j, cudaStreamWaitEvent(cs, sl.k2, 0));
     JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, cs));
     j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
@@ -563,6 +615,7 @@ void destroy_job(frc_job* j) {
     if (sl.k0) cudaEventDestroy(sl.k0);
     if (sl.k1) cudaEventDestroy(sl.k1);
     if (sl.k2) cudaEventDestroy(sl.k2);
+    if (sl.k3) cudaEventDestroy(sl.k3);
     if (sl.done) cudaEventDestroy(sl.done);
   }
   if (j->ev_h2d0) cudaEventDestroy(j->ev_h2d0);
@@ -698,7 +751,11 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   *out = nullptr;
   if (!tree || !abnd || !opts) { g_create_error = "frc_create: NULL argument"; return FRC_ERR_ARG; }
   frc_job* j = new frc_job();
-  auto bail = [&](int rc) { g_create_error = j->err; destroy_job(j); return rc; };
+  bool csr_workers_busy = false;  // the table is validated + staged by the pool while this thread handles the tree
+  auto bail = [&](int rc) {
+    if (csr_workers_busy) { j->ctx->pool->wait(); csr_workers_busy = false; }
+    g_create_error = j->err; destroy_job(j); return rc;
+  };
   const bool trace = getenv("FRC_TRACE") != nullptr;
   auto tp0 = std::chrono::steady_clock::now();
   auto mark = [&](const char* what) {
@@ -734,7 +791,162 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   const int32_t B = tree->n_nodes;
   if (B < 1 || !tree->parent || !tree->length) return bail(fail(j, FRC_ERR_ARG, "empty tree"));
   if (tree->parent[0] != -1) return bail(fail(j, FRC_ERR_ARG, "parent[0] must be -1 (root has pre-order id 0)"));
-  std::vector<int32_t> child_cnt(B, 0), height(B, 0);
+  // ------------------------------------------------------------ validate table
+  const int64_t N = abnd->n_samples;
+  if (N < 0 || (N > 0 && !abnd->row_ptr)) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
+  if (N > (1LL << 31) - 256) return bail(fail(j, FRC_ERR_UNSUPPORTED, "too many samples"));
+  const int64_t nnz = N > 0 ? abnd->row_ptr[N] : 0;
+  if (N > 0 && abnd->row_ptr[0] != 0) return bail(fail(j, FRC_ERR_ARG, "row_ptr[0] != 0"));
+  if (nnz < 0 || (nnz > 0 && (!abnd->col || !abnd->val))) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
+  for (int64_t s = 0; s < N; ++s)
+    if (abnd->row_ptr[s + 1] < abnd->row_ptr[s] || abnd->row_ptr[s + 1] > nnz)
+      return bail(fail(j, FRC_ERR_ARG, "row_ptr is not monotone"));
+  // (entries are validated while they are copied into the pinned staging buffer, below)
+
+  // -------------------------------------------------------------------- context
+  int rc = FRC_OK;
+  if (ctx) {
+    if (ctx->in_use) return bail(fail(j, FRC_ERR_STATE, "context already has a live job"));
+    j->ctx = ctx;
+  } else {
+    rc = frc_ctx_create(opts->device, &j->ctx);
+    if (rc) { j->err = g_create_error; j->ctx = nullptr; return bail(rc); }
+    j->own_ctx = true;
+  }
+  frc_ctx* c = j->ctx;
+  c->in_use = true;
+  CREATE_CUDA(cudaSetDevice(c->device));
+
+  // ------------------------------------ table: validate + stage on the worker pool
+  // The CSR entries (the bulk of the input) are checked and copied into pinned staging memory by the
+  // pool while this thread validates the tree, plans the operand columns and bands, and sets up
+  // the device side; the two meet just before the embedding is queued.
+  const int64_t n_pairs = N >= 2 ? tri(N) : 0;
+  if (opts->path == FRC_PATH_EXACT) j->exact = true;
+  else if (opts->path == FRC_PATH_FAST) j->exact = false;
+  else j->exact = n_pairs == 0 || (static_cast<double>(n_pairs) * B <= static_cast<double>(kExactWorkLimit));
+  const bool need_val = j->exact || j->weighted;
+  struct Seg { size_t off, bytes; };
+  size_t csr_total = 0;
+  auto cseg = [&](size_t bytes) { Seg s{csr_total, bytes}; csr_total += (bytes + 255) & ~size_t(255); return s; };
+  const int32_t kp_pad = static_cast<int32_t>(round_up(B, kKBlock));
+  const Seg s_rowptr = cseg(sizeof(int64_t) * (N + 1)), s_col = cseg(sizeof(int32_t) * nnz),
+            s_val = cseg(need_val ? sizeof(double) * nnz : 0),
+            // tree topology, filled by one more pool share (tree_share below)
+            s_parent = cseg(sizeof(int32_t) * B), s_len = cseg(sizeof(double) * B),
+            s_cptr = cseg(sizeof(int32_t) * (B + 1)), s_cidx = cseg(sizeof(int32_t) * B),
+            s_lvl = cseg(sizeof(int32_t) * B), s_lpar = cseg(sizeof(int32_t) * B),
+            s_lptr = cseg(sizeof(int32_t) * (static_cast<size_t>(B) + 2)), s_lenf = cseg(sizeof(float) * kp_pad);
+  char* stage_csr = pin_alloc<char>(j, csr_total, &rc);
+  if (!stage_csr) return bail(rc);
+  char* d_csr = dev_alloc<char>(j, csr_total, &rc);
+  if (!d_csr) return bail(rc);
+  {
+    int64_t* rp = reinterpret_cast<int64_t*>(stage_csr + s_rowptr.off);
+    if (N > 0) memcpy(rp, abnd->row_ptr, sizeof(int64_t) * (N + 1)); else rp[0] = 0;
+  }
+  // one worker prepares the tree topology arrays, the others take the CSR entries
+  const int csr_shares = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->pool->size() - 2), nnz / 32768)));
+  int32_t tree_H = -1;  // height of the tree; -1: the share found a parent outside [0, v) (reported by the walk below)
+  auto tree_share = [&, stage_csr]() {
+    const int32_t* parent = tree->parent;
+    std::vector<int32_t> child_cnt(B, 0), height(B, 0);
+    for (int32_t v = 1; v < B; ++v) {
+      const int32_t p = parent[v];
+      if (p < 0 || p >= v) return;
+      child_cnt[p]++;
+    }
+    for (int32_t v = B - 1; v >= 1; --v) height[parent[v]] = std::max(height[parent[v]], height[v] + 1);
+    const int32_t H = height[0];
+    memcpy(stage_csr + s_parent.off, parent, sizeof(int32_t) * B);
+    memcpy(stage_csr + s_len.off, tree->length, sizeof(double) * B);
+    int32_t* cptr = reinterpret_cast<int32_t*>(stage_csr + s_cptr.off);
+    int32_t* cidx = reinterpret_cast<int32_t*>(stage_csr + s_cidx.off);
+    cptr[0] = 0;
+    for (int32_t v = 0; v < B; ++v) cptr[v + 1] = cptr[v] + child_cnt[v];
+    std::vector<int32_t> fill(cptr, cptr + B);
+    for (int32_t v = 1; v < B; ++v) cidx[fill[parent[v]]++] = v;  // ascending id = file order
+    j->level_ptr.assign(H + 2, 0);
+    for (int32_t v = 0; v < B; ++v) j->level_ptr[height[v] + 1]++;
+    for (int32_t h = 0; h <= H; ++h) j->level_ptr[h + 1] += j->level_ptr[h];
+    int32_t* lvl = reinterpret_cast<int32_t*>(stage_csr + s_lvl.off);
+    std::vector<int32_t> lfill(j->level_ptr.begin(), j->level_ptr.end() - 1);
+    for (int32_t v = 0; v < B; ++v) lvl[lfill[height[v]]++] = v;
+    int32_t* lpar = reinterpret_cast<int32_t*>(stage_csr + s_lpar.off);
+    for (int32_t k = 0; k < B; ++k) lpar[k] = lvl[k] ? parent[lvl[k]] : 0;
+    float* lf = reinterpret_cast<float*>(stage_csr + s_lenf.off);
+    for (int32_t v = 0; v < kp_pad; ++v) lf[v] = v < B ? static_cast<float>(tree->length[v]) : 0.f;
+    memcpy(stage_csr + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
+    tree_H = H;
+  };
+  std::vector<std::string> csr_errs(csr_shares);
+  std::vector<double> csr_us(csr_shares + 1, 0.0);
+  // duplicate detection: stamp[leaf] = epoch-tagged sample id; the arrays persist in the
+  // context, so nothing is cleared between jobs
+  const int64_t stamp_tag = c->stamp_epoch;
+  c->stamp_epoch += N + 1;
+  const std::function<void(int)> csr_work = [&, stage_csr](int t) {
+    const auto w0 = std::chrono::steady_clock::now();
+    if (t == csr_shares) {
+      tree_share();
+      csr_us[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+      return;
+    }
+    int32_t* dcol = reinterpret_cast<int32_t*>(stage_csr + s_col.off);
+    double* dval = need_val ? reinterpret_cast<double*>(stage_csr + s_val.off) : nullptr;
+    const int TS = csr_shares;
+    // a leaf listed twice in a row only matters when values are used (presence is an OR)
+    const bool check_dup = need_val;
+    const int32_t* parent = tree->parent;
+    auto row_at = [&](int64_t target) {
+      return static_cast<int64_t>(std::lower_bound(abnd->row_ptr, abnd->row_ptr + N, target) - abnd->row_ptr);
+    };
+    const int64_t s0 = t == 0 ? 0 : row_at(nnz * t / TS), s1 = t == TS - 1 ? N : row_at(nnz * (t + 1) / TS);
+    std::vector<int64_t>& stamp = c->stamps[t];
+    if (check_dup && static_cast<int32_t>(stamp.size()) < B) stamp.assign(B, -1);
+    bool failed = false;
+    for (int64_t s = s0; s < s1 && !failed; ++s) {
+      const int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
+      const int64_t mark_s = stamp_tag + s;
+      for (int64_t k = b; k < e; ++k) {
+        const int32_t cc = abnd->col[k];
+        const double v = abnd->val[k];
+        const char* what = nullptr;
+        if (cc < 0 || cc >= B) what = "node id out of range";
+        // pre-order ids: the first child of a node is the next id (the numbering itself is being
+        // checked by the calling thread at this moment; a bad tree fails the call before this result counts)
+        else if (cc + 1 < B && parent[cc + 1] == cc) what = "node is not a leaf";
+        else if (!(v > 0) || std::isinf(v)) what = "bad value";
+        else if (check_dup && stamp[cc] == mark_s) what = "leaf listed twice";
+        if (what) {
+          csr_errs[t] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
+                        std::to_string(cc) + "): " + what;
+          failed = true;
+          break;
+        }
+        if (check_dup) stamp[cc] = mark_s;
+#if defined(__x86_64__)
+        // streaming stores: the staging buffer is read next by the DMA engine, not by a core
+        _mm_stream_si32(dcol + k, cc);
+        if (dval) _mm_stream_si64(reinterpret_cast<long long*>(dval + k), static_cast<long long>(__builtin_bit_cast(int64_t, v)));
+#else
+        dcol[k] = cc;
+        if (dval) dval[k] = v;
+#endif
+      }
+    }
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+    csr_us[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+  };
+  csr_workers_busy = true;
+  const bool tree_share_pooled = c->pool->size() >= 3;
+  c->pool->start(csr_shares + (tree_share_pooled ? 1 : 0), csr_work);
+  if (c->pool->size() == 1) csr_workers_busy = false;  // (no workers: the shares ran inline)
+  mark("table checks, context, CSR workers started");
+
+  // ------------------------------------------------------------- validate tree (full walk)
   {
     // pre-order check: parent[v] must lie on the path root..v-1, i.e. be the node of its depth on the
     // current root-to-(v-1) path.  Branch-free per node (the stack-popping form cost 14 ns per node in
@@ -748,7 +960,6 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       if ((d > depth[v - 1] || on_path[d] != p) && !bad_order) bad_order = v;
       depth[v] = d + 1;
       on_path[d + 1] = v;
-      child_cnt[p]++;
     }
     if (bad_parent) return bail(fail(j, FRC_ERR_ARG, "parent[" + std::to_string(bad_parent) + "] is not a smaller node id"));
     if (bad_order) return bail(fail(j, FRC_ERR_ARG, "node ids are not a pre-order numbering (node " + std::to_string(bad_order) + ")"));
@@ -759,22 +970,8 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (!(l == l) || std::isinf(l)) bad_len = true;
     else if (l < 0) neg_len = true;
   }
-  for (int32_t v = B - 1; v >= 1; --v) height[tree->parent[v]] = std::max(height[tree->parent[v]], height[v] + 1);
-  const int32_t H = height[0];
-
+  if (!tree_share_pooled) tree_share();
   mark("validate tree");
-  // ------------------------------------------------------------ validate table
-  const int64_t N = abnd->n_samples;
-  if (N < 0 || (N > 0 && !abnd->row_ptr)) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
-  if (N > (1LL << 31) - 256) return bail(fail(j, FRC_ERR_UNSUPPORTED, "too many samples"));
-  const int64_t nnz = N > 0 ? abnd->row_ptr[N] : 0;
-  if (N > 0 && abnd->row_ptr[0] != 0) return bail(fail(j, FRC_ERR_ARG, "row_ptr[0] != 0"));
-  if (nnz < 0 || (nnz > 0 && (!abnd->col || !abnd->val))) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
-  for (int64_t s = 0; s < N; ++s)
-    if (abnd->row_ptr[s + 1] < abnd->row_ptr[s] || abnd->row_ptr[s + 1] > nnz)
-      return bail(fail(j, FRC_ERR_ARG, "row_ptr is not monotone"));
-  // (entries are validated while they are copied into the pinned staging buffer, below)
-
   // --------------------------------------------------------------- choose path
   j->N = N; j->B = B; j->nnz = nnz;
   j->sharded = (opts->flags & FRC_FLAG_SHARD_EMBED) != 0 && world > 1;
@@ -787,10 +984,6 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->np = std::max<int64_t>(kTile, round_up(N, j->sharded ? kTile * static_cast<int64_t>(world) : kTile));
   j->kp = static_cast<int32_t>(round_up(B, kKBlock));
   j->nw = static_cast<int32_t>(j->np / 32);
-  const int64_t n_pairs = N >= 2 ? tri(N) : 0;
-  if (opts->path == FRC_PATH_EXACT) j->exact = true;
-  else if (opts->path == FRC_PATH_FAST) j->exact = false;
-  else j->exact = n_pairs == 0 || (static_cast<double>(n_pairs) * B <= static_cast<double>(kExactWorkLimit));
   if (!j->exact && bad_len)
     return bail(fail(j, FRC_ERR_UNSUPPORTED, "non-finite branch length: only the exact path handles it"));
   j->prescale = !neg_len;
@@ -798,7 +991,6 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   j->shard_nw = j->sharded ? j->nw / world : j->nw;
   j->shard_w0 = j->sharded ? rank * j->shard_nw : 0;
   j->info.path_taken = j->exact ? FRC_PATH_EXACT : FRC_PATH_FAST;
-  j->info.tree_height = H;
   j->info.n_pairs_total = n_pairs;
   j->info.n_nodes_padded = j->exact ? B : j->kp;
 
@@ -974,34 +1166,12 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     }
   }
   mark("row_ptr check + bands/tiles");
-  // -------------------------------------------------------------------- context
-  int rc = FRC_OK;
-  if (ctx) {
-    if (ctx->in_use) return bail(fail(j, FRC_ERR_STATE, "context already has a live job"));
-    j->ctx = ctx;
-  } else {
-    rc = frc_ctx_create(opts->device, &j->ctx);
-    if (rc) { j->err = g_create_error; j->ctx = nullptr; return bail(rc); }
-    j->own_ctx = true;
-  }
-  frc_ctx* c = j->ctx;
-  c->in_use = true;
-  CREATE_CUDA(cudaSetDevice(c->device));
-
-  mark("context");
   // ------------------------------------------------- pack + upload the inputs
-  const bool need_val = j->exact || j->weighted;
-  struct Seg { size_t off, bytes; };
+  // (the column plan and the tile lists; the CSR block and the tree topology are staged by the pool)
   size_t total = 0;
   auto seg = [&](size_t bytes) { Seg s{total, bytes}; total += (bytes + 255) & ~size_t(255); return s; };
-  Seg s_rowptr = seg(sizeof(int64_t) * (N + 1)), s_col = seg(sizeof(int32_t) * nnz),
-      s_val = seg(need_val ? sizeof(double) * nnz : 0), s_parent = seg(sizeof(int32_t) * B),
-      s_len = seg(sizeof(double) * B), s_cptr = seg(sizeof(int32_t) * (B + 1)),
-      s_cidx = seg(sizeof(int32_t) * B), s_lvl = seg(sizeof(int32_t) * B),
-      s_q0 = seg(j->kp), s_hi = seg(sizeof(uint16_t) * j->kp), s_lo = seg(sizeof(uint16_t) * j->kp),
-      s_lenq = seg(sizeof(double) * j->kp),
-      s_lenf = seg(sizeof(float) * j->kp), s_tiles = seg(sizeof(Tile) * j->tiles.size()),
-      s_lptr = seg(sizeof(int32_t) * (H + 2)), s_lpar = seg(sizeof(int32_t) * B),
+  Seg s_q0 = seg(j->kp), s_hi = seg(sizeof(uint16_t) * j->kp), s_lo = seg(sizeof(uint16_t) * j->kp),
+      s_lenq = seg(sizeof(double) * j->kp), s_tiles = seg(sizeof(Tile) * j->tiles.size()),
       s_order = seg(sizeof(int32_t) * col_order.size()), s_cexp = seg(sizeof(int32_t) * col_exp.size()),
       s_lcol = seg(sizeof(double) * len_col.size()), s_cend = seg(sizeof(int32_t) * chunk_end.size()),
       s_cscale = seg(sizeof(double) * chunk_scale.size()), s_need = seg(need_blocks.size()),
@@ -1010,33 +1180,12 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   if (!stage) return bail(rc);
   j->d_inputs = dev_alloc<char>(j, total, &rc);
   if (!j->d_inputs) return bail(rc);
-  j->input_bytes = total;
+  j->input_bytes = total + csr_total;
   {
-    int64_t* rp = reinterpret_cast<int64_t*>(stage + s_rowptr.off);
-    if (N > 0) memcpy(rp, abnd->row_ptr, sizeof(int64_t) * (N + 1)); else rp[0] = 0;
-    mark("staging alloc + row_ptr copy");
-    // everything derived from the tree alone; runs on the calling thread while the pool validates the table
-    auto prep_tree = [&]() {
-    memcpy(stage + s_parent.off, tree->parent, sizeof(int32_t) * B);
-    memcpy(stage + s_len.off, tree->length, sizeof(double) * B);
-    int32_t* cptr = reinterpret_cast<int32_t*>(stage + s_cptr.off);
-    int32_t* cidx = reinterpret_cast<int32_t*>(stage + s_cidx.off);
-    cptr[0] = 0;
-    for (int32_t v = 0; v < B; ++v) cptr[v + 1] = cptr[v] + child_cnt[v];
-    std::vector<int32_t> fill(cptr, cptr + B);
-    for (int32_t v = 1; v < B; ++v) cidx[fill[tree->parent[v]]++] = v;  // ascending id = file order
-    j->level_ptr.assign(H + 2, 0);
-    for (int32_t v = 0; v < B; ++v) j->level_ptr[height[v] + 1]++;
-    for (int32_t h = 0; h <= H; ++h) j->level_ptr[h + 1] += j->level_ptr[h];
-    int32_t* lvl = reinterpret_cast<int32_t*>(stage + s_lvl.off);
-    std::vector<int32_t> lfill(j->level_ptr.begin(), j->level_ptr.end() - 1);
-    for (int32_t v = 0; v < B; ++v) lvl[lfill[height[v]]++] = v;
-    int32_t* lpar = reinterpret_cast<int32_t*>(stage + s_lpar.off);
-    for (int32_t k = 0; k < B; ++k) lpar[k] = lvl[k] ? tree->parent[lvl[k]] : 0;
+    {
     uint16_t* hi = reinterpret_cast<uint16_t*>(stage + s_hi.off);
     uint16_t* lo = reinterpret_cast<uint16_t*>(stage + s_lo.off);
     double* lq = reinterpret_cast<double*>(stage + s_lenq.off);
-    float* lf = reinterpret_cast<float*>(stage + s_lenf.off);
     if (!j->i8) {  // (u8: k_quantize_lengths fills q0/q1/q2 and lenq on the device)
       for (int32_t v = 0; v < B; ++v) {
         double l = tree->length[v];
@@ -1047,7 +1196,6 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
       }
       for (int32_t v = B; v < j->kp; ++v) { hi[v] = 0; lo[v] = 0; lq[v] = 0.0; }
     }
-    for (int32_t v = 0; v < j->kp; ++v) lf[v] = v < B ? static_cast<float>(tree->length[v]) : 0.f;
     if (!col_order.empty()) memcpy(stage + s_order.off, col_order.data(), s_order.bytes);
     if (!col_exp.empty()) memcpy(stage + s_cexp.off, col_exp.data(), s_cexp.bytes);
     if (!len_col.empty()) memcpy(stage + s_lcol.off, len_col.data(), s_lcol.bytes);
@@ -1056,73 +1204,9 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (!need_blocks.empty()) memcpy(stage + s_need.off, need_blocks.data(), s_need.bytes);
     if (!chunk_shift.empty()) memcpy(stage + s_cshift.off, chunk_shift.data(), s_cshift.bytes);
     if (!j->tiles.empty()) memcpy(stage + s_tiles.off, j->tiles.data(), sizeof(Tile) * j->tiles.size());
-    memcpy(stage + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
-    };
-    // validate + copy the CSR entries in one pass, samples split over host threads
-    {
-      int32_t* dcol = reinterpret_cast<int32_t*>(stage + s_col.off);
-      double* dval = need_val ? reinterpret_cast<double*>(stage + s_val.off) : nullptr;
-      const int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->pool->size(), nnz / 32768)));
-      // with enough workers the caller (t == 0) prepares the tree arrays instead of taking a CSR share
-      const bool split = T >= 4;
-      const int TS = split ? T - 1 : T;  // CSR shares
-      std::vector<std::string> errs(T);
-      // duplicate detection: stamp[leaf] = epoch-tagged sample id; the arrays persist in the
-      // context, so nothing is cleared between jobs
-      const int64_t tag = c->stamp_epoch;
-      c->stamp_epoch += N + 1;
-      // a leaf listed twice in a row only matters when values are used (presence is an OR)
-      const bool check_dup = need_val;
-      std::function<void(int)> work = [&](int t) {
-        if (split) {
-          if (t == 0) { prep_tree(); return; }
-          --t;
-        }
-        auto row_at = [&](int64_t target) {
-          return static_cast<int64_t>(std::lower_bound(abnd->row_ptr, abnd->row_ptr + N, target) - abnd->row_ptr);
-        };
-        const int64_t s0 = t == 0 ? 0 : row_at(nnz * t / TS), s1 = t == TS - 1 ? N : row_at(nnz * (t + 1) / TS);
-        std::vector<int64_t>& stamp = c->stamps[t];
-        if (check_dup && static_cast<int32_t>(stamp.size()) < B) stamp.assign(B, -1);
-        for (int64_t s = s0; s < s1; ++s) {
-          const int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
-          const int64_t mark_s = tag + s;
-          for (int64_t k = b; k < e; ++k) {
-            const int32_t cc = abnd->col[k];
-            const double v = abnd->val[k];
-            const char* what = nullptr;
-            if (cc < 0 || cc >= B) what = "node id out of range";
-            else if (child_cnt[cc] != 0) what = "node is not a leaf";
-            else if (!(v > 0) || std::isinf(v)) what = "bad value";
-            else if (check_dup && stamp[cc] == mark_s) what = "leaf listed twice";
-            if (what) {
-              errs[t] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
-                        std::to_string(cc) + "): " + what;
-              return;
-            }
-            if (check_dup) stamp[cc] = mark_s;
-#if defined(__x86_64__)
-            // streaming stores: the staging buffer is read next by the DMA engine, not by a core
-            _mm_stream_si32(dcol + k, cc);
-            if (dval) _mm_stream_si64(reinterpret_cast<long long*>(dval + k), static_cast<long long>(__builtin_bit_cast(int64_t, v)));
-#else
-            dcol[k] = cc;
-            if (dval) dval[k] = v;
-#endif
-          }
-        }
-#if defined(__x86_64__)
-        _mm_sfence();
-#endif
-      };
-      c->pool->run(T, work);
-      if (!split) prep_tree();
-      for (auto& e : errs)
-        if (!e.empty()) return bail(fail(j, FRC_ERR_ARG, e));
     }
-    mark("validate+copy CSR entries (+ tree arrays on the calling thread)");
   }
-  mark("tree arrays, hi/lo, tiles");
+  mark("column plan + tiles staged");
   CREATE_CUDA(cudaEventCreate(&j->ev_h2d0));
   CREATE_CUDA(cudaEventCreate(&j->ev_h2d1));
   CREATE_CUDA(cudaEventCreate(&j->ev_embed0));
@@ -1133,19 +1217,18 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   CREATE_CUDA(cudaEventCreateWithFlags(&j->ev_rsum, cudaEventDisableTiming));
   CREATE_CUDA(cudaEventRecord(j->ev_h2d0, c->stream[0]));
   CREATE_CUDA(cudaMemcpyAsync(j->d_inputs, stage, total, cudaMemcpyHostToDevice, c->stream[0]));
-  CREATE_CUDA(cudaEventRecord(j->ev_h2d1, c->stream[0]));
-  j->info.h2d_bytes = static_cast<int64_t>(total);
+  j->info.h2d_bytes = static_cast<int64_t>(total + csr_total);
   char* d = j->d_inputs;
   j->dcsr.n_samples = N; j->dcsr.nnz = nnz;
-  j->dcsr.row_ptr = reinterpret_cast<int64_t*>(d + s_rowptr.off);
-  j->dcsr.col = reinterpret_cast<int32_t*>(d + s_col.off);
-  j->dcsr.val = need_val ? reinterpret_cast<double*>(d + s_val.off) : nullptr;
-  j->dtree.n_nodes = B; j->dtree.height = H;
-  j->dtree.parent = reinterpret_cast<int32_t*>(d + s_parent.off);
-  j->dtree.length = reinterpret_cast<double*>(d + s_len.off);
-  j->dtree.child_ptr = reinterpret_cast<int32_t*>(d + s_cptr.off);
-  j->dtree.child_idx = reinterpret_cast<int32_t*>(d + s_cidx.off);
-  j->dtree.level_nodes = reinterpret_cast<int32_t*>(d + s_lvl.off);
+  j->dcsr.row_ptr = reinterpret_cast<int64_t*>(d_csr + s_rowptr.off);
+  j->dcsr.col = reinterpret_cast<int32_t*>(d_csr + s_col.off);
+  j->dcsr.val = need_val ? reinterpret_cast<double*>(d_csr + s_val.off) : nullptr;
+  j->dtree.n_nodes = B; j->dtree.height = 0;  // (height: set when the tree share is joined)
+  j->dtree.parent = reinterpret_cast<int32_t*>(d_csr + s_parent.off);
+  j->dtree.length = reinterpret_cast<double*>(d_csr + s_len.off);
+  j->dtree.child_ptr = reinterpret_cast<int32_t*>(d_csr + s_cptr.off);
+  j->dtree.child_idx = reinterpret_cast<int32_t*>(d_csr + s_cidx.off);
+  j->dtree.level_nodes = reinterpret_cast<int32_t*>(d_csr + s_lvl.off);
   j->d_q0 = d + s_q0.off;
   j->d_q1 = d + s_hi.off;
   j->d_q2 = d + s_lo.off;
@@ -1162,10 +1245,10 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     const auto mm = std::minmax_element(chunk_scale.begin(), chunk_scale.end());
     j->d_chunks.biased = *mm.second <= *mm.first * 256.0;
   }
-  j->d_lenf = reinterpret_cast<float*>(d + s_lenf.off);
+  j->d_lenf = reinterpret_cast<float*>(d_csr + s_lenf.off);
   j->d_tiles = reinterpret_cast<Tile*>(d + s_tiles.off);
-  j->d_level_ptr = reinterpret_cast<int32_t*>(d + s_lptr.off);
-  j->dtree.level_parent = reinterpret_cast<int32_t*>(d + s_lpar.off);
+  j->d_level_ptr = reinterpret_cast<int32_t*>(d_csr + s_lptr.off);
+  j->dtree.level_parent = reinterpret_cast<int32_t*>(d_csr + s_lpar.off);
 
   mark("events + H2D enqueue");
   // ------------------------------------------------------------ device buffers
@@ -1266,15 +1349,27 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   }
   { const char* e = getenv("FRC_ZERO_COPY"); j->zero_copy = e && atoi(e) == 1; }
   {
+    // fast-path distances have fp32 precision: send them over PCIe as fp32, widen on the host (wire.cu)
+    const char* e = getenv("FRC_WIRE");  // "f64": keep doubles on the bus
+    j->wire32 = !j->exact && !(opts->flags & FRC_FLAG_NO_D2H) && !j->zero_copy && !(e && !strcmp(e, "f64"));
+  }
+  {
     int64_t want = std::max<int64_t>(kMinSlots, std::min<int64_t>(kSlots, kSlotBytesBudget / (max_band * 8)));
     j->n_slots = static_cast<int>(std::min<int64_t>(want, std::max<int64_t>(2, static_cast<int64_t>(j->mine.size()) + 1)));
   }
   if (j->mine.empty()) j->n_slots = 0;
+  if (j->wire32 && j->n_slots > 0 && !(j->wide = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
   for (int k = 0; k < j->n_slots; ++k) {
     Slot& sl = j->slots[k];
-    if (!(opts->flags & FRC_FLAG_NO_D2H) && !(sl.host = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
+    if (!(opts->flags & FRC_FLAG_NO_D2H) && !j->wire32 && !(sl.host = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
     if (j->zero_copy && sl.host) sl.dev = sl.host;  // kernels store straight into pinned host memory (UVA)
     else if (!(sl.dev = dev_alloc<double>(j, max_band, &rc))) return bail(rc);
+    if (j->wire32) {
+      if (!(sl.dev32 = dev_alloc<float>(j, max_band, &rc))) return bail(rc);
+      if (!(sl.host32 = pin_alloc<float>(j, max_band, &rc))) return bail(rc);
+      if (!(sl.n_bad_host = pin_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
+      *sl.n_bad_host = 0;
+    }
     if (!j->exact) {
       if (!(sl.flagged = dev_alloc<uint32_t>(j, max_band, &rc))) return bail(rc);
       if (!(sl.n_flagged_host = pin_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
@@ -1282,12 +1377,23 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     }
     cudaError_t e;
     if ((e = cudaEventCreate(&sl.k0)) != cudaSuccess || (e = cudaEventCreate(&sl.k1)) != cudaSuccess ||
-        (e = cudaEventCreate(&sl.k2)) != cudaSuccess ||
+        (e = cudaEventCreate(&sl.k2)) != cudaSuccess || (e = cudaEventCreate(&sl.k3)) != cudaSuccess ||
         (e = cudaEventCreate(&sl.done)) != cudaSuccess)
       return bail(fail(j, FRC_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e)));
   }
 
   mark("device buffers, tensor maps, slots");
+  // -------------------------------------------- join the table workers, upload the CSR block
+  if (csr_workers_busy) { c->pool->wait(); csr_workers_busy = false; }
+  if (trace) { fprintf(stderr, "[frc_create] CSR share times (us):"); for (double u : csr_us) fprintf(stderr, " %.0f", u); fprintf(stderr, "\n"); }
+  for (auto& e : csr_errs)
+    if (!e.empty()) return bail(fail(j, FRC_ERR_ARG, e));
+  if (tree_H < 0) return bail(fail(j, FRC_ERR_ARG, "tree topology could not be prepared"));  // (unreachable after the walk above)
+  j->dtree.height = tree_H;
+  j->info.tree_height = tree_H;
+  CREATE_CUDA(cudaMemcpyAsync(d_csr, stage_csr, csr_total, cudaMemcpyHostToDevice, c->stream[0]));
+  CREATE_CUDA(cudaEventRecord(j->ev_h2d1, c->stream[0]));
+  mark("CSR workers joined, CSR upload queued");
   // ----------------------------------------------------------------- go
   if ((rc = run_embedding(j)) != FRC_OK) return bail(rc);
   if ((rc = start_pairs(j)) != FRC_OK) return bail(rc);
@@ -1318,7 +1424,10 @@ int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* c
   }
   const size_t idx = j->next_deliver;
   Slot& sl = j->slots[idx % j->n_slots];
+  const bool trace_next = getenv("FRC_TRACE") != nullptr;
+  const auto tn0 = std::chrono::steady_clock::now();
   JOB_CUDA(j, cudaEventSynchronize(sl.done));
+  const auto tn1 = std::chrono::steady_clock::now();
   float ms = 0.f;
   JOB_CUDA(j, cudaEventElapsedTime(&ms, sl.k0, sl.k1));
   j->info.pairs_ms += ms;
@@ -1331,7 +1440,7 @@ int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* c
     j->run_timed = true;
   }
   if (sl.n_flagged_host) j->info.flagged_pairs += static_cast<int64_t>(*sl.n_flagged_host);
-  if (getenv("FRC_TRACE")) {
+  if (trace_next) {
     fprintf(stderr, "[host] deliver band %zu at %.3f ms\n", idx,
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - j->t_host0).count());
     float a = 0, b = 0, c2 = 0, d = 0;
@@ -1343,7 +1452,33 @@ int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* c
             static_cast<long long>(j->bands[j->mine[idx]].count));
   }
   const Band& b = j->bands[j->mine[idx]];
-  *data = (j->opts.flags & FRC_FLAG_NO_D2H) ? sl.dev : sl.host;
+  if (j->wire32) {
+    if (*sl.n_bad_host) {
+      // some value of this band does not survive fp32 (underflow): fetch the doubles themselves
+      JOB_CUDA(j, cudaMemcpy(j->wide, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost));
+      j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
+    } else {
+      Pool* pool = j->ctx->pool.get();
+      int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(pool->size(), b.count / 65536)));
+      const float* src = sl.host32;
+      double* dst = j->wide;
+      const int64_t n = b.count;
+      bool stream_stores = n * 8 > (32LL << 20);  // larger than the cores' L2s together
+      if (const char* e = getenv("FRC_WIDEN_NT")) stream_stores = atoi(e) != 0;
+      if (const char* e = getenv("FRC_WIDEN_THREADS")) T = std::max(1, std::min(T, atoi(e)));
+      pool->run(T, [=](int t) {
+        const int64_t lo = n * t / T / 16 * 16, hi = t + 1 == T ? n : n * (t + 1) / T / 16 * 16;
+        widen_band(src + lo, dst + lo, hi - lo, stream_stores);
+      });
+    }
+  }
+  if (trace_next) {
+    const auto tn2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[host] band %zu: waited %.1f us for the copy, bookkeeping + widening %.1f us\n", idx,
+            std::chrono::duration<double, std::micro>(tn1 - tn0).count(),
+            std::chrono::duration<double, std::micro>(tn2 - tn1).count());
+  }
+  *data = (j->opts.flags & FRC_FLAG_NO_D2H) ? sl.dev : j->wire32 ? j->wide : sl.host;
   *first_index = b.first;
   *count = b.count;
   j->held_slot = static_cast<int>(idx % j->n_slots);

@@ -121,6 +121,11 @@ class Context:
     """Reusable device context (streams + memory pools)."""
 
     def __init__(self, device: int = -1):
+        # several ranks on one host (torchrun): split the host cores between their worker pools
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        if local_world > 1 and "FRC_HOST_THREADS" not in os.environ:
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            os.environ["FRC_HOST_THREADS"] = str(max(2, min(16, cores // local_world)))
         h = C.c_void_p()
         rc = lib().frc_ctx_create(device, C.byref(h))
         if rc:

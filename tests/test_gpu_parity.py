@@ -231,7 +231,60 @@ def test_fast_weighted_small_distances(gpu_ctx, normalize):
     assert flagged >= 21
     e = rel_err(got, want)
     assert e.max() < 1e-5, f"max rel err {e.max():.3e}"
-    assert np.abs(got[:21] - want[:21]).max() <= 1e-9 * want[:21].max() + 1e-15
+    # fixed-point recompute, then one fp32 rounding on the PCIe leg (wire.cu)
+    assert (np.abs(got[:21] - want[:21]) <= 1.2e-7 * want[:21] + 1e-15).all()
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_fp32_wire_against_f64_wire(gpu_ctx, monkeypatch, weighted):
+    """Fast-path distances cross PCIe as fp32 and are widened on the host (wire.cu).  Against doubles on the
+    bus: half the bytes, values identical except for one fp32 rounding of the pairs the exact fix-up rewrote."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(1500, 301)
+    rp, col, val = synth.random_table(tree, 1100, 0.03, 302)
+    m = rp[1]
+    col[m:2 * m] = col[:m]            # an identical pair (d = 0 exactly) and a near copy (fix-up territory)
+    val[m:2 * m] = val[:m]
+    col[2 * m:3 * m] = col[:m]
+    val[2 * m:3 * m] = val[:m] * (1.0 + 1e-3 * (np.arange(m) % 5 == 0))
+
+    def run(band_rows=0):
+        with engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=gpu_ctx,
+                        band_rows=band_rows) as job:
+            got = np.concatenate([a for _, a in job.chunks()])
+            return got, job.info()
+
+    narrow, ni = run()
+    ragged, _ = run(band_rows=128)       # many small bands, odd lengths and alignments
+    monkeypatch.setenv("FRC_WIRE", "f64")
+    wide, wi = run()
+    pairs = 1100 * 1099 // 2
+    assert ni.d2h_bytes == 4 * pairs and wi.d2h_bytes == 8 * pairs
+    assert narrow[0] == 0.0 and wide[0] == 0.0
+    assert np.array_equal(narrow, ragged)
+    assert (np.abs(narrow - wide) <= 6e-8 * wide).all()
+    assert np.array_equal(narrow, wide.astype(np.float32).astype(np.float64))
+    if not weighted:  # the tensor-core epilogue already produces fp32 ratios: nothing is lost on the bus
+        assert (narrow == wide).sum() >= pairs - ni.flagged_pairs
+    assert rel_err(narrow, oracle_flat(tree, (rp, col, val), weighted)).max() < 1e-5
+
+
+def test_fp32_wire_falls_back_when_a_value_underflows(gpu_ctx):
+    """A distance below fp32's range must still arrive: the band is then fetched as doubles."""
+    from frackyfrac_b200 import engine, hostlib
+
+    tree = hostlib.Tree("((a:1e-60,b:1e-60):1,(c:1,d:2):0.5);")
+    tab = hostlib.Table("a:1\tc:1\nb:1\tc:1\nc:1\td:1\na:1\td:3\n", sparse=True)
+    rp, col, val = tab.resolve(tree)
+    want = oracle_flat(tree, (rp, col, val), False)
+    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx) as job:
+        got = np.concatenate([a for _, a in job.chunks()])
+        info = job.info()
+    assert 0 < want[0] < 1e-59
+    assert abs(got[0] - want[0]) <= 1e-5 * want[0]
+    assert rel_err(got, want).max() < 1e-5
+    assert info.d2h_bytes == 4 * 6 + 8 * 6   # the fp32 band, then the same band as doubles
 
 
 @pytest.mark.parametrize("slab", [128, 256])
