@@ -845,65 +845,93 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     int64_t* rp = reinterpret_cast<int64_t*>(stage_csr + s_rowptr.off);
     if (N > 0) memcpy(rp, abnd->row_ptr, sizeof(int64_t) * (N + 1)); else rp[0] = 0;
   }
-  // one worker prepares the tree topology arrays, the others take the CSR entries
-  const int csr_shares = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->pool->size() - 2), nnz / 32768)));
-  int32_t tree_H = -1;  // height of the tree; -1: the share found a parent outside [0, v) (reported by the walk below)
-  auto tree_share = [&, stage_csr]() {
+  // two workers prepare the tree (children lists; pre-order check + level order), the others take the CSR entries
+  const int csr_shares = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->pool->size() - 3), nnz / 32768)));
+  int32_t tree_H = -1;                      // height of the tree, from the levels share
+  int32_t bad_parent = 0, bad_order = 0;    // first offending node ids, from the levels share
+  bool children_ok = false;
+  auto tree_children_share = [&, stage_csr]() {
     const int32_t* parent = tree->parent;
-    std::vector<int32_t> child_cnt(B, 0), height(B, 0);
+    std::vector<int32_t> child_cnt(B, 0);
     for (int32_t v = 1; v < B; ++v) {
       const int32_t p = parent[v];
-      if (p < 0 || p >= v) return;
+      if (p < 0 || p >= v) return;  // (reported by the levels share)
       child_cnt[p]++;
     }
-    for (int32_t v = B - 1; v >= 1; --v) height[parent[v]] = std::max(height[parent[v]], height[v] + 1);
-    const int32_t H = height[0];
     memcpy(stage_csr + s_parent.off, parent, sizeof(int32_t) * B);
     memcpy(stage_csr + s_len.off, tree->length, sizeof(double) * B);
     int32_t* cptr = reinterpret_cast<int32_t*>(stage_csr + s_cptr.off);
     int32_t* cidx = reinterpret_cast<int32_t*>(stage_csr + s_cidx.off);
     cptr[0] = 0;
     for (int32_t v = 0; v < B; ++v) cptr[v + 1] = cptr[v] + child_cnt[v];
-    std::vector<int32_t> fill(cptr, cptr + B);
+    std::vector<int32_t>& fill = child_cnt;  // reused: next free slot of every node's child list
+    for (int32_t v = 0; v < B; ++v) fill[v] = cptr[v];
     for (int32_t v = 1; v < B; ++v) cidx[fill[parent[v]]++] = v;  // ascending id = file order
+    float* lf = reinterpret_cast<float*>(stage_csr + s_lenf.off);
+    for (int32_t v = 0; v < kp_pad; ++v) lf[v] = v < B ? static_cast<float>(tree->length[v]) : 0.f;
+    children_ok = true;
+  };
+  auto tree_levels_share = [&, stage_csr]() {
+    const int32_t* parent = tree->parent;
+    // pre-order check: parent[v] must lie on the path root..v-1, i.e. be the node of its depth on the
+    // current root-to-(v-1) path.  Branch-free per node (the stack-popping form cost 14 ns per node in
+    // mispredictions).
+    std::vector<int32_t> depth(B, 0), on_path(B, 0), height(B, 0);  // on_path[d] = node at depth d of the current path
+    for (int32_t v = 1; v < B; ++v) {
+      const int32_t p = parent[v];
+      if (p < 0 || p >= v) { bad_parent = v; return; }
+      const int32_t d = depth[p];
+      if ((d > depth[v - 1] || on_path[d] != p) && !bad_order) bad_order = v;
+      depth[v] = d + 1;
+      on_path[d + 1] = v;
+    }
+    if (bad_order) return;
+    for (int32_t v = B - 1; v >= 1; --v) height[parent[v]] = std::max(height[parent[v]], height[v] + 1);
+    const int32_t H = height[0];
     j->level_ptr.assign(H + 2, 0);
     for (int32_t v = 0; v < B; ++v) j->level_ptr[height[v] + 1]++;
     for (int32_t h = 0; h <= H; ++h) j->level_ptr[h + 1] += j->level_ptr[h];
     int32_t* lvl = reinterpret_cast<int32_t*>(stage_csr + s_lvl.off);
-    std::vector<int32_t> lfill(j->level_ptr.begin(), j->level_ptr.end() - 1);
+    std::vector<int32_t>& lfill = depth;  // reused: next free slot of every level
+    for (int32_t h = 0; h <= H; ++h) lfill[h] = j->level_ptr[h];
     for (int32_t v = 0; v < B; ++v) lvl[lfill[height[v]]++] = v;
     int32_t* lpar = reinterpret_cast<int32_t*>(stage_csr + s_lpar.off);
     for (int32_t k = 0; k < B; ++k) lpar[k] = lvl[k] ? parent[lvl[k]] : 0;
-    float* lf = reinterpret_cast<float*>(stage_csr + s_lenf.off);
-    for (int32_t v = 0; v < kp_pad; ++v) lf[v] = v < B ? static_cast<float>(tree->length[v]) : 0.f;
     memcpy(stage_csr + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
     tree_H = H;
   };
-  std::vector<std::string> csr_errs(csr_shares);
-  std::vector<double> csr_us(csr_shares + 1, 0.0);
+  // The entries are cut into many more chunks than workers and handed out through a counter: a worker
+  // on a busy or slow core (the slowest static share took 1.5-2.4x the median) just takes fewer.
+  int csr_per_share = 8;
+  if (const char* e = getenv("FRC_CSR_CHUNKS")) csr_per_share = std::max(1, atoi(e));
+  const int csr_chunks = nnz >= 65536 ? static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(csr_shares * static_cast<int64_t>(csr_per_share), nnz / 8192))) : 1;
+  std::atomic<int> csr_next{0};
+  std::vector<std::string> csr_errs(csr_chunks);
+  std::vector<double> csr_us(csr_shares + 2, 0.0);
   // duplicate detection: stamp[leaf] = epoch-tagged sample id; the arrays persist in the
   // context, so nothing is cleared between jobs
   const int64_t stamp_tag = c->stamp_epoch;
   c->stamp_epoch += N + 1;
   const std::function<void(int)> csr_work = [&, stage_csr](int t) {
     const auto w0 = std::chrono::steady_clock::now();
-    if (t == csr_shares) {
-      tree_share();
+    if (t >= csr_shares) {
+      if (t == csr_shares) tree_children_share(); else tree_levels_share();
       csr_us[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
       return;
     }
     int32_t* dcol = reinterpret_cast<int32_t*>(stage_csr + s_col.off);
     double* dval = need_val ? reinterpret_cast<double*>(stage_csr + s_val.off) : nullptr;
-    const int TS = csr_shares;
+    const int TS = csr_chunks;
     // a leaf listed twice in a row only matters when values are used (presence is an OR)
     const bool check_dup = need_val;
     const int32_t* parent = tree->parent;
     auto row_at = [&](int64_t target) {
       return static_cast<int64_t>(std::lower_bound(abnd->row_ptr, abnd->row_ptr + N, target) - abnd->row_ptr);
     };
-    const int64_t s0 = t == 0 ? 0 : row_at(nnz * t / TS), s1 = t == TS - 1 ? N : row_at(nnz * (t + 1) / TS);
     std::vector<int64_t>& stamp = c->stamps[t];
     if (check_dup && static_cast<int32_t>(stamp.size()) < B) stamp.assign(B, -1);
+    for (int ch = csr_next.fetch_add(1, std::memory_order_relaxed); ch < TS; ch = csr_next.fetch_add(1, std::memory_order_relaxed)) {
+    const int64_t s0 = ch == 0 ? 0 : row_at(nnz * ch / TS), s1 = ch == TS - 1 ? N : row_at(nnz * (ch + 1) / TS);
     bool failed = false;
     for (int64_t s = s0; s < s1 && !failed; ++s) {
       const int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
@@ -919,7 +947,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
         else if (!(v > 0) || std::isinf(v)) what = "bad value";
         else if (check_dup && stamp[cc] == mark_s) what = "leaf listed twice";
         if (what) {
-          csr_errs[t] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
+          csr_errs[ch] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
                         std::to_string(cc) + "): " + what;
           failed = true;
           break;
@@ -935,43 +963,27 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
 #endif
       }
     }
+    }
 #if defined(__x86_64__)
     _mm_sfence();
 #endif
     csr_us[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
   };
   csr_workers_busy = true;
-  const bool tree_share_pooled = c->pool->size() >= 3;
-  c->pool->start(csr_shares + (tree_share_pooled ? 1 : 0), csr_work);
+  const bool tree_share_pooled = c->pool->size() >= 4;
+  c->pool->start(csr_shares + (tree_share_pooled ? 2 : 0), csr_work);
   if (c->pool->size() == 1) csr_workers_busy = false;  // (no workers: the shares ran inline)
   mark("table checks, context, CSR workers started");
 
-  // ------------------------------------------------------------- validate tree (full walk)
-  {
-    // pre-order check: parent[v] must lie on the path root..v-1, i.e. be the node of its depth on the
-    // current root-to-(v-1) path.  Branch-free per node (the stack-popping form cost 14 ns per node in
-    // mispredictions: 0.2 ms of the 2.8 ms end-to-end time at cfg2).
-    std::vector<int32_t> depth(B, 0), on_path(B, 0);  // on_path[d] = node at depth d of the current path
-    int32_t bad_parent = 0, bad_order = 0;
-    for (int32_t v = 1; v < B; ++v) {
-      const int32_t p = tree->parent[v];
-      if (p < 0 || p >= v) { bad_parent = v; break; }
-      const int32_t d = depth[p];
-      if ((d > depth[v - 1] || on_path[d] != p) && !bad_order) bad_order = v;
-      depth[v] = d + 1;
-      on_path[d + 1] = v;
-    }
-    if (bad_parent) return bail(fail(j, FRC_ERR_ARG, "parent[" + std::to_string(bad_parent) + "] is not a smaller node id"));
-    if (bad_order) return bail(fail(j, FRC_ERR_ARG, "node ids are not a pre-order numbering (node " + std::to_string(bad_order) + ")"));
-  }
+  // ------------------------------------------------------------- branch lengths (the walk runs in the pool)
   bool neg_len = false, bad_len = false;
   for (int32_t v = 0; v < B; ++v) {
     double l = tree->length[v];
     if (!(l == l) || std::isinf(l)) bad_len = true;
     else if (l < 0) neg_len = true;
   }
-  if (!tree_share_pooled) tree_share();
-  mark("validate tree");
+  if (!tree_share_pooled) { tree_children_share(); tree_levels_share(); }
+  mark("branch lengths checked");
   // --------------------------------------------------------------- choose path
   j->N = N; j->B = B; j->nnz = nnz;
   j->sharded = (opts->flags & FRC_FLAG_SHARD_EMBED) != 0 && world > 1;
@@ -1028,10 +1040,18 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
         if (tree->length[v] > 0) e_max = std::max(e_max, ilog(tree->length[v]));
       int gb = 3;  // binades per group: x = len * 2^-e in [2^20, 2^23), >= 110 candidate factors a
       if (const char* e = getenv("FRC_U8_GROUP_BINADES")) gb = std::max(1, std::min(16, atoi(e)));
-      auto group_of = [&](double l) { return std::min(kGroups - 1, (e_max - ilog(l)) / gb); };
-      int32_t cnt[kGroups] = {0};
-      for (int32_t v = 0; v < B; ++v)
-        if (tree->length[v] > 0) cnt[group_of(tree->length[v])]++;
+      // group of every node, through a table over the exponent distance (an integer division per node
+      // and pass was most of this plan's 0.15 ms at 2e4 nodes); 255 = no column (length 0)
+      uint8_t group_tab[2112];
+      for (int d = 0; d < 2112; ++d) group_tab[d] = static_cast<uint8_t>(std::min(kGroups - 1, d / gb));
+      std::vector<uint8_t> grp(B);
+      int32_t cnt[kGroups + 1] = {0};
+      for (int32_t v = 0; v < B; ++v) {
+        const double l = tree->length[v];
+        const uint8_t g = l > 0 ? group_tab[e_max - ilog(l)] : static_cast<uint8_t>(kGroups);
+        grp[v] = g;
+        cnt[g]++;
+      }
       // Groups -> accumulation chunks.  Every chunk costs a TMEM drain (>= 2k cycles: 128 KB at
       // 64 B/clk) that only hides behind a long enough MMA run, so a group opens a chunk of its own
       // only when it is large; smaller groups below it join the current chunk at that chunk's
@@ -1072,10 +1092,9 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
           if (chunk_of[g] >= 0) { fill[g] = next[chunk_of[g]]; next[chunk_of[g]] += cnt[g]; }
       }
       for (int32_t v = 0; v < B; ++v) {
-        const double l = tree->length[v];
-        if (!(l > 0)) continue;
-        const int32_t k = fill[group_of(l)]++;
-        col_order[k] = v; len_col[k] = l;
+        if (grp[v] == kGroups) continue;
+        const int32_t k = fill[grp[v]]++;
+        col_order[k] = v; len_col[k] = tree->length[v];
       }
       for (int k = 0; k < n_ch; ++k) {
         const int c = ch_order[k];
@@ -1386,9 +1405,11 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   // -------------------------------------------- join the table workers, upload the CSR block
   if (csr_workers_busy) { c->pool->wait(); csr_workers_busy = false; }
   if (trace) { fprintf(stderr, "[frc_create] CSR share times (us):"); for (double u : csr_us) fprintf(stderr, " %.0f", u); fprintf(stderr, "\n"); }
+  if (bad_parent) return bail(fail(j, FRC_ERR_ARG, "parent[" + std::to_string(bad_parent) + "] is not a smaller node id"));
+  if (bad_order) return bail(fail(j, FRC_ERR_ARG, "node ids are not a pre-order numbering (node " + std::to_string(bad_order) + ")"));
   for (auto& e : csr_errs)
     if (!e.empty()) return bail(fail(j, FRC_ERR_ARG, e));
-  if (tree_H < 0) return bail(fail(j, FRC_ERR_ARG, "tree topology could not be prepared"));  // (unreachable after the walk above)
+  if (tree_H < 0 || !children_ok) return bail(fail(j, FRC_ERR_ARG, "tree topology could not be prepared"));  // (unreachable)
   j->dtree.height = tree_H;
   j->info.tree_height = tree_H;
   CREATE_CUDA(cudaMemcpyAsync(d_csr, stage_csr, csr_total, cudaMemcpyHostToDevice, c->stream[0]));
@@ -1466,10 +1487,30 @@ int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* c
       bool stream_stores = n * 8 > (32LL << 20);  // larger than the cores' L2s together
       if (const char* e = getenv("FRC_WIDEN_NT")) stream_stores = atoi(e) != 0;
       if (const char* e = getenv("FRC_WIDEN_THREADS")) T = std::max(1, std::min(T, atoi(e)));
+      double share_us[64] = {0};
+      double* su = trace_next && T <= 64 ? share_us : nullptr;
+      // chunks handed out through a counter (a worker on a busy core takes fewer); walking the band in
+      // the same order every time keeps most of a chunk's destination lines in the core that wrote them last
+      int64_t kChunk = 16384;
+      if (const char* e = getenv("FRC_WIDEN_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(e)) / 16 * 16;  // (static shares: >= n / T)
+      const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+      std::atomic<int64_t> next{0};
+      std::atomic<int64_t>* nx = &next;
       pool->run(T, [=](int t) {
-        const int64_t lo = n * t / T / 16 * 16, hi = t + 1 == T ? n : n * (t + 1) / T / 16 * 16;
-        widen_band(src + lo, dst + lo, hi - lo, stream_stores);
+        const auto w0 = std::chrono::steady_clock::now();
+        // the first round is static so that thread t starts where it started for the previous band
+        for (int64_t ch = t < n_chunks ? t : n_chunks; ch < n_chunks;) {
+          const int64_t lo = ch * kChunk, hi = std::min(n, lo + kChunk);
+          widen_band(src + lo, dst + lo, hi - lo, stream_stores);
+          ch = T + nx->fetch_add(1, std::memory_order_relaxed);
+        }
+        if (su) su[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
       });
+      if (su) {
+        fprintf(stderr, "[host] band %zu widen shares (us):", idx);
+        for (int t = 0; t < T; ++t) fprintf(stderr, " %.0f", su[t]);
+        fprintf(stderr, "  (whole call %.0f)\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tn1).count());
+      }
     }
   }
   if (trace_next) {

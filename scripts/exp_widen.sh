@@ -1,17 +1,15 @@
 #!/bin/bash
-# e2e against how the host widens the fp32 bands (store kind, worker count).
+# e2e against how the host widens the fp32 bands (chunk size of the dynamic hand-out; 110000 = one static share per thread).
 out=gpurun_out/widen_e2e.txt; : > $out
 run() { label=$1; shift
   env "$@" python bench.py --steps 100 --warmup 5 --no-cpu 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('$label e2e %.3e (%.3f ms)'%(d['e2e']['value'],d['e2e']['ms_per_step']))" >> $out
 }
-run "cached t16" FRC_WIDEN_NT=0
-run "nt     t16" FRC_WIDEN_NT=1
-run "cached t8 " FRC_WIDEN_NT=0 FRC_WIDEN_THREADS=8
-run "nt     t8 " FRC_WIDEN_NT=1 FRC_WIDEN_THREADS=8
-run "cached t12" FRC_WIDEN_NT=0 FRC_WIDEN_THREADS=12
-run "nt     t12" FRC_WIDEN_NT=1 FRC_WIDEN_THREADS=12
-run "cached t4 " FRC_WIDEN_NT=0 FRC_WIDEN_THREADS=4
-run "cached t16" FRC_WIDEN_NT=0
-run "nt     t16" FRC_WIDEN_NT=1
+run "chunk 16384 " FRC_WIDEN_CHUNK=16384
+run "chunk 110000" FRC_WIDEN_CHUNK=110000
+run "chunk 4096  " FRC_WIDEN_CHUNK=4096
+run "chunk 32768 " FRC_WIDEN_CHUNK=32768
+run "chunk 16384 " FRC_WIDEN_CHUNK=16384
+run "chunk 110000" FRC_WIDEN_CHUNK=110000
+run "chunk 8192  " FRC_WIDEN_CHUNK=8192
