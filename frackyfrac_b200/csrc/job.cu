@@ -172,6 +172,7 @@ class Pool {
   bool stop_ = false;
 };
 
+constexpr int64_t kWidePiece = 2LL << 20;        // fp32 wire: pairs widened per frc_next call (16 MB of doubles: cache-resident)
 constexpr int kSlots = 8;                       // output ring: enough for the compute to run ahead of the D2H
 constexpr int kMinSlots = 3;
 constexpr int64_t kSlotBytesBudget = 1LL << 30;  // bytes the output ring may take beyond kMinSlots (pinned allocation is slow: ~0.4 s per GB)
@@ -238,7 +239,8 @@ struct frc_job {
   bool fused_embed = true;
   bool zero_copy = false;
   bool wire32 = false;  // bands cross PCIe as fp32 and are widened on the host (wire.cu)
-  double* wide = nullptr;  // wire32: the one band-sized double buffer frc_next hands out
+  double* wide = nullptr;  // wire32: the one double buffer frc_next hands out (<= kWidePiece values)
+  int64_t piece_first = 0, piece_off = 0, piece_end = 0;  // wire32: progress through the held band
   int64_t ws_slab = 0;        // fast weighted: samples per fp64 embedding slab
   bool peer_push = false;     // sharded unweighted: the bits kernel stores into every rank's bitsT (no NCCL for the bits)
   uint32_t* d_bits2[2] = {nullptr, nullptr};  // double-buffered by run parity (a rank may be one step ahead)
@@ -589,6 +591,7 @@ int enqueue_band(frc_job* j, size_t idx) {
 int start_pairs(frc_job* j) {
   j->next_enqueue = j->next_deliver = 0;
   j->held_slot = -1;
+  j->piece_off = j->piece_end = 0;
   j->info.pairs_ms = 0;
   j->info.fixup_ms = 0;
   j->info.run_ms = 0;
@@ -1377,7 +1380,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     j->n_slots = static_cast<int>(std::min<int64_t>(want, std::max<int64_t>(2, static_cast<int64_t>(j->mine.size()) + 1)));
   }
   if (j->mine.empty()) j->n_slots = 0;
-  if (j->wire32 && j->n_slots > 0 && !(j->wide = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
+  if (j->wire32 && j->n_slots > 0 && !(j->wide = pin_alloc<double>(j, std::min(max_band, kWidePiece), &rc))) return bail(rc);
   for (int k = 0; k < j->n_slots; ++k) {
     Slot& sl = j->slots[k];
     if (!(opts->flags & FRC_FLAG_NO_D2H) && !j->wire32 && !(sl.host = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
@@ -1424,10 +1427,61 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
 #undef CREATE_CUDA
 }
 
+// fp32 wire: widens pairs [off, off + n) of the band in slot `sl` into j->wide (wire.cu).  A band larger
+// than kWidePiece is handed out in pieces, so that the buffer always fits the cores' caches.
+static int widen_piece(frc_job* j, Slot& sl, int64_t off, int64_t n, bool trace) {
+  if (*sl.n_bad_host) {
+    // some value of this band does not survive fp32 (underflow): fetch the doubles themselves
+    JOB_CUDA(j, cudaMemcpy(j->wide, sl.dev + off, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * n;
+    return FRC_OK;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  Pool* pool = j->ctx->pool.get();
+  int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(pool->size(), n / 65536)));
+  if (const char* e = getenv("FRC_WIDEN_THREADS")) T = std::max(1, std::min(T, atoi(e)));
+  const float* src = sl.host32 + off;
+  double* dst = j->wide;
+  double share_us[64] = {0};
+  double* su = trace && T <= 64 ? share_us : nullptr;
+  // chunks handed out through a counter (a worker on a busy core takes fewer); the first round is
+  // static so that thread t starts where it started last time and finds its destination lines in its L2
+  constexpr int64_t kChunk = 16384;
+  const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+  std::atomic<int64_t> next{0};
+  std::atomic<int64_t>* nx = &next;
+  pool->run(T, [=](int t) {
+    const auto w0 = std::chrono::steady_clock::now();
+    for (int64_t ch = t < n_chunks ? t : n_chunks; ch < n_chunks;) {
+      const int64_t lo = ch * kChunk, hi = std::min(n, lo + kChunk);
+      widen_band(src + lo, dst + lo, hi - lo, /*stream_stores=*/false);
+      ch = T + nx->fetch_add(1, std::memory_order_relaxed);
+    }
+    if (su) su[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+  });
+  if (su) {
+    fprintf(stderr, "[host] widen %lld pairs, shares (us):", static_cast<long long>(n));
+    for (int t = 0; t < T; ++t) fprintf(stderr, " %.0f", su[t]);
+    fprintf(stderr, "  (whole %.0f)\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+  }
+  return FRC_OK;
+}
+
 int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* count) {
   if (!j || !data || !first_index || !count) return FRC_ERR_ARG;
   *data = nullptr; *first_index = 0; *count = 0;
   JOB_CUDA(j, cudaSetDevice(j->ctx->device));
+  // a band larger than the widening buffer is handed out piece by piece
+  if (j->held_slot >= 0 && j->wire32 && j->piece_off < j->piece_end) {
+    const int64_t n = std::min(kWidePiece, j->piece_end - j->piece_off);
+    int rc = widen_piece(j, j->slots[j->held_slot], j->piece_off, n, getenv("FRC_TRACE") != nullptr);
+    if (rc) return rc;
+    *data = j->wide;
+    *first_index = j->piece_first + j->piece_off;
+    *count = n;
+    j->piece_off += n;
+    return FRC_OK;
+  }
   // the band handed out by the previous call is released now
   if (j->held_slot >= 0) {
     j->held_slot = -1;
@@ -1473,45 +1527,12 @@ int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* c
             static_cast<long long>(j->bands[j->mine[idx]].count));
   }
   const Band& b = j->bands[j->mine[idx]];
+  int64_t deliver_n = b.count;
   if (j->wire32) {
-    if (*sl.n_bad_host) {
-      // some value of this band does not survive fp32 (underflow): fetch the doubles themselves
-      JOB_CUDA(j, cudaMemcpy(j->wide, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost));
-      j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
-    } else {
-      Pool* pool = j->ctx->pool.get();
-      int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(pool->size(), b.count / 65536)));
-      const float* src = sl.host32;
-      double* dst = j->wide;
-      const int64_t n = b.count;
-      bool stream_stores = n * 8 > (32LL << 20);  // larger than the cores' L2s together
-      if (const char* e = getenv("FRC_WIDEN_NT")) stream_stores = atoi(e) != 0;
-      if (const char* e = getenv("FRC_WIDEN_THREADS")) T = std::max(1, std::min(T, atoi(e)));
-      double share_us[64] = {0};
-      double* su = trace_next && T <= 64 ? share_us : nullptr;
-      // chunks handed out through a counter (a worker on a busy core takes fewer); walking the band in
-      // the same order every time keeps most of a chunk's destination lines in the core that wrote them last
-      int64_t kChunk = 16384;
-      if (const char* e = getenv("FRC_WIDEN_CHUNK")) kChunk = std::max<int64_t>(1024, atoll(e)) / 16 * 16;  // (static shares: >= n / T)
-      const int64_t n_chunks = (n + kChunk - 1) / kChunk;
-      std::atomic<int64_t> next{0};
-      std::atomic<int64_t>* nx = &next;
-      pool->run(T, [=](int t) {
-        const auto w0 = std::chrono::steady_clock::now();
-        // the first round is static so that thread t starts where it started for the previous band
-        for (int64_t ch = t < n_chunks ? t : n_chunks; ch < n_chunks;) {
-          const int64_t lo = ch * kChunk, hi = std::min(n, lo + kChunk);
-          widen_band(src + lo, dst + lo, hi - lo, stream_stores);
-          ch = T + nx->fetch_add(1, std::memory_order_relaxed);
-        }
-        if (su) su[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
-      });
-      if (su) {
-        fprintf(stderr, "[host] band %zu widen shares (us):", idx);
-        for (int t = 0; t < T; ++t) fprintf(stderr, " %.0f", su[t]);
-        fprintf(stderr, "  (whole call %.0f)\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tn1).count());
-      }
-    }
+    deliver_n = std::min(kWidePiece, b.count);
+    j->piece_first = b.first; j->piece_off = deliver_n; j->piece_end = b.count;
+    int rc = widen_piece(j, sl, 0, deliver_n, trace_next);
+    if (rc) return rc;
   }
   if (trace_next) {
     const auto tn2 = std::chrono::steady_clock::now();
@@ -1521,7 +1542,7 @@ int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* c
   }
   *data = (j->opts.flags & FRC_FLAG_NO_D2H) ? sl.dev : j->wire32 ? j->wide : sl.host;
   *first_index = b.first;
-  *count = b.count;
+  *count = deliver_n;
   j->held_slot = static_cast<int>(idx % j->n_slots);
   ++j->next_deliver;
   return FRC_OK;

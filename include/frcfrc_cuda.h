@@ -159,7 +159,10 @@ int frc_create(frc_ctx_t *ctx, const frc_tree_t *tree, const frc_csr_t *abnd,
  * flat lower-triangle vector, index(i,j) = i(i-1)/2 + j for j < i
  * (common/common.go:21-31), in strictly increasing index order.  `*data` is
  * engine-owned pinned host memory (device memory with FRC_FLAG_NO_D2H), valid
- * until the next call on this job.  *count == 0 means the stream has ended. */
+ * until the next call on this job.  *count == 0 means the stream has ended.
+ * A run is one tile band of the plan (frc_plan_bands) or, for the fast paths on
+ * the host route, a piece of one of at most 2^21 values: those distances cross
+ * PCIe as fp32 and are widened here into a cache-sized buffer (csrc/wire.cu). */
 int frc_next(frc_job_t *job, const double **data, int64_t *first_index, int64_t *count);
 
 /* Re-runs embedding + pair stage on the inputs already resident in HBM

@@ -270,6 +270,25 @@ def test_fp32_wire_against_f64_wire(gpu_ctx, monkeypatch, weighted):
     assert rel_err(narrow, oracle_flat(tree, (rp, col, val), weighted)).max() < 1e-5
 
 
+def test_fp32_wire_delivers_large_bands_in_pieces(gpu_ctx):
+    """A band larger than the host widening buffer (2 M pairs) arrives over several frc_next calls: contiguous,
+    in order, and with the same values as the default band plan."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(300, 311)
+    rp, col, val = synth.random_table(tree, 2500, 0.05, 312)
+    pairs = 2500 * 2499 // 2
+    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx,
+                    band_rows=4096) as job:
+        runs = [(first, a.copy()) for first, a in job.chunks(copy=False)]
+        info = job.info()
+    assert info.n_bands_mine == 1 and [len(a) for _, a in runs] == [2 << 20, pairs - (2 << 20)]
+    assert [f for f, _ in runs] == [0, 2 << 20]
+    one_band = np.concatenate([a for _, a in runs])
+    assert np.array_equal(one_band, gpu_flat(tree, (rp, col, val), False, path=engine.PATH_FAST, ctx=gpu_ctx))
+    assert rel_err(one_band, oracle_flat(tree, (rp, col, val), False)).max() < 1e-5
+
+
 def test_fp32_wire_falls_back_when_a_value_underflows(gpu_ctx):
     """A distance below fp32's range must still arrive: the band is then fetched as doubles."""
     from frackyfrac_b200 import engine, hostlib
