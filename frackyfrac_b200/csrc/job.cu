@@ -848,8 +848,10 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     int64_t* rp = reinterpret_cast<int64_t*>(stage_csr + s_rowptr.off);
     if (N > 0) memcpy(rp, abnd->row_ptr, sizeof(int64_t) * (N + 1)); else rp[0] = 0;
   }
-  // two workers prepare the tree (children lists; pre-order check + level order), the others take the CSR entries
-  const int csr_shares = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::max(1, c->pool->size() - 3), nnz / 32768)));
+  // One task list for the pool: two tree tasks (children lists; pre-order check + level order), then the
+  // CSR entries in chunks, all handed out through one counter; the calling thread joins in when its own
+  // part is done, so the split adapts to any pool size (4 threads per rank on a 32-core 8-GPU host).
+  const int n_workers = c->pool->size() - 1;
   int32_t tree_H = -1;                      // height of the tree, from the levels share
   int32_t bad_parent = 0, bad_order = 0;    // first offending node ids, from the levels share
   bool children_ok = false;
@@ -905,23 +907,16 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   };
   // The entries are cut into many more chunks than workers and handed out through a counter: a worker
   // on a busy or slow core (the slowest static share took 1.5-2.4x the median) just takes fewer.
-  int csr_per_share = 8;
-  if (const char* e = getenv("FRC_CSR_CHUNKS")) csr_per_share = std::max(1, atoi(e));
-  const int csr_chunks = nnz >= 65536 ? static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(csr_shares * static_cast<int64_t>(csr_per_share), nnz / 8192))) : 1;
-  std::atomic<int> csr_next{0};
+  const int csr_chunks = nnz >= 65536 ? static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->pool->size() * 8LL, nnz / 8192))) : 1;
+  std::atomic<int> task_next{0};
   std::vector<std::string> csr_errs(csr_chunks);
-  std::vector<double> csr_us(csr_shares + 2, 0.0);
+  std::vector<double> csr_us(c->pool->size(), 0.0);
   // duplicate detection: stamp[leaf] = epoch-tagged sample id; the arrays persist in the
   // context, so nothing is cleared between jobs
   const int64_t stamp_tag = c->stamp_epoch;
   c->stamp_epoch += N + 1;
   const std::function<void(int)> csr_work = [&, stage_csr](int t) {
     const auto w0 = std::chrono::steady_clock::now();
-    if (t >= csr_shares) {
-      if (t == csr_shares) tree_children_share(); else tree_levels_share();
-      csr_us[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
-      return;
-    }
     int32_t* dcol = reinterpret_cast<int32_t*>(stage_csr + s_col.off);
     double* dval = need_val ? reinterpret_cast<double*>(stage_csr + s_val.off) : nullptr;
     const int TS = csr_chunks;
@@ -933,7 +928,10 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     };
     std::vector<int64_t>& stamp = c->stamps[t];
     if (check_dup && static_cast<int32_t>(stamp.size()) < B) stamp.assign(B, -1);
-    for (int ch = csr_next.fetch_add(1, std::memory_order_relaxed); ch < TS; ch = csr_next.fetch_add(1, std::memory_order_relaxed)) {
+    for (int task = task_next.fetch_add(1, std::memory_order_relaxed); task < TS + 2; task = task_next.fetch_add(1, std::memory_order_relaxed)) {
+    if (task == 0) { tree_levels_share(); continue; }
+    if (task == 1) { tree_children_share(); continue; }
+    const int ch = task - 2;
     const int64_t s0 = ch == 0 ? 0 : row_at(nnz * ch / TS), s1 = ch == TS - 1 ? N : row_at(nnz * (ch + 1) / TS);
     bool failed = false;
     for (int64_t s = s0; s < s1 && !failed; ++s) {
@@ -970,12 +968,12 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
 #if defined(__x86_64__)
     _mm_sfence();
 #endif
-    csr_us[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
+    csr_us[t] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
   };
-  csr_workers_busy = true;
-  const bool tree_share_pooled = c->pool->size() >= 4;
-  c->pool->start(csr_shares + (tree_share_pooled ? 2 : 0), csr_work);
-  if (c->pool->size() == 1) csr_workers_busy = false;  // (no workers: the shares ran inline)
+  if (n_workers > 0) {
+    csr_workers_busy = true;
+    c->pool->start(n_workers, csr_work);
+  }
   mark("table checks, context, CSR workers started");
 
   // ------------------------------------------------------------- branch lengths (the walk runs in the pool)
@@ -985,7 +983,6 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
     if (!(l == l) || std::isinf(l)) bad_len = true;
     else if (l < 0) neg_len = true;
   }
-  if (!tree_share_pooled) { tree_children_share(); tree_levels_share(); }
   mark("branch lengths checked");
   // --------------------------------------------------------------- choose path
   j->N = N; j->B = B; j->nnz = nnz;
@@ -1406,6 +1403,7 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
 
   mark("device buffers, tensor maps, slots");
   // -------------------------------------------- join the table workers, upload the CSR block
+  csr_work(n_workers);  // whatever is left of the task list (everything, without workers)
   if (csr_workers_busy) { c->pool->wait(); csr_workers_busy = false; }
   if (trace) { fprintf(stderr, "[frc_create] CSR share times (us):"); for (double u : csr_us) fprintf(stderr, " %.0f", u); fprintf(stderr, "\n"); }
   if (bad_parent) return bail(fail(j, FRC_ERR_ARG, "parent[" + std::to_string(bad_parent) + "] is not a smaller node id"));
