@@ -1369,8 +1369,13 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   { const char* e = getenv("FRC_ZERO_COPY"); j->zero_copy = e && atoi(e) == 1; }
   {
     // fast-path distances have fp32 precision: send them over PCIe as fp32, widen on the host (wire.cu)
-    const char* e = getenv("FRC_WIRE");  // "f64": keep doubles on the bus
-    j->wire32 = !j->exact && !(opts->flags & FRC_FLAG_NO_D2H) && !j->zero_copy && !(e && !strcmp(e, "f64"));
+    // The widening is host CPU work the copy engine did for free with doubles on the bus: it pays when
+    // this rank has the cores for it.  Measured: 16 threads 1.7 vs 2.8 ms per cfg2 call, 8 threads per
+    // rank (2 GPUs) 9.9 vs 7.0e9 pairs/s, but 4 threads per rank (8 GPUs on a 32-core host) 8.1e9 against
+    // 1.0e10 with doubles.  FRC_WIRE=f64 / f32 overrides.
+    const char* e = getenv("FRC_WIRE");
+    const bool want32 = e ? !strcmp(e, "f32") : c->pool->size() >= 8;
+    j->wire32 = !j->exact && !(opts->flags & FRC_FLAG_NO_D2H) && !j->zero_copy && want32;
   }
   {
     int64_t want = std::max<int64_t>(kMinSlots, std::min<int64_t>(kSlots, kSlotBytesBudget / (max_band * 8)));

@@ -255,6 +255,7 @@ def test_fp32_wire_against_f64_wire(gpu_ctx, monkeypatch, weighted):
             got = np.concatenate([a for _, a in job.chunks()])
             return got, job.info()
 
+    monkeypatch.setenv("FRC_WIRE", "f32")   # (the default picks it when the rank has >= 8 host threads)
     narrow, ni = run()
     ragged, _ = run(band_rows=128)       # many small bands, odd lengths and alignments
     monkeypatch.setenv("FRC_WIRE", "f64")
@@ -270,10 +271,12 @@ def test_fp32_wire_against_f64_wire(gpu_ctx, monkeypatch, weighted):
     assert rel_err(narrow, oracle_flat(tree, (rp, col, val), weighted)).max() < 1e-5
 
 
-def test_fp32_wire_delivers_large_bands_in_pieces(gpu_ctx):
+def test_fp32_wire_delivers_large_bands_in_pieces(gpu_ctx, monkeypatch):
     """A band larger than the host widening buffer (2 M pairs) arrives over several frc_next calls: contiguous,
     in order, and with the same values as the default band plan."""
     from frackyfrac_b200 import engine, synth
+
+    monkeypatch.setenv("FRC_WIRE", "f32")
 
     tree = synth.random_tree(300, 311)
     rp, col, val = synth.random_table(tree, 2500, 0.05, 312)
@@ -289,9 +292,11 @@ def test_fp32_wire_delivers_large_bands_in_pieces(gpu_ctx):
     assert rel_err(one_band, oracle_flat(tree, (rp, col, val), False)).max() < 1e-5
 
 
-def test_fp32_wire_falls_back_when_a_value_underflows(gpu_ctx):
+def test_fp32_wire_falls_back_when_a_value_underflows(gpu_ctx, monkeypatch):
     """A distance below fp32's range must still arrive: the band is then fetched as doubles."""
     from frackyfrac_b200 import engine, hostlib
+
+    monkeypatch.setenv("FRC_WIRE", "f32")
 
     tree = hostlib.Tree("((a:1e-60,b:1e-60):1,(c:1,d:2):0.5);")
     tab = hostlib.Table("a:1\tc:1\nb:1\tc:1\nc:1\td:1\na:1\td:3\n", sparse=True)
