@@ -22,3 +22,12 @@ CLI = [("uwtd1", False, False), ("uwtd1", True, False), ("uwtd2", False, False),
 
 def sparse_text(abnd):
     return "".join("\t".join(f"{k}:{v}" for k, v in m.items()) + "\n" for m in abnd)
+
+
+# (fixture, table suffix, sparse, want tag, weighted, unnormalised): tests/golden/make_golden.py (oracle answers on
+# seeded synthetic inputs, committed)
+SYNTH = [("synth_a", ".sparse", True, "uw", False, False), ("synth_a", ".dense", False, "uw", False, False),
+         ("synth_a", ".sparse", True, "w", True, False), ("synth_a", ".dense", False, "w", True, False),
+         ("synth_a", ".sparse", True, "wl", True, True),
+         ("synth_b", ".sparse", True, "uw", False, False), ("synth_b", ".sparse", True, "w", True, False),
+         ("synth_b", ".sparse", True, "wl", True, True)]

@@ -61,6 +61,28 @@ def test_cli_binary_golden(built, tmp_path, fixture, sparse, weighted):
     assert out.read_text() == _read(fixture + ".want")
 
 
+@pytest.mark.parametrize("fixture,suffix,sparse,tag,weighted,nnorm", kat.SYNTH)
+def test_synthetic_golden_through_the_gpu(built, gpu_ctx, tmp_path, fixture, suffix, sparse, tag, weighted, nnorm):
+    """Committed synthetic fixtures (tests/golden/make_golden.py): the CLI stand-in reproduces the bytes (these sizes
+    take the exact fp64 kernel), and the fast kernels land within 1e-5 of the committed values."""
+    from frackyfrac_b200 import engine, hostlib
+
+    want_text = _read(f"{fixture}.{tag}.want")
+    out = tmp_path / "got"
+    cmd = [hostlib.CLI_PATH, "-t", os.path.join(GOLDEN, fixture + ".tree"), "-i", os.path.join(GOLDEN, fixture + suffix),
+           "-o", str(out)]
+    cmd += (["-s"] if sparse else []) + (["-w"] if weighted else []) + (["-l"] if nnorm else [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.read_text() == want_text
+    tree = hostlib.Tree(_read(fixture + ".tree"))
+    rp, col, val = hostlib.Table(_read(fixture + suffix), sparse=sparse).resolve(tree)
+    want = np.array([float(x) for x in want_text.split()])
+    got = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, not nnorm, path=engine.PATH_FAST, ctx=gpu_ctx)
+    assert rel_err(got, want).max() < 1e-5
+    assert (got[want == 0] == 0).all()
+
+
 def test_cli_binary_compressed_files(built, tmp_path):
     """aio.Open / aio.Create pick the codec from the suffix (frcfrc.go:93,100-109): gzip'd tree and table in,
     gzip'd and zstd'd distances out; the decoded output equals the golden .want, also with a multi-block output."""

@@ -44,6 +44,28 @@ def test_cli_golden(built, fixture, sparse, weighted):
     assert r.returncode == 0 and r.stdout == _read(fixture + ".want")
 
 
+@pytest.mark.parametrize("fixture,suffix,sparse,tag,weighted,nnorm", kat.SYNTH)
+def test_synthetic_golden_bytes(built, fixture, suffix, sparse, tag, weighted, nnorm):
+    """The committed synthetic fixtures (tests/golden/make_golden.py): the oracle, through its library and its
+    CLI, must keep producing exactly these bytes — a change to the checker cannot move the target unnoticed."""
+    from oracle import oracle as orc
+
+    tree = orc.Tree.parse(_read(fixture + ".tree"))
+    tab = orc.Table.parse(_read(fixture + suffix), sparse)
+    orc.validate_species(tab, tree)
+    want = _read(f"{fixture}.{tag}.want")
+    for threads in (1, 3):
+        d = orc.unifrac(tab, tree, weighted, 2 if nnorm else 1, threads)
+        assert "".join(orc.format_go(float(v)) + "\n" for v in d) == want
+    if nnorm:
+        return  # the oracle's CLI restates the reference's -l literally (unsorted lists, normalize=0); the fixture
+                # holds -l as documented (normalize=2), which is what the engine implements (DESIGN.md, A-notes)
+    cmd = [orc.CLI_PATH, "-t", os.path.join(GOLDEN, fixture + ".tree"), "-i", os.path.join(GOLDEN, fixture + suffix)]
+    cmd += (["-s"] if sparse else []) + (["-w"] if weighted else [])
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == want
+
+
 def test_pair_order_is_iterpairs(built):
     """common/common_test.go:8-18: (2,1),(4,1),(4,2),(8,1),(8,2),(8,4) -> row-major lower triangle."""
     from oracle import oracle as orc
