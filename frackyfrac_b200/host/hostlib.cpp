@@ -15,10 +15,17 @@ namespace frchost {
 
 // ------------------------------------------------------------------- Newick
 namespace {
-bool nwk_delim(unsigned char c) {
-  return c == '(' || c == ')' || c == ',' || c == ':' || c == ';' || c == '[' || c == ']';
-}
-bool is_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
+// character classes of the Newick scanner: 1 = structural delimiter, 2 = white space
+struct NwkLut {
+  uint8_t t[256] = {};
+  constexpr NwkLut() {
+    for (char c : {'(', ')', ',', ':', ';', '[', ']'}) t[static_cast<unsigned char>(c)] = 1;
+    for (char c : {' ', '\t', '\n', '\r', '\f', '\v'}) t[static_cast<unsigned char>(c)] = 2;
+  }
+};
+constexpr NwkLut kNwk;
+inline bool is_space(unsigned char c) { return kNwk.t[c] == 2; }
+inline bool nwk_token_end(unsigned char c) { return kNwk.t[c] != 0; }  // delimiter or space
 }  // namespace
 
 FlatTree parse_newick(const char* s, size_t len) {
@@ -33,6 +40,12 @@ FlatTree parse_newick(const char* s, size_t len) {
   };
   // A node gets its id when it is opened, which is pre-order: "(" opens the
   // first child of the current node, "," opens the next sibling.
+  {
+    // one node per ',' or '(' (+ the root): reserving spares the name vector its reallocation moves
+    size_t nodes = 1;
+    for (size_t k = 0; k < len; ++k) nodes += (s[k] == ',') | (s[k] == '(');
+    t.parent.reserve(nodes); t.length.reserve(nodes); t.name.reserve(nodes); t.n_children.reserve(nodes);
+  }
   int32_t cur = add(-1);
   size_t i = 0;
   bool done = false;
@@ -56,11 +69,21 @@ FlatTree parse_newick(const char* s, size_t len) {
         ++i;
         while (i < len && is_space(static_cast<unsigned char>(s[i]))) ++i;
         size_t st = i;
-        while (i < len && !nwk_delim(static_cast<unsigned char>(s[i])) && !is_space(static_cast<unsigned char>(s[i]))) ++i;
-        std::string tok(s + st, i - st);
-        char* end = nullptr;
-        double d = strtod(tok.c_str(), &end);
-        if (tok.empty() || *end) throw std::runtime_error("newick: bad branch length \"" + tok + "\"");
+        while (i < len && !nwk_token_end(static_cast<unsigned char>(s[i]))) ++i;
+        // plain decimals (every tree a program writes) through from_chars: correctly rounded like strtod,
+        // no allocation, no locale; whatever it does not consume entirely takes the strtod path as before
+        double d = 0.0;
+        const unsigned char c0 = i > st ? static_cast<unsigned char>(s[st]) : 0;
+        const unsigned char c1 = i > st + 1 ? static_cast<unsigned char>(s[st + 1]) : 0;
+        auto r = std::from_chars(s + st, s + i, d);
+        const bool plain = (std::isdigit(c0) || c0 == '.' || (c0 == '-' && (std::isdigit(c1) || c1 == '.'))) &&
+                           r.ec == std::errc() && r.ptr == s + i;
+        if (!plain) {
+          std::string tok(s + st, i - st);
+          char* end = nullptr;
+          d = strtod(tok.c_str(), &end);
+          if (tok.empty() || *end) throw std::runtime_error("newick: bad branch length \"" + tok + "\"");
+        }
         t.length[cur] = d;
         break;
       }
@@ -79,7 +102,7 @@ FlatTree parse_newick(const char* s, size_t len) {
       }
       default: {
         size_t st = i;
-        while (i < len && !nwk_delim(static_cast<unsigned char>(s[i])) && !is_space(static_cast<unsigned char>(s[i]))) ++i;
+        while (i < len && !nwk_token_end(static_cast<unsigned char>(s[i]))) ++i;
         t.name[cur].assign(s + st, i - st);
       }
     }

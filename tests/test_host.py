@@ -24,6 +24,19 @@ def test_newick_flattening_matches_oracle(built):
         assert np.array_equal(h.parent, p) and np.array_equal(h.length, l), txt[:40]
         assert h.parent[0] == -1 and (h.parent[1:] < np.arange(1, len(p))).all()
     assert hostlib.Tree("('it''s':1,b:2);").names()[1] == "it's"
+    # branch-length tokens: the from_chars fast path and the strtod path must agree with the oracle's strtod
+    forms = ["0", "7", "0.1", ".5", "5.", "1e-3", "1E5", "2.5e+3", "-2", "-.25", "+3", "0x1p3", "1e999", "1e-999",
+             "inf", "-inf", "Infinity", "nan", "0.30000000000000004", "123456789012345678901234567890",
+             "4.9406564584124654e-324", "1.7976931348623157e308", "00012.5000"]
+    txt = "(" + ",".join(f"n{k}:{f}" for k, f in enumerate(forms)) + ");"
+    h, (p, l) = hostlib.Tree(txt), orc.Tree.parse(txt).flatten()
+    assert np.array_equal(h.parent, p) and np.array_equal(h.length, l, equal_nan=True)
+    assert h.length[1:].tolist()[:9] == [0.0, 7.0, 0.1, 0.5, 5.0, 1e-3, 1e5, 2500.0, -2.0]
+    for bad_len in ["1d5", "1e", "--1", "1.2.3", "e5", "0x", "1_000"]:
+        with pytest.raises(hostlib.HostError):
+            hostlib.Tree(f"(a:{bad_len},b:1);")
+        with pytest.raises(orc.OracleError):
+            orc.Tree.parse(f"(a:{bad_len},b:1);")
     for bad in ["(a,b)", "(a,b));", "((a,b);", "(a:x,b);", ""]:
         with pytest.raises(hostlib.HostError):
             hostlib.Tree(bad)
