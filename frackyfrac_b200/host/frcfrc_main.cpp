@@ -10,6 +10,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "frcfrc_cuda.h"
 #include "hostlib.hpp"
@@ -136,18 +137,19 @@ int main(int argc, char** argv) {
     if (frc_create(nullptr, &ft, &fc, &fo, &job) != FRC_OK) die(frc_last_error(nullptr));
     lap("frc_create (+ CUDA init)");
     fputs("Calculating distances\n", stderr);
-    std::string text;
+    std::vector<std::string> parts;  // one formatted piece per -p worker, written in order
     for (;;) {
       const double* d; int64_t first, n;
       auto a0 = std::chrono::steady_clock::now();
       if (frc_next(job, &d, &first, &n) != FRC_OK) { std::string m = frc_last_error(job); frc_destroy(job); die(m); }
       if (n == 0) break;
       auto a1 = std::chrono::steady_clock::now();
-      text.clear();
-      frchost::format_lines_parallel(d, n, static_cast<int>(fl.nt), text);  // -p threads format, one writer
+      frchost::format_parts_parallel(d, n, static_cast<int>(fl.nt), parts);  // -p threads format, one writer
       auto a2 = std::chrono::steady_clock::now();
       std::string werr;
-      try { w.write(text.data(), text.size()); } catch (const std::exception& e) { werr = e.what(); }
+      try {
+        for (const std::string& p : parts) w.write(p.data(), p.size());
+      } catch (const std::exception& e) { werr = e.what(); }
       auto a3 = std::chrono::steady_clock::now();
       next_ms += std::chrono::duration<double, std::milli>(a1 - a0).count();
       fmt_ms += std::chrono::duration<double, std::milli>(a2 - a1).count();

@@ -509,19 +509,24 @@ int format_go(double v, char* buf) {
 }
 
 void append_lines(const double* d, int64_t n, std::string& out) {
-  char b[40];
+  // formatted in blocks on the stack: one append per ~200 values instead of one per line
+  char b[8192];
+  size_t o = 0;
   for (int64_t k = 0; k < n; ++k) {
-    int l = format_go(d[k], b);
-    b[l] = '\n';
-    out.append(b, static_cast<size_t>(l) + 1);
+    if (o + 40 > sizeof b) { out.append(b, o); o = 0; }
+    o += static_cast<size_t>(format_go(d[k], b + o));
+    b[o++] = '\n';
   }
+  out.append(b, o);
 }
 
-void format_lines_parallel(const double* d, int64_t n, int threads, std::string& out) {
+void format_parts_parallel(const double* d, int64_t n, int threads, std::vector<std::string>& parts) {
   if (threads < 1) threads = 1;
-  if (threads == 1 || n < 4096) { append_lines(d, n, out); return; }
-  threads = static_cast<int>(std::min<int64_t>(threads, n / 2048));
-  std::vector<std::string> parts(threads);
+  if (n < 4096) threads = 1;
+  threads = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(threads, n / 2048)));
+  if (static_cast<int>(parts.size()) < threads) parts.resize(threads);
+  for (auto& p : parts) p.clear();  // (capacity is kept: a caller that reuses `parts` allocates once)
+  if (threads == 1) { append_lines(d, n, parts[0]); return; }
   std::vector<std::thread> th;
   for (int t = 0; t < threads; ++t) {
     const int64_t b = n * t / threads, e = n * (t + 1) / threads;
@@ -530,8 +535,15 @@ void format_lines_parallel(const double* d, int64_t n, int threads, std::string&
       append_lines(d + b, e - b, parts[t]);
     });
   }
+  for (auto& x : th) x.join();
+}
+
+void format_lines_parallel(const double* d, int64_t n, int threads, std::string& out) {
+  if (threads <= 1 || n < 4096) { append_lines(d, n, out); return; }
+  std::vector<std::string> parts;
+  format_parts_parallel(d, n, threads, parts);
   size_t total = out.size();
-  for (int t = 0; t < threads; ++t) { th[t].join(); total += parts[t].size(); }
+  for (auto& p : parts) total += p.size();
   out.reserve(total);
   for (auto& p : parts) out.append(p);
 }

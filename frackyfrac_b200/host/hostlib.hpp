@@ -57,6 +57,11 @@ void append_lines(const double* d, int64_t n, std::string& out);
 // end-to-end bottleneck).
 void format_lines_parallel(const double* d, int64_t n, int threads, std::string& out);
 
+// The same bytes as consecutive pieces, parts[0] + parts[1] + ...: the writer hands each piece to the file
+// as it is, which spares a single-threaded concatenation of the whole band (250 MB of text at cfg2).
+// Unused trailing entries of `parts` are left empty; reusing `parts` across calls reuses its buffers.
+void format_parts_parallel(const double* d, int64_t n, int threads, std::vector<std::string>& parts);
+
 // aio.Open stand-in (frcfrc.go:93,109): the whole file, decoded by suffix (".gz", ".zst"); "" = stdin.
 std::string read_file(const std::string& path);
 
