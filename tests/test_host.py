@@ -91,6 +91,14 @@ def test_go_format_matches_oracle(built):
                            [0.0, 1.0, np.nan, 1e-5, 1e-4, 2 / 3, 22 / 36, 0.1 + 0.2]])
     for v in vals:
         assert hostlib.format_go(float(v)) == orc.format_go(float(v))
+    # a third, independent implementation: for 0 < v < 1 CPython's repr() is the same text as Go's %v
+    # (shortest round-trip digits, exponent form below 1e-4 with at least two exponent digits)
+    more = np.concatenate([rng.random(20000), rng.random(5000).astype(np.float32).astype(np.float64),
+                           10.0 ** -rng.uniform(0, 300, 3000), np.nextafter(1e-4, [0.0, 1.0]), [5e-324, 2.2250738585072014e-308]])
+    for v in more[(more > 0) & (more < 1)]:
+        assert hostlib.format_go(float(v)) == repr(float(v)), repr(float(v))
+    assert [hostlib.format_go(v) for v in (0.0, 1.0, float("nan"), 100000.0, 1e6, 123456789.0, -0.5)] == \
+        ["0", "1", "NaN", "100000", "1e+06", "1.23456789e+08", "-0.5"]
 
 
 def test_cli_flag_rules(built):
