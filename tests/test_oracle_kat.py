@@ -190,3 +190,71 @@ def test_empty_and_degenerate(built):
     d = orc.unifrac(orc.Table.parse("\n\na:1\na:2\nb:1\n", True), tree, True)
     assert np.isnan(d[0]) and d[1] == 1.0 and d[5] == 0.0 and d[9] == 1.0
     assert orc.format_go(d[0]) == "NaN"
+
+
+def _random_case(rng):
+    """A small tree as text (shared leaf names, named internal nodes, zero and root lengths) and sample maps."""
+    n_leaves = int(rng.integers(2, 14))
+    pool = [f"s{k}" for k in range(max(2, n_leaves - 2))]          # fewer names than leaves: some repeat (A6)
+    nodes = [f"{pool[int(rng.integers(len(pool)))]}:{int(rng.integers(0, 9)) / 2}" for _ in range(n_leaves)]
+    k = 0
+    while len(nodes) > 1:
+        take = int(rng.integers(2, min(4, len(nodes)) + 1))
+        idx = sorted(rng.choice(len(nodes), size=take, replace=False).tolist(), reverse=True)
+        kids = [nodes.pop(i) for i in idx][::-1]
+        name = f"i{k}" if rng.random() < 0.5 else ""
+        nodes.append(f"({','.join(kids)}){name}:{int(rng.integers(0, 9)) / 4}")
+        k += 1
+    text = nodes[0] if rng.random() < 0.5 else nodes[0].rsplit(":", 1)[0]   # with / without a root length (A5)
+    samples = []
+    for _ in range(int(rng.integers(2, 7))):
+        m = {}
+        for nm in pool + [f"i{q}" for q in range(k)]:
+            if rng.random() < 0.35:
+                m[nm] = float(rng.integers(1, 40)) if rng.random() < 0.7 else float(rng.random() * 3 + 0.01)
+        samples.append(m)
+    if rng.random() < 0.3:
+        samples[0] = {}                                               # an empty sample (A8: NaN rows)
+    return text + ";", samples
+
+
+def test_c_oracle_against_the_python_restatement(built):
+    """oracle/py_restatement.py keeps the reference's own structures (maps, recursion, merge-join); the C oracle is
+    dense and threaded.  Same inputs, same summation order -> identical bits, in every mode."""
+    from frackyfrac_b200 import hostlib
+    from oracle import oracle as orc
+    from oracle import py_restatement as pyr
+
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for _ in range(150):
+        text, samples = _random_case(rng)
+        ht = hostlib.Tree(text)
+        names = ht.names()
+        known = set(names)
+        samples = [{k: v for k, v in m.items() if k in known} for m in samples]
+        tab_text = "".join("\t".join(f"{k}:{v!r}" for k, v in m.items()) + "\n" for m in samples)
+        tree = orc.Tree.parse(text)
+        tab = orc.Table.parse(tab_text, True)
+        orc.validate_species(tab, tree)
+        for weighted in (False, True):
+            for normalize in ((1,) if not weighted else (0, 1, 2)):
+                want = pyr.unifrac(samples, ht.parent.tolist(), ht.length.tolist(), names, weighted, normalize)
+                got = orc.unifrac(tab, tree, weighted, normalize, 2)
+                assert len(got) == len(want)
+                for g, w in zip(got.tolist(), want):
+                    assert g == w or (g != g and w != w), (text, tab_text, weighted, normalize, g, w)
+                checked += len(want)
+    assert checked > 3000
+    # and the reference's three unit KATs through the restatement itself
+    for case in kat.UNIT:
+        ht = hostlib.Tree(case["tree"])
+        got = pyr.unifrac([{k: float(v) for k, v in m.items()} for m in case["abnd"]], ht.parent.tolist(),
+                          ht.length.tolist(), ht.names(), case["weighted"], 1)
+        assert got == case["want"]
+    # ... and the reference's six CLI fixtures, byte for byte
+    for fixture, sparse, weighted in kat.CLI:
+        ht = hostlib.Tree(_read(fixture + ".tree"))
+        maps = hostlib.Table(_read(fixture + (".sparse" if sparse else ".dense")), sparse).maps()
+        d = pyr.unifrac(maps, ht.parent.tolist(), ht.length.tolist(), ht.names(), weighted, 1)
+        assert "".join(orc.format_go(v) + "\n" for v in d) == _read(fixture + ".want")
