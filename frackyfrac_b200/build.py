@@ -44,7 +44,7 @@ def _stale(target: str, sources: list[str]) -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, "libfrcfrc_cuda.so")
-    headers = [os.path.join(CSRC, h) for h in ("frc_internal.h", "ptx.cuh")]
+    headers = [os.path.join(CSRC, h) for h in ("frc_internal.h", "ptx.cuh", "host_pool.h")]
     headers.append(os.path.join(ROOT, "include", "frcfrc_cuda.h"))
     objs = []
     for src in CUDA_SOURCES:

@@ -96,3 +96,25 @@ def test_band_plan_covers_the_triangle(built):
     # explicit band_rows: uniform bands of whole tiles
     f, c = engine.plan_bands(700, 0, 1, band_rows=128)
     assert len(f) == 6 and c[0] == 128 * 127 // 2
+
+
+def test_host_pool_under_tsan(tmp_path):
+    """The context's worker pool (csrc/host_pool.h: spinning workers, run / start / wait) drives frc_create's table
+    staging and frc_next's widening; a race there would be a rare hang on the GPU box.  ThreadSanitizer harness,
+    CPU only (tests/pool_tsan.cpp)."""
+    import shutil
+
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no g++")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = tmp_path / "pool_tsan"
+    r = subprocess.run([cxx, "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread",
+                        "-I", os.path.join(here, "..", "frackyfrac_b200", "csrc"), "-o", str(exe),
+                        os.path.join(here, "pool_tsan.cpp")], capture_output=True, text=True)
+    if r.returncode != 0 and "tsan" in (r.stderr + r.stdout).lower():
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout + r.stderr
+    assert "ThreadSanitizer" not in r.stderr, r.stderr
