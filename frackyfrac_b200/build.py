@@ -3,6 +3,7 @@
   frackyfrac_b200/_build/libfrcfrc_cuda.so   CUDA engine + C ABI (include/frcfrc_cuda.h)
   frackyfrac_b200/_build/libfrcfrc_host.so   C++ host side (Newick / table readers, Go %v writer)
   frackyfrac_b200/_build/frcfrc              C++ stand-in for the Go CLI (same flags and output)
+  frackyfrac_b200/_build/sprspr              C++ stand-in for the dense -> sparse converter (sprspr/sprspr.go)
 
 nvcc cross-compiles without a GPU, so this runs on the CPU-only build box; the
 .so files travel to the GPU box with the repo snapshot.
@@ -84,6 +85,10 @@ def build_host(force: bool = False) -> tuple[str, str]:
                         os.path.join(HOST, "hostlib.cpp"), os.path.join(HOST, "fileio.cpp"),
                         "-L", OUT, "-lfrcfrc_cuda", "-lz", "-ldl",
                         "-Wl,-rpath,$ORIGIN"], check=True)
+    sprspr = os.path.join(OUT, "sprspr")
+    if force or _stale(sprspr, srcs):
+        subprocess.run([*common, "-o", sprspr, os.path.join(HOST, "sprspr_main.cpp"),
+                        os.path.join(HOST, "hostlib.cpp"), os.path.join(HOST, "fileio.cpp"), "-lz", "-ldl"], check=True)
     return lib, exe
 
 

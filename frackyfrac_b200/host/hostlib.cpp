@@ -548,6 +548,22 @@ void format_lines_parallel(const double* d, int64_t n, int threads, std::string&
   for (auto& p : parts) out.append(p);
 }
 
+// sprspr's toSparse (sprspr/sprspr.go:19-36): one line per sample, "name:%g" joined by tabs.  The reference
+// ranges over a Go map (random order, its test sorts the fields before comparing: sprspr_test.go:26-31); here the
+// fields come in first-assignment order, i.e. the header's column order.
+void to_sparse_lines(const Table& t, std::string& out) {
+  char num[40];
+  for (int64_t s = 0; s < t.n_samples(); ++s) {
+    for (int64_t k = t.row_ptr[s]; k < t.row_ptr[s + 1]; ++k) {
+      if (k > t.row_ptr[s]) out.push_back('\t');
+      out.append(t.species[t.sp[k]]);
+      out.push_back(':');
+      out.append(num, static_cast<size_t>(format_go(t.val[k], num)));  // %g and %v print a float64 alike
+    }
+    out.push_back('\n');
+  }
+}
+
 }  // namespace frchost
 
 // -------------------------------------------------------------------- C ABI
@@ -614,5 +630,19 @@ char* frch_format_lines(const double* d, int64_t n, int threads, size_t* len) {
   return p;
 }
 void frch_free(void* p) { free(p); }
+
+// Dense table text -> sparse table text (sprspr); malloc'd, free with frch_free; NULL + frch_last_error on bad input.
+char* frch_to_sparse(const char* text, size_t len, int threads, size_t* out_len) {
+  try {
+    frchost::Table t = frchost::parse_table(text, len, /*sparse=*/false, threads);
+    std::string out;
+    frchost::to_sparse_lines(t, out);
+    char* p = static_cast<char*>(malloc(out.size() + 1));
+    memcpy(p, out.data(), out.size());
+    p[out.size()] = 0;
+    *out_len = out.size();
+    return p;
+  } catch (const std::exception& e) { g_err = e.what(); return nullptr; }
+}
 
 }  // extern "C"

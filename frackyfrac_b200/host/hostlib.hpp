@@ -46,6 +46,9 @@ struct Csr {
 };
 Csr resolve(const Table& t, const FlatTree& tree, int threads = 1);
 
+// sprspr/sprspr.go:19-36: the table as sparse-format text, one "name:%g" field per non-zero entry.
+void to_sparse_lines(const Table& t, std::string& out);
+
 // Go's fmt %v for float64, no newline.  Returns the length written (<= 32).
 int format_go(double v, char* buf);
 

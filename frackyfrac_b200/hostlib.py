@@ -14,6 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libfrcfrc_host.so")
 CLI_PATH = os.path.join(_HERE, "_build", "frcfrc")
+SPRSPR_PATH = os.path.join(_HERE, "_build", "sprspr")
 
 _lib = None
 
@@ -72,6 +73,8 @@ def lib():
         L.frch_format_lines.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_size_t)]
         L.frch_format_lines.restype = C.c_void_p
         L.frch_free.argtypes = [C.c_void_p]
+        L.frch_to_sparse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
+        L.frch_to_sparse.restype = C.c_void_p
         L.frch_read_file.argtypes = [C.c_char_p, C.POINTER(C.c_size_t)]
         L.frch_read_file.restype = C.c_void_p
         L.frch_write_file.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int]
@@ -183,3 +186,16 @@ def write_file(path: str, chunks: list[bytes], threads: int = 1) -> None:
     sizes = (C.c_size_t * len(chunks))(*[len(c) for c in chunks])
     if lib().frch_write_file(os.fsencode(path), arr, sizes, len(chunks), threads):
         raise HostError(lib().frch_last_error().decode())
+
+
+def to_sparse(text: str | bytes, threads: int = 1) -> bytes:
+    """sprspr: a dense table as sparse-format text (sprspr/sprspr.go:19-36)."""
+    b = text.encode() if isinstance(text, str) else text
+    n = C.c_size_t()
+    p = lib().frch_to_sparse(b, len(b), threads, C.byref(n))
+    if not p:
+        raise HostError(lib().frch_last_error().decode())
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        lib().frch_free(p)

@@ -259,3 +259,32 @@ def test_float_token_forms_match_the_oracle_parser(built):
             except Exception:
                 outcomes.append("error")
         assert outcomes[0] == outcomes[1], (tok, outcomes)
+
+
+def test_sprspr_converter_follows_the_reference_test(built, tmp_path):
+    """sprspr/sprspr_test.go:12-37: three dense inputs and their sparse renderings (fields compared after sorting,
+    because the reference ranges over a Go map), through the library and through the stand-in binary; plus the
+    round trip dense -> sparse -> maps on a bigger table and the reference's error exit."""
+    from frackyfrac_b200 import hostlib, synth
+
+    cases = [("s1\n1.3", "s1:1.3"),
+             ("s1\ts2\n0\t4\n3\t0\n", "s2:4\ns1:3"),
+             ("s1\ts2\ts3\n4\t3\t2\n5\t0\t8\n0\t0\t10", "s1:4\ts2:3\ts3:2\ns1:5\ts3:8\ns3:10")]
+
+    def canon(text):
+        rows = text.removesuffix("\n").split("\n")
+        return "\n".join("\t".join(sorted(r.split("\t"))) for r in rows)
+
+    for dense, want in cases:
+        assert canon(hostlib.to_sparse(dense).decode()) == want
+        r = subprocess.run([hostlib.SPRSPR_PATH], input=dense, capture_output=True, text=True)
+        assert r.returncode == 0 and canon(r.stdout) == want
+        assert r.stderr.startswith("SparseySparse converts dense format abundance tables to sparse format.\n")
+    tree = synth.random_tree(60, 3)
+    rp, col, val = synth.random_table(tree, 25, 0.2, 4, integer_counts=False)
+    dense = synth.to_dense_text(tree, rp, col, val)
+    sparse = hostlib.to_sparse(dense, threads=3)
+    assert hostlib.Table(sparse, True).maps() == hostlib.Table(dense, False).maps()
+    assert sparse == hostlib.to_sparse(dense, threads=1)
+    r = subprocess.run([hostlib.SPRSPR_PATH], input="a b\n1\n", capture_output=True, text=True)
+    assert r.returncode == 2 and r.stderr.rstrip().split("\n")[-1].startswith("ERROR: ")
