@@ -90,3 +90,8 @@ void widen_band(const float* src, double* dst, int64_t n, bool stream_stores) {
 }
 
 }  // namespace frc
+
+// Host-only entry for the CPU test-suite (no device needed): the widening routine frc_next runs.
+extern "C" void frc_debug_widen(const float* src, double* dst, int64_t n, int stream_stores) {
+  frc::widen_band(src, dst, n, stream_stores != 0);
+}

@@ -118,3 +118,30 @@ def test_host_pool_under_tsan(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout + r.stderr
     assert "ThreadSanitizer" not in r.stderr, r.stderr
+
+
+def test_host_widening_of_fp32_bands(built):
+    """The host half of the fp32 PCIe leg (csrc/wire.cu widen_band: AVX2 cvtps2pd, plain or non-temporal stores)
+    must be exact for every float — subnormals, infinities, NaN, signed zeros — at any length and alignment."""
+    from frackyfrac_b200 import engine
+
+    L = engine.lib()
+    L.frc_debug_widen.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    L.frc_debug_widen.restype = None
+    rng = np.random.default_rng(77)
+    bits = rng.integers(0, 2**32, 70_000, dtype=np.uint64).astype(np.uint32)
+    special = np.array([0, 0x80000000, 1, 0x007FFFFF, 0x00800000, 0x7F7FFFFF, 0x7F800000, 0xFF800000, 0x7FC00000,
+                        0x3F800000, 0x3DCCCCCD], np.uint32)
+    src_all = np.concatenate([special, bits]).view(np.float32)
+    for n in (0, 1, 7, 8, 9, 31, 1000, 16384, 16385, len(src_all) - 3):
+        for s_off in (0, 1, 3):
+            for d_off in (0, 1, 2, 3):
+                for stream in (0, 1):
+                    src = src_all[s_off:s_off + n]
+                    buf = np.full(n + 8, -7.0)
+                    dst = buf[d_off:d_off + n]
+                    L.frc_debug_widen(src.ctypes.data, dst.ctypes.data, n, stream)
+                    with np.errstate(invalid="ignore"):   # (signalling NaNs among the random bit patterns)
+                        want = src.astype(np.float64)
+                    assert np.array_equal(dst.view(np.uint64), want.view(np.uint64)), (n, s_off, d_off, stream)
+                    assert (buf[:d_off] == -7.0).all() and (buf[d_off + n:] == -7.0).all()   # nothing outside the range
