@@ -145,3 +145,33 @@ def test_host_widening_of_fp32_bands(built):
                         want = src.astype(np.float64)
                     assert np.array_equal(dst.view(np.uint64), want.view(np.uint64)), (n, s_off, d_off, stream)
                     assert (buf[:d_off] == -7.0).all() and (buf[d_off + n:] == -7.0).all()   # nothing outside the range
+
+
+def test_argument_errors_come_before_the_device(built):
+    """frc_create checks its options and the shape of its inputs before it touches CUDA: on a box without a GPU the
+    caller still gets the precise FRC_ERR_ARG (1) for a bad call, and a device error only for a good one."""
+    import torch
+
+    from frackyfrac_b200 import engine
+
+    if torch.cuda.is_available():
+        pytest.skip("runs on the CPU box (on a GPU the same checks are covered by test_bad_arguments_are_errors)")
+    parent, length = np.array([-1, 0, 0], np.int32), np.array([0, 1, 1.0])
+    rp, col, val = np.array([0, 1, 2], np.int64), np.array([1, 2], np.int32), np.array([1.0, 1.0])
+
+    def code(**kw):
+        a = dict(parent=parent, length=length, row_ptr=rp, col=col, val=val, weighted=False)
+        a.update(kw)
+        with pytest.raises(engine.FrcError) as e:
+            engine.Job(a.pop("parent"), a.pop("length"), a.pop("row_ptr"), a.pop("col"), a.pop("val"), **a)
+        return e.value.code, str(e.value)
+
+    assert code(normalize=False)[0] == 1 and "-l can only be used with weighted" in code(normalize=False)[1]   # frcfrc.go:84-86
+    assert code(path=7)[0] == 1
+    assert code(rank=3, world=2)[0] == 1
+    assert code(band_rows=-5)[0] == 1
+    assert code(parent=np.array([0, 0, 0], np.int32))[0] == 1           # root must have parent -1
+    assert code(row_ptr=np.array([0, 2, 1], np.int64), col=np.array([1], np.int32), val=np.array([1.0]))[0] == 1
+    assert code(row_ptr=np.array([1, 1, 2], np.int64))[0] == 1          # row_ptr[0] != 0
+    good = code()
+    assert good[0] in (2, 5), good                                      # only now the missing device shows
