@@ -32,7 +32,7 @@ def newick(draw, depth=0):
     return out + draw(WS)
 
 
-@settings(max_examples=int(__import__("os").environ.get("FRC_FUZZ_EXAMPLES", "300")), deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=int(__import__("os").environ.get("FRC_FUZZ_EXAMPLES", "300")), deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(newick(), st.sampled_from([";", ";", ";\n", "", ";;", "; (a,b);"]))
 def test_newick_readers_agree(built, body, tail):
     from frackyfrac_b200 import hostlib
@@ -98,13 +98,13 @@ def _both(text, sparse):
                 assert g[k] == w[k] or (g[k] != g[k] and w[k] != w[k]), repr(text)
 
 
-@settings(max_examples=int(__import__("os").environ.get("FRC_FUZZ_EXAMPLES", "300")), deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=int(__import__("os").environ.get("FRC_FUZZ_EXAMPLES", "300")), deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(sparse_table())
 def test_sparse_table_readers_agree(built, text):
     _both(text, True)
 
 
-@settings(max_examples=int(__import__("os").environ.get("FRC_FUZZ_EXAMPLES", "300")), deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=int(__import__("os").environ.get("FRC_FUZZ_EXAMPLES", "300")), deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(dense_table())
 def test_dense_table_readers_agree(built, text):
     _both(text, False)
