@@ -152,6 +152,7 @@ int launch_exact_pairs(const double* E, const double* length, int32_t n_nodes, i
 // *n_bad_mapped (mapped pinned memory) is incremented when a value does not survive fp32.
 int launch_narrow_band(const double* in, float* out, int64_t n, unsigned long long* n_bad_mapped, int num_sms,
                        cudaStream_t s);
+int launch_round_band(double* io, int64_t n, int num_sms, cudaStream_t s);  // the same rounding in place (doubles on the bus)
 void widen_band(const float* src, double* dst, int64_t n, bool stream_stores);  // host
 
 // ---- weighted.cu ------------------------------------------------------------

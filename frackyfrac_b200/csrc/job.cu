@@ -482,7 +482,15 @@ int enqueue_band(frc_job* j, size_t idx) {
     j->info.d2h_bytes += static_cast<int64_t>(sizeof(float)) * b.count;
     JOB_CUDA(j, cudaEventRecord(sl.done, cs));
   } else if (!(j->opts.flags & FRC_FLAG_NO_D2H) && sl.dev != sl.host) {
-    JOB_CUDA(j, cudaStreamWaitEvent(cs, sl.k2, 0));
+    cudaEvent_t ready = sl.k2;
+    if (!j->exact) {
+      // doubles on the bus carry the values the fp32 route would deliver (wire.cu: same bytes for any rank count)
+      launches += launch_round_band(sl.dev, b.count, c->num_sms, s);
+      JOB_CUDA(j, cudaGetLastError());
+      JOB_CUDA(j, cudaEventRecord(sl.k3, s));
+      ready = sl.k3;
+    }
+    JOB_CUDA(j, cudaStreamWaitEvent(cs, ready, 0));
     JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, cs));
     j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
     JOB_CUDA(j, cudaEventRecord(sl.done, cs));
@@ -1346,8 +1354,13 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
 // than kWidePiece is handed out in pieces, so that the buffer always fits the cores' caches.
 static int widen_piece(frc_job* j, Slot& sl, int64_t off, int64_t n, bool trace) {
   if (*sl.n_bad_host) {
-    // some value of this band does not survive fp32 (underflow): fetch the doubles themselves
-    JOB_CUDA(j, cudaMemcpy(j->wide, sl.dev + off, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    // some value of this band does not survive fp32 (underflow): fetch the doubles themselves, rounded like
+    // the rest wherever fp32 can carry them
+    cudaStream_t fs = j->ctx->stream[0];
+    j->info.kernel_launches += launch_round_band(sl.dev + off, n, j->ctx->num_sms, fs);
+    JOB_CUDA(j, cudaGetLastError());
+    JOB_CUDA(j, cudaMemcpyAsync(j->wide, sl.dev + off, sizeof(double) * n, cudaMemcpyDeviceToHost, fs));
+    JOB_CUDA(j, cudaStreamSynchronize(fs));
     j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * n;
     return FRC_OK;
   }

@@ -50,6 +50,19 @@ __global__ void __launch_bounds__(256) k_narrow_band(const double* __restrict__ 
   if (bad) atomicAdd_system(n_bad, 1ULL);  // rare: straight into mapped pinned memory
 }
 
+// Doubles on the bus (ranks with few host threads): the same rounding, in place, so that the host sees the same
+// values whichever format crossed PCIe — the output bytes must not depend on how many ranks share a host
+// (identical for 1, 2, 4 and 8 GPUs).  A value fp32 cannot carry stays as it is, as on the fp32 route.
+__global__ void __launch_bounds__(256) k_round_band(double* __restrict__ io, int64_t n) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const double d = io[k];
+    const float f = static_cast<float>(d);
+    const bool bad = fabs(static_cast<double>(f) - d) > fabs(d) * 0x1p-23;
+    if (!bad) io[k] = static_cast<double>(f);
+  }
+}
+
 // kStream: non-temporal stores for a destination larger than the caches (no read-for-ownership, no
 // write-back of lines nobody re-reads soon); plain stores when the destination is the one band-sized
 // buffer that stays cache-resident from band to band.
@@ -79,6 +92,14 @@ int launch_narrow_band(const double* in, float* out, int64_t n, unsigned long lo
   const int64_t want = (n + 256 * 4 - 1) / (256 * 4);
   const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(num_sms) * 8));
   k_narrow_band<<<grid, 256, 0, s>>>(in, out, n, n_bad_mapped);
+  return 1;
+}
+
+int launch_round_band(double* io, int64_t n, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int64_t want = (n + 255) / 256;
+  const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(num_sms) * 8));
+  k_round_band<<<grid, 256, 0, s>>>(io, n);
   return 1;
 }
 

@@ -260,7 +260,7 @@ def test_fast_weighted_small_distances(gpu_ctx, normalize):
 @pytest.mark.parametrize("weighted", [False, True])
 def test_fp32_wire_against_f64_wire(gpu_ctx, monkeypatch, weighted):
     """Fast-path distances cross PCIe as fp32 and are widened on the host (wire.cu).  Against doubles on the
-    bus: half the bytes, values identical except for one fp32 rounding of the pairs the exact fix-up rewrote."""
+    bus: half the bytes, identical values (the doubles route rounds in place on the device)."""
     from frackyfrac_b200 import engine, synth
 
     tree = synth.random_tree(1500, 301)
@@ -286,10 +286,10 @@ def test_fp32_wire_against_f64_wire(gpu_ctx, monkeypatch, weighted):
     assert ni.d2h_bytes == 4 * pairs and wi.d2h_bytes == 8 * pairs
     assert narrow[0] == 0.0 and wide[0] == 0.0
     assert np.array_equal(narrow, ragged)
-    assert (np.abs(narrow - wide) <= 6e-8 * wide).all()
-    assert np.array_equal(narrow, wide.astype(np.float32).astype(np.float64))
-    if not weighted:  # the tensor-core epilogue already produces fp32 ratios: nothing is lost on the bus
-        assert (narrow == wide).sum() >= pairs - ni.flagged_pairs
+    # the bus format must not show in the output (ranks with few host threads keep doubles on the bus, and the
+    # stream has to be byte-identical for 1, 2, 4 and 8 GPUs: SURVEY 8e) - the doubles are rounded the same way
+    assert np.array_equal(narrow, wide, equal_nan=True)
+    assert np.array_equal(narrow, narrow.astype(np.float32).astype(np.float64))
     assert rel_err(narrow, oracle_flat(tree, (rp, col, val), weighted)).max() < 1e-5
 
 
