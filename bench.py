@@ -299,7 +299,7 @@ def run_ours(args, world, rank, local_rank):
     def e2e_step():
         with engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
                         rank=rank, world=world, flags=uw_flags) as j:
-            n = j.drain()
+            n = j.drain()   # native format of the fast paths: fp32 bands straight from the pinned ring (frc_next_f32)
             i = j.info()
         return n, i
 

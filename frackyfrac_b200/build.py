@@ -21,7 +21,7 @@ OUT = os.path.join(HERE, "_build")
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 
-CUDA_SOURCES = ["job.cu", "embed.cu", "exact.cu", "weighted.cu", "unweighted_tc.cu", "unweighted_bits.cu", "comm.cu", "wire.cu"]
+CUDA_SOURCES = ["job.cu", "plan.cpp", "embed.cu", "exact.cu", "weighted.cu", "unweighted_tc.cu", "unweighted_bits.cu", "comm.cu", "wire.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -45,12 +45,12 @@ def _stale(target: str, sources: list[str]) -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, "libfrcfrc_cuda.so")
-    headers = [os.path.join(CSRC, h) for h in ("frc_internal.h", "ptx.cuh", "host_pool.h")]
+    headers = [os.path.join(CSRC, h) for h in ("frc_internal.h", "ptx.cuh", "host_pool.h", "plan.h", "wire.cuh")]
     headers.append(os.path.join(ROOT, "include", "frcfrc_cuda.h"))
     objs = []
     for src in CUDA_SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OUT, src.replace(".cu", ".o"))
+        o = os.path.join(OUT, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
             cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("FRC_BUILD_DEFS", "").split(), "-c", s, "-o", o]

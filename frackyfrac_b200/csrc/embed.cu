@@ -519,7 +519,7 @@ k_expand_operands_u8(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
 __global__ void k_quantize_lengths(const double* __restrict__ len_col, const int32_t* __restrict__ col_exp,
                                    int32_t kp, uint8_t* __restrict__ qa, uint8_t* __restrict__ qh,
                                    uint8_t* __restrict__ ql, uint32_t* __restrict__ qam,
-                                   double* __restrict__ lenq, double* __restrict__ flag_u) {
+                                   double* __restrict__ lenq, double* __restrict__ qerr) {
   const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= kp) return;
   const double len = len_col[k];
@@ -550,8 +550,26 @@ __global__ void k_quantize_lengths(const double* __restrict__ len_col, const int
   // columns (small lengths merged into a chunk of larger ones, or an unlucky search) are summed
   // into A, and a pair with U < 1e6 * A (A could exceed 1e-6 of U, hence of V) is recomputed
   // exactly: |rel err d| <= 2 * (2e-6 + 1e-6) = 6e-6 for every pair that is not.
+  // (summed in a FIXED order by k_sum_flag_u: the threshold must be the same bits on every run, rank and
+  // device, or a pair sitting on it could take different routes and break "same bytes for any world")
   const double err = fabs(q - len);
-  if (err > 2e-6 * len) atomicAdd(flag_u, 1e6 * err);
+  qerr[k] = err > 2e-6 * len ? 1e6 * err : 0.0;
+}
+
+// flag_u[0] = sum of qerr[0..kp) in a fixed order: thread t adds its strided columns in ascending order,
+// then a fixed binary tree over the 1024 partial sums.
+__global__ void __launch_bounds__(1024) k_sum_flag_u(const double* __restrict__ qerr, int32_t kp,
+                                                     double* __restrict__ flag_u) {
+  __shared__ double part[1024];
+  double acc = 0.0;
+  for (int32_t k = threadIdx.x; k < kp; k += 1024) acc += qerr[k];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) flag_u[0] = part[0];
 }
 
 }  // namespace
@@ -679,6 +697,10 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 
 
 // (nw = word columns this rank builds)
+void embed_setup() {
+  cudaFuncSetAttribute(k_embed_presence_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw) {
   return static_cast<size_t>(n_nodes) * 4 <= 200 * 1024 ? 0 : static_cast<int64_t>(n_nodes) * nw;
 }
@@ -689,12 +711,7 @@ int launch_embed_presence_fused(const DevTree& t, const int32_t* level_ptr_dev, 
                                 cudaStream_t s) {
   (void)nw;
   const size_t smem = (static_cast<size_t>(t.n_nodes) * 4 + 15) & ~size_t(15);
-  if (smem <= 200 * 1024) {
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(k_embed_presence_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr = true;
-    }
+  if (smem <= 200 * 1024) {  // (shared-memory attribute: embed_setup, once per device context)
     k_embed_presence_fused<true><<<w_count, 512, smem, s>>>(a.row_ptr, a.col, a.n_samples, t.level_nodes,
                                                             t.level_parent, level_ptr_dev, t.height, t.n_nodes, kp,
                                                             order, node_scratch, bitsT, w0, bitsS, peers);
@@ -747,11 +764,11 @@ int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int6
 }
 
 int launch_quantize_lengths(const double* len_col, const int32_t* col_exp, int32_t kp, uint8_t* qa,
-                            uint8_t* qh, uint8_t* ql, uint32_t* qam, double* lenq, double* flag_u,
+                            uint8_t* qh, uint8_t* ql, uint32_t* qam, double* lenq, double* qerr, double* flag_u,
                             cudaStream_t s) {
-  cudaMemsetAsync(flag_u, 0, sizeof(double), s);
-  k_quantize_lengths<<<(kp + 127) / 128, 128, 0, s>>>(len_col, col_exp, kp, qa, qh, ql, qam, lenq, flag_u);
-  return 1;
+  k_quantize_lengths<<<(kp + 127) / 128, 128, 0, s>>>(len_col, col_exp, kp, qa, qh, ql, qam, lenq, qerr);
+  k_sum_flag_u<<<1, 1024, 0, s>>>(qerr, kp, flag_u);
+  return 2;
 }
 
 }  // namespace frc

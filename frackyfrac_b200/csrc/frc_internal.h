@@ -44,6 +44,16 @@ struct PeerPtrs {
 // One tile of the lower triangle: rows [128*ti, +128) x cols [128*tj, +128), tj <= ti.
 struct Tile { int32_t ti, tj; };
 
+// The fast paths store fp32 distances.  A fix-up kernel that meets a value fp32 cannot carry to 2^-23
+// relative (|d| < 1.2e-38: pathological trees only) also reports it here, in mapped pinned host memory:
+// frc_next patches it into the widened doubles, frc_chunk_exceptions hands it to fp32 consumers.
+struct Exceptions {
+  unsigned long long* count = nullptr;  // entries appended (may exceed cap: the host then fails the call)
+  int64_t* index = nullptr;             // flat pair index
+  double* value = nullptr;
+  int32_t cap = 0;
+};
+
 // ---- embed.cu ---------------------------------------------------------------
 // fp64 branch embedding, node-major E[B][ld] (unifrac.go:32-53): leaf rows
 // scattered from the CSR, then one pass per tree level, children summed in
@@ -98,6 +108,7 @@ int launch_expand_operands(const uint32_t* bits, int32_t n_nodes, int32_t nw, in
 // `node_scratch` holds the per-CTA node-indexed column when the tree is too large for shared
 // memory (presence_node_scratch_words(n_nodes, nw) words, 0 when shared memory is used).
 int64_t presence_node_scratch_words(int32_t n_nodes, int32_t nw);
+void embed_setup();  // cudaFuncSetAttribute calls for the CURRENT device (once per device context)
 // qam / col_exp non-null (u8): integer row sums from q[k] = a*m and the per-column exponents.
 // Only the word columns [w0, w0 + w_count) (32 samples each) are built: the sample shard of this rank.
 // bitsS != null: also the sample-major form bitsS[np][kp / 32] that the bits-fed pair kernel reads.
@@ -122,9 +133,10 @@ int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int6
 // exponent col_exp[k], find the 8-bit a and 16-bit m = 256*qh + ql minimising
 // |a * m * 2^e - len| ; lenq[k] = a * m * 2^e (exact in fp64).
 // flag_u[0] = 1e6 * sum of |lenq - len| over the columns whose relative quantisation error
-// exceeds 2e-6 (pairs with a unique length below that are recomputed exactly).
+// exceeds 2e-6 (pairs with a unique length below that are recomputed exactly), summed in a fixed
+// order through qerr[kp] (device scratch): the same bits on every run, rank and device.
 int launch_quantize_lengths(const double* len_col, const int32_t* col_exp, int32_t kp, uint8_t* qa,
-                            uint8_t* qh, uint8_t* ql, uint32_t* qam, double* lenq, double* flag_u,
+                            uint8_t* qh, uint8_t* ql, uint32_t* qam, double* lenq, double* qerr, double* flag_u,
                             cudaStream_t s);
 
 // ---- comm.cu ----------------------------------------------------------------
@@ -146,13 +158,20 @@ bool comm_barrier(Comm* c, cudaStream_t s, std::string* err);
 // fp64 reference-order distances for pairs [first, first+count) of the triangle.
 int launch_exact_pairs(const double* E, const double* length, int32_t n_nodes, int64_t ld,
                        bool weighted, int64_t first, int64_t count, double* out, cudaStream_t s);
+// Flag -l AS CODED in the reference (normalize = 0): without normalizeFlatNodes the per-sample lists stay in
+// the order abundanceToFlatNodes appended them (post-order, unifrac.go:32-53) and unifracDistWeighted's
+// merge-join (:174-205) compares ids of lists that are not sorted.  Reproduced literally:
+//   launch_postorder_lists  per sample, the (id, raw subtree sum) entries with sum > 0 in post-order, from the
+//                           fp64 embedding E[B][ld] (two passes: count -> host prefix is avoided by a device
+//                           scan over samples; list_ptr has n_samples + 1 entries)
+//   launch_unsorted_pairs   one thread per pair runs the reference's two-pointer walk over the two lists.
+int launch_postorder_lists(const double* E, const int32_t* post_order, int32_t n_nodes, int64_t ld, int64_t n_samples,
+                           int64_t* list_ptr, int32_t* list_id, double* list_val, cudaStream_t s);
+int launch_unsorted_pairs(const int64_t* list_ptr, const int32_t* list_id, const double* list_val,
+                          const double* length, int64_t first, int64_t count, double* out, cudaStream_t s);
 
 // ---- wire.cu ----------------------------------------------------------------
-// fp32 on PCIe for the fast paths: device narrows a finished band, the host widens it again.
-// *n_bad_mapped (mapped pinned memory) is incremented when a value does not survive fp32.
-int launch_narrow_band(const double* in, float* out, int64_t n, unsigned long long* n_bad_mapped, int num_sms,
-                       cudaStream_t s);
-int launch_round_band(double* io, int64_t n, int num_sms, cudaStream_t s);  // the same rounding in place (doubles on the bus)
+// fp32 on PCIe for the fast paths: the pair kernels store fp32, frc_next widens on the host.
 void widen_band(const float* src, double* dst, int64_t n, bool stream_stores);  // host
 
 // ---- weighted.cu ------------------------------------------------------------
@@ -160,15 +179,15 @@ void widen_band(const float* src, double* dst, int64_t n, bool stream_stores);  
 // Pairs with d < flag_below are appended to flagged[] for the fix-up pass (as the unweighted kernel).
 int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
                           const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
-                          int64_t first, double* out, double flag_below, uint32_t* flagged,
-                          unsigned long long* n_flagged, cudaStream_t s);
+                          int64_t first, float* out, double flag_below, uint32_t* flagged,
+                          unsigned long long* n_flagged, int num_sms, cudaStream_t s);
 // fp64 / fixed-point recompute of the flagged pairs from the CSR rows (total: per-sample normaliser,
 // null for -l); ws = ws_ctas zeroed int64 arrays of n_nodes entries, left zeroed.
 int launch_weighted_fixup(const DevCsr& a, const DevTree& t, const double* total, const double* W,
                           const uint32_t* flagged, const unsigned long long* n_flagged,
-                          unsigned long long* count_host, int64_t first, long long* ws, int ws_ctas, double* out,
-                          cudaStream_t s);
-void weighted_setup();  // cudaFuncSetAttribute calls, once per process
+                          unsigned long long* count_host, int64_t first, long long* ws, int ws_ctas, float* out,
+                          const Exceptions& ex, cudaStream_t s);
+void weighted_setup();  // cudaFuncSetAttribute calls for the CURRENT device (once per device context)
 
 // ---- unweighted_tc.cu -------------------------------------------------------
 struct TcOperands;  // opaque: tensor maps + chunk table
@@ -192,14 +211,13 @@ int tc_chunk_kblocks();  // bf16: K blocks per fp32 accumulation run (FRC_TC_CHU
 // every pair with d < flag_below is appended to flagged[] (count in *n_flagged;
 // capacity = pairs of the band, so it cannot overflow) for the fix-up pass.
 int launch_unweighted_tc(const TcOperands* ops, const double* r, const Tile* tiles, int32_t n_tiles,
-                         int64_t n_samples, int64_t first, double* out, double flag_below,
-                         uint32_t* flagged, unsigned long long* n_flagged, int num_sms, int ctas,
-                         cudaStream_t s);
+                         int64_t n_samples, int64_t first, float* out, double flag_below,
+                         uint32_t* flagged, unsigned long long* n_flagged, int num_sms, cudaStream_t s);
 // fp64 recompute of the flagged pairs from the presence rows and true lengths.
 int launch_unweighted_fixup(const TcOperands* ops, const uint32_t* flagged,
                             const unsigned long long* n_flagged, unsigned long long* count_host,
-                            int64_t first, double* out, int num_sms, cudaStream_t s);
-bool tc_setup(std::string* err);  // smem attribute + driver entry points, once per process
+                            int64_t first, float* out, const Exceptions& ex, int num_sms, cudaStream_t s);
+bool tc_setup(std::string* err);  // driver entry point (once per process) + smem attributes for the CURRENT device
 
 // ---- unweighted_bits.cu -----------------------------------------------------
 // The same pair tiles with the u8 operand tiles expanded inside the kernel from the bit rows
@@ -211,10 +229,11 @@ BitsOperands* bits_operands_create(const uint32_t* bitsS, int64_t np, int32_t kp
                                    double unit, std::string* err);
 void bits_operands_destroy(BitsOperands* o);
 int launch_unweighted_bits(const BitsOperands* ops, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
-                           int64_t first, double* out, uint32_t* flagged, unsigned long long* n_flagged,
+                           int64_t first, float* out, uint32_t* flagged, unsigned long long* n_flagged,
                            int num_sms, cudaStream_t s);
 int launch_unweighted_fixup_bits(const BitsOperands* ops, const uint32_t* flagged, const unsigned long long* n_flagged,
-                                 unsigned long long* count_host, int64_t first, double* out, int num_sms,
-                                 cudaStream_t s);
+                                 unsigned long long* count_host, int64_t first, float* out, const Exceptions& ex,
+                                 int num_sms, cudaStream_t s);
+bool bits_setup(std::string* err);  // as tc_setup, for the bits-fed kernel
 
 }  // namespace frc

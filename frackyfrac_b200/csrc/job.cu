@@ -1,11 +1,23 @@
 // Host side of libfrcfrc_cuda: the C ABI of include/frcfrc_cuda.h.
 //
-// A job is one unifrac() call (frcfrc/unifrac.go:97-124): validate + copy the
-// flattened tree and CSR abundances, upload them in one pinned transfer, build
-// the branch embedding on the device, then compute the lower triangle in bands
-// of consecutive rows.  Bands alternate between two streams, each followed by
-// its own pinned D2H copy, and are handed to the caller strictly in flat-index
-// order by frc_next (the ordered iter.Seq of unifrac.go:209-228).
+// A job is one unifrac() call (frcfrc/unifrac.go:97-124).  It is made of PARTS, one per GPU this
+// process drives (one part unless opts.n_devices > 1):
+//
+//   frc_create   validate the options and the table header                  (this thread)
+//                stage: check + copy the CSR entries and walk the tree       (worker pool, once per job
+//                       into ONE portable pinned buffer every device reads    whatever the device count)
+//                plan:  operand columns, bands, owners  -> csrc/plan.cpp     (this thread, meanwhile)
+//                prepare(part): tiles, device buffers, ring slots, upload    (one pool task per device)
+//                       of the plan, tensor maps, length quantisation
+//                launch(part): upload the inputs, embedding (+ exchange of   (one pool task per device)
+//                       the sample shards between the devices), first bands
+//   frc_next*    bands of consecutive rows are contiguous flat ranges; every part computes the bands it
+//                owns on two alternating streams, each followed by its own D2H into a pinned ring slot,
+//                and the job hands them out strictly in flat-index order (the ordered iter.Seq of
+//                unifrac.go:209-228) from whichever part owns the next one.
+//
+// Fast-path kernels store fp32 (wire.cu); frc_next_f32 hands the pinned slot out as it is, frc_next
+// widens it on the host.  The exact path is fp64 end to end.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -14,10 +26,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <condition_variable>
 #include <functional>
 #include <memory>
-#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -29,6 +39,7 @@
 #include "../../include/frcfrc_cuda.h"
 #include "frc_internal.h"
 #include "host_pool.h"
+#include "plan.h"
 
 using namespace frc;
 using frc_host::Pool;
@@ -51,12 +62,13 @@ struct Arena {
       if (b.cap - b.off >= bytes) { void* r = b.p + b.off; b.off += bytes; return r; }
     size_t cap = std::max(bytes, min_block);
     char* p = nullptr;
-    cudaError_t e = pinned ? cudaHostAlloc(reinterpret_cast<void**>(&p), cap, cudaHostAllocDefault)
+    // portable: one staging buffer feeds the uploads of every device of a multi-GPU job
+    cudaError_t e = pinned ? cudaHostAlloc(reinterpret_cast<void**>(&p), cap, cudaHostAllocPortable)
                            : cudaMalloc(reinterpret_cast<void**>(&p), cap);
     if (e != cudaSuccess && cap > bytes) {  // retry without the rounding-up
       cudaGetLastError();
       cap = bytes;
-      e = pinned ? cudaHostAlloc(reinterpret_cast<void**>(&p), cap, cudaHostAllocDefault)
+      e = pinned ? cudaHostAlloc(reinterpret_cast<void**>(&p), cap, cudaHostAllocPortable)
                  : cudaMalloc(reinterpret_cast<void**>(&p), cap);
     }
     if (e != cudaSuccess) { cudaGetLastError(); *err = e; return nullptr; }
@@ -84,97 +96,176 @@ float bf16_to_float(uint16_t h) {
   return f;
 }
 
-constexpr int64_t kWidePiece = 2LL << 20;        // fp32 wire: pairs widened per frc_next call (16 MB of doubles: cache-resident)
+constexpr int64_t kWidePiece = 2LL << 20;        // frc_next on a fast path: pairs widened per call (16 MB of doubles: cache-resident)
 constexpr int kSlots = 8;                       // output ring: enough for the compute to run ahead of the D2H
 constexpr int kMinSlots = 3;
 constexpr int64_t kSlotBytesBudget = 1LL << 30;  // bytes the output ring may take beyond kMinSlots (pinned allocation is slow: ~0.4 s per GB)
-constexpr double kFlagBelow = 0.125;            // fast unweighted: recompute d below this exactly
+constexpr double kFlagBelow = 0.125;            // fast unweighted (fp64 / bf16 modes): recompute d below this exactly
 constexpr double kFlagBelowW = 0.03125;         // fast weighted: fp32 error is ~6e-8 / d -> 2e-6 at this d
 constexpr int64_t kExactWorkLimit = 1LL << 28;  // AUTO: pairs * nodes at or below this -> exact
+constexpr int kMaxExceptions = 4096;            // per band: distances fp32 cannot carry (wire.cuh)
+constexpr int kFixupCtas = 32;                  // weighted fix-up: CTAs (one int64[B] workspace each, per stream)
+constexpr int kMaxParts = 8;                    // devices per job (PeerPtrs holds 8)
+
+// Environment knobs (tests and experiments; DESIGN.md has the table).  Read ONCE per frc_create: nothing
+// on the per-band path calls getenv.
+struct Knobs {
+  bool trace = false;
+  int bands_per_rank = 0;     // FRC_BANDS
+  int widen_threads = 0;      // FRC_WIDEN_THREADS
+  int ws_slab = 0;            // FRC_WS_SLAB
+  bool uw_bf16 = false;       // FRC_UW_KERNEL=bf16
+  bool u8_acc_f64 = false;    // FRC_U8_ACC=f64
+  bool feed_bits = false;     // FRC_UW_FEED=bits
+  bool embed_levels = false;  // FRC_EMBED_LEVELS=1
+  int peer_push = -1;         // FRC_PEER_PUSH (multi-process sharding: 0 = NCCL all-gather of the bits)
+  int group_binades = 3;      // FRC_U8_GROUP_BINADES
+  int shard = -1;             // FRC_SHARD (in-process multi-GPU: 0 = every device rebuilds the embedding)
+  static Knobs read() {
+    Knobs k;
+    auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; };
+    auto is = [](const char* name, const char* v) { const char* e = getenv(name); return e && !strcmp(e, v); };
+    k.trace = getenv("FRC_TRACE") != nullptr;
+    k.bands_per_rank = std::max(0, num("FRC_BANDS", 0));
+    k.widen_threads = std::max(0, num("FRC_WIDEN_THREADS", 0));
+    k.ws_slab = std::max(0, num("FRC_WS_SLAB", 0));
+    k.uw_bf16 = is("FRC_UW_KERNEL", "bf16");
+    k.u8_acc_f64 = is("FRC_U8_ACC", "f64");
+    k.feed_bits = is("FRC_UW_FEED", "bits");
+    k.embed_levels = num("FRC_EMBED_LEVELS", 0) == 1;
+    k.peer_push = num("FRC_PEER_PUSH", -1);
+    k.group_binades = num("FRC_U8_GROUP_BINADES", 3);
+    k.shard = num("FRC_SHARD", -1);
+    return k;
+  }
+};
+
+// The calling thread's current device is restored when an entry point returns (a job may drive several).
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 }  // namespace
 
-struct frc_ctx {
+// One GPU of a context: streams + reusable memory.
+struct DevCtx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream[3] = {nullptr, nullptr, nullptr};  // two compute streams + one copy (D2H) stream
-  Arena dev, pin;
+  Arena dev, pin, sym;
+};
+
+struct frc_ctx {
+  std::vector<DevCtx*> devs;
+  Arena pin;  // staging of a job's inputs and plan: portable pinned memory, read by every device's upload
   std::unique_ptr<Pool> pool;
   std::vector<std::vector<int64_t>> stamps;  // per-worker duplicate-detection scratch
   int64_t stamp_epoch = 0;
   bool in_use = false;
-  Comm* comm = nullptr;  // NCCL communicator over the ranks of a multi-GPU run (frc_ctx_comm_init)
-  // "symmetric heap": buffers every rank allocates identically, so block index + offset name the same
-  // buffer on every rank; each block is mapped from the peers with CUDA IPC (peer stores over NVLink)
-  Arena sym;
+  bool peer_ok = false;   // every device of the context can address every other's memory (NVLink / PCIe P2P)
+  Comm* comm = nullptr;   // NCCL communicator over the PROCESSES of a multi-process run (frc_ctx_comm_init)
+  // multi-process "symmetric heap": buffers every rank allocates identically (devs[0]->sym), so block index +
+  // offset name the same buffer on every rank; each block is mapped from the peers with CUDA IPC
   std::vector<std::vector<char*>> sym_peer;  // [block][rank] mapped base (own rank: the local base)
 };
 
-struct Band { int64_t row0, row1, first, count; int32_t tile_off, n_tiles; };
+namespace {
 
 struct Slot {
-  double* dev = nullptr;
-  double* host = nullptr;
-  float* dev32 = nullptr;   // fp32 wire (wire.cu): narrowed copy of the band and its pinned landing buffer
+  double* dev64 = nullptr;   // exact path: the band in HBM / its pinned landing buffer
+  double* host64 = nullptr;
+  float* dev32 = nullptr;    // fast paths
   float* host32 = nullptr;
-  unsigned long long* n_bad_host = nullptr;  // values of this band fp32 cannot carry (mapped pinned)
   uint32_t* flagged = nullptr;
   unsigned long long* n_flagged_host = nullptr;
-  cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr, k3 = nullptr, done = nullptr;
+  Exceptions ex;             // mapped pinned
+  cudaEvent_t k0 = nullptr, k1 = nullptr, k2 = nullptr, done = nullptr;
   int band = -1;  // index into mine[]
 };
 
-struct frc_job {
-  frc_ctx* ctx = nullptr;
-  bool own_ctx = false;
+struct Seg { size_t off = 0, bytes = 0; };
+struct SegAlloc {
+  size_t total = 0;
+  Seg operator()(size_t bytes) { Seg s{total, bytes}; total += (bytes + 255) & ~size_t(255); return s; }
+};
+
+// What the parts of a job share: options, sizes, the plan and the pinned staging buffers (read-only
+// once frc_create's staging phase has joined).
+struct Shared {
   frc_opts_t opts{};
+  Knobs knobs;
+  int64_t N = 0, np = 0, nnz = 0;
+  int32_t B = 0, kp = 0, nw = 0;
+  bool exact = false, weighted = false, prescale = true, need_val = false;
+  bool unsorted_l = false;    // normalize == 0: the reference's -l as coded (post-order lists, exact.cu)
+  bool d2h = true;
+  int n_parts = 1;
+  int world = 1, rank0 = 0;   // band ownership: `world` owners; part p owns owner id rank0 + p
+  enum Exchange { kNone, kInProcess, kNccl } exchange = kNone;  // how the sample shards of the embedding meet
+  bool fused_embed = true, bits_feed = false;
+  ColumnPlan cols;
+  std::vector<Band> bands;   // whole triangle (owners filled in)
+  std::vector<int32_t> level_ptr;
+  int32_t tree_height = 0;
+  // inputs: [row_ptr | tree arrays ... | col | val] in one pinned buffer, same layout on every device
+  char* stage_in = nullptr;
+  Seg in_rowptr, in_parent, in_len, in_cptr, in_cidx, in_lvl, in_lpar, in_lptr, in_lenf, in_post, in_col, in_val;
+  size_t in_bytes = 0;
+  // plan: operand columns, chunks
+  char* stage_plan = nullptr;
+  Seg pl_q0, pl_hi, pl_lo, pl_lenq, pl_order, pl_cexp, pl_lcol, pl_cend, pl_cscale, pl_cshift;
+  size_t plan_bytes = 0;
+};
+
+}  // namespace
+
+struct frc_job;
+
+namespace {
+
+// One device's share of a job.
+struct Part {
+  frc_job* job = nullptr;
+  const Shared* sh = nullptr;
+  DevCtx* dc = nullptr;
+  int index = 0;   // position in job->parts
+  int owner = 0;   // band owner id of this part
+  int rc = FRC_OK;
   std::string err;
   frc_info_t info{};
 
-  int64_t N = 0, np = 0, nnz = 0;
-  int32_t B = 0, kp = 0, nw = 0;
-  bool exact = false, weighted = false, prescale = true;
+  std::vector<int> mine;    // indices into sh->bands, ascending
+  std::vector<Band> bands;  // copies of the bands in `mine` with this part's tile offsets
+  std::vector<Tile> tiles;
 
-  std::vector<int32_t> level_ptr;  // host
-  std::vector<Band> bands;         // whole triangle
-  std::vector<int> mine;           // indices into bands
-  std::vector<Tile> tiles;         // host copy (uploaded)
+  // sample shard of the embedding this part builds (word columns of 32 samples; everything unless sharded)
+  int32_t shard_w0 = 0, shard_nw = 0;
+  int64_t csr_k0 = 0, csr_k1 = 0;  // CSR entries this part uploads
 
-  // device
   DevTree dtree;
   DevCsr dcsr;
-  char* d_inputs = nullptr;
-  size_t input_bytes = 0;
+  char* d_in = nullptr;
+  char* d_plan = nullptr;
   Tile* d_tiles = nullptr;
   int32_t* d_level_ptr = nullptr;
-  unsigned long long* d_flag_counts = nullptr;  // one per band of this rank
-  bool fused_embed = true;
-  bool zero_copy = false;
-  bool wire32 = false;  // bands cross PCIe as fp32 and are widened on the host (wire.cu)
-  double* wide = nullptr;  // wire32: the one double buffer frc_next hands out (<= kWidePiece values)
-  int64_t piece_first = 0, piece_off = 0, piece_end = 0;  // wire32: progress through the held band
-  int64_t ws_slab = 0;        // fast weighted: samples per fp64 embedding slab
-  bool peer_push = false;     // sharded unweighted: the bits kernel stores into every rank's bitsT (no NCCL for the bits)
-  uint32_t* d_bits2[2] = {nullptr, nullptr};  // double-buffered by run parity (a rank may be one step ahead)
+  int32_t* d_post = nullptr;
+  unsigned long long* d_flag_counts = nullptr;  // one per band of this part
+  int64_t ws_slab = 0;
+  bool peer_push = false;     // multi-process sharding: the bits kernel stores into every rank's bitsT over IPC mappings
+  uint32_t* d_bits2[2] = {nullptr, nullptr};  // (double-buffered by run parity: a rank may be one pass ahead)
   PeerPtrs peers[2];
   int64_t run_count = 0;
-  bool sharded = false;       // embedding built for this rank's sample shard, then all-gathered
-  int32_t shard_w0 = 0, shard_nw = 0;  // word columns (32 samples) of the shard
-  int tc_ctas = 1;  // CTAs per tensor-core tile group (2 = cta_group::2 pairs)
-  bool i8 = false;  // fast unweighted: u8 block-floating-point operands (kind::i8) instead of bf16 hi/lo
-  // per operand column (fast unweighted): q0/q1/q2 = bf16 (unused, len_hi, len_lo) or u8 (a, m_hi, m_lo)
   void *d_q0 = nullptr, *d_q1 = nullptr, *d_q2 = nullptr;
   int32_t *d_order = nullptr, *d_col_exp = nullptr;
-  uint32_t* d_qam = nullptr;  // u8: a * m per operand column
-  bool intacc = false;        // u8: chunk scales within 2^16 -> integer accumulation / integer row sums
-  bool bits_feed = false;     // operand tiles expanded inside the pair kernel from bit rows (no operands in HBM)
+  uint32_t* d_qam = nullptr;
   uint32_t* d_bitsS = nullptr;
   BitsOperands* bo = nullptr;
-  int32_t e_min = 0;          // smallest chunk exponent (integer unit = 2^e_min)
   long long* d_r_int = nullptr;
-  long long* d_fix_ws = nullptr;  // fast weighted fix-up: one zeroed int64[B] per SM
-  uint8_t* d_need = nullptr;  // per block of 256 samples: which operands this rank's tiles read (world > 1)
-  double *d_lenq = nullptr, *d_len_col = nullptr, *d_flag_u = nullptr;
+  long long* d_fix_ws[2] = {nullptr, nullptr};  // weighted fix-up: one zeroed int64[B] per CTA, per compute stream
+  uint8_t* d_need = nullptr;
+  double *d_lenq = nullptr, *d_len_col = nullptr, *d_flag_u = nullptr, *d_qerr = nullptr;
   TcChunks d_chunks;
   float* d_lenf = nullptr;
   double *d_E = nullptr, *d_total = nullptr, *d_W = nullptr, *d_r = nullptr, *d_scratch = nullptr;
@@ -182,405 +273,461 @@ struct frc_job {
   uint32_t *d_bits = nullptr, *d_node_scratch = nullptr;
   void *d_P = nullptr, *d_Bh = nullptr, *d_Bl = nullptr;
   TcOperands* tc = nullptr;
+  // -l as coded: per-sample post-order lists
+  int64_t* d_list_ptr = nullptr;
+  int32_t* d_list_id = nullptr;
+  double* d_list_val = nullptr;
+  int64_t list_cap = 0;
 
   Slot slots[kSlots];
   int n_slots = 0;
+  int64_t max_band = 1;
   size_t next_enqueue = 0, next_deliver = 0;
-  int held_slot = -1;  // slot whose buffer the caller currently reads
   cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_embed0 = nullptr, ev_embed1 = nullptr;
   cudaEvent_t ev_run1 = nullptr, ev_join = nullptr, ev_bits = nullptr, ev_rsum = nullptr;
-  bool run_timed = false;
-  bool embed_timed = false;
+  cudaEvent_t ev_shard = nullptr;  // in-process exchange: this part's shard has been stored into every device
+  bool run_timed = false, embed_timed = false;
   std::chrono::steady_clock::time_point t_host0;
+};
+
+}  // namespace
+
+struct frc_job {
+  frc_ctx* ctx = nullptr;
+  bool own_ctx = false;
+  Shared sh;
+  std::vector<std::unique_ptr<Part>> parts;
+  std::string err;
+  frc_info_t info{};
+  // delivery: the bands this process yields, in flat-index order
+  struct Item { int part, idx; };
+  std::vector<Item> order;
+  size_t next_item = 0;
+  int held_part = -1;   // part whose slot the caller currently reads
+  int held_slot = -1;
+  int read_mode = 0;    // 0 = not decided, 1 = frc_next (float64), 2 = frc_next_f32
+  double* wide = nullptr;  // frc_next on a fast path: the one double buffer handed out (<= kWidePiece values)
+  int64_t piece_first = 0, piece_off = 0, piece_end = 0;
+  double create_ms = 0;
 };
 
 namespace {
 
-#define JOB_CUDA(job, expr)                                                                  \
+#define PART_CUDA(p, expr)                                                                   \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
     if (_e != cudaSuccess) {                                                                 \
-      (job)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                       \
+      (p)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                         \
       cudaGetLastError();                                                                    \
-      return _e == cudaErrorMemoryAllocation ? FRC_ERR_OOM : FRC_ERR_CUDA;                   \
+      return (p)->rc = (_e == cudaErrorMemoryAllocation ? FRC_ERR_OOM : FRC_ERR_CUDA);       \
     }                                                                                        \
   } while (0)
 
+int pfail(Part* p, int code, const std::string& msg) { p->err = msg; return p->rc = code; }
 int fail(frc_job* j, int code, const std::string& msg) { j->err = msg; return code; }
 
-// Which rank computes which band: bands are as equal as whole tile rows allow, and the rest of
-// the imbalance is removed by dealing them largest-first to the least loaded rank (deterministic,
-// the same on every rank and in frc_plan_bands).
-std::vector<int> band_owners(const std::vector<int64_t>& rows, int world) {
-  const size_t n = rows.size() > 0 ? rows.size() - 1 : 0;
-  std::vector<int> owner(n, 0);
-  if (world <= 1) return owner;
-  std::vector<size_t> order(n);
-  std::vector<int64_t> cnt(n);
-  for (size_t k = 0; k < n; ++k) {
-    order[k] = k;
-    cnt[k] = tri(rows[k + 1]) - (rows[k] >= 2 ? tri(rows[k]) : 0);
-  }
-  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cnt[a] > cnt[b]; });
-  std::vector<int64_t> load(world, 0);
-  for (size_t k : order) {
-    int best = 0;
-    for (int r = 1; r < world; ++r)
-      if (load[r] < load[best]) best = r;
-    owner[k] = best;
-    load[best] += cnt[k];
-  }
-  return owner;
-}
-
-// Row boundaries of the bands of the triangle (multiples of the tile size, first 0, last N).
-//   requested > 0 : uniform bands of that many rows (rounded up to whole tiles);
-//   otherwise     : bands of (nearly) EQUAL PAIR COUNT, boundaries at N * sqrt(k / n) -- equal work per
-//                   launch, so the ranks are balanced and no band is a sliver that cannot fill the GPU.
-//                   Distances stay in HBM (no D2H to overlap): one band, or two per rank;
-//                   with D2H: about 8 per rank so that copies overlap the kernels.  More bands when one
-//                   would exceed 96 MB (streamed) / 1.5 GB (kept in HBM) of distances.
-std::vector<int64_t> band_boundaries(int64_t N, int64_t requested, int world, bool d2h) {
-  std::vector<int64_t> rows;
-  rows.push_back(0);
-  if (N <= 0) return rows;
-  if (requested > 0) {
-    const int64_t step = round_up(requested, kTile);
-    for (int64_t r = step; r < N; r += step) rows.push_back(r);
-    rows.push_back(N);
-    return rows;
-  }
-  const int64_t tile_rows = (N + kTile - 1) / kTile;
-  int64_t n = d2h ? 8LL * world : (world == 1 ? 1 : 2LL * world);
-  if (const char* e = getenv("FRC_BANDS")) { if (d2h && atoi(e) > 0) n = static_cast<int64_t>(atoi(e)) * world; }
-  const double total_bytes = 8.0 * static_cast<double>(N) * static_cast<double>(N - 1) / 2.0;
-  // streamed to the host: bands of <= 96 MB keep the pinned ring small (pinning memory costs ~0.4 s
-  // per GB, paid by the first job of a context) and are still several waves of tiles each
-  const double band_cap = d2h ? 96.0 * 1024 * 1024 : 1536.0 * 1024 * 1024;
-  const int64_t by_size = static_cast<int64_t>(std::ceil(total_bytes / band_cap));
-  if (by_size > n) n = round_up(by_size, 2LL * world);
-  n = std::max<int64_t>(1, std::min(n, std::max<int64_t>(world, tile_rows / 2)));
-  for (int64_t k = 1; k < n; ++k) {
-    int64_t r = static_cast<int64_t>(std::llround(static_cast<double>(N) * std::sqrt(static_cast<double>(k) / n) / kTile)) * kTile;
-    r = std::max(r, rows.back() + kTile);
-    if (r >= N) break;
-    rows.push_back(r);
-  }
-  rows.push_back(N);
-  return rows;
-}
-
 template <class T>
-T* dev_alloc(frc_job* j, size_t n, int* rc) {
+T* dev_alloc(Part* p, size_t n) {
   cudaError_t e = cudaSuccess;
-  void* p = j->ctx->dev.alloc(n * sizeof(T), &e);
-  if (!p) {
-    j->err = "device allocation of " + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e);
-    *rc = FRC_ERR_OOM;
+  void* q = p->dc->dev.alloc(n * sizeof(T), &e);
+  if (!q) {
+    p->err = "device allocation of " + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e);
+    p->rc = FRC_ERR_OOM;
   }
-  return static_cast<T*>(p);
+  return static_cast<T*>(q);
 }
 template <class T>
-T* pin_alloc(frc_job* j, size_t n, int* rc) {
+T* pin_alloc(Part* p, size_t n) {
   cudaError_t e = cudaSuccess;
-  void* p = j->ctx->pin.alloc(n * sizeof(T), &e);
-  if (!p) {
-    j->err = "pinned host allocation of " + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e);
-    *rc = FRC_ERR_OOM;
+  void* q = p->dc->pin.alloc(n * sizeof(T), &e);
+  if (!q) {
+    p->err = "pinned host allocation of " + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e);
+    p->rc = FRC_ERR_OOM;
   }
-  return static_cast<T*>(p);
+  return static_cast<T*>(q);
 }
 
-// Maps the blocks of the symmetric heap that the peers have not seen yet (collective: every rank
-// allocates the same sequence, so every rank gains the same blocks at the same time).
-int sym_sync(frc_job* j) {
-  frc_ctx* c = j->ctx;
+// Runs fn(part index) for every part: on the pool when there are several (each task binds its own
+// device), inline otherwise.  Returns the first failing part's status.
+int for_parts(frc_job* j, const std::function<int(Part*)>& fn) {
+  const int n = static_cast<int>(j->parts.size());
+  if (n == 1) {
+    cudaSetDevice(j->parts[0]->dc->device);
+    fn(j->parts[0].get());
+  } else {
+    Pool* pool = j->ctx->pool.get();
+    const int T = std::min(n, pool->size());
+    std::atomic<int> next{0};
+    pool->run(T, [&](int) {
+      for (int k = next.fetch_add(1); k < n; k = next.fetch_add(1)) {
+        cudaSetDevice(j->parts[k]->dc->device);
+        fn(j->parts[k].get());
+      }
+    });
+  }
+  for (auto& p : j->parts)
+    if (p->rc) { j->err = p->err; return p->rc; }
+  return FRC_OK;
+}
+
+// Multi-process sharding: maps the blocks of the symmetric heap that the peers have not seen yet (collective:
+// every rank allocates the same sequence, so every rank gains the same blocks at the same time).
+int sym_sync(Part* p) {
+  frc_ctx* c = p->job->ctx;
+  DevCtx* dc = p->dc;
   const int world = comm_world(c->comm), rank = comm_rank(c->comm);
-  while (c->sym_peer.size() < c->sym.blocks.size()) {
+  while (c->sym_peer.size() < dc->sym.blocks.size()) {
     const size_t b = c->sym_peer.size();
     cudaIpcMemHandle_t mine;
-    JOB_CUDA(j, cudaIpcGetMemHandle(&mine, c->sym.blocks[b].p));
+    PART_CUDA(p, cudaIpcGetMemHandle(&mine, dc->sym.blocks[b].p));
     std::vector<cudaIpcMemHandle_t> all(world);
     std::string cerr;
-    if (!comm_all_gather_host(c->comm, &mine, sizeof(mine), all.data(), c->stream[0], &cerr))
-      return fail(j, FRC_ERR_CUDA, cerr);
+    if (!comm_all_gather_host(c->comm, &mine, sizeof(mine), all.data(), dc->stream[0], &cerr))
+      return pfail(p, FRC_ERR_CUDA, cerr);
     std::vector<char*> bases(world, nullptr);
     for (int r = 0; r < world; ++r) {
-      if (r == rank) { bases[r] = c->sym.blocks[b].p; continue; }
-      void* p = nullptr;
-      JOB_CUDA(j, cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
-      bases[r] = static_cast<char*>(p);
+      if (r == rank) { bases[r] = dc->sym.blocks[b].p; continue; }
+      void* q = nullptr;
+      PART_CUDA(p, cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess));
+      bases[r] = static_cast<char*>(q);
     }
     c->sym_peer.push_back(bases);
   }
   return FRC_OK;
 }
 
-// Queue the embedding stage on stream 0.
-int run_embedding(frc_job* j) {
-  frc_ctx* c = j->ctx;
-  cudaStream_t s = c->stream[0];
+// ------------------------------------------------------------------ embedding
+// Stage 1 of the embedding on stream 0 of the part: everything up to (and including) the point where this
+// part's sample shard has been made visible to the other devices.  Unsharded jobs run the whole embedding here.
+int embed_stage1(Part* p) {
+  const Shared& sh = *p->sh;
+  DevCtx* dc = p->dc;
+  frc_ctx* c = p->job->ctx;
+  cudaStream_t s = dc->stream[0];
   int launches = 0;
-  j->t_host0 = std::chrono::steady_clock::now();
-  if (j->d_flag_counts)
-    JOB_CUDA(j, cudaMemsetAsync(j->d_flag_counts, 0, sizeof(unsigned long long) * (j->mine.size() + 1), s));
-  JOB_CUDA(j, cudaEventRecord(j->ev_embed0, s));
-  if (j->exact) {
-    launches += launch_embed_f64(j->dtree, j->level_ptr.data(), j->dcsr, j->d_E, j->np, 0, s);
-    if (j->opts.normalize != 0) {
-      launches += launch_totals_f64(j->d_E, j->B, j->np, j->N, j->d_total, s);
-      launches += launch_normalize_f64(j->d_E, j->B, j->np, j->N, j->d_total, s);
+  p->t_host0 = std::chrono::steady_clock::now();
+  if (p->d_flag_counts)
+    PART_CUDA(p, cudaMemsetAsync(p->d_flag_counts, 0, sizeof(unsigned long long) * (p->mine.size() + 1), s));
+  PART_CUDA(p, cudaEventRecord(p->ev_embed0, s));
+  const bool inproc = sh.exchange == Shared::kInProcess;
+  const int n_parts = sh.n_parts;
+  if (sh.exact) {
+    launches += launch_embed_f64(p->dtree, sh.level_ptr.data(), p->dcsr, p->d_E, sh.np, 0, s);
+    // (normalisation cannot change membership, which is all the unweighted kernel reads -- and a
+    // proportion that underflows to 0 would drop a node the reference keeps)
+    if (sh.opts.normalize == 1 && sh.weighted) {
+      launches += launch_totals_f64(p->d_E, sh.B, sh.np, sh.N, p->d_total, s);
+      launches += launch_normalize_f64(p->d_E, sh.B, sh.np, sh.N, p->d_total, s);
     }
-    j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
-  } else if (j->weighted) {
+    if (sh.unsorted_l) {
+      // per-sample lists in post-order; their total size is only known after the counting pass
+      launches += launch_postorder_lists(p->d_E, p->d_post, sh.B, sh.np, sh.N, p->d_list_ptr, nullptr, nullptr, s);
+      int64_t total = 0;
+      PART_CUDA(p, cudaMemcpyAsync(&total, p->d_list_ptr + sh.N, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      PART_CUDA(p, cudaStreamSynchronize(s));
+      if (total > p->list_cap) {
+        p->list_cap = total;
+        if (!(p->d_list_id = dev_alloc<int32_t>(p, static_cast<size_t>(total) + 1))) return p->rc;
+        if (!(p->d_list_val = dev_alloc<double>(p, static_cast<size_t>(total) + 1))) return p->rc;
+      }
+      launches += launch_postorder_lists(p->d_E, p->d_post, sh.B, sh.np, sh.N, p->d_list_ptr, p->d_list_id,
+                                         p->d_list_val, s);
+    }
+    p->info.embed_bytes = 2LL * sh.B * sh.np * 8 + 12LL * sh.nnz;
+  } else if (sh.weighted) {
     // fast weighted: the fp64 embedding is built one slab of samples at a time (E[B][slab] stays
     // <= 2 GB whatever the sample count) and leaves as the fp32 tile-panel operand + denominators;
-    // a rank of a sharded run only builds the slabs of its own sample shard
-    const bool norm = j->opts.normalize != 0;
-    const int64_t per_rank = j->np / (j->sharded ? j->opts.world : 1);
-    const int64_t s_begin = j->sharded ? j->opts.rank * per_rank : 0, s_stop = s_begin + per_rank;
-    for (int64_t sb = s_begin; sb < s_stop; sb += j->ws_slab) {
-      const int64_t ld = std::min<int64_t>(j->ws_slab, s_stop - sb);
-      launches += launch_embed_f64(j->dtree, j->level_ptr.data(), j->dcsr, j->d_E, ld, sb, s);
-      if (norm) launches += launch_totals_fast_f64(j->d_E, j->B, ld, j->d_total + sb, j->d_scratch, s);
-      launches += launch_weighted_operand_panels(j->d_E, j->dtree.length, j->B, j->kp, ld, sb,
-                                                 norm ? j->d_total + sb : nullptr, j->prescale, j->d_A, j->d_W,
-                                                 j->d_scratch, s);
+    // a part of a sharded job only builds the slabs of its own sample shard
+    const bool norm = sh.opts.normalize == 1;
+    const int64_t s_begin = static_cast<int64_t>(p->shard_w0) * 32, s_stop = s_begin + static_cast<int64_t>(p->shard_nw) * 32;
+    for (int64_t sb = s_begin; sb < s_stop; sb += p->ws_slab) {
+      const int64_t ld = std::min<int64_t>(p->ws_slab, s_stop - sb);
+      launches += launch_embed_f64(p->dtree, sh.level_ptr.data(), p->dcsr, p->d_E, ld, sb, s);
+      if (norm) launches += launch_totals_fast_f64(p->d_E, sh.B, ld, p->d_total + sb, p->d_scratch, s);
+      launches += launch_weighted_operand_panels(p->d_E, p->dtree.length, sh.B, sh.kp, ld, sb,
+                                                 norm ? p->d_total + sb : nullptr, sh.prescale, p->d_A, p->d_W,
+                                                 p->d_scratch, s);
     }
-    if (j->sharded) {
-      void* bufs[3] = {j->d_A, j->d_W, j->d_total};
-      const size_t bytes[3] = {static_cast<size_t>(per_rank) * j->kp * sizeof(float),
-                               static_cast<size_t>(per_rank) * sizeof(double),
-                               static_cast<size_t>(per_rank) * sizeof(double)};
+    const size_t per = static_cast<size_t>(p->shard_nw) * 32;
+    const size_t bytes[3] = {per * sh.kp * sizeof(float), per * sizeof(double), per * sizeof(double)};
+    if (sh.exchange == Shared::kNccl) {
+      void* bufs[3] = {p->d_A, p->d_W, p->d_total};
       std::string cerr;
-      if (!comm_all_gather_inplace(c->comm, bufs, bytes, norm ? 3 : 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
-      j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (norm ? bytes[2] : 0)) * (j->opts.world - 1);
+      if (!comm_all_gather_inplace(c->comm, bufs, bytes, norm ? 3 : 2, s, &cerr)) return pfail(p, FRC_ERR_CUDA, cerr);
+      p->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (norm ? bytes[2] : 0)) * (sh.world - 1);
+    } else if (inproc) {
+      // the shard's panels, denominators and normalisers go to the same place in every other device's
+      // HBM: device-to-device copies over NVLink on the copy engines
+      for (int q = 0; q < n_parts; ++q) {
+        if (q == p->index) continue;
+        Part* o = p->job->parts[q].get();
+        PART_CUDA(p, cudaMemcpyPeerAsync(o->d_A + s_begin * sh.kp, o->dc->device, p->d_A + s_begin * sh.kp, dc->device, bytes[0], s));
+        PART_CUDA(p, cudaMemcpyPeerAsync(o->d_W + s_begin, o->dc->device, p->d_W + s_begin, dc->device, bytes[1], s));
+        if (norm)
+          PART_CUDA(p, cudaMemcpyPeerAsync(o->d_total + s_begin, o->dc->device, p->d_total + s_begin, dc->device, bytes[2], s));
+      }
+      p->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (norm ? bytes[2] : 0)) * (n_parts - 1);
     }
     // write each element once, read it once when folded into its parent (+ CSR)
-    j->info.embed_bytes = 2LL * j->B * j->np * 8 + 12LL * j->nnz;
-  } else {
-    if (j->fused_embed) {
-      const int cur = static_cast<int>(j->run_count & 1);
-      if (j->peer_push) {
-        j->d_bits = j->d_bits2[cur];
-        if (j->run_count == 0) {  // nobody may still be reading these buffers for an earlier job
-          std::string cerr;
-          if (!comm_barrier(c->comm, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
+    p->info.embed_bytes = 2LL * sh.B * (static_cast<int64_t>(p->shard_nw) * 32) * 8 + 12LL * (p->csr_k1 - p->csr_k0);
+  } else if (sh.fused_embed) {
+    const int cur = static_cast<int>(p->run_count & 1);
+    if (p->peer_push) {
+      p->d_bits = p->d_bits2[cur];
+      if (p->run_count == 0) {  // nobody may still be reading these buffers for an earlier job
+        std::string cerr;
+        if (!comm_barrier(c->comm, s, &cerr)) return pfail(p, FRC_ERR_CUDA, cerr);
+      }
+    }
+    ++p->run_count;
+    PeerPtrs peers;  // n = 0: local stores only
+    if (p->peer_push) peers = p->peers[cur];
+    else if (inproc && !sh.bits_feed) {
+      // in-process sharding: the kernel stores its finished bit columns straight into every device's
+      // bitsT (peer access over NVLink): the all-gather is fused into the producing kernel
+      peers.n = n_parts; peers.self = p->index;
+      for (int q = 0; q < n_parts; ++q) peers.p[q] = p->job->parts[q]->d_bits;
+    }
+    launches += launch_embed_presence_fused(p->dtree, p->d_level_ptr, p->dcsr, sh.nw, p->shard_w0, p->shard_nw,
+                                            sh.kp, p->d_order, p->d_node_scratch, p->d_bits, p->d_bitsS, peers, s);
+    // the row sums (integer-ALU-bound) and the operand expansion (HBM-bound) both only read the bit
+    // columns: they run side by side on the two compute streams unless an exchange sits between
+    const bool split = sh.exchange == Shared::kNone;
+    cudaStream_t rs = split ? dc->stream[1] : s;
+    if (split) {
+      PART_CUDA(p, cudaEventRecord(p->ev_bits, s));
+      PART_CUDA(p, cudaStreamWaitEvent(rs, p->ev_bits, 0));
+    }
+    launches += launch_presence_rowsum_t(p->d_bits, sh.B, sh.nw, p->shard_w0, p->shard_nw, sh.kp, p->d_lenq,
+                                         sh.cols.i8 ? p->d_qam : nullptr, p->d_col_exp, p->d_scratch, p->d_r,
+                                         sh.cols.e_min, sh.cols.intacc ? p->d_r_int : nullptr, rs);
+    const size_t rbytes = static_cast<size_t>(p->shard_nw) * 32 * sizeof(double);
+    const size_t bbytes = static_cast<size_t>(p->shard_nw) * sh.kp * sizeof(uint32_t);
+    if (sh.exchange == Shared::kNccl) {
+      // the one exchange step of the path: presence bit columns + row sums of every rank's sample
+      // shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
+      // (bits-fed kernel: the sample-major bit rows are what is exchanged, same size)
+      void* bufs[2] = {sh.cols.intacc ? static_cast<void*>(p->d_r_int) : static_cast<void*>(p->d_r),
+                       sh.bits_feed ? p->d_bitsS : p->d_bits};
+      const size_t bytes[2] = {rbytes, bbytes};
+      // peer_push: the bit columns already sit in every rank's bitsT (stored there by the embedding
+      // kernel itself); the small all-gather of the row sums is also the point where the ranks meet
+      std::string cerr;
+      if (!comm_all_gather_inplace(c->comm, bufs, bytes, p->peer_push ? 1 : 2, s, &cerr)) return pfail(p, FRC_ERR_CUDA, cerr);
+      p->info.gather_bytes = static_cast<int64_t>(rbytes + bbytes) * (sh.world - 1);
+    } else if (inproc) {
+      // row sums of the shard (8 bytes per sample) and, for the bits-fed kernel, the shard's bit rows:
+      // small device-to-device copies to every other device
+      const int64_t s_begin = static_cast<int64_t>(p->shard_w0) * 32;
+      for (int q = 0; q < n_parts; ++q) {
+        if (q == p->index) continue;
+        Part* o = p->job->parts[q].get();
+        if (sh.cols.intacc)
+          PART_CUDA(p, cudaMemcpyPeerAsync(o->d_r_int + s_begin, o->dc->device, p->d_r_int + s_begin, dc->device, rbytes, s));
+        else
+          PART_CUDA(p, cudaMemcpyPeerAsync(o->d_r + s_begin, o->dc->device, p->d_r + s_begin, dc->device, rbytes, s));
+        if (sh.bits_feed) {
+          const size_t roww = static_cast<size_t>(sh.kp / 32);
+          PART_CUDA(p, cudaMemcpyPeerAsync(o->d_bitsS + s_begin * roww, o->dc->device, p->d_bitsS + s_begin * roww,
+                                           dc->device, bbytes, s));
         }
       }
-      ++j->run_count;
-      static const PeerPtrs no_peers;
-      launches += launch_embed_presence_fused(j->dtree, j->d_level_ptr, j->dcsr, j->nw, j->shard_w0, j->shard_nw,
-                                              j->kp, j->d_order, j->d_node_scratch, j->d_bits, j->d_bitsS,
-                                              j->peer_push ? j->peers[cur] : no_peers, s);
-      // the row sums (integer-ALU-bound) and the operand expansion (HBM-bound) both only read the bit
-      // columns: they run side by side on the two compute streams unless an all-gather sits between
-      cudaStream_t rs = j->sharded ? s : c->stream[1];
-      if (!j->sharded) {
-        JOB_CUDA(j, cudaEventRecord(j->ev_bits, s));
-        JOB_CUDA(j, cudaStreamWaitEvent(rs, j->ev_bits, 0));
-      }
-      launches += launch_presence_rowsum_t(j->d_bits, j->B, j->nw, j->shard_w0, j->shard_nw, j->kp, j->d_lenq,
-                                           j->i8 ? j->d_qam : nullptr, j->d_col_exp, j->d_scratch, j->d_r, j->e_min,
-                                           j->intacc ? j->d_r_int : nullptr, rs);
-      if (j->sharded) {
-        // the one exchange step of the path: presence bit columns + row sums of every rank's
-        // sample shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
-        // (bits-fed kernel: the sample-major bit rows are what is exchanged, same size)
-        void* bufs[2] = {j->intacc ? static_cast<void*>(j->d_r_int) : static_cast<void*>(j->d_r),
-                         j->bits_feed ? j->d_bitsS : j->d_bits};
-        const size_t bytes[2] = {static_cast<size_t>(j->shard_nw) * 32 * sizeof(double),
-                                 static_cast<size_t>(j->shard_nw) * j->kp * sizeof(uint32_t)};
-        // peer_push: the bit columns already sit in every rank's bitsT (stored there by the embedding
-        // kernel itself); the small all-gather of the row sums is also the point where the ranks meet
-        std::string cerr;
-        if (!comm_all_gather_inplace(c->comm, bufs, bytes, j->peer_push ? 1 : 2, s, &cerr)) return fail(j, FRC_ERR_CUDA, cerr);
-        j->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1]) * (j->opts.world - 1);
-      }
-      if (!j->bits_feed)
-        launches += launch_expand_operands_t(j->d_bits, j->nw, j->kp, j->np, j->i8, j->d_q0, j->d_q1, j->d_q2,
-                                             j->d_P, j->d_Bh, j->d_Bl, j->d_need, s);
-      if (!j->sharded) {
-        JOB_CUDA(j, cudaEventRecord(j->ev_rsum, rs));
-        JOB_CUDA(j, cudaStreamWaitEvent(s, j->ev_rsum, 0));
-      }
-    } else {
-      launches += launch_embed_bits(j->dtree, j->level_ptr.data(), j->dcsr, j->d_bits, j->nw, s);
-      launches += launch_presence_rowsum(j->d_bits, j->B, j->nw, j->d_lenq, j->d_r, j->d_scratch, s);
-      launches += launch_expand_operands(j->d_bits, j->B, j->nw, j->kp, j->np,
-                                         static_cast<const uint16_t*>(j->d_q1), static_cast<const uint16_t*>(j->d_q2),
-                                         static_cast<uint16_t*>(j->d_P), static_cast<uint16_t*>(j->d_Bh),
-                                         static_cast<uint16_t*>(j->d_Bl), s);
+      p->info.gather_bytes = static_cast<int64_t>(rbytes + bbytes) * (n_parts - 1);
     }
-    // bits written + read once per level pass, three bf16 operands written once (+ CSR cols)
-    j->info.embed_bytes = 2LL * j->B * j->nw * 4 + 3LL * j->np * j->kp * (j->i8 ? 1 : 2) + 4LL * j->nnz;
+    if (!split) {
+      // bits written + read once per level pass (+ CSR cols): this part's shard
+      p->info.embed_bytes = 2LL * sh.B * p->shard_nw * 4 + 4LL * (p->csr_k1 - p->csr_k0);
+    }
   }
-  JOB_CUDA(j, cudaGetLastError());
-  JOB_CUDA(j, cudaEventRecord(j->ev_embed1, s));
-  JOB_CUDA(j, cudaStreamWaitEvent(c->stream[1], j->ev_embed1, 0));
-  j->info.kernel_launches += launches;
-  j->embed_timed = false;
+  PART_CUDA(p, cudaGetLastError());
+  if (inproc) PART_CUDA(p, cudaEventRecord(p->ev_shard, s));
+  p->info.kernel_launches += launches;
   return FRC_OK;
 }
 
-// Queue band mine[idx] into its slot.
-int enqueue_band(frc_job* j, size_t idx) {
-  frc_ctx* c = j->ctx;
-  if (getenv("FRC_TRACE"))
-    fprintf(stderr, "[host] enqueue band %zu at %.3f ms\n", idx,
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - j->t_host0).count());
-  const Band& b = j->bands[j->mine[idx]];
-  Slot& sl = j->slots[idx % j->n_slots];
-  cudaStream_t s = c->stream[idx % 2];
+// Stage 2: wait for the other devices' shards, then whatever every device does for ALL samples.
+int embed_stage2(Part* p) {
+  const Shared& sh = *p->sh;
+  DevCtx* dc = p->dc;
+  cudaStream_t s = dc->stream[0];
+  int launches = 0;
+  if (sh.exchange == Shared::kInProcess)
+    for (auto& o : p->job->parts)
+      if (o.get() != p) PART_CUDA(p, cudaStreamWaitEvent(s, o->ev_shard, 0));
+  if (!sh.exact && !sh.weighted) {
+    if (sh.fused_embed) {
+      if (!sh.bits_feed)
+        launches += launch_expand_operands_t(p->d_bits, sh.nw, sh.kp, sh.np, sh.cols.i8, p->d_q0, p->d_q1, p->d_q2,
+                                             p->d_P, p->d_Bh, p->d_Bl, p->d_need, s);
+      if (sh.exchange == Shared::kNone) {
+        PART_CUDA(p, cudaEventRecord(p->ev_rsum, dc->stream[1]));
+        PART_CUDA(p, cudaStreamWaitEvent(s, p->ev_rsum, 0));
+        p->info.embed_bytes = 2LL * sh.B * sh.nw * 4 + 4LL * sh.nnz;
+      }
+      // + three operands written once, the bit columns read once more
+      if (!sh.bits_feed) p->info.embed_bytes += 3LL * sh.np * sh.kp * (sh.cols.i8 ? 1 : 2) + 4LL * sh.nw * sh.kp;
+    } else {
+      launches += launch_embed_bits(p->dtree, sh.level_ptr.data(), p->dcsr, p->d_bits, sh.nw, s);
+      launches += launch_presence_rowsum(p->d_bits, sh.B, sh.nw, p->d_lenq, p->d_r, p->d_scratch, s);
+      launches += launch_expand_operands(p->d_bits, sh.B, sh.nw, sh.kp, sh.np,
+                                         static_cast<const uint16_t*>(p->d_q1), static_cast<const uint16_t*>(p->d_q2),
+                                         static_cast<uint16_t*>(p->d_P), static_cast<uint16_t*>(p->d_Bh),
+                                         static_cast<uint16_t*>(p->d_Bl), s);
+      p->info.embed_bytes = 2LL * sh.B * sh.nw * 4 + 3LL * sh.np * sh.kp * 2 + 4LL * sh.nnz;
+    }
+  }
+  PART_CUDA(p, cudaGetLastError());
+  PART_CUDA(p, cudaEventRecord(p->ev_embed1, s));
+  PART_CUDA(p, cudaStreamWaitEvent(dc->stream[1], p->ev_embed1, 0));
+  p->info.kernel_launches += launches;
+  p->embed_timed = false;
+  return FRC_OK;
+}
+
+// Queue band mine[idx] of the part into its slot.
+int enqueue_band(Part* p, size_t idx) {
+  const Shared& sh = *p->sh;
+  DevCtx* dc = p->dc;
+  if (sh.knobs.trace)
+    fprintf(stderr, "[host] dev %d enqueue band %zu at %.3f ms\n", dc->device, idx,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - p->t_host0).count());
+  const Band& b = p->bands[idx];
+  Slot& sl = p->slots[idx % p->n_slots];
+  const int si = static_cast<int>(idx % 2);
+  cudaStream_t s = dc->stream[si];
   sl.band = static_cast<int>(idx);
   int launches = 0;
-  JOB_CUDA(j, cudaEventRecord(sl.k0, s));
-  if (j->exact) {
-    launches += launch_exact_pairs(j->d_E, j->dtree.length, j->B, j->np, j->weighted, b.first, b.count,
-                                   sl.dev, s);
-  } else if (j->weighted) {
-    unsigned long long* cnt = j->d_flag_counts + idx;
-    launches += launch_weighted_tiles(j->d_A, j->np, j->kp, j->d_lenf, j->prescale, j->d_W,
-                                      j->d_tiles + b.tile_off, b.n_tiles, j->N, b.first, sl.dev, kFlagBelowW,
-                                      sl.flagged, cnt, s);
-    JOB_CUDA(j, cudaEventRecord(sl.k1, s));
-    launches += launch_weighted_fixup(j->dcsr, j->dtree, j->opts.normalize ? j->d_total : nullptr, j->d_W,
-                                      sl.flagged, cnt, sl.n_flagged_host, b.first, j->d_fix_ws, c->num_sms, sl.dev, s);
+  PART_CUDA(p, cudaEventRecord(sl.k0, s));
+  if (sh.exact) {
+    if (sh.unsorted_l)
+      launches += launch_unsorted_pairs(p->d_list_ptr, p->d_list_id, p->d_list_val, p->dtree.length, b.first, b.count,
+                                        sl.dev64, s);
+    else
+      launches += launch_exact_pairs(p->d_E, p->dtree.length, sh.B, sh.np, sh.weighted, b.first, b.count, sl.dev64, s);
+    PART_CUDA(p, cudaEventRecord(sl.k1, s));
   } else {
     // no copy-engine work between the kernels: a memset or an 8-byte D2H would queue behind the
     // previous band's bulk D2H and stall this band (measured).  Counters are per band, zeroed once
     // per run; the fix-up kernel publishes the count through mapped pinned memory.
-    unsigned long long* cnt = j->d_flag_counts + idx;
-    if (j->bits_feed) {
-      launches += launch_unweighted_bits(j->bo, j->d_tiles + b.tile_off, b.n_tiles, j->N, b.first, sl.dev,
-                                         sl.flagged, cnt, c->num_sms, s);
-      JOB_CUDA(j, cudaEventRecord(sl.k1, s));
-      launches += launch_unweighted_fixup_bits(j->bo, sl.flagged, cnt, sl.n_flagged_host, b.first, sl.dev,
-                                               c->num_sms, s);
+    unsigned long long* cnt = p->d_flag_counts + idx;
+    *sl.ex.count = 0;  // (the slot's previous band has been delivered)
+    if (sh.weighted) {
+      launches += launch_weighted_tiles(p->d_A, sh.np, sh.kp, p->d_lenf, sh.prescale, p->d_W, p->d_tiles + b.tile_off,
+                                        b.n_tiles, sh.N, b.first, sl.dev32, kFlagBelowW, sl.flagged, cnt, dc->num_sms, s);
+      PART_CUDA(p, cudaEventRecord(sl.k1, s));
+      // (one workspace per compute stream: consecutive bands run their fix-ups concurrently)
+      launches += launch_weighted_fixup(p->dcsr, p->dtree, sh.opts.normalize == 1 ? p->d_total : nullptr, p->d_W,
+                                        sl.flagged, cnt, sl.n_flagged_host, b.first, p->d_fix_ws[si], kFixupCtas,
+                                        sl.dev32, sl.ex, s);
+    } else if (sh.bits_feed) {
+      launches += launch_unweighted_bits(p->bo, p->d_tiles + b.tile_off, b.n_tiles, sh.N, b.first, sl.dev32,
+                                         sl.flagged, cnt, dc->num_sms, s);
+      PART_CUDA(p, cudaEventRecord(sl.k1, s));
+      launches += launch_unweighted_fixup_bits(p->bo, sl.flagged, cnt, sl.n_flagged_host, b.first, sl.dev32, sl.ex,
+                                               dc->num_sms, s);
     } else {
-      launches += launch_unweighted_tc(j->tc, j->d_r, j->d_tiles + b.tile_off, b.n_tiles, j->N,
-                                       b.first, sl.dev, kFlagBelow, sl.flagged, cnt, c->num_sms, j->tc_ctas, s);
-      JOB_CUDA(j, cudaEventRecord(sl.k1, s));
-      launches += launch_unweighted_fixup(j->tc, sl.flagged, cnt, sl.n_flagged_host, b.first, sl.dev,
-                                          c->num_sms, s);
+      launches += launch_unweighted_tc(p->tc, p->d_r, p->d_tiles + b.tile_off, b.n_tiles, sh.N, b.first, sl.dev32,
+                                       kFlagBelow, sl.flagged, cnt, dc->num_sms, s);
+      PART_CUDA(p, cudaEventRecord(sl.k1, s));
+      launches += launch_unweighted_fixup(p->tc, sl.flagged, cnt, sl.n_flagged_host, b.first, sl.dev32, sl.ex,
+                                          dc->num_sms, s);
     }
   }
-  JOB_CUDA(j, cudaGetLastError());
-  if (j->exact) JOB_CUDA(j, cudaEventRecord(sl.k1, s));
-  JOB_CUDA(j, cudaEventRecord(sl.k2, s));
+  PART_CUDA(p, cudaGetLastError());
+  PART_CUDA(p, cudaEventRecord(sl.k2, s));
   // bulk D2H runs on its own stream so the compute streams never hold copy-engine work
   // (a kernel queued behind a copy in the same stream cannot overlap that copy)
-  cudaStream_t cs = c->stream[2];
-  if (j->wire32) {
-    // the band crosses PCIe as fp32 (wire.cu); frc_next widens it into sl.host
-    *sl.n_bad_host = 0;
-    launches += launch_narrow_band(sl.dev, sl.dev32, b.count, sl.n_bad_host, c->num_sms, s);
-    JOB_CUDA(j, cudaGetLastError());
-    JOB_CUDA(j, cudaEventRecord(sl.k3, s));
-    JOB_CUDA(j, cudaStreamWaitEvent(cs, sl.k3, 0));
-    JOB_CUDA(j, cudaMemcpyAsync(sl.host32, sl.dev32, sizeof(float) * b.count, cudaMemcpyDeviceToHost, cs));
-    j->info.d2h_bytes += static_cast<int64_t>(sizeof(float)) * b.count;
-    JOB_CUDA(j, cudaEventRecord(sl.done, cs));
-  } else if (!(j->opts.flags & FRC_FLAG_NO_D2H) && sl.dev != sl.host) {
-    cudaEvent_t ready = sl.k2;
-    if (!j->exact) {
-      // doubles on the bus carry the values the fp32 route would deliver (wire.cu: same bytes for any rank count)
-      launches += launch_round_band(sl.dev, b.count, c->num_sms, s);
-      JOB_CUDA(j, cudaGetLastError());
-      JOB_CUDA(j, cudaEventRecord(sl.k3, s));
-      ready = sl.k3;
+  if (sh.d2h) {
+    cudaStream_t cs = dc->stream[2];
+    PART_CUDA(p, cudaStreamWaitEvent(cs, sl.k2, 0));
+    if (sh.exact) {
+      PART_CUDA(p, cudaMemcpyAsync(sl.host64, sl.dev64, sizeof(double) * b.count, cudaMemcpyDeviceToHost, cs));
+      p->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
+    } else {
+      PART_CUDA(p, cudaMemcpyAsync(sl.host32, sl.dev32, sizeof(float) * b.count, cudaMemcpyDeviceToHost, cs));
+      p->info.d2h_bytes += static_cast<int64_t>(sizeof(float)) * b.count;
     }
-    JOB_CUDA(j, cudaStreamWaitEvent(cs, ready, 0));
-    JOB_CUDA(j, cudaMemcpyAsync(sl.host, sl.dev, sizeof(double) * b.count, cudaMemcpyDeviceToHost, cs));
-    j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * b.count;
-    JOB_CUDA(j, cudaEventRecord(sl.done, cs));
+    PART_CUDA(p, cudaEventRecord(sl.done, cs));
   } else {
-    JOB_CUDA(j, cudaEventRecord(sl.done, s));
+    PART_CUDA(p, cudaEventRecord(sl.done, s));
   }
-  j->info.kernel_launches += launches;
-  if (idx + 1 == j->mine.size()) {
+  p->info.kernel_launches += launches;
+  if (idx + 1 == p->mine.size()) {
     // last band queued: join all streams and stamp the end of the run on stream 0
-    JOB_CUDA(j, cudaEventRecord(j->ev_join, c->stream[1]));
-    JOB_CUDA(j, cudaStreamWaitEvent(c->stream[0], j->ev_join, 0));
-    JOB_CUDA(j, cudaStreamWaitEvent(c->stream[0], sl.done, 0));
-    JOB_CUDA(j, cudaEventRecord(j->ev_run1, c->stream[0]));
+    PART_CUDA(p, cudaEventRecord(p->ev_join, dc->stream[1]));
+    PART_CUDA(p, cudaStreamWaitEvent(dc->stream[0], p->ev_join, 0));
+    PART_CUDA(p, cudaStreamWaitEvent(dc->stream[0], sl.done, 0));
+    PART_CUDA(p, cudaEventRecord(p->ev_run1, dc->stream[0]));
   }
   return FRC_OK;
 }
 
-int start_pairs(frc_job* j) {
-  j->next_enqueue = j->next_deliver = 0;
-  j->held_slot = -1;
-  j->piece_off = j->piece_end = 0;
-  j->info.pairs_ms = 0;
-  j->info.fixup_ms = 0;
-  j->info.run_ms = 0;
-  j->run_timed = false;
-  j->info.flagged_pairs = 0;
-  j->info.d2h_bytes = 0;
+int start_pairs(Part* p) {
+  p->next_enqueue = p->next_deliver = 0;
+  p->info.pairs_ms = 0;
+  p->info.fixup_ms = 0;
+  p->info.run_ms = 0;
+  p->run_timed = false;
+  p->info.flagged_pairs = 0;
+  p->info.exceptions = 0;
+  p->info.d2h_bytes = 0;
+  if (p->mine.empty()) {  // nothing to compute: the run ends with the embedding
+    PART_CUDA(p, cudaEventRecord(p->ev_run1, p->dc->stream[0]));
+    return FRC_OK;
+  }
   // keep one slot free for the band the caller is still reading
-  while (j->next_enqueue < j->mine.size() && j->next_enqueue < static_cast<size_t>(j->n_slots - 1)) {
-    int rc = enqueue_band(j, j->next_enqueue);
-    if (rc) return rc;
-    ++j->next_enqueue;
+  while (p->next_enqueue < p->mine.size() && p->next_enqueue < static_cast<size_t>(p->n_slots - 1)) {
+    if (enqueue_band(p, p->next_enqueue)) return p->rc;
+    ++p->next_enqueue;
   }
   return FRC_OK;
+}
+
+void destroy_part(Part* p) {
+  if (!p) return;
+  if (p->dc) {
+    cudaSetDevice(p->dc->device);
+    for (auto s : p->dc->stream) if (s) cudaStreamSynchronize(s);
+    cudaGetLastError();
+  }
+  for (auto& sl : p->slots) {
+    if (sl.k0) cudaEventDestroy(sl.k0);
+    if (sl.k1) cudaEventDestroy(sl.k1);
+    if (sl.k2) cudaEventDestroy(sl.k2);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
+  for (cudaEvent_t e : {p->ev_h2d0, p->ev_h2d1, p->ev_embed0, p->ev_embed1, p->ev_run1, p->ev_join, p->ev_bits,
+                        p->ev_rsum, p->ev_shard})
+    if (e) cudaEventDestroy(e);
+  tc_operands_destroy(p->tc);
+  bits_operands_destroy(p->bo);
+  if (p->dc) {
+    p->dc->dev.reset();
+    p->dc->pin.reset();
+    p->dc->sym.reset();
+  }
 }
 
 void destroy_job(frc_job* j) {
   if (!j) return;
+  // every device must be idle before any part's memory is recycled (peers store into each other's buffers)
+  for (auto& p : j->parts)
+    if (p->dc) {
+      cudaSetDevice(p->dc->device);
+      for (auto s : p->dc->stream) if (s) cudaStreamSynchronize(s);
+    }
+  cudaGetLastError();
+  for (auto& p : j->parts) destroy_part(p.get());
   if (j->ctx) {
-    cudaSetDevice(j->ctx->device);
-    for (auto s : j->ctx->stream) if (s) cudaStreamSynchronize(s);
-    cudaGetLastError();
-  }
-  for (auto& sl : j->slots) {
-    if (sl.k0) cudaEventDestroy(sl.k0);
-    if (sl.k1) cudaEventDestroy(sl.k1);
-    if (sl.k2) cudaEventDestroy(sl.k2);
-    if (sl.k3) cudaEventDestroy(sl.k3);
-    if (sl.done) cudaEventDestroy(sl.done);
-  }
-  if (j->ev_h2d0) cudaEventDestroy(j->ev_h2d0);
-  if (j->ev_h2d1) cudaEventDestroy(j->ev_h2d1);
-  if (j->ev_embed0) cudaEventDestroy(j->ev_embed0);
-  if (j->ev_embed1) cudaEventDestroy(j->ev_embed1);
-  if (j->ev_run1) cudaEventDestroy(j->ev_run1);
-  if (j->ev_join) cudaEventDestroy(j->ev_join);
-  if (j->ev_bits) cudaEventDestroy(j->ev_bits);
-  if (j->ev_rsum) cudaEventDestroy(j->ev_rsum);
-  tc_operands_destroy(j->tc);
-  bits_operands_destroy(j->bo);
-  if (j->ctx) {
-    j->ctx->dev.reset();
     j->ctx->pin.reset();
-    j->ctx->sym.reset();
     j->ctx->in_use = false;
     if (j->own_ctx) frc_ctx_destroy(j->ctx);
   }
   delete j;
 }
 
-}  // namespace
-
-extern "C" {
-
-int frc_abi_version(void) { return FRC_ABI_VERSION; }
-
-const char* frc_last_error(const frc_job_t* job) { return job ? job->err.c_str() : g_create_error.c_str(); }
-
-int frc_ctx_create(int32_t device, frc_ctx_t** out) {
-  if (!out) { g_create_error = "frc_ctx_create: out is NULL"; return FRC_ERR_ARG; }
-  *out = nullptr;
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) {
-    cudaGetLastError();
-    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
-    return FRC_ERR_CUDA;
-  }
-  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
-  if (device >= count) { g_create_error = "device ordinal out of range"; return FRC_ERR_ARG; }
+int make_dev_ctx(int device, DevCtx** out) {
+  cudaError_t e;
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
     g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
@@ -595,51 +742,131 @@ int frc_ctx_create(int32_t device, frc_ctx_t** out) {
     g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
     return FRC_ERR_CUDA;
   }
-  frc_ctx* c = new frc_ctx();
-  c->device = device;
-  c->num_sms = prop.multiProcessorCount;
-  c->dev.pinned = false; c->dev.min_block = 64u << 20;
-  c->sym.pinned = false; c->sym.min_block = 32u << 20;
-  c->pin.pinned = true;  c->pin.min_block = 8u << 20;
-  {
-    int hw = static_cast<int>(std::thread::hardware_concurrency());
-    int n = std::max(1, std::min(16, hw)) - 1;
-    if (const char* e = getenv("FRC_HOST_THREADS")) n = std::max(1, atoi(e)) - 1;
-    c->pool.reset(new Pool(n));
-    c->stamps.resize(n + 1);
-  }
-  for (auto& s : c->stream)
+  DevCtx* d = new DevCtx();
+  d->device = device;
+  d->num_sms = prop.multiProcessorCount;
+  d->dev.pinned = false; d->dev.min_block = 64u << 20;
+  d->sym.pinned = false; d->sym.min_block = 32u << 20;
+  d->pin.pinned = true;  d->pin.min_block = 8u << 20;
+  *out = d;
+  for (auto& s : d->stream)
     if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) {
       g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
-      frc_ctx_destroy(c);
       return FRC_ERR_CUDA;
     }
+  // function attributes live in the device's context: once per device, not once per process
   std::string terr;
-  if (!tc_setup(&terr)) { g_create_error = terr; frc_ctx_destroy(c); return FRC_ERR_CUDA; }
+  if (!tc_setup(&terr) || !bits_setup(&terr)) { g_create_error = terr; return FRC_ERR_CUDA; }
   weighted_setup();
+  embed_setup();
   if ((e = cudaGetLastError()) != cudaSuccess) {
     g_create_error = std::string("kernel attribute setup: ") + cudaGetErrorString(e);
-    frc_ctx_destroy(c);
     return FRC_ERR_CUDA;
+  }
+  return FRC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int frc_abi_version(void) { return FRC_ABI_VERSION; }
+
+const char* frc_last_error(const frc_job_t* job) { return job ? job->err.c_str() : g_create_error.c_str(); }
+
+int frc_ctx_create_multi(int32_t n_devices, const int32_t* devices, frc_ctx_t** out) {
+  if (!out) { g_create_error = "frc_ctx_create: out is NULL"; return FRC_ERR_ARG; }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
+    return FRC_ERR_CUDA;
+  }
+  DeviceGuard guard;
+  std::vector<int> ids;
+  if (n_devices < 0) {  // every visible sm_100 device
+    for (int d = 0; d < count && static_cast<int>(ids.size()) < kMaxParts; ++d) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ids.push_back(d);
+    }
+    if (ids.empty()) { g_create_error = "no sm_100 device visible (libfrcfrc_cuda is built for B200 only)"; return FRC_ERR_UNSUPPORTED; }
+  } else {
+    if (n_devices == 0) n_devices = 1;
+    if (n_devices > kMaxParts) { g_create_error = "at most 8 devices per job"; return FRC_ERR_UNSUPPORTED; }
+    for (int k = 0; k < n_devices; ++k) {
+      int d = devices ? devices[k] : k;
+      if (n_devices == 1 && d < 0) { if (guard.prev >= 0) d = guard.prev; else d = 0; }
+      if (d < 0 || d >= count) { g_create_error = "device ordinal out of range"; return FRC_ERR_ARG; }
+      for (int x : ids) if (x == d) { g_create_error = "device listed twice"; return FRC_ERR_ARG; }
+      ids.push_back(d);
+    }
+  }
+  frc_ctx* c = new frc_ctx();
+  c->pin.pinned = true; c->pin.min_block = 8u << 20;
+  for (int d : ids) {
+    DevCtx* dc = nullptr;
+    int rc = make_dev_ctx(d, &dc);
+    if (dc) c->devs.push_back(dc);
+    if (rc) { frc_ctx_destroy(c); return rc; }
+  }
+  if (c->devs.size() > 1) {
+    // peer access between every pair (NVLink on an HGX board): lets the embedding kernel of one device store
+    // into the others' HBM.  Without it the devices work independently (each rebuilds the embedding).
+    bool ok = true;
+    for (DevCtx* a : c->devs)
+      for (DevCtx* b : c->devs) {
+        if (a == b) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, a->device, b->device) != cudaSuccess || !can) { ok = false; continue; }
+        cudaSetDevice(a->device);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(b->device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+        cudaGetLastError();
+      }
+    c->peer_ok = ok;
+  }
+  {
+    int hw = static_cast<int>(std::thread::hardware_concurrency());
+    int n = std::max(1, std::min(16, hw));
+    if (c->devs.size() > 1) n = std::max(n, std::min(hw, 32));  // several rings to serve
+    if (const char* ev = getenv("FRC_HOST_THREADS")) n = std::max(1, atoi(ev));
+    c->pool.reset(new Pool(n - 1));
+    c->stamps.resize(n);
   }
   *out = c;
   return FRC_OK;
 }
 
+int frc_ctx_create(int32_t device, frc_ctx_t** out) { return frc_ctx_create_multi(1, &device, out); }
+
 void frc_ctx_destroy(frc_ctx_t* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard guard;
   c->pool.reset();
-  for (auto s : c->stream) if (s) cudaStreamSynchronize(s);
-  for (size_t b = 0; b < c->sym_peer.size(); ++b)
-    for (size_t r = 0; r < c->sym_peer[b].size(); ++r)
-      if (c->sym_peer[b][r] && c->sym_peer[b][r] != c->sym.blocks[b].p) cudaIpcCloseMemHandle(c->sym_peer[b][r]);
-  c->sym_peer.clear();
-  c->sym.release();
-  comm_destroy(c->comm);
-  c->comm = nullptr;
-  for (auto s : c->stream) if (s) cudaStreamDestroy(s);
-  c->dev.release();
+  for (DevCtx* d : c->devs) {
+    cudaSetDevice(d->device);
+    for (auto s : d->stream) if (s) cudaStreamSynchronize(s);
+  }
+  if (!c->devs.empty()) {
+    DevCtx* d0 = c->devs[0];
+    cudaSetDevice(d0->device);
+    for (size_t b = 0; b < c->sym_peer.size(); ++b)
+      for (size_t r = 0; r < c->sym_peer[b].size(); ++r)
+        if (c->sym_peer[b][r] && c->sym_peer[b][r] != d0->sym.blocks[b].p) cudaIpcCloseMemHandle(c->sym_peer[b][r]);
+    c->sym_peer.clear();
+    comm_destroy(c->comm);
+    c->comm = nullptr;
+  }
+  for (DevCtx* d : c->devs) {
+    cudaSetDevice(d->device);
+    d->sym.release();
+    for (auto s : d->stream) if (s) cudaStreamDestroy(s);
+    d->dev.release();
+    d->pin.release();
+    delete d;
+  }
   c->pin.release();
   cudaGetLastError();
   delete c;
@@ -658,7 +885,9 @@ int frc_ctx_comm_init(frc_ctx_t* ctx, const char* id, int32_t rank, int32_t worl
     return FRC_ERR_ARG;
   }
   if (ctx->in_use) { g_create_error = "context has a live job"; return FRC_ERR_STATE; }
-  cudaSetDevice(ctx->device);
+  if (ctx->devs.size() != 1) { g_create_error = "a communicator joins one-device contexts (one process per GPU)"; return FRC_ERR_STATE; }
+  DeviceGuard guard;
+  cudaSetDevice(ctx->devs[0]->device);
   comm_destroy(ctx->comm);
   ctx->comm = nullptr;
   std::string err;
@@ -667,167 +896,516 @@ int frc_ctx_comm_init(frc_ctx_t* ctx, const char* id, int32_t rank, int32_t worl
   return FRC_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// ------------------------------------------------------------------ frc_create, unit by unit
+// (1) options and table header; fills the sizes of `sh`.  No CUDA call.
+int validate_header(frc_job* j, const frc_tree_t* tree, const frc_csr_t* abnd, const frc_opts_t* opts) {
+  Shared& sh = j->sh;
+  if (opts->mode != FRC_UNWEIGHTED && opts->mode != FRC_WEIGHTED) return fail(j, FRC_ERR_ARG, "bad mode");
+  if (opts->path < FRC_PATH_AUTO || opts->path > FRC_PATH_EXACT) return fail(j, FRC_ERR_ARG, "bad path");
+  if (opts->normalize < 0 || opts->normalize > 2) return fail(j, FRC_ERR_ARG, "bad normalize");
+  if (opts->normalize != 1 && opts->mode != FRC_WEIGHTED)  // frcfrc.go:84-86
+    return fail(j, FRC_ERR_ARG, "-l can only be used with weighted unifrac");
+  if (opts->normalize == 0 && opts->path == FRC_PATH_FAST)
+    return fail(j, FRC_ERR_UNSUPPORTED, "normalize = 0 (flag -l as coded in the reference: unsorted merge-join) only "
+                                        "exists on the exact path; normalize = 2 is the documented -l");
+  const int world = opts->world <= 0 ? 1 : opts->world;
+  const int rank = opts->world <= 0 ? 0 : opts->rank;
+  if (rank < 0 || rank >= world) return fail(j, FRC_ERR_ARG, "rank outside [0, world)");
+  if (opts->band_rows < 0) return fail(j, FRC_ERR_ARG, "band_rows < 0");
+  const int32_t B = tree->n_nodes;
+  if (B < 1 || !tree->parent || !tree->length) return fail(j, FRC_ERR_ARG, "empty tree");
+  if (tree->parent[0] != -1) return fail(j, FRC_ERR_ARG, "parent[0] must be -1 (root has pre-order id 0)");
+  const int64_t N = abnd->n_samples;
+  if (N < 0 || (N > 0 && !abnd->row_ptr)) return fail(j, FRC_ERR_ARG, "bad abundance table");
+  if (N > (1LL << 31) - 256) return fail(j, FRC_ERR_UNSUPPORTED, "too many samples");
+  const int64_t nnz = N > 0 ? abnd->row_ptr[N] : 0;
+  if (N > 0 && abnd->row_ptr[0] != 0) return fail(j, FRC_ERR_ARG, "row_ptr[0] != 0");
+  if (nnz < 0 || (nnz > 0 && (!abnd->col || !abnd->val))) return fail(j, FRC_ERR_ARG, "bad abundance table");
+  for (int64_t s = 0; s < N; ++s)
+    if (abnd->row_ptr[s + 1] < abnd->row_ptr[s] || abnd->row_ptr[s + 1] > nnz)
+      return fail(j, FRC_ERR_ARG, "row_ptr is not monotone");
+  // (entries are validated while they are copied into the pinned staging buffer)
+  sh.opts = *opts;
+  sh.opts.devices = nullptr;  // (borrowed pointer: not kept)
+  sh.weighted = opts->mode == FRC_WEIGHTED;
+  sh.N = N; sh.B = B; sh.nnz = nnz;
+  sh.world = world; sh.rank0 = rank;
+  sh.d2h = !(opts->flags & FRC_FLAG_NO_D2H);
+  const int64_t n_pairs = N >= 2 ? tri(N) : 0;
+  sh.unsorted_l = opts->normalize == 0;
+  if (opts->path == FRC_PATH_EXACT || sh.unsorted_l) sh.exact = true;
+  else if (opts->path == FRC_PATH_FAST) sh.exact = false;
+  else sh.exact = n_pairs == 0 || (static_cast<double>(n_pairs) * B <= static_cast<double>(kExactWorkLimit));
+  sh.need_val = sh.exact || sh.weighted;
+  return FRC_OK;
+}
+
+// (2) layout of the staged inputs.
+void layout_inputs(Shared& sh) {
+  SegAlloc seg;
+  const int32_t B = sh.B;
+  const int32_t kp_pad = static_cast<int32_t>(round_up(B, kKBlock));
+  sh.in_rowptr = seg(sizeof(int64_t) * (sh.N + 1));
+  sh.in_parent = seg(sizeof(int32_t) * B);
+  sh.in_len = seg(sizeof(double) * B);
+  sh.in_cptr = seg(sizeof(int32_t) * (B + 1));
+  sh.in_cidx = seg(sizeof(int32_t) * B);
+  sh.in_lvl = seg(sizeof(int32_t) * B);
+  sh.in_lpar = seg(sizeof(int32_t) * B);
+  sh.in_lptr = seg(sizeof(int32_t) * (static_cast<size_t>(B) + 2));
+  sh.in_lenf = seg(sizeof(float) * kp_pad);
+  sh.in_post = seg(sh.unsorted_l ? sizeof(int32_t) * B : 0);
+  sh.in_col = seg(sizeof(int32_t) * sh.nnz);   // the two bulk arrays last: a sharded part uploads a slice of them
+  sh.in_val = seg(sh.need_val ? sizeof(double) * sh.nnz : 0);
+  sh.in_bytes = seg.total;
+}
+
+// (3) the plan that does not depend on the table: operand columns; then bands + owners.
+int plan_job(frc_job* j, const frc_tree_t* tree, bool neg_len) {
+  Shared& sh = j->sh;
+  frc_ctx* c = j->ctx;
+  const int n_parts = sh.n_parts;
+  const bool fast_uw = !sh.exact && !sh.weighted;
+  sh.fused_embed = !sh.knobs.embed_levels;
+  // how the sample shards of the embedding meet
+  sh.exchange = Shared::kNone;
+  if (!sh.exact) {
+    if (n_parts > 1 && c->peer_ok && sh.knobs.shard != 0 && (sh.weighted || sh.fused_embed)) sh.exchange = Shared::kInProcess;
+    if (n_parts == 1 && sh.world > 1 && (sh.opts.flags & FRC_FLAG_SHARD_EMBED)) {
+      if (!c->comm || comm_world(c->comm) != sh.world || comm_rank(c->comm) != sh.rank0)
+        return fail(j, FRC_ERR_STATE, "FRC_FLAG_SHARD_EMBED needs a context whose communicator "
+                                      "(frc_ctx_comm_init) matches opts->rank / opts->world");
+      if (fast_uw && !sh.fused_embed) return fail(j, FRC_ERR_UNSUPPORTED, "FRC_EMBED_LEVELS=1 cannot build a sample shard");
+      sh.exchange = Shared::kNccl;
+    }
+  }
+  const int shards = sh.exchange == Shared::kInProcess ? n_parts : sh.exchange == Shared::kNccl ? sh.world : 1;
+  // sharded: every owner builds np / shards samples, a whole number of tiles
+  sh.np = std::max<int64_t>(kTile, round_up(sh.N, kTile * static_cast<int64_t>(shards)));
+  sh.nw = static_cast<int32_t>(sh.np / 32);
+  sh.kp = static_cast<int32_t>(round_up(sh.B, kKBlock));
+  sh.prescale = !neg_len;
+  if (fast_uw) {
+    const bool want_i8 = sh.fused_embed && !neg_len && !(sh.opts.flags & FRC_FLAG_UW_BF16) && !sh.knobs.uw_bf16;
+    sh.cols = plan_columns(tree->length, sh.B, want_i8, sh.knobs.group_binades, sh.knobs.u8_acc_f64, tc_chunk_kblocks());
+    sh.kp = sh.cols.kp;
+    sh.bits_feed = sh.cols.intacc && ((sh.opts.flags & FRC_FLAG_UW_BITS) != 0 || sh.knobs.feed_bits);
+    if (sh.cols.intacc && !sh.bits_feed) {
+      // capacity: when the three u8 operand arrays would not fit the free HBM (with room for the
+      // output ring), the pair kernel expands its tiles from the bit rows instead (8x less memory,
+      // about half the speed: DESIGN.md)
+      const double need = 3.0 * static_cast<double>(sh.np) * sh.kp;
+      if (need > 32.0 * (1 << 30)) {  // (cudaMemGetInfo costs milliseconds: only asked when it can matter)
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(c->devs[0]->device);
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need > 0.80 * static_cast<double>(free_b)) sh.bits_feed = true;
+        cudaGetLastError();
+      }
+    }
+  }
+  const int owners = sh.n_parts > 1 ? sh.n_parts : sh.world;
+  sh.bands = make_bands(sh.N, sh.opts.band_rows, owners, sh.d2h, sh.knobs.bands_per_rank, 8);
+  for (const Band& b : sh.bands)
+    if (b.count >= (1LL << 32)) return fail(j, FRC_ERR_UNSUPPORTED, "band too large; lower band_rows");
+  return FRC_OK;
+}
+
+// (4) the plan arrays every device receives, into pinned staging memory.
+int stage_plan(frc_job* j, const frc_tree_t* tree) {
+  Shared& sh = j->sh;
+  const ColumnPlan& cp = sh.cols;
+  SegAlloc seg;
+  sh.pl_q0 = seg(sh.kp); sh.pl_hi = seg(sizeof(uint16_t) * sh.kp); sh.pl_lo = seg(sizeof(uint16_t) * sh.kp);
+  sh.pl_lenq = seg(sizeof(double) * sh.kp);
+  sh.pl_order = seg(sizeof(int32_t) * cp.col_order.size()); sh.pl_cexp = seg(sizeof(int32_t) * cp.col_exp.size());
+  sh.pl_lcol = seg(sizeof(double) * cp.len_col.size()); sh.pl_cend = seg(sizeof(int32_t) * cp.chunk_end.size());
+  sh.pl_cscale = seg(sizeof(double) * cp.chunk_scale.size()); sh.pl_cshift = seg(sizeof(int32_t) * cp.chunk_shift.size());
+  sh.plan_bytes = seg.total;
+  cudaError_t e = cudaSuccess;
+  sh.stage_plan = static_cast<char*>(j->ctx->pin.alloc(sh.plan_bytes, &e));
+  if (!sh.stage_plan) return fail(j, FRC_ERR_OOM, std::string("pinned staging: ") + cudaGetErrorString(e));
+  char* st = sh.stage_plan;
+  if (!sh.exact && !sh.weighted && !cp.i8) {  // (u8: k_quantize_lengths fills q0/q1/q2 and lenq on the device)
+    uint16_t* hi = reinterpret_cast<uint16_t*>(st + sh.pl_hi.off);
+    uint16_t* lo = reinterpret_cast<uint16_t*>(st + sh.pl_lo.off);
+    double* lq = reinterpret_cast<double*>(st + sh.pl_lenq.off);
+    for (int32_t v = 0; v < sh.B; ++v) {
+      const double l = tree->length[v];
+      hi[v] = bf16_rn(static_cast<float>(l));
+      const double res = l - static_cast<double>(bf16_to_float(hi[v]));
+      lo[v] = (l == l && !std::isinf(l)) ? bf16_rn(static_cast<float>(res)) : 0;
+      lq[v] = static_cast<double>(bf16_to_float(hi[v])) + static_cast<double>(bf16_to_float(lo[v]));
+    }
+    for (int32_t v = sh.B; v < sh.kp; ++v) { hi[v] = 0; lo[v] = 0; lq[v] = 0.0; }
+  }
+  auto put = [&](const Seg& s, const void* src) { if (s.bytes) memcpy(st + s.off, src, s.bytes); };
+  put(sh.pl_order, cp.col_order.data()); put(sh.pl_cexp, cp.col_exp.data()); put(sh.pl_lcol, cp.len_col.data());
+  put(sh.pl_cend, cp.chunk_end.data()); put(sh.pl_cscale, cp.chunk_scale.data()); put(sh.pl_cshift, cp.chunk_shift.data());
+  return FRC_OK;
+}
+
+// (5) per device: tiles of its bands, device buffers, ring slots, upload of the plan, tensor maps.
+int prepare_part(Part* p) {
+  const Shared& sh = *p->sh;
+  DevCtx* dc = p->dc;
+  frc_ctx* c = p->job->ctx;
+  const int32_t B = sh.B;
+  PART_CUDA(p, cudaSetDevice(dc->device));
+  // ---- bands + tiles of this owner
+  p->max_band = 1;
+  for (size_t k = 0; k < sh.bands.size(); ++k)
+    if (sh.bands[k].owner == p->owner) {
+      p->mine.push_back(static_cast<int>(k));
+      p->bands.push_back(sh.bands[k]);
+      p->info.n_pairs_mine += sh.bands[k].count;
+      p->max_band = std::max(p->max_band, sh.bands[k].count);
+    }
+  const bool fast_uw = !sh.exact && !sh.weighted;
+  if (!sh.exact)
+    for (Band& b : p->bands) append_band_tiles(b, fast_uw, p->tiles);
+  const int owners = sh.n_parts > 1 ? sh.n_parts : sh.world;
+  std::vector<uint8_t> need;
+  if (fast_uw && owners > 1 && sh.fused_embed) need = operand_need_blocks(p->tiles, sh.np, true);
+  // ---- sample shard
+  const int shards = sh.exchange == Shared::kNone ? 1 : owners;
+  p->shard_nw = sh.nw / shards;
+  p->shard_w0 = sh.exchange == Shared::kNone ? 0 : p->owner * p->shard_nw;
+  // CSR entries this part uploads: its own rows when only the embedding reads the table (the weighted
+  // fix-up walks the rows of any flagged pair, so weighted parts keep the whole table)
+  p->csr_k0 = 0; p->csr_k1 = sh.nnz;
+  if (sh.exchange != Shared::kNone && fast_uw && sh.N > 0) {
+    const int64_t* rp = reinterpret_cast<const int64_t*>(sh.stage_in + sh.in_rowptr.off);
+    const int64_t s0 = std::min<int64_t>(sh.N, static_cast<int64_t>(p->shard_w0) * 32);
+    const int64_t s1 = std::min<int64_t>(sh.N, s0 + static_cast<int64_t>(p->shard_nw) * 32);
+    // (row_ptr is copied into the staging buffer before any task starts)
+    p->csr_k0 = rp[s0]; p->csr_k1 = rp[s1];
+  }
+  // ---- per-part staging: tiles + need blocks
+  SegAlloc seg;
+  const Seg s_tiles = seg(sizeof(Tile) * p->tiles.size()), s_need = seg(need.size());
+  char* st = pin_alloc<char>(p, seg.total);
+  if (!st) return p->rc;
+  char* d_small = dev_alloc<char>(p, seg.total);
+  if (!d_small) return p->rc;
+  if (!p->tiles.empty()) memcpy(st + s_tiles.off, p->tiles.data(), s_tiles.bytes);
+  if (!need.empty()) memcpy(st + s_need.off, need.data(), s_need.bytes);
+  if (!(p->d_plan = dev_alloc<char>(p, sh.plan_bytes))) return p->rc;
+  if (!(p->d_in = dev_alloc<char>(p, sh.in_bytes))) return p->rc;
+  for (cudaEvent_t* e : {&p->ev_h2d0, &p->ev_h2d1, &p->ev_embed0, &p->ev_embed1, &p->ev_run1})
+    PART_CUDA(p, cudaEventCreate(e));
+  for (cudaEvent_t* e : {&p->ev_join, &p->ev_bits, &p->ev_rsum, &p->ev_shard})
+    PART_CUDA(p, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  cudaStream_t s0 = dc->stream[0];
+  PART_CUDA(p, cudaEventRecord(p->ev_h2d0, s0));
+  PART_CUDA(p, cudaMemcpyAsync(p->d_plan, sh.stage_plan, sh.plan_bytes, cudaMemcpyHostToDevice, s0));
+  if (seg.total) PART_CUDA(p, cudaMemcpyAsync(d_small, st, seg.total, cudaMemcpyHostToDevice, s0));
+  p->info.h2d_bytes = static_cast<int64_t>(sh.plan_bytes + seg.total);
+  // ---- device views
+  char* d = p->d_plan;
+  char* di = p->d_in;
+  p->dcsr.n_samples = sh.N; p->dcsr.nnz = sh.nnz;
+  p->dcsr.row_ptr = reinterpret_cast<int64_t*>(di + sh.in_rowptr.off);
+  p->dcsr.col = reinterpret_cast<int32_t*>(di + sh.in_col.off);
+  p->dcsr.val = sh.need_val ? reinterpret_cast<double*>(di + sh.in_val.off) : nullptr;
+  p->dtree.n_nodes = B; p->dtree.height = 0;  // (height: set when the tree walk has joined)
+  p->dtree.parent = reinterpret_cast<int32_t*>(di + sh.in_parent.off);
+  p->dtree.length = reinterpret_cast<double*>(di + sh.in_len.off);
+  p->dtree.child_ptr = reinterpret_cast<int32_t*>(di + sh.in_cptr.off);
+  p->dtree.child_idx = reinterpret_cast<int32_t*>(di + sh.in_cidx.off);
+  p->dtree.level_nodes = reinterpret_cast<int32_t*>(di + sh.in_lvl.off);
+  p->dtree.level_parent = reinterpret_cast<int32_t*>(di + sh.in_lpar.off);
+  p->d_level_ptr = reinterpret_cast<int32_t*>(di + sh.in_lptr.off);
+  p->d_lenf = reinterpret_cast<float*>(di + sh.in_lenf.off);
+  p->d_post = sh.unsorted_l ? reinterpret_cast<int32_t*>(di + sh.in_post.off) : nullptr;
+  p->d_q0 = d + sh.pl_q0.off;
+  p->d_q1 = d + sh.pl_hi.off;
+  p->d_q2 = d + sh.pl_lo.off;
+  p->d_lenq = reinterpret_cast<double*>(d + sh.pl_lenq.off);
+  p->d_order = reinterpret_cast<int32_t*>(d + sh.pl_order.off);
+  p->d_col_exp = reinterpret_cast<int32_t*>(d + sh.pl_cexp.off);
+  p->d_len_col = reinterpret_cast<double*>(d + sh.pl_lcol.off);
+  p->d_chunks.end = reinterpret_cast<int32_t*>(d + sh.pl_cend.off);
+  p->d_chunks.scale = reinterpret_cast<double*>(d + sh.pl_cscale.off);
+  p->d_chunks.n = static_cast<int32_t>(sh.cols.chunk_end.size());
+  p->d_chunks.shift = sh.cols.chunk_shift.empty() ? nullptr : reinterpret_cast<int32_t*>(d + sh.pl_cshift.off);
+  p->d_chunks.biased = sh.cols.i8 && sh.cols.biased;
+  p->d_tiles = reinterpret_cast<Tile*>(d_small + s_tiles.off);
+  p->d_need = need.empty() ? nullptr : reinterpret_cast<uint8_t*>(d_small + s_need.off);
+
+  // ---- device buffers
+  const int chunks = weighted_scratch_chunks(B);
+  const bool i8 = sh.cols.i8, intacc = sh.cols.intacc;
+  if (sh.exact || sh.weighted) {
+    // exact: the whole fp64 embedding; fast weighted: one slab of samples at a time, <= 2 GB
+    const int64_t per = static_cast<int64_t>(p->shard_nw) * 32;
+    p->ws_slab = sh.exact ? sh.np : std::min<int64_t>(per, std::max<int64_t>(kTile, (2LL << 30) / (8LL * B) / kTile * kTile));
+    if (!sh.exact && sh.knobs.ws_slab > 0)  // tests: force several slabs on a small problem
+      p->ws_slab = std::min<int64_t>(per, round_up(sh.knobs.ws_slab, kTile));
+    if (!(p->d_E = dev_alloc<double>(p, static_cast<size_t>(B) * p->ws_slab))) return p->rc;
+    if (!(p->d_total = dev_alloc<double>(p, sh.np))) return p->rc;
+    if (sh.unsorted_l && !(p->d_list_ptr = dev_alloc<int64_t>(p, sh.N + 2))) return p->rc;
+    if (!sh.exact) {
+      if (!(p->d_A = dev_alloc<float>(p, static_cast<size_t>(sh.kp) * sh.np))) return p->rc;
+      if (!(p->d_W = dev_alloc<double>(p, sh.np))) return p->rc;
+      if (!(p->d_scratch = dev_alloc<double>(p, static_cast<size_t>(chunks) * sh.np))) return p->rc;
+      if (!(p->d_flag_counts = dev_alloc<unsigned long long>(p, p->mine.size() + 1))) return p->rc;
+      const size_t ws_words = static_cast<size_t>(kFixupCtas) * B;
+      for (int k = 0; k < 2; ++k) {
+        if (!(p->d_fix_ws[k] = dev_alloc<long long>(p, ws_words))) return p->rc;
+        PART_CUDA(p, cudaMemsetAsync(p->d_fix_ws[k], 0, sizeof(long long) * ws_words, s0));
+      }
+    }
+  } else {
+    // fused: published columns bitsT[nw][kp] (+ node-indexed scratch for trees beyond shared memory);
+    // FRC_EMBED_LEVELS=1: node-major bits[B][nw], one launch per tree level
+    const size_t words = sh.fused_embed ? static_cast<size_t>(sh.kp) * sh.nw : static_cast<size_t>(B) * sh.nw;
+    p->peer_push = sh.exchange == Shared::kNccl && !sh.bits_feed && sh.world <= 8 && sh.knobs.peer_push != 0;
+    if (p->peer_push) {
+      // two buffers from the symmetric heap (same block + offset on every rank), mapped from the peers
+      for (int k = 0; k < 2; ++k) {
+        cudaError_t e = cudaSuccess;
+        p->d_bits2[k] = static_cast<uint32_t*>(dc->sym.alloc(words * sizeof(uint32_t), &e));
+        if (!p->d_bits2[k]) return pfail(p, FRC_ERR_OOM, std::string("symmetric heap: ") + cudaGetErrorString(e));
+      }
+      if (sym_sync(p) != FRC_OK) return p->rc;
+      for (int k = 0; k < 2; ++k) {
+        size_t blk = 0;
+        for (; blk < dc->sym.blocks.size(); ++blk) {
+          char* base = dc->sym.blocks[blk].p;
+          if (reinterpret_cast<char*>(p->d_bits2[k]) >= base &&
+              reinterpret_cast<char*>(p->d_bits2[k]) < base + dc->sym.blocks[blk].cap) break;
+        }
+        const size_t off = reinterpret_cast<char*>(p->d_bits2[k]) - dc->sym.blocks[blk].p;
+        p->peers[k].n = sh.world; p->peers[k].self = sh.rank0;
+        for (int r = 0; r < sh.world; ++r) p->peers[k].p[r] = reinterpret_cast<uint32_t*>(c->sym_peer[blk][r] + off);
+      }
+      p->d_bits = p->d_bits2[0];
+    } else if (!(p->d_bits = dev_alloc<uint32_t>(p, std::max<size_t>(words, 64)))) return p->rc;
+    const size_t ns = sh.fused_embed ? static_cast<size_t>(presence_node_scratch_words(B, p->shard_nw)) : 0;
+    if (ns && !(p->d_node_scratch = dev_alloc<uint32_t>(p, ns))) return p->rc;
+    const size_t opsz = sh.bits_feed ? 256 : static_cast<size_t>(sh.np) * sh.kp * (i8 ? 1 : 2);
+    if (!(p->d_P = dev_alloc<char>(p, opsz))) return p->rc;
+    if (!(p->d_Bh = dev_alloc<char>(p, opsz))) return p->rc;
+    if (!(p->d_Bl = dev_alloc<char>(p, opsz))) return p->rc;
+    if (sh.bits_feed && !(p->d_bitsS = dev_alloc<uint32_t>(p, static_cast<size_t>(sh.np) * (sh.kp / 32)))) return p->rc;
+    if (!(p->d_r = dev_alloc<double>(p, sh.np))) return p->rc;
+    if (!(p->d_scratch = dev_alloc<double>(p, static_cast<size_t>(chunks) * sh.np))) return p->rc;
+    if (!(p->d_flag_counts = dev_alloc<unsigned long long>(p, p->mine.size() + 1))) return p->rc;
+    if (i8 && !(p->d_flag_u = dev_alloc<double>(p, 1))) return p->rc;
+    if (i8 && !(p->d_qerr = dev_alloc<double>(p, sh.kp))) return p->rc;
+    if (i8 && !(p->d_qam = dev_alloc<uint32_t>(p, sh.kp))) return p->rc;
+    if (intacc && !(p->d_r_int = dev_alloc<long long>(p, sh.np))) return p->rc;
+    std::string terr;
+    if (!sh.bits_feed) {
+      p->tc = tc_operands_create(p->d_P, p->d_Bh, p->d_Bl, sh.np, sh.kp, i8, p->d_chunks, p->d_len_col, p->d_flag_u, &terr);
+      if (!p->tc) return pfail(p, FRC_ERR_CUDA, terr);
+      if (intacc) tc_operands_set_int(p->tc, p->d_r_int, std::ldexp(1.0, sh.cols.e_min));
+    } else {
+      p->bo = bits_operands_create(p->d_bitsS, sh.np, sh.kp, static_cast<const uint8_t*>(p->d_q0),
+                                   static_cast<const uint8_t*>(p->d_q1), static_cast<const uint8_t*>(p->d_q2),
+                                   p->d_chunks, p->d_len_col, p->d_flag_u, p->d_r_int, std::ldexp(1.0, sh.cols.e_min), &terr);
+      if (!p->bo) return pfail(p, FRC_ERR_CUDA, terr);
+    }
+    if (i8) {  // a function of the tree only: once per job, not per restart
+      p->info.kernel_launches += launch_quantize_lengths(
+          p->d_len_col, p->d_col_exp, sh.kp, static_cast<uint8_t*>(p->d_q0), static_cast<uint8_t*>(p->d_q1),
+          static_cast<uint8_t*>(p->d_q2), p->d_qam, p->d_lenq, p->d_qerr, p->d_flag_u, s0);
+      PART_CUDA(p, cudaGetLastError());
+    }
+  }
+  // ---- output ring
+  {
+    const int vb = sh.exact ? 8 : 4;
+    const int64_t want = std::max<int64_t>(kMinSlots, std::min<int64_t>(kSlots, kSlotBytesBudget / (p->max_band * vb)));
+    p->n_slots = static_cast<int>(std::min<int64_t>(want, std::max<int64_t>(2, static_cast<int64_t>(p->mine.size()) + 1)));
+  }
+  if (p->mine.empty()) p->n_slots = 0;
+  for (int k = 0; k < p->n_slots; ++k) {
+    Slot& sl = p->slots[k];
+    if (sh.exact) {
+      if (!(sl.dev64 = dev_alloc<double>(p, p->max_band))) return p->rc;
+      if (sh.d2h && !(sl.host64 = pin_alloc<double>(p, p->max_band))) return p->rc;
+    } else {
+      if (!(sl.dev32 = dev_alloc<float>(p, p->max_band))) return p->rc;
+      if (sh.d2h && !(sl.host32 = pin_alloc<float>(p, p->max_band))) return p->rc;
+      if (!(sl.flagged = dev_alloc<uint32_t>(p, p->max_band))) return p->rc;
+      if (!(sl.n_flagged_host = pin_alloc<unsigned long long>(p, 1))) return p->rc;
+      *sl.n_flagged_host = 0;
+      if (!(sl.ex.count = pin_alloc<unsigned long long>(p, 1))) return p->rc;
+      if (!(sl.ex.index = pin_alloc<int64_t>(p, kMaxExceptions))) return p->rc;
+      if (!(sl.ex.value = pin_alloc<double>(p, kMaxExceptions))) return p->rc;
+      sl.ex.cap = kMaxExceptions;
+      *sl.ex.count = 0;
+    }
+    for (cudaEvent_t* e : {&sl.k0, &sl.k1, &sl.k2, &sl.done}) PART_CUDA(p, cudaEventCreate(e));
+  }
+  return FRC_OK;
+}
+
+// (6a) per device: upload the staged inputs, first stage of the embedding.
+int launch_part_stage1(Part* p) {
+  const Shared& sh = *p->sh;
+  DevCtx* dc = p->dc;
+  cudaStream_t s0 = dc->stream[0];
+  p->dtree.height = sh.tree_height;
+  p->info.tree_height = sh.tree_height;
+  // row_ptr + tree arrays, then this part's slice of the entries
+  PART_CUDA(p, cudaMemcpyAsync(p->d_in, sh.stage_in, sh.in_col.off, cudaMemcpyHostToDevice, s0));
+  int64_t up = static_cast<int64_t>(sh.in_col.off);
+  const int64_t k0 = p->csr_k0, n = p->csr_k1 - p->csr_k0;
+  if (n > 0) {
+    PART_CUDA(p, cudaMemcpyAsync(p->d_in + sh.in_col.off + 4 * k0, sh.stage_in + sh.in_col.off + 4 * k0, 4 * n,
+                                 cudaMemcpyHostToDevice, s0));
+    up += 4 * n;
+    if (sh.need_val) {
+      PART_CUDA(p, cudaMemcpyAsync(p->d_in + sh.in_val.off + 8 * k0, sh.stage_in + sh.in_val.off + 8 * k0, 8 * n,
+                                   cudaMemcpyHostToDevice, s0));
+      up += 8 * n;
+    }
+  }
+  p->info.h2d_bytes += up;
+  PART_CUDA(p, cudaEventRecord(p->ev_h2d1, s0));
+  return embed_stage1(p);
+}
+int launch_part_stage2(Part* p) {
+  if (embed_stage2(p)) return p->rc;
+  return start_pairs(p);
+}
+
+void aggregate_info(frc_job* j) {
+  frc_info_t& a = j->info;
+  const Shared& sh = j->sh;
+  a = frc_info_t{};
+  a.path_taken = sh.exact ? FRC_PATH_EXACT : FRC_PATH_FAST;
+  a.n_bands_total = static_cast<int32_t>(sh.bands.size());
+  a.tree_height = sh.tree_height;
+  a.n_pairs_total = sh.N >= 2 ? tri(sh.N) : 0;
+  a.n_nodes_padded = sh.exact ? sh.B : sh.kp;
+  a.operand_kind = (!sh.exact && !sh.weighted) ? (sh.cols.i8 ? (sh.bits_feed ? 3 : 2) : 1) : 0;
+  a.n_devices = static_cast<int32_t>(j->parts.size());
+  a.value_bytes = sh.exact ? 8 : 4;
+  a.create_ms = j->create_ms;
+  for (auto& p : j->parts) {
+    const frc_info_t& i = p->info;
+    a.n_bands_mine += static_cast<int32_t>(p->mine.size());
+    a.n_pairs_mine += i.n_pairs_mine;
+    a.kernel_launches += i.kernel_launches;
+    a.h2d_ms = std::max(a.h2d_ms, i.h2d_ms);
+    a.embed_ms = std::max(a.embed_ms, i.embed_ms);
+    a.pairs_ms += i.pairs_ms;
+    a.fixup_ms += i.fixup_ms;
+    a.run_ms = std::max(a.run_ms, i.run_ms);
+    a.h2d_bytes += i.h2d_bytes;
+    a.d2h_bytes += i.d2h_bytes;
+    a.embed_bytes += i.embed_bytes;
+    a.flagged_pairs += i.flagged_pairs;
+    a.gather_bytes += i.gather_bytes;
+    a.exceptions += i.exceptions;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
 int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, const frc_opts_t* opts,
                frc_job_t** out) {
   g_create_error.clear();
   if (!out) { g_create_error = "frc_create: out is NULL"; return FRC_ERR_ARG; }
   *out = nullptr;
   if (!tree || !abnd || !opts) { g_create_error = "frc_create: NULL argument"; return FRC_ERR_ARG; }
+  DeviceGuard guard;
+  const auto t_create0 = std::chrono::steady_clock::now();
   frc_job* j = new frc_job();
-  bool csr_workers_busy = false;  // the table is validated + staged by the pool while this thread handles the tree
+  Shared& sh = j->sh;
+  bool workers_busy = false;  // the table is validated + staged by the pool while this thread plans
   auto bail = [&](int rc) {
-    if (csr_workers_busy) { j->ctx->pool->wait(); csr_workers_busy = false; }
+    if (workers_busy) { j->ctx->pool->wait(); workers_busy = false; }
     g_create_error = j->err; destroy_job(j); return rc;
   };
-  const bool trace = getenv("FRC_TRACE") != nullptr;
-  auto tp0 = std::chrono::steady_clock::now();
+  sh.knobs = Knobs::read();
+  const bool trace = sh.knobs.trace;
+  auto tp0 = t_create0;
   auto mark = [&](const char* what) {
     if (!trace) return;
     auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[frc_create] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - tp0).count());
+    fprintf(stderr, "[frc_create] %-32s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - tp0).count());
     tp0 = now;
   };
-#define CREATE_CUDA(expr)                                                                    \
-  do {                                                                                       \
-    cudaError_t _e = (expr);                                                                 \
-    if (_e != cudaSuccess) {                                                                 \
-      cudaGetLastError();                                                                    \
-      return bail(fail(j, _e == cudaErrorMemoryAllocation ? FRC_ERR_OOM : FRC_ERR_CUDA,      \
-                       std::string(#expr) + ": " + cudaGetErrorString(_e)));                 \
-    }                                                                                        \
-  } while (0)
-  j->opts = *opts;
 
-  // ---------------------------------------------------------- validate options
-  if (opts->mode != FRC_UNWEIGHTED && opts->mode != FRC_WEIGHTED) return bail(fail(j, FRC_ERR_ARG, "bad mode"));
-  if (opts->path < FRC_PATH_AUTO || opts->path > FRC_PATH_EXACT) return bail(fail(j, FRC_ERR_ARG, "bad path"));
-  if (opts->normalize != 0 && opts->normalize != 1) return bail(fail(j, FRC_ERR_ARG, "bad normalize"));
-  if (opts->normalize == 0 && opts->mode != FRC_WEIGHTED)  // frcfrc.go:84-86
-    return bail(fail(j, FRC_ERR_ARG, "-l can only be used with weighted unifrac"));
-  int world = opts->world <= 0 ? 1 : opts->world;
-  int rank = opts->world <= 0 ? 0 : opts->rank;
-  if (rank < 0 || rank >= world) return bail(fail(j, FRC_ERR_ARG, "rank outside [0, world)"));
-  if (opts->band_rows < 0) return bail(fail(j, FRC_ERR_ARG, "band_rows < 0"));
-  j->weighted = opts->mode == FRC_WEIGHTED;
+  // ------------------------------------------------------------ (1) options, table header
+  int rc = validate_header(j, tree, abnd, opts);
+  if (rc) return bail(rc);
+  const int32_t B = sh.B;
+  const int64_t N = sh.N, nnz = sh.nnz;
 
-  // ------------------------------------------------------------- validate tree
-  const int32_t B = tree->n_nodes;
-  if (B < 1 || !tree->parent || !tree->length) return bail(fail(j, FRC_ERR_ARG, "empty tree"));
-  if (tree->parent[0] != -1) return bail(fail(j, FRC_ERR_ARG, "parent[0] must be -1 (root has pre-order id 0)"));
-  // ------------------------------------------------------------ validate table
-  const int64_t N = abnd->n_samples;
-  if (N < 0 || (N > 0 && !abnd->row_ptr)) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
-  if (N > (1LL << 31) - 256) return bail(fail(j, FRC_ERR_UNSUPPORTED, "too many samples"));
-  const int64_t nnz = N > 0 ? abnd->row_ptr[N] : 0;
-  if (N > 0 && abnd->row_ptr[0] != 0) return bail(fail(j, FRC_ERR_ARG, "row_ptr[0] != 0"));
-  if (nnz < 0 || (nnz > 0 && (!abnd->col || !abnd->val))) return bail(fail(j, FRC_ERR_ARG, "bad abundance table"));
-  for (int64_t s = 0; s < N; ++s)
-    if (abnd->row_ptr[s + 1] < abnd->row_ptr[s] || abnd->row_ptr[s + 1] > nnz)
-      return bail(fail(j, FRC_ERR_ARG, "row_ptr is not monotone"));
-  // (entries are validated while they are copied into the pinned staging buffer, below)
-
-  // -------------------------------------------------------------------- context
-  int rc = FRC_OK;
+  // ------------------------------------------------------------ context
   if (ctx) {
     if (ctx->in_use) return bail(fail(j, FRC_ERR_STATE, "context already has a live job"));
     j->ctx = ctx;
   } else {
-    rc = frc_ctx_create(opts->device, &j->ctx);
+    if (opts->n_devices > 1 || opts->n_devices < 0) rc = frc_ctx_create_multi(opts->n_devices, opts->devices, &j->ctx);
+    else rc = frc_ctx_create(opts->n_devices == 1 && opts->devices ? opts->devices[0] : opts->device, &j->ctx);
     if (rc) { j->err = g_create_error; j->ctx = nullptr; return bail(rc); }
     j->own_ctx = true;
   }
   frc_ctx* c = j->ctx;
   c->in_use = true;
-  CREATE_CUDA(cudaSetDevice(c->device));
+  sh.n_parts = static_cast<int>(c->devs.size());
+  if (sh.n_parts > 1 && sh.world > 1)
+    return bail(fail(j, FRC_ERR_UNSUPPORTED, "a multi-device job cannot also be a rank of a multi-process run (world > 1)"));
+  for (int k = 0; k < sh.n_parts; ++k) {
+    j->parts.emplace_back(new Part());
+    Part* p = j->parts.back().get();
+    p->job = j; p->sh = &sh; p->dc = c->devs[k]; p->index = k;
+    p->owner = sh.n_parts > 1 ? k : sh.rank0;
+  }
 
-  // ------------------------------------ table: validate + stage on the worker pool
-  // The CSR entries (the bulk of the input) are checked and copied into pinned staging memory by the
-  // pool while this thread validates the tree, plans the operand columns and bands, and sets up
-  // the device side; the two meet just before the embedding is queued.
-  const int64_t n_pairs = N >= 2 ? tri(N) : 0;
-  if (opts->path == FRC_PATH_EXACT) j->exact = true;
-  else if (opts->path == FRC_PATH_FAST) j->exact = false;
-  else j->exact = n_pairs == 0 || (static_cast<double>(n_pairs) * B <= static_cast<double>(kExactWorkLimit));
-  const bool need_val = j->exact || j->weighted;
-  struct Seg { size_t off, bytes; };
-  size_t csr_total = 0;
-  auto cseg = [&](size_t bytes) { Seg s{csr_total, bytes}; csr_total += (bytes + 255) & ~size_t(255); return s; };
-  const int32_t kp_pad = static_cast<int32_t>(round_up(B, kKBlock));
-  const Seg s_rowptr = cseg(sizeof(int64_t) * (N + 1)), s_col = cseg(sizeof(int32_t) * nnz),
-            s_val = cseg(need_val ? sizeof(double) * nnz : 0),
-            // tree topology, filled by one more pool share (tree_share below)
-            s_parent = cseg(sizeof(int32_t) * B), s_len = cseg(sizeof(double) * B),
-            s_cptr = cseg(sizeof(int32_t) * (B + 1)), s_cidx = cseg(sizeof(int32_t) * B),
-            s_lvl = cseg(sizeof(int32_t) * B), s_lpar = cseg(sizeof(int32_t) * B),
-            s_lptr = cseg(sizeof(int32_t) * (static_cast<size_t>(B) + 2)), s_lenf = cseg(sizeof(float) * kp_pad);
-  char* stage_csr = pin_alloc<char>(j, csr_total, &rc);
-  if (!stage_csr) return bail(rc);
-  char* d_csr = dev_alloc<char>(j, csr_total, &rc);
-  if (!d_csr) return bail(rc);
+  // ------------------------------------------------------------ (2) staging buffer; row_ptr right away
+  layout_inputs(sh);
   {
-    int64_t* rp = reinterpret_cast<int64_t*>(stage_csr + s_rowptr.off);
+    cudaError_t e = cudaSuccess;
+    sh.stage_in = static_cast<char*>(c->pin.alloc(sh.in_bytes, &e));
+    if (!sh.stage_in) return bail(fail(j, FRC_ERR_OOM, std::string("pinned staging of the inputs: ") + cudaGetErrorString(e)));
+    int64_t* rp = reinterpret_cast<int64_t*>(sh.stage_in + sh.in_rowptr.off);
     if (N > 0) memcpy(rp, abnd->row_ptr, sizeof(int64_t) * (N + 1)); else rp[0] = 0;
   }
-  // One task list for the pool: two tree tasks (children lists; pre-order check + level order), then the
-  // CSR entries in chunks, all handed out through one counter; the calling thread joins in when its own
-  // part is done, so the split adapts to any pool size (4 threads per rank on a 32-core 8-GPU host).
-  const int n_workers = c->pool->size() - 1;
-  int32_t tree_H = -1;                      // height of the tree, from the levels share
-  int32_t bad_parent = 0, bad_order = 0;    // first offending node ids, from the levels share
+  char* const stage_in = sh.stage_in;
+
+  // One task list for the pool: the tree walks, the preparation of devices 1.. (they wait for the plan),
+  // then the CSR entries in chunks, all handed out through one counter; the calling thread plans, prepares
+  // device 0 and then joins in, so the split adapts to any pool size.
+  TreeLevels levels;
   bool children_ok = false;
-  auto tree_children_share = [&, stage_csr]() {
-    const int32_t* parent = tree->parent;
-    std::vector<int32_t> child_cnt(B, 0);
-    for (int32_t v = 1; v < B; ++v) {
-      const int32_t p = parent[v];
-      if (p < 0 || p >= v) return;  // (reported by the levels share)
-      child_cnt[p]++;
-    }
-    memcpy(stage_csr + s_parent.off, parent, sizeof(int32_t) * B);
-    memcpy(stage_csr + s_len.off, tree->length, sizeof(double) * B);
-    int32_t* cptr = reinterpret_cast<int32_t*>(stage_csr + s_cptr.off);
-    int32_t* cidx = reinterpret_cast<int32_t*>(stage_csr + s_cidx.off);
-    cptr[0] = 0;
-    for (int32_t v = 0; v < B; ++v) cptr[v + 1] = cptr[v] + child_cnt[v];
-    std::vector<int32_t>& fill = child_cnt;  // reused: next free slot of every node's child list
-    for (int32_t v = 0; v < B; ++v) fill[v] = cptr[v];
-    for (int32_t v = 1; v < B; ++v) cidx[fill[parent[v]]++] = v;  // ascending id = file order
-    float* lf = reinterpret_cast<float*>(stage_csr + s_lenf.off);
+  std::atomic<int> plan_ready{0};  // 1 = planned, -1 = planning failed
+  auto tree_children_share = [&]() {
+    if (!tree_children(tree->parent, B, reinterpret_cast<int32_t*>(stage_in + sh.in_cptr.off),
+                       reinterpret_cast<int32_t*>(stage_in + sh.in_cidx.off))) return;
+    memcpy(stage_in + sh.in_parent.off, tree->parent, sizeof(int32_t) * B);
+    memcpy(stage_in + sh.in_len.off, tree->length, sizeof(double) * B);
+    float* lf = reinterpret_cast<float*>(stage_in + sh.in_lenf.off);
+    const int32_t kp_pad = static_cast<int32_t>(round_up(B, kKBlock));
     for (int32_t v = 0; v < kp_pad; ++v) lf[v] = v < B ? static_cast<float>(tree->length[v]) : 0.f;
+    if (sh.unsorted_l) tree_post_order(tree->parent, B, reinterpret_cast<int32_t*>(stage_in + sh.in_post.off));
     children_ok = true;
   };
-  auto tree_levels_share = [&, stage_csr]() {
-    const int32_t* parent = tree->parent;
-    // pre-order check: parent[v] must lie on the path root..v-1, i.e. be the node of its depth on the
-    // current root-to-(v-1) path.  Branch-free per node (the stack-popping form cost 14 ns per node in
-    // mispredictions).
-    std::vector<int32_t> depth(B, 0), on_path(B, 0), height(B, 0);  // on_path[d] = node at depth d of the current path
-    for (int32_t v = 1; v < B; ++v) {
-      const int32_t p = parent[v];
-      if (p < 0 || p >= v) { bad_parent = v; return; }
-      const int32_t d = depth[p];
-      if ((d > depth[v - 1] || on_path[d] != p) && !bad_order) bad_order = v;
-      depth[v] = d + 1;
-      on_path[d + 1] = v;
-    }
-    if (bad_order) return;
-    for (int32_t v = B - 1; v >= 1; --v) height[parent[v]] = std::max(height[parent[v]], height[v] + 1);
-    const int32_t H = height[0];
-    j->level_ptr.assign(H + 2, 0);
-    for (int32_t v = 0; v < B; ++v) j->level_ptr[height[v] + 1]++;
-    for (int32_t h = 0; h <= H; ++h) j->level_ptr[h + 1] += j->level_ptr[h];
-    int32_t* lvl = reinterpret_cast<int32_t*>(stage_csr + s_lvl.off);
-    std::vector<int32_t>& lfill = depth;  // reused: next free slot of every level
-    for (int32_t h = 0; h <= H; ++h) lfill[h] = j->level_ptr[h];
-    for (int32_t v = 0; v < B; ++v) lvl[lfill[height[v]]++] = v;
-    int32_t* lpar = reinterpret_cast<int32_t*>(stage_csr + s_lpar.off);
-    for (int32_t k = 0; k < B; ++k) lpar[k] = lvl[k] ? parent[lvl[k]] : 0;
-    memcpy(stage_csr + s_lptr.off, j->level_ptr.data(), sizeof(int32_t) * (H + 2));
-    tree_H = H;
+  auto tree_levels_share = [&]() {
+    levels = tree_levels(tree->parent, B, reinterpret_cast<int32_t*>(stage_in + sh.in_lvl.off),
+                         reinterpret_cast<int32_t*>(stage_in + sh.in_lpar.off));
+    if (levels.height >= 0)
+      memcpy(stage_in + sh.in_lptr.off, levels.level_ptr.data(), sizeof(int32_t) * (levels.height + 2));
   };
   // The entries are cut into many more chunks than workers and handed out through a counter: a worker
   // on a busy or slow core (the slowest static share took 1.5-2.4x the median) just takes fewer.
+  // A rank of a multi-process sharded unweighted job only reads its own rows: only those are checked and staged.
+  int64_t stage_k0 = 0, stage_k1 = nnz;
   const int csr_chunks = nnz >= 65536 ? static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->pool->size() * 8LL, nnz / 8192))) : 1;
+  const int n_prep = sh.n_parts - 1;
+  const int n_tasks = 2 + n_prep + csr_chunks;
   std::atomic<int> task_next{0};
   std::vector<std::string> csr_errs(csr_chunks);
   std::vector<double> csr_us(c->pool->size(), 0.0);
@@ -835,543 +1413,197 @@ int frc_create(frc_ctx_t* ctx, const frc_tree_t* tree, const frc_csr_t* abnd, co
   // context, so nothing is cleared between jobs
   const int64_t stamp_tag = c->stamp_epoch;
   c->stamp_epoch += N + 1;
-  const std::function<void(int)> csr_work = [&, stage_csr](int t) {
+  const std::function<void(int)> work = [&](int t) {
     const auto w0 = std::chrono::steady_clock::now();
-    int32_t* dcol = reinterpret_cast<int32_t*>(stage_csr + s_col.off);
-    double* dval = need_val ? reinterpret_cast<double*>(stage_csr + s_val.off) : nullptr;
+    int32_t* dcol = reinterpret_cast<int32_t*>(stage_in + sh.in_col.off);
+    double* dval = sh.need_val ? reinterpret_cast<double*>(stage_in + sh.in_val.off) : nullptr;
     const int TS = csr_chunks;
     // a leaf listed twice in a row only matters when values are used (presence is an OR)
-    const bool check_dup = need_val;
+    const bool check_dup = sh.need_val;
     const int32_t* parent = tree->parent;
     auto row_at = [&](int64_t target) {
       return static_cast<int64_t>(std::lower_bound(abnd->row_ptr, abnd->row_ptr + N, target) - abnd->row_ptr);
     };
     std::vector<int64_t>& stamp = c->stamps[t];
     if (check_dup && static_cast<int32_t>(stamp.size()) < B) stamp.assign(B, -1);
-    for (int task = task_next.fetch_add(1, std::memory_order_relaxed); task < TS + 2; task = task_next.fetch_add(1, std::memory_order_relaxed)) {
-    if (task == 0) { tree_levels_share(); continue; }
-    if (task == 1) { tree_children_share(); continue; }
-    const int ch = task - 2;
-    const int64_t s0 = ch == 0 ? 0 : row_at(nnz * ch / TS), s1 = ch == TS - 1 ? N : row_at(nnz * (ch + 1) / TS);
-    bool failed = false;
-    for (int64_t s = s0; s < s1 && !failed; ++s) {
-      const int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
-      const int64_t mark_s = stamp_tag + s;
-      for (int64_t k = b; k < e; ++k) {
-        const int32_t cc = abnd->col[k];
-        const double v = abnd->val[k];
-        const char* what = nullptr;
-        if (cc < 0 || cc >= B) what = "node id out of range";
-        // pre-order ids: the first child of a node is the next id (the numbering itself is being
-        // checked by the calling thread at this moment; a bad tree fails the call before this result counts)
-        else if (cc + 1 < B && parent[cc + 1] == cc) what = "node is not a leaf";
-        else if (!(v > 0) || std::isinf(v)) what = "bad value";
-        else if (check_dup && stamp[cc] == mark_s) what = "leaf listed twice";
-        if (what) {
-          csr_errs[ch] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
-                        std::to_string(cc) + "): " + what;
-          failed = true;
-          break;
-        }
-        if (check_dup) stamp[cc] = mark_s;
-#if defined(__x86_64__)
-        // streaming stores: the staging buffer is read next by the DMA engine, not by a core
-        _mm_stream_si32(dcol + k, cc);
-        if (dval) _mm_stream_si64(reinterpret_cast<long long*>(dval + k), static_cast<long long>(__builtin_bit_cast(int64_t, v)));
-#else
-        dcol[k] = cc;
-        if (dval) dval[k] = v;
-#endif
+    for (int task = task_next.fetch_add(1, std::memory_order_relaxed); task < n_tasks;
+         task = task_next.fetch_add(1, std::memory_order_relaxed)) {
+      if (task == 0) { tree_levels_share(); continue; }
+      if (task == 1) { tree_children_share(); continue; }
+      if (task < 2 + n_prep) {
+        int ready;
+        while ((ready = plan_ready.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+        if (ready > 0) prepare_part(j->parts[task - 1].get());
+        continue;
       }
-    }
+      const int ch = task - 2 - n_prep;
+      const int64_t span = stage_k1 - stage_k0;
+      const int64_t s0 = row_at(stage_k0 + span * ch / TS), s1 = ch == TS - 1 ? row_at(stage_k1) : row_at(stage_k0 + span * (ch + 1) / TS);
+      bool failed = false;
+      for (int64_t s = s0; s < s1 && !failed; ++s) {
+        const int64_t b = abnd->row_ptr[s], e = abnd->row_ptr[s + 1];
+        const int64_t mark_s = stamp_tag + s;
+        for (int64_t k = b; k < e; ++k) {
+          const int32_t cc = abnd->col[k];
+          const double v = abnd->val[k];
+          const char* what = nullptr;
+          if (cc < 0 || cc >= B) what = "node id out of range";
+          // pre-order ids: the first child of a node is the next id (the numbering itself is being
+          // checked by another task at this moment; a bad tree fails the call before this result counts)
+          else if (cc + 1 < B && parent[cc + 1] == cc) what = "node is not a leaf";
+          else if (!(v > 0) || std::isinf(v)) what = "bad value";
+          else if (check_dup && stamp[cc] == mark_s) what = "leaf listed twice";
+          if (what) {
+            csr_errs[ch] = "sample #" + std::to_string(s + 1) + ": entry " + std::to_string(k - b + 1) + " (node " +
+                           std::to_string(cc) + "): " + what;
+            failed = true;
+            break;
+          }
+          if (check_dup) stamp[cc] = mark_s;
+#if defined(__x86_64__)
+          // streaming stores: the staging buffer is read next by the DMA engines, not by a core
+          _mm_stream_si32(dcol + k, cc);
+          if (dval) _mm_stream_si64(reinterpret_cast<long long*>(dval + k), static_cast<long long>(__builtin_bit_cast(int64_t, v)));
+#else
+          dcol[k] = cc;
+          if (dval) dval[k] = v;
+#endif
+        }
+      }
     }
 #if defined(__x86_64__)
     _mm_sfence();
 #endif
     csr_us[t] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
   };
-  if (n_workers > 0) {
-    csr_workers_busy = true;
-    c->pool->start(n_workers, csr_work);
+  // multi-process sharded unweighted: the rows of this rank's shard only (decided before the tasks start;
+  // np is not planned yet, so the shard bounds are computed here the way plan_job will)
+  if (!sh.exact && !sh.weighted && sh.n_parts == 1 && sh.world > 1 && (opts->flags & FRC_FLAG_SHARD_EMBED) && N > 0) {
+    const int64_t np = std::max<int64_t>(kTile, round_up(N, kTile * static_cast<int64_t>(sh.world)));
+    const int64_t per = np / sh.world;
+    const int64_t s0 = std::min<int64_t>(N, sh.rank0 * per), s1 = std::min<int64_t>(N, s0 + per);
+    stage_k0 = abnd->row_ptr[s0]; stage_k1 = abnd->row_ptr[s1];
   }
-  mark("table checks, context, CSR workers started");
+  const int n_workers = c->pool->size() - 1;
+  if (n_workers > 0) {
+    workers_busy = true;
+    c->pool->start(n_workers, work);
+  }
+  mark("header checks, context, workers started");
 
-  // ------------------------------------------------------------- branch lengths (the walk runs in the pool)
+  // ------------------------------------------------------------ (3) plan (the walks and the staging run in the pool)
   bool neg_len = false, bad_len = false;
   for (int32_t v = 0; v < B; ++v) {
-    double l = tree->length[v];
+    const double l = tree->length[v];
     if (!(l == l) || std::isinf(l)) bad_len = true;
     else if (l < 0) neg_len = true;
   }
-  mark("branch lengths checked");
-  // --------------------------------------------------------------- choose path
-  j->N = N; j->B = B; j->nnz = nnz;
-  j->sharded = (opts->flags & FRC_FLAG_SHARD_EMBED) != 0 && world > 1;
-  if (j->sharded) {
-    if (!ctx || !ctx->comm || comm_world(ctx->comm) != world || comm_rank(ctx->comm) != rank)
-      return bail(fail(j, FRC_ERR_STATE, "FRC_FLAG_SHARD_EMBED needs a context whose communicator "
-                                         "(frc_ctx_comm_init) matches opts->rank / opts->world"));
-  }
-  // sharded: every rank owns np / world samples, a whole number of tiles
-  j->np = std::max<int64_t>(kTile, round_up(N, j->sharded ? kTile * static_cast<int64_t>(world) : kTile));
-  j->kp = static_cast<int32_t>(round_up(B, kKBlock));
-  j->nw = static_cast<int32_t>(j->np / 32);
-  if (!j->exact && bad_len)
-    return bail(fail(j, FRC_ERR_UNSUPPORTED, "non-finite branch length: only the exact path handles it"));
-  j->prescale = !neg_len;
-  if (j->sharded && j->exact) j->sharded = false;  // (the exact path rebuilds the embedding per rank)
-  j->shard_nw = j->sharded ? j->nw / world : j->nw;
-  j->shard_w0 = j->sharded ? rank * j->shard_nw : 0;
-  j->info.path_taken = j->exact ? FRC_PATH_EXACT : FRC_PATH_FAST;
-  j->info.n_pairs_total = n_pairs;
-  j->info.n_nodes_padded = j->exact ? B : j->kp;
-
-  // ---------------------------------------------------------------------- bands
-  {
-    const char* e = getenv("FRC_TC_CTAS");
-    // CTA pairs (cta_group::2) by default; FRC_TC_CTAS=1 selects the single-CTA kernel
-    j->tc_ctas = (!(e && atoi(e) == 1) && !j->exact && !j->weighted) ? 2 : 1;
-  }
-  // ------------------------------------- operand columns of the fast unweighted path
-  // Column k of the K-major operands holds node col_order[k] (-1: padding).  bf16: identity
-  // order, uniform accumulation chunks.  u8: nodes grouped by binade pairs of their length so
-  // that one power-of-two scale per chunk leaves every length a 21..24-bit integer a * m
-  // (zero-length nodes contribute nothing and get no column).
-  std::vector<int32_t> col_order, col_exp, chunk_end, chunk_shift;
-  std::vector<double> len_col, chunk_scale;
-  if (!j->exact && !j->weighted) {
-    { const char* e = getenv("FRC_EMBED_LEVELS"); j->fused_embed = !(e && atoi(e) == 1); }
-    if (j->sharded && !j->fused_embed)
-      return bail(fail(j, FRC_ERR_UNSUPPORTED, "FRC_EMBED_LEVELS=1 cannot build a sample shard"));
-    const char* ek = getenv("FRC_UW_KERNEL");  // "bf16" forces the bf16 hi/lo kernel
-    j->i8 = j->tc_ctas == 2 && j->fused_embed && !neg_len && !(opts->flags & FRC_FLAG_UW_BF16) &&
-            !(ek && strcmp(ek, "bf16") == 0);
-    if (j->i8) {
-      constexpr int kGroups = 24, kBlockCols = 128, kMaxChunkBlocks = 128;
-      // floor(log2(l)) of a positive finite double straight from its exponent field (denormals: -1023,
-      // they all land in the last group)
-      auto ilog = [](double l) {
-        uint64_t u;
-        memcpy(&u, &l, 8);
-        return static_cast<int>((u >> 52) & 0x7FF) - 1023;
-      };
-      int e_max = INT32_MIN;
-      for (int32_t v = 0; v < B; ++v)
-        if (tree->length[v] > 0) e_max = std::max(e_max, ilog(tree->length[v]));
-      int gb = 3;  // binades per group: x = len * 2^-e in [2^20, 2^23), >= 110 candidate factors a
-      if (const char* e = getenv("FRC_U8_GROUP_BINADES")) gb = std::max(1, std::min(16, atoi(e)));
-      // group of every node, through a table over the exponent distance (an integer division per node
-      // and pass was most of this plan's 0.15 ms at 2e4 nodes); 255 = no column (length 0)
-      uint8_t group_tab[2112];
-      for (int d = 0; d < 2112; ++d) group_tab[d] = static_cast<uint8_t>(std::min(kGroups - 1, d / gb));
-      std::vector<uint8_t> grp(B);
-      int32_t cnt[kGroups + 1] = {0};
-      for (int32_t v = 0; v < B; ++v) {
-        const double l = tree->length[v];
-        const uint8_t g = l > 0 ? group_tab[e_max - ilog(l)] : static_cast<uint8_t>(kGroups);
-        grp[v] = g;
-        cnt[g]++;
-      }
-      // Groups -> accumulation chunks.  Every chunk costs a TMEM drain (>= 2k cycles: 128 KB at
-      // 64 B/clk) that only hides behind a long enough MMA run, so a group opens a chunk of its own
-      // only when it is large; smaller groups below it join the current chunk at that chunk's
-      // (larger) scale.  Their lengths then keep fewer significant bits; k_quantize_lengths sums the
-      // absolute error of every column that misses 4e-6 relative, and pairs whose unique length is
-      // too small for that sum to be harmless are recomputed exactly (flag_u).
-      constexpr int32_t kMinChunkCols = 1024;
-      int chunk_of[kGroups], chunk_exp[kGroups], n_ch = 0;
-      int32_t ch_cols[kGroups] = {0};
-      for (int g = 0; g < kGroups; ++g) {
-        if (cnt[g] == 0) { chunk_of[g] = -1; continue; }
-        if (n_ch == 0 || cnt[g] >= kMinChunkCols) {
-          chunk_exp[n_ch] = e_max - gb * g - 22;  // top of the group: len < 2^(e_max-gb*g+1) -> x < 2^23
-          ++n_ch;
-        }
-        chunk_of[g] = n_ch - 1;
-        ch_cols[n_ch - 1] += cnt[g];
-      }
-      // Chunks are laid out along K from the largest to the smallest (the order is free): the MMA
-      // run of a large chunk then covers the ratio epilogue of the previous tile plus the drain of
-      // the small chunk before it, and the two TMEM buffers are never both waiting for the epilogue
-      // warps (with the small chunk first the third chunk of a tile needed its buffer ~57k cycles
-      // after the previous tile ended, exactly when the ratio epilogue released it).
-      int ch_order[kGroups];
-      for (int c = 0; c < n_ch; ++c) ch_order[c] = c;
-      std::stable_sort(ch_order, ch_order + n_ch, [&](int a, int b) { return ch_cols[a] > ch_cols[b]; });
-      int32_t ch_off[kGroups + 1] = {0}, ch_at[kGroups], fill[kGroups];
-      for (int k = 0; k < n_ch; ++k) {
-        ch_at[ch_order[k]] = ch_off[k];
-        ch_off[k + 1] = ch_off[k] + static_cast<int32_t>(round_up(ch_cols[ch_order[k]], kBlockCols));
-      }
-      j->kp = std::max<int32_t>(ch_off[n_ch], kBlockCols);
-      col_order.assign(j->kp, -1); col_exp.assign(j->kp, 0); len_col.assign(j->kp, 0.0);
-      {  // columns of a chunk: its groups from large to small lengths, node id order inside a group
-        int32_t next[kGroups];
-        for (int c = 0; c < n_ch; ++c) next[c] = ch_at[c];
-        for (int g = 0; g < kGroups; ++g)
-          if (chunk_of[g] >= 0) { fill[g] = next[chunk_of[g]]; next[chunk_of[g]] += cnt[g]; }
-      }
-      for (int32_t v = 0; v < B; ++v) {
-        if (grp[v] == kGroups) continue;
-        const int32_t k = fill[grp[v]]++;
-        col_order[k] = v; len_col[k] = tree->length[v];
-      }
-      for (int k = 0; k < n_ch; ++k) {
-        const int c = ch_order[k];
-        for (int32_t q = ch_off[k]; q < ch_off[k + 1]; ++q) col_exp[q] = chunk_exp[c];
-        for (int32_t kb = ch_off[k] / kBlockCols; kb < ch_off[k + 1] / kBlockCols;) {
-          kb = std::min(ch_off[k + 1] / kBlockCols, kb + kMaxChunkBlocks);  // plane sums stay < 2^31
-          chunk_end.push_back(kb);
-          chunk_scale.push_back(std::ldexp(1.0, chunk_exp[c]));
-        }
-      }
-      if (chunk_end.empty()) { chunk_end.push_back(1); chunk_scale.push_back(1.0); }
-      {  // integer mode when all chunk scales lie within 2^16 (sums then stay below 2^60)
-        int lo = INT32_MAX, hi = INT32_MIN;
-        for (double sc : chunk_scale) { const int e = std::ilogb(sc); lo = std::min(lo, e); hi = std::max(hi, e); }
-        const char* ev = getenv("FRC_U8_ACC");  // "f64" forces the fp64 accumulation path (tests)
-        j->intacc = hi - lo <= 16 && !(ev && strcmp(ev, "f64") == 0);
-        j->e_min = lo;
-        for (double sc : chunk_scale) chunk_shift.push_back(std::ilogb(sc) - lo);
-        const char* ef = getenv("FRC_UW_FEED");  // "bits": expand the operand tiles inside the pair kernel
-        j->bits_feed = j->intacc && (((opts->flags & FRC_FLAG_UW_BITS) != 0) || (ef && strcmp(ef, "bits") == 0));
-      }
-    } else {
-      col_order.assign(j->kp, -1); len_col.assign(j->kp, 0.0);
-      for (int32_t v = 0; v < B; ++v) { col_order[v] = v; len_col[v] = tree->length[v]; }
-      const int32_t nkb = j->kp / kKBlock, per = tc_chunk_kblocks();
-      for (int32_t kb = 0; kb < nkb;) { kb = std::min(nkb, kb + per); chunk_end.push_back(kb); chunk_scale.push_back(1.0); }
-    }
-    j->info.n_nodes_padded = j->kp;
-    j->info.operand_kind = j->i8 ? (j->bits_feed ? 3 : 2) : 1;
-  }
-  const std::vector<int64_t> brows = band_boundaries(N, opts->band_rows, world, !(opts->flags & FRC_FLAG_NO_D2H));
-  for (size_t kb = 0; kb + 1 < brows.size(); ++kb) {
-    Band b;
-    b.row0 = brows[kb]; b.row1 = brows[kb + 1];
-    b.first = b.row0 >= 2 ? tri(b.row0) : 0;
-    b.count = tri(b.row1) - b.first;
-    b.tile_off = 0; b.n_tiles = 0;
-    if (b.count > 0) j->bands.push_back(b);
-  }
-  int64_t max_band = 1;
-  const std::vector<int> owners = band_owners(brows, world);
-  for (size_t k = 0; k < j->bands.size(); ++k)
-    if (owners[k] == rank) {
-      j->mine.push_back(static_cast<int>(k));
-      j->info.n_pairs_mine += j->bands[k].count;
-      max_band = std::max(max_band, j->bands[k].count);
-    }
-  if (max_band >= (1LL << 32)) return bail(fail(j, FRC_ERR_UNSUPPORTED, "band too large; lower band_rows"));
-  j->info.n_bands_total = static_cast<int32_t>(j->bands.size());
-  j->info.n_bands_mine = static_cast<int32_t>(j->mine.size());
-  if (!j->exact)
-    for (int k : j->mine) {
-      Band& b = j->bands[k];
-      b.tile_off = static_cast<int32_t>(j->tiles.size());
-      int32_t t0 = static_cast<int32_t>(b.row0 / kTile), t1 = static_cast<int32_t>((b.row1 - 1) / kTile);
-      // column-major inside the band: CTAs running together share the few
-      // i-tiles of the band and neighbouring j-tiles (L2 reuse of both operands)
-      if (j->tc_ctas == 2) {
-        // pair tiles: (ti, tj) and (ti, tj+1) with tj even; needed when tj <= ti.  The clusters
-        // that run together (74 on a B200) take consecutive list entries, so the list walks
-        // compact super-tiles of ~9 tile rows x ~8 tile-pair columns: the wave then shares
-        // 9 + 8 operand panels instead of 2 + 37 and its working set fits the 126 MB L2.
-        const int32_t rows_blk = std::min<int32_t>(9, t1 - t0 + 1);
-        const int32_t cols_blk = std::max<int32_t>(1, 74 / rows_blk);  // in tile pairs
-        for (int32_t tb = t0; tb <= t1; tb += rows_blk) {
-          const int32_t te = std::min(t1, tb + rows_blk - 1);
-          for (int32_t pb = 0; 2 * pb <= te; pb += cols_blk)
-            for (int32_t tp = pb; tp < pb + cols_blk && 2 * tp <= te; ++tp)
-              for (int32_t ti = std::max(2 * tp, tb); ti <= te; ++ti) j->tiles.push_back({ti, 2 * tp});
-        }
-      } else {
-        for (int32_t tj = 0; tj <= t1; ++tj)
-          for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) j->tiles.push_back({ti, tj});
-      }
-      b.n_tiles = static_cast<int32_t>(j->tiles.size()) - b.tile_off;
-    }
-
-  // which operand rows this rank's tiles read (fast unweighted, world > 1): a tile (ti, tj) reads the
-  // Bh / Bl rows of its row samples and the A rows of its column samples (both tiles of a pair)
-  std::vector<uint8_t> need_blocks;
-  if (!j->exact && !j->weighted && world > 1 && j->fused_embed) {
-    need_blocks.assign(static_cast<size_t>((j->np + 255) / 256), 0);
-    const int32_t pairw = j->tc_ctas == 2 ? 2 : 1;
-    for (const Tile& t : j->tiles) {
-      need_blocks[t.ti / 2] |= 2;
-      for (int32_t c = 0; c < pairw; ++c)
-        if ((static_cast<int64_t>(t.tj) + c) * kTile < j->np) need_blocks[(t.tj + c) / 2] |= 1;
-    }
-  }
-  mark("row_ptr check + bands/tiles");
-  // ------------------------------------------------- pack + upload the inputs
-  // (the column plan and the tile lists; the CSR block and the tree topology are staged by the pool)
-  size_t total = 0;
-  auto seg = [&](size_t bytes) { Seg s{total, bytes}; total += (bytes + 255) & ~size_t(255); return s; };
-  Seg s_q0 = seg(j->kp), s_hi = seg(sizeof(uint16_t) * j->kp), s_lo = seg(sizeof(uint16_t) * j->kp),
-      s_lenq = seg(sizeof(double) * j->kp), s_tiles = seg(sizeof(Tile) * j->tiles.size()),
-      s_order = seg(sizeof(int32_t) * col_order.size()), s_cexp = seg(sizeof(int32_t) * col_exp.size()),
-      s_lcol = seg(sizeof(double) * len_col.size()), s_cend = seg(sizeof(int32_t) * chunk_end.size()),
-      s_cscale = seg(sizeof(double) * chunk_scale.size()), s_need = seg(need_blocks.size()),
-      s_cshift = seg(sizeof(int32_t) * chunk_shift.size());
-  char* stage = pin_alloc<char>(j, total, &rc);
-  if (!stage) return bail(rc);
-  j->d_inputs = dev_alloc<char>(j, total, &rc);
-  if (!j->d_inputs) return bail(rc);
-  j->input_bytes = total + csr_total;
-  {
-    {
-    uint16_t* hi = reinterpret_cast<uint16_t*>(stage + s_hi.off);
-    uint16_t* lo = reinterpret_cast<uint16_t*>(stage + s_lo.off);
-    double* lq = reinterpret_cast<double*>(stage + s_lenq.off);
-    if (!j->i8) {  // (u8: k_quantize_lengths fills q0/q1/q2 and lenq on the device)
-      for (int32_t v = 0; v < B; ++v) {
-        double l = tree->length[v];
-        hi[v] = bf16_rn(static_cast<float>(l));
-        double res = l - static_cast<double>(bf16_to_float(hi[v]));
-        lo[v] = (l == l && !std::isinf(l)) ? bf16_rn(static_cast<float>(res)) : 0;
-        lq[v] = static_cast<double>(bf16_to_float(hi[v])) + static_cast<double>(bf16_to_float(lo[v]));
-      }
-      for (int32_t v = B; v < j->kp; ++v) { hi[v] = 0; lo[v] = 0; lq[v] = 0.0; }
-    }
-    if (!col_order.empty()) memcpy(stage + s_order.off, col_order.data(), s_order.bytes);
-    if (!col_exp.empty()) memcpy(stage + s_cexp.off, col_exp.data(), s_cexp.bytes);
-    if (!len_col.empty()) memcpy(stage + s_lcol.off, len_col.data(), s_lcol.bytes);
-    if (!chunk_end.empty()) memcpy(stage + s_cend.off, chunk_end.data(), s_cend.bytes);
-    if (!chunk_scale.empty()) memcpy(stage + s_cscale.off, chunk_scale.data(), s_cscale.bytes);
-    if (!need_blocks.empty()) memcpy(stage + s_need.off, need_blocks.data(), s_need.bytes);
-    if (!chunk_shift.empty()) memcpy(stage + s_cshift.off, chunk_shift.data(), s_cshift.bytes);
-    if (!j->tiles.empty()) memcpy(stage + s_tiles.off, j->tiles.data(), sizeof(Tile) * j->tiles.size());
-    }
-  }
-  mark("column plan + tiles staged");
-  CREATE_CUDA(cudaEventCreate(&j->ev_h2d0));
-  CREATE_CUDA(cudaEventCreate(&j->ev_h2d1));
-  CREATE_CUDA(cudaEventCreate(&j->ev_embed0));
-  CREATE_CUDA(cudaEventCreate(&j->ev_embed1));
-  CREATE_CUDA(cudaEventCreate(&j->ev_run1));
-  CREATE_CUDA(cudaEventCreateWithFlags(&j->ev_join, cudaEventDisableTiming));
-  CREATE_CUDA(cudaEventCreateWithFlags(&j->ev_bits, cudaEventDisableTiming));
-  CREATE_CUDA(cudaEventCreateWithFlags(&j->ev_rsum, cudaEventDisableTiming));
-  CREATE_CUDA(cudaEventRecord(j->ev_h2d0, c->stream[0]));
-  CREATE_CUDA(cudaMemcpyAsync(j->d_inputs, stage, total, cudaMemcpyHostToDevice, c->stream[0]));
-  j->info.h2d_bytes = static_cast<int64_t>(total + csr_total);
-  char* d = j->d_inputs;
-  j->dcsr.n_samples = N; j->dcsr.nnz = nnz;
-  j->dcsr.row_ptr = reinterpret_cast<int64_t*>(d_csr + s_rowptr.off);
-  j->dcsr.col = reinterpret_cast<int32_t*>(d_csr + s_col.off);
-  j->dcsr.val = need_val ? reinterpret_cast<double*>(d_csr + s_val.off) : nullptr;
-  j->dtree.n_nodes = B; j->dtree.height = 0;  // (height: set when the tree share is joined)
-  j->dtree.parent = reinterpret_cast<int32_t*>(d_csr + s_parent.off);
-  j->dtree.length = reinterpret_cast<double*>(d_csr + s_len.off);
-  j->dtree.child_ptr = reinterpret_cast<int32_t*>(d_csr + s_cptr.off);
-  j->dtree.child_idx = reinterpret_cast<int32_t*>(d_csr + s_cidx.off);
-  j->dtree.level_nodes = reinterpret_cast<int32_t*>(d_csr + s_lvl.off);
-  j->d_q0 = d + s_q0.off;
-  j->d_q1 = d + s_hi.off;
-  j->d_q2 = d + s_lo.off;
-  j->d_lenq = reinterpret_cast<double*>(d + s_lenq.off);
-  j->d_order = reinterpret_cast<int32_t*>(d + s_order.off);
-  j->d_col_exp = reinterpret_cast<int32_t*>(d + s_cexp.off);
-  j->d_len_col = reinterpret_cast<double*>(d + s_lcol.off);
-  j->d_chunks.end = reinterpret_cast<int32_t*>(d + s_cend.off);
-  j->d_chunks.scale = reinterpret_cast<double*>(d + s_cscale.off);
-  j->d_chunks.n = static_cast<int32_t>(chunk_end.size());
-  j->d_chunks.shift = chunk_shift.empty() ? nullptr : reinterpret_cast<int32_t*>(d + s_cshift.off);
-  j->d_need = need_blocks.empty() ? nullptr : reinterpret_cast<uint8_t*>(d + s_need.off);
-  if (j->i8 && !chunk_scale.empty()) {
-    const auto mm = std::minmax_element(chunk_scale.begin(), chunk_scale.end());
-    j->d_chunks.biased = *mm.second <= *mm.first * 256.0;
-  }
-  j->d_lenf = reinterpret_cast<float*>(d_csr + s_lenf.off);
-  j->d_tiles = reinterpret_cast<Tile*>(d + s_tiles.off);
-  j->d_level_ptr = reinterpret_cast<int32_t*>(d_csr + s_lptr.off);
-  j->dtree.level_parent = reinterpret_cast<int32_t*>(d_csr + s_lpar.off);
-
-  mark("events + H2D enqueue");
-  // ------------------------------------------------------------ device buffers
-  const int chunks = weighted_scratch_chunks(B);
-  if (j->exact || j->weighted) {
-    // exact: the whole fp64 embedding; fast weighted: one slab of samples at a time, <= 2 GB
-    const int64_t per_rank = j->np / (j->sharded ? world : 1);
-    j->ws_slab = j->exact ? j->np
-                          : std::min<int64_t>(per_rank, std::max<int64_t>(kTile, (2LL << 30) / (8LL * B) / kTile * kTile));
-    if (const char* e = getenv("FRC_WS_SLAB"))  // tests: force several slabs on a small problem
-      if (!j->exact && atoi(e) > 0) j->ws_slab = std::min<int64_t>(per_rank, round_up(atoi(e), kTile));
-    if (!(j->d_E = dev_alloc<double>(j, static_cast<size_t>(B) * j->ws_slab, &rc))) return bail(rc);
-    if (!(j->d_total = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
-    if (!j->exact) {
-      if (!(j->d_A = dev_alloc<float>(j, static_cast<size_t>(j->kp) * j->np, &rc))) return bail(rc);
-      if (!(j->d_W = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
-      if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
-      if (!(j->d_flag_counts = dev_alloc<unsigned long long>(j, j->mine.size() + 1, &rc))) return bail(rc);
-      const size_t ws_words = static_cast<size_t>(c->num_sms) * B;
-      if (!(j->d_fix_ws = dev_alloc<long long>(j, ws_words, &rc))) return bail(rc);
-      CREATE_CUDA(cudaMemsetAsync(j->d_fix_ws, 0, sizeof(long long) * ws_words, c->stream[0]));
-    }
-  } else {
-    {
-      // fused: published columns bitsT[nw][kp] (+ node-indexed scratch for trees beyond shared memory);
-      // FRC_EMBED_LEVELS=1: node-major bits[B][nw], one launch per tree level
-      size_t words = j->fused_embed ? static_cast<size_t>(j->kp) * j->nw : static_cast<size_t>(B) * j->nw;
-      const char* ep = getenv("FRC_PEER_PUSH");  // "0": exchange the bit columns with NCCL instead
-      j->peer_push = j->sharded && j->fused_embed && !j->bits_feed && world <= 8 && !(ep && atoi(ep) == 0);
-      if (j->peer_push) {
-        // two buffers from the symmetric heap (same block + offset on every rank), mapped from the peers
-        for (int k = 0; k < 2; ++k) {
-          cudaError_t e = cudaSuccess;
-          j->d_bits2[k] = static_cast<uint32_t*>(c->sym.alloc(words * sizeof(uint32_t), &e));
-          if (!j->d_bits2[k]) return bail(fail(j, FRC_ERR_OOM, std::string("symmetric heap: ") + cudaGetErrorString(e)));
-        }
-        if ((rc = sym_sync(j)) != FRC_OK) return bail(rc);
-        for (int k = 0; k < 2; ++k) {
-          size_t blk = 0;
-          for (; blk < c->sym.blocks.size(); ++blk) {
-            char* base = c->sym.blocks[blk].p;
-            if (reinterpret_cast<char*>(j->d_bits2[k]) >= base &&
-                reinterpret_cast<char*>(j->d_bits2[k]) < base + c->sym.blocks[blk].cap) break;
-          }
-          const size_t off = reinterpret_cast<char*>(j->d_bits2[k]) - c->sym.blocks[blk].p;
-          j->peers[k].n = world; j->peers[k].self = rank;
-          for (int r = 0; r < world; ++r) j->peers[k].p[r] = reinterpret_cast<uint32_t*>(c->sym_peer[blk][r] + off);
-        }
-        j->d_bits = j->d_bits2[0];
-      } else if (!(j->d_bits = dev_alloc<uint32_t>(j, std::max<size_t>(words, 64), &rc))) return bail(rc);
-      const size_t ns = j->fused_embed ? static_cast<size_t>(presence_node_scratch_words(B, j->shard_nw)) : 0;
-      if (ns && !(j->d_node_scratch = dev_alloc<uint32_t>(j, ns, &rc))) return bail(rc);
-    }
-    if (j->intacc && !j->bits_feed) {
-      // capacity: when the three u8 operand arrays would not fit the free HBM (with room for the
-      // output ring), the pair kernel expands its tiles from the bit rows instead (8x less memory,
-      // about half the speed: DESIGN.md)
-      const double need = 3.0 * static_cast<double>(j->np) * j->kp;
-      if (need > 32.0 * (1 << 30)) {  // (cudaMemGetInfo costs milliseconds: only asked when it can matter)
-        size_t free_b = 0, total_b = 0;
-        CREATE_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        if (need > 0.80 * static_cast<double>(free_b)) j->bits_feed = true;
-      }
-      j->info.operand_kind = j->bits_feed ? 3 : 2;
-    }
-    const size_t opsz = j->bits_feed ? 256 : static_cast<size_t>(j->np) * j->kp * (j->i8 ? 1 : 2);
-    if (!(j->d_P = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
-    if (!(j->d_Bh = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
-    if (!(j->d_Bl = dev_alloc<char>(j, opsz, &rc))) return bail(rc);
-    if (j->bits_feed && !(j->d_bitsS = dev_alloc<uint32_t>(j, static_cast<size_t>(j->np) * (j->kp / 32), &rc)))
-      return bail(rc);
-    if (!(j->d_r = dev_alloc<double>(j, j->np, &rc))) return bail(rc);
-    if (!(j->d_scratch = dev_alloc<double>(j, static_cast<size_t>(chunks) * j->np, &rc))) return bail(rc);
-    if (!(j->d_flag_counts = dev_alloc<unsigned long long>(j, j->mine.size() + 1, &rc))) return bail(rc);
-    std::string terr;
-    if (j->i8 && !(j->d_flag_u = dev_alloc<double>(j, 1, &rc))) return bail(rc);
-    if (j->i8 && !(j->d_qam = dev_alloc<uint32_t>(j, j->kp, &rc))) return bail(rc);
-    if (j->intacc) {
-      if (!(j->d_r_int = dev_alloc<long long>(j, j->np, &rc))) return bail(rc);
-    }
-    if (!j->bits_feed) {
-      j->tc = tc_operands_create(j->d_P, j->d_Bh, j->d_Bl, j->np, j->kp, j->i8, j->d_chunks, j->d_len_col,
-                                 j->d_flag_u, &terr);
-      if (!j->tc) return bail(fail(j, FRC_ERR_CUDA, terr));
-    } else {
-      j->bo = bits_operands_create(j->d_bitsS, j->np, j->kp, static_cast<const uint8_t*>(j->d_q0),
-                                   static_cast<const uint8_t*>(j->d_q1), static_cast<const uint8_t*>(j->d_q2),
-                                   j->d_chunks, j->d_len_col, j->d_flag_u, j->d_r_int, std::ldexp(1.0, j->e_min), &terr);
-      if (!j->bo) return bail(fail(j, FRC_ERR_CUDA, terr));
-    }
-    if (j->intacc && j->tc) tc_operands_set_int(j->tc, j->d_r_int, std::ldexp(1.0, j->e_min));
-    if (j->i8) {  // a function of the tree only: once per job, not per restart
-      j->info.kernel_launches += launch_quantize_lengths(
-          j->d_len_col, j->d_col_exp, j->kp, static_cast<uint8_t*>(j->d_q0), static_cast<uint8_t*>(j->d_q1),
-          static_cast<uint8_t*>(j->d_q2), j->d_qam, j->d_lenq, j->d_flag_u, c->stream[0]);
-      CREATE_CUDA(cudaGetLastError());
-    }
-  }
-  { const char* e = getenv("FRC_ZERO_COPY"); j->zero_copy = e && atoi(e) == 1; }
-  {
-    // fast-path distances have fp32 precision: send them over PCIe as fp32, widen on the host (wire.cu)
-    // The widening is host CPU work the copy engine did for free with doubles on the bus: it pays when
-    // this rank has the cores for it.  Measured: 16 threads 1.7 vs 2.8 ms per cfg2 call, 8 threads per
-    // rank (2 GPUs) 9.9 vs 7.0e9 pairs/s, but 4 threads per rank (8 GPUs on a 32-core host) 8.1e9 against
-    // 1.0e10 with doubles.  FRC_WIRE=f64 / f32 overrides.
-    const char* e = getenv("FRC_WIRE");
-    const bool want32 = e ? !strcmp(e, "f32") : c->pool->size() >= 8;
-    j->wire32 = !j->exact && !(opts->flags & FRC_FLAG_NO_D2H) && !j->zero_copy && want32;
-  }
-  {
-    int64_t want = std::max<int64_t>(kMinSlots, std::min<int64_t>(kSlots, kSlotBytesBudget / (max_band * 8)));
-    j->n_slots = static_cast<int>(std::min<int64_t>(want, std::max<int64_t>(2, static_cast<int64_t>(j->mine.size()) + 1)));
-  }
-  if (j->mine.empty()) j->n_slots = 0;
-  if (j->wire32 && j->n_slots > 0 && !(j->wide = pin_alloc<double>(j, std::min(max_band, kWidePiece), &rc))) return bail(rc);
-  for (int k = 0; k < j->n_slots; ++k) {
-    Slot& sl = j->slots[k];
-    if (!(opts->flags & FRC_FLAG_NO_D2H) && !j->wire32 && !(sl.host = pin_alloc<double>(j, max_band, &rc))) return bail(rc);
-    if (j->zero_copy && sl.host) sl.dev = sl.host;  // kernels store straight into pinned host memory (UVA)
-    else if (!(sl.dev = dev_alloc<double>(j, max_band, &rc))) return bail(rc);
-    if (j->wire32) {
-      if (!(sl.dev32 = dev_alloc<float>(j, max_band, &rc))) return bail(rc);
-      if (!(sl.host32 = pin_alloc<float>(j, max_band, &rc))) return bail(rc);
-      if (!(sl.n_bad_host = pin_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
-      *sl.n_bad_host = 0;
-    }
-    if (!j->exact) {
-      if (!(sl.flagged = dev_alloc<uint32_t>(j, max_band, &rc))) return bail(rc);
-      if (!(sl.n_flagged_host = pin_alloc<unsigned long long>(j, 1, &rc))) return bail(rc);
-      *sl.n_flagged_host = 0;
-    }
-    cudaError_t e;
-    if ((e = cudaEventCreate(&sl.k0)) != cudaSuccess || (e = cudaEventCreate(&sl.k1)) != cudaSuccess ||
-        (e = cudaEventCreate(&sl.k2)) != cudaSuccess || (e = cudaEventCreate(&sl.k3)) != cudaSuccess ||
-        (e = cudaEventCreate(&sl.done)) != cudaSuccess)
-      return bail(fail(j, FRC_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e)));
-  }
-
-  mark("device buffers, tensor maps, slots");
-  // -------------------------------------------- join the table workers, upload the CSR block
-  csr_work(n_workers);  // whatever is left of the task list (everything, without workers)
-  if (csr_workers_busy) { c->pool->wait(); csr_workers_busy = false; }
-  if (trace) { fprintf(stderr, "[frc_create] CSR share times (us):"); for (double u : csr_us) fprintf(stderr, " %.0f", u); fprintf(stderr, "\n"); }
-  if (bad_parent) return bail(fail(j, FRC_ERR_ARG, "parent[" + std::to_string(bad_parent) + "] is not a smaller node id"));
-  if (bad_order) return bail(fail(j, FRC_ERR_ARG, "node ids are not a pre-order numbering (node " + std::to_string(bad_order) + ")"));
+  auto plan_failed = [&](int code) { plan_ready.store(-1, std::memory_order_release); return bail(code); };
+  if (!sh.exact && bad_len)
+    return plan_failed(fail(j, FRC_ERR_UNSUPPORTED, "non-finite branch length: only the exact path handles it"));
+  if ((rc = plan_job(j, tree, neg_len)) != FRC_OK) return plan_failed(rc);
+  if ((rc = stage_plan(j, tree)) != FRC_OK) return plan_failed(rc);
+  mark("column plan + bands");
+  plan_ready.store(1, std::memory_order_release);
+  // ------------------------------------------------------------ (5) device 0 on this thread
+  prepare_part(j->parts[0].get());
+  mark("device 0 prepared");
+  work(n_workers);  // whatever is left of the task list (everything, without workers)
+  if (workers_busy) { c->pool->wait(); workers_busy = false; }
+  if (trace) { fprintf(stderr, "[frc_create] share times (us):"); for (double u : csr_us) fprintf(stderr, " %.0f", u); fprintf(stderr, "\n"); }
+  if (levels.bad_parent) return bail(fail(j, FRC_ERR_ARG, "parent[" + std::to_string(levels.bad_parent) + "] is not a smaller node id"));
+  if (levels.bad_order) return bail(fail(j, FRC_ERR_ARG, "node ids are not a pre-order numbering (node " + std::to_string(levels.bad_order) + ")"));
   for (auto& e : csr_errs)
     if (!e.empty()) return bail(fail(j, FRC_ERR_ARG, e));
-  if (tree_H < 0 || !children_ok) return bail(fail(j, FRC_ERR_ARG, "tree topology could not be prepared"));  // (unreachable)
-  j->dtree.height = tree_H;
-  j->info.tree_height = tree_H;
-  CREATE_CUDA(cudaMemcpyAsync(d_csr, stage_csr, csr_total, cudaMemcpyHostToDevice, c->stream[0]));
-  CREATE_CUDA(cudaEventRecord(j->ev_h2d1, c->stream[0]));
-  mark("CSR workers joined, CSR upload queued");
-  // ----------------------------------------------------------------- go
-  if ((rc = run_embedding(j)) != FRC_OK) return bail(rc);
-  if ((rc = start_pairs(j)) != FRC_OK) return bail(rc);
-  mark("enqueue embedding + first bands");
+  if (levels.height < 0 || !children_ok) return bail(fail(j, FRC_ERR_ARG, "tree topology could not be prepared"));  // (unreachable)
+  for (auto& p : j->parts)
+    if (p->rc) { j->err = p->err; return bail(p->rc); }
+  sh.level_ptr = levels.level_ptr;
+  sh.tree_height = levels.height;
+  // the delivery order: bands of this process in flat-index order
+  {
+    std::vector<int> cursor(sh.n_parts, 0);
+    for (const Band& b : sh.bands)
+      for (int k = 0; k < sh.n_parts; ++k)
+        if (j->parts[k]->owner == b.owner) { j->order.push_back({k, cursor[k]++}); break; }
+  }
+  if (!sh.exact && sh.d2h) {
+    int64_t mb = 1;
+    for (auto& p : j->parts) mb = std::max(mb, p->max_band);
+    cudaError_t e = cudaSuccess;
+    j->wide = static_cast<double*>(c->pin.alloc(sizeof(double) * std::min(mb, kWidePiece), &e));
+    if (!j->wide) return bail(fail(j, FRC_ERR_OOM, std::string("pinned widening buffer: ") + cudaGetErrorString(e)));
+  }
+  mark("workers joined");
+  // ------------------------------------------------------------ (6) go
+  if ((rc = for_parts(j, launch_part_stage1)) != FRC_OK) return bail(rc);
+  if ((rc = for_parts(j, launch_part_stage2)) != FRC_OK) return bail(rc);
+  mark("uploads, embedding, first bands queued");
+  j->create_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create0).count();
   *out = j;
   return FRC_OK;
-#undef CREATE_CUDA
 }
 
-// fp32 wire: widens pairs [off, off + n) of the band in slot `sl` into j->wide (wire.cu).  A band larger
-// than kWidePiece is handed out in pieces, so that the buffer always fits the cores' caches.
-static int widen_piece(frc_job* j, Slot& sl, int64_t off, int64_t n, bool trace) {
-  if (*sl.n_bad_host) {
-    // some value of this band does not survive fp32 (underflow): fetch the doubles themselves, rounded like
-    // the rest wherever fp32 can carry them
-    cudaStream_t fs = j->ctx->stream[0];
-    j->info.kernel_launches += launch_round_band(sl.dev + off, n, j->ctx->num_sms, fs);
-    JOB_CUDA(j, cudaGetLastError());
-    JOB_CUDA(j, cudaMemcpyAsync(j->wide, sl.dev + off, sizeof(double) * n, cudaMemcpyDeviceToHost, fs));
-    JOB_CUDA(j, cudaStreamSynchronize(fs));
-    j->info.d2h_bytes += static_cast<int64_t>(sizeof(double)) * n;
-    return FRC_OK;
+}  // extern "C"
+
+namespace {
+
+// Waits for band idx of the part and does the per-band bookkeeping.
+int part_wait_band(Part* p, size_t idx, Slot** out) {
+  const Shared& sh = *p->sh;
+  PART_CUDA(p, cudaSetDevice(p->dc->device));
+  if (idx >= p->next_enqueue) {  // only when the ring has 2 slots and this is the first call
+    if (enqueue_band(p, p->next_enqueue)) return p->rc;
+    ++p->next_enqueue;
   }
+  Slot& sl = p->slots[idx % p->n_slots];
+  const auto tn0 = std::chrono::steady_clock::now();
+  PART_CUDA(p, cudaEventSynchronize(sl.done));
+  float ms = 0.f;
+  PART_CUDA(p, cudaEventElapsedTime(&ms, sl.k0, sl.k1));
+  p->info.pairs_ms += ms;
+  PART_CUDA(p, cudaEventElapsedTime(&ms, sl.k1, sl.k2));
+  p->info.fixup_ms += ms;
+  if (idx + 1 == p->mine.size() && !p->run_timed) {
+    PART_CUDA(p, cudaEventSynchronize(p->ev_run1));
+    PART_CUDA(p, cudaEventElapsedTime(&ms, p->ev_embed0, p->ev_run1));
+    p->info.run_ms = ms;
+    p->run_timed = true;
+  }
+  if (sl.n_flagged_host) p->info.flagged_pairs += static_cast<int64_t>(*sl.n_flagged_host);
+  if (sl.ex.count) {
+    const unsigned long long n = *sl.ex.count;
+    if (n > static_cast<unsigned long long>(sl.ex.cap))
+      return pfail(p, FRC_ERR_UNSUPPORTED, "more than " + std::to_string(sl.ex.cap) + " distances of one band lie below "
+                                           "fp32's range (|d| < 1.2e-38): run this input with path = FRC_PATH_EXACT");
+    p->info.exceptions += static_cast<int64_t>(n);
+  }
+  if (sh.knobs.trace) {
+    float a = 0, b = 0, c2 = 0, d = 0;
+    cudaEventElapsedTime(&a, p->ev_embed0, sl.k0);
+    cudaEventElapsedTime(&b, p->ev_embed0, sl.k1);
+    cudaEventElapsedTime(&c2, p->ev_embed0, sl.k2);
+    cudaEventElapsedTime(&d, p->ev_embed0, sl.done);
+    fprintf(stderr, "[dev %d band %3zu] host: deliver at %.3f ms after waiting %.1f us; device: start %.3f kernel_end %.3f "
+                    "fixup_end %.3f d2h_end %.3f ms (pairs %lld)\n", p->dc->device, idx,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - p->t_host0).count(),
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tn0).count(), a, b, c2, d,
+            static_cast<long long>(p->bands[idx].count));
+  }
+  *out = &sl;
+  return FRC_OK;
+}
+
+// frc_next on a fast path: widens pairs [off, off + n) of the held band into j->wide (wire.cu) and patches the
+// exceptions that fall into the piece.
+void widen_piece(frc_job* j, const Slot& sl, int64_t band_first, int64_t off, int64_t n) {
+  const bool trace = j->sh.knobs.trace;
   const auto t0 = std::chrono::steady_clock::now();
   Pool* pool = j->ctx->pool.get();
-  int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(pool->size(), n / 65536)));
-  if (const char* e = getenv("FRC_WIDEN_THREADS")) T = std::max(1, std::min(T, atoi(e)));
+  int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min(pool->size(), 16), n / 65536)));
+  if (j->sh.knobs.widen_threads > 0) T = std::max(1, std::min(T, j->sh.knobs.widen_threads));
   const float* src = sl.host32 + off;
   double* dst = j->wide;
-  double share_us[64] = {0};
-  double* su = trace && T <= 64 ? share_us : nullptr;
   // chunks handed out through a counter (a worker on a busy core takes fewer); the first round is
   // static so that thread t starts where it started last time and finds its destination lines in its L2
   constexpr int64_t kChunk = 16384;
@@ -1379,150 +1611,167 @@ static int widen_piece(frc_job* j, Slot& sl, int64_t off, int64_t n, bool trace)
   std::atomic<int64_t> next{0};
   std::atomic<int64_t>* nx = &next;
   pool->run(T, [=](int t) {
-    const auto w0 = std::chrono::steady_clock::now();
     for (int64_t ch = t < n_chunks ? t : n_chunks; ch < n_chunks;) {
       const int64_t lo = ch * kChunk, hi = std::min(n, lo + kChunk);
       widen_band(src + lo, dst + lo, hi - lo, /*stream_stores=*/false);
       ch = T + nx->fetch_add(1, std::memory_order_relaxed);
     }
-    if (su) su[t] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - w0).count();
   });
-  if (su) {
-    fprintf(stderr, "[host] widen %lld pairs, shares (us):", static_cast<long long>(n));
-    for (int t = 0; t < T; ++t) fprintf(stderr, " %.0f", su[t]);
-    fprintf(stderr, "  (whole %.0f)\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+  const int64_t n_ex = std::min<int64_t>(static_cast<int64_t>(*sl.ex.count), sl.ex.cap);
+  for (int64_t k = 0; k < n_ex; ++k) {
+    const int64_t at = sl.ex.index[k] - band_first - off;
+    if (at >= 0 && at < n) dst[at] = sl.ex.value[k];
   }
-  return FRC_OK;
+  if (trace)
+    fprintf(stderr, "[host] widened %lld pairs on %d threads in %.0f us\n", static_cast<long long>(n), T,
+            std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
 }
 
-int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* count) {
-  if (!j || !data || !first_index || !count) return FRC_ERR_ARG;
+// Common body of frc_next / frc_next_f32.  mode 1: float64 out, mode 2: float32 out.
+int next_chunk(frc_job* j, int mode, const void** data, int64_t* first_index, int64_t* count) {
+  const Shared& sh = j->sh;
   *data = nullptr; *first_index = 0; *count = 0;
-  JOB_CUDA(j, cudaSetDevice(j->ctx->device));
+  if (j->read_mode == 0) j->read_mode = mode;
+  if (j->read_mode != mode) return fail(j, FRC_ERR_STATE, "frc_next and frc_next_f32 cannot be mixed on one pass of a job");
+  if (mode == 2 && sh.exact)
+    return fail(j, FRC_ERR_STATE, "this job took the exact path (bit-exact float64): read it with frc_next");
+  if (mode == 1 && !sh.exact && !sh.d2h)
+    return fail(j, FRC_ERR_STATE, "FRC_FLAG_NO_D2H on a fast path keeps fp32 in HBM: read it with frc_next_f32");
+  DeviceGuard guard;
   // a band larger than the widening buffer is handed out piece by piece
-  if (j->held_slot >= 0 && j->wire32 && j->piece_off < j->piece_end) {
+  if (mode == 1 && j->held_part >= 0 && !sh.exact && j->piece_off < j->piece_end) {
     const int64_t n = std::min(kWidePiece, j->piece_end - j->piece_off);
-    int rc = widen_piece(j, j->slots[j->held_slot], j->piece_off, n, getenv("FRC_TRACE") != nullptr);
-    if (rc) return rc;
+    widen_piece(j, j->parts[j->held_part]->slots[j->held_slot], j->piece_first, j->piece_off, n);
     *data = j->wide;
     *first_index = j->piece_first + j->piece_off;
     *count = n;
     j->piece_off += n;
     return FRC_OK;
   }
-  // the band handed out by the previous call is released now
-  if (j->held_slot >= 0) {
-    j->held_slot = -1;
-    if (j->next_enqueue < j->mine.size()) {
-      int rc = enqueue_band(j, j->next_enqueue);
-      if (rc) return rc;
-      ++j->next_enqueue;
+  // the band handed out by the previous call is released now: its slot takes the part's next band
+  if (j->held_part >= 0) {
+    Part* hp = j->parts[j->held_part].get();
+    j->held_part = -1; j->held_slot = -1;
+    if (hp->next_enqueue < hp->mine.size()) {
+      cudaSetDevice(hp->dc->device);
+      if (enqueue_band(hp, hp->next_enqueue)) return fail(j, hp->rc, hp->err);
+      ++hp->next_enqueue;
     }
   }
-  if (j->next_deliver >= j->mine.size()) return FRC_OK;  // end of stream
-  if (j->next_deliver >= j->next_enqueue) {               // only when n_slots == 2 and first call
-    int rc = enqueue_band(j, j->next_enqueue);
-    if (rc) return rc;
-    ++j->next_enqueue;
-  }
-  const size_t idx = j->next_deliver;
-  Slot& sl = j->slots[idx % j->n_slots];
-  const bool trace_next = getenv("FRC_TRACE") != nullptr;
-  const auto tn0 = std::chrono::steady_clock::now();
-  JOB_CUDA(j, cudaEventSynchronize(sl.done));
-  const auto tn1 = std::chrono::steady_clock::now();
-  float ms = 0.f;
-  JOB_CUDA(j, cudaEventElapsedTime(&ms, sl.k0, sl.k1));
-  j->info.pairs_ms += ms;
-  JOB_CUDA(j, cudaEventElapsedTime(&ms, sl.k1, sl.k2));
-  j->info.fixup_ms += ms;
-  if (j->next_deliver + 1 == j->mine.size() && !j->run_timed) {
-    JOB_CUDA(j, cudaEventSynchronize(j->ev_run1));
-    JOB_CUDA(j, cudaEventElapsedTime(&ms, j->ev_embed0, j->ev_run1));
-    j->info.run_ms = ms;
-    j->run_timed = true;
-  }
-  if (sl.n_flagged_host) j->info.flagged_pairs += static_cast<int64_t>(*sl.n_flagged_host);
-  if (trace_next) {
-    fprintf(stderr, "[host] deliver band %zu at %.3f ms\n", idx,
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - j->t_host0).count());
-    float a = 0, b = 0, c2 = 0, d = 0;
-    cudaEventElapsedTime(&a, j->ev_embed0, sl.k0);
-    cudaEventElapsedTime(&b, j->ev_embed0, sl.k1);
-    cudaEventElapsedTime(&c2, j->ev_embed0, sl.k2);
-    cudaEventElapsedTime(&d, j->ev_embed0, sl.done);
-    fprintf(stderr, "[band %3zu] start %.3f kernel_end %.3f fixup_end %.3f d2h_end %.3f ms (pairs %lld)\n", idx, a, b, c2, d,
-            static_cast<long long>(j->bands[j->mine[idx]].count));
-  }
-  const Band& b = j->bands[j->mine[idx]];
+  if (j->next_item >= j->order.size()) return FRC_OK;  // end of stream
+  const frc_job::Item it = j->order[j->next_item];
+  Part* p = j->parts[it.part].get();
+  Slot* sl = nullptr;
+  if (part_wait_band(p, static_cast<size_t>(it.idx), &sl)) return fail(j, p->rc, p->err);
+  const Band& b = p->bands[it.idx];
   int64_t deliver_n = b.count;
-  if (j->wire32) {
+  if (sh.exact) {
+    *data = sh.d2h ? sl->host64 : sl->dev64;
+  } else if (mode == 2) {
+    *data = sh.d2h ? sl->host32 : sl->dev32;
+  } else {
     deliver_n = std::min(kWidePiece, b.count);
     j->piece_first = b.first; j->piece_off = deliver_n; j->piece_end = b.count;
-    int rc = widen_piece(j, sl, 0, deliver_n, trace_next);
-    if (rc) return rc;
+    widen_piece(j, *sl, b.first, 0, deliver_n);
+    *data = j->wide;
   }
-  if (trace_next) {
-    const auto tn2 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[host] band %zu: waited %.1f us for the copy, bookkeeping + widening %.1f us\n", idx,
-            std::chrono::duration<double, std::micro>(tn1 - tn0).count(),
-            std::chrono::duration<double, std::micro>(tn2 - tn1).count());
-  }
-  *data = (j->opts.flags & FRC_FLAG_NO_D2H) ? sl.dev : j->wire32 ? j->wide : sl.host;
   *first_index = b.first;
   *count = deliver_n;
-  j->held_slot = static_cast<int>(idx % j->n_slots);
-  ++j->next_deliver;
+  j->held_part = it.part;
+  j->held_slot = static_cast<int>(it.idx % p->n_slots);
+  ++p->next_deliver;
+  ++j->next_item;
+  return FRC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int frc_next(frc_job_t* j, const double** data, int64_t* first_index, int64_t* count) {
+  if (!j || !data || !first_index || !count) return FRC_ERR_ARG;
+  const void* d = nullptr;
+  const int rc = next_chunk(j, 1, &d, first_index, count);
+  *data = static_cast<const double*>(d);
+  return rc;
+}
+
+int frc_next_f32(frc_job_t* j, const float** data, int64_t* first_index, int64_t* count) {
+  if (!j || !data || !first_index || !count) return FRC_ERR_ARG;
+  const void* d = nullptr;
+  const int rc = next_chunk(j, 2, &d, first_index, count);
+  *data = static_cast<const float*>(d);
+  return rc;
+}
+
+int frc_chunk_exceptions(frc_job_t* j, const int64_t** index, const double** value, int64_t* count) {
+  if (!j || !index || !value || !count) return FRC_ERR_ARG;
+  *index = nullptr; *value = nullptr; *count = 0;
+  if (j->held_part < 0 || j->sh.exact) return FRC_OK;
+  const Slot& sl = j->parts[j->held_part]->slots[j->held_slot];
+  *index = sl.ex.index;
+  *value = sl.ex.value;
+  *count = std::min<int64_t>(static_cast<int64_t>(*sl.ex.count), sl.ex.cap);
   return FRC_OK;
 }
 
 int frc_restart(frc_job_t* j) {
   if (!j) return FRC_ERR_ARG;
-  JOB_CUDA(j, cudaSetDevice(j->ctx->device));
-  for (auto s : j->ctx->stream) JOB_CUDA(j, cudaStreamSynchronize(s));
-  j->info.kernel_launches = 0;
-  // stream 0 must not start before stream 1 drained (it did: both are idle)
-  int rc = run_embedding(j);
+  DeviceGuard guard;
+  // every stream of every device idle before the buffers are rewritten (peers store into each other's memory)
+  for (auto& p : j->parts) {
+    cudaSetDevice(p->dc->device);
+    for (auto s : p->dc->stream)
+      if (cudaStreamSynchronize(s) != cudaSuccess) return fail(j, FRC_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(cudaGetLastError()));
+    p->info.kernel_launches = 0;
+  }
+  j->next_item = 0;
+  j->held_part = j->held_slot = -1;
+  j->read_mode = 0;
+  j->piece_off = j->piece_end = 0;
+  int rc = for_parts(j, embed_stage1);
   if (rc) return rc;
-  return start_pairs(j);
+  return for_parts(j, launch_part_stage2);
 }
 
 int frc_job_info(const frc_job_t* cj, frc_info_t* info) {
   if (!cj || !info) return FRC_ERR_ARG;
   frc_job* j = const_cast<frc_job*>(cj);
-  if (!j->embed_timed && j->ev_embed1) {
-    cudaSetDevice(j->ctx->device);
-    if (cudaEventSynchronize(j->ev_embed1) == cudaSuccess) {
-      float a = 0.f, b = 0.f;
-      if (cudaEventElapsedTime(&a, j->ev_h2d0, j->ev_h2d1) == cudaSuccess) j->info.h2d_ms = a;
-      if (cudaEventElapsedTime(&b, j->ev_embed0, j->ev_embed1) == cudaSuccess) j->info.embed_ms = b;
-      j->embed_timed = true;
+  DeviceGuard guard;
+  for (auto& p : j->parts) {
+    if (!p->embed_timed && p->ev_embed1) {
+      cudaSetDevice(p->dc->device);
+      if (cudaEventSynchronize(p->ev_embed1) == cudaSuccess) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, p->ev_h2d0, p->ev_h2d1) == cudaSuccess) p->info.h2d_ms = a;
+        if (cudaEventElapsedTime(&b, p->ev_embed0, p->ev_embed1) == cudaSuccess) p->info.embed_ms = b;
+        p->embed_timed = true;
+      }
+      cudaGetLastError();
     }
-    cudaGetLastError();
   }
+  aggregate_info(j);
   *info = j->info;
   return FRC_OK;
 }
 
-void frc_destroy(frc_job_t* j) { destroy_job(j); }
+void frc_destroy(frc_job_t* j) {
+  DeviceGuard guard;
+  destroy_job(j);
+}
 
 int64_t frc_plan_bands(int64_t n_samples, int64_t band_rows, int32_t rank, int32_t world, uint32_t flags,
                        int64_t* first_index, int64_t* count, int64_t cap) {
   if (world <= 0) { world = 1; rank = 0; }
   if (n_samples < 0 || band_rows < 0 || rank < 0 || rank >= world) return -FRC_ERR_ARG;
-  const std::vector<int64_t> brows = band_boundaries(n_samples, band_rows, world, !(flags & FRC_FLAG_NO_D2H));
-  const std::vector<int> owners = band_owners(brows, world);
+  const Knobs knobs = Knobs::read();
+  const std::vector<Band> bands = make_bands(n_samples, band_rows, world, !(flags & FRC_FLAG_NO_D2H), knobs.bands_per_rank, 8);
   int64_t n = 0;
-  for (size_t kb = 0; kb + 1 < brows.size(); ++kb) {
-    const int64_t r0 = brows[kb], r1 = brows[kb + 1];
-    const int64_t first = r0 >= 2 ? tri(r0) : 0;
-    const int64_t cnt = tri(r1) - first;
-    if (cnt <= 0) continue;
-    if (owners[kb] == rank) {
-      if (n < cap && first_index && count) { first_index[n] = first; count[n] = cnt; }
+  for (const Band& b : bands)
+    if (b.owner == rank) {
+      if (n < cap && first_index && count) { first_index[n] = b.first; count[n] = b.count; }
       ++n;
     }
-  }
   return n;
 }
 

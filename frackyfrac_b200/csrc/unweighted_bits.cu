@@ -21,6 +21,7 @@
 
 #include "frc_internal.h"
 #include "ptx.cuh"
+#include "wire.cuh"
 
 namespace frc {
 namespace {
@@ -41,16 +42,6 @@ constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);  // 896
 constexpr int EPI_COLS = 32;
 constexpr int DN = 2 * BN;
 constexpr uint32_t TMEM_COLS = 2 * DN;
-
-__device__ __forceinline__ double widen_f32(float f) {
-  const uint32_t u = __float_as_uint(f);
-  const uint32_t e = (u >> 23) & 0xFFu;
-  uint32_t hi = (u & 0x80000000u) | (((u & 0x7FFFFFFFu) >> 3) + 0x38000000u);
-  uint32_t lo = u << 29;
-  if (e == 0u) { hi = u & 0x80000000u; lo = 0u; }
-  if (e == 0xFFu) { hi = 0x7FF80000u; lo = 0u; }
-  return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
-}
 
 // 4 bits (b0..b3 of `nib`, other bits must be zero) -> byte masks 0xFF / 0x00: one multiply puts bit g
 // into the sign of byte g, one PRMT replicates the signs.
@@ -73,7 +64,7 @@ k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* _
                    const int32_t* __restrict__ chunk_end, const int32_t* __restrict__ chunk_shift,
                    int32_t n_chunks, const long long* __restrict__ r_int, double unit,
                    const Tile* __restrict__ tiles, int32_t n_tiles, int64_t n_samples, int64_t first,
-                   double* __restrict__ out, const double* __restrict__ flag_u_ptr,
+                   float* __restrict__ out, const double* __restrict__ flag_u_ptr,
                    uint32_t* __restrict__ flagged, unsigned long long* __restrict__ n_flagged) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -324,7 +315,7 @@ k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* _
           for (int x = 0; x < 8; ++x) {
             const int64_t i = i0 + n0 + x;
             if (i < n_samples && j < i) {
-              out[off] = widen_f32(dv[x]);
+              out[off] = dv[x];
               if (fu[x]) {
                 unsigned long long slot = atomicAdd(n_flagged, 1ULL);
                 flagged[slot] = static_cast<uint32_t>(off);
@@ -349,7 +340,8 @@ k_unweighted_bits2(const __grid_constant__ CUtensorMap mapBits, const uint8_t* _
 __global__ void __launch_bounds__(256)
 k_unweighted_fixup_bits(const uint32_t* __restrict__ bitsS, int32_t kp, const double* __restrict__ len_col,
                         const uint32_t* __restrict__ flagged, const unsigned long long* __restrict__ n_flagged,
-                        unsigned long long* __restrict__ count_host, int64_t first, double* __restrict__ out) {
+                        unsigned long long* __restrict__ count_host, int64_t first, float* __restrict__ out,
+                        const Exceptions ex) {
   const unsigned long long total = *n_flagged;
   if (blockIdx.x == 0 && threadIdx.x == 0) *count_host = total;
   const int lane = threadIdx.x & 31;
@@ -377,7 +369,7 @@ k_unweighted_fixup_bits(const uint32_t* __restrict__ bitsS, int32_t kp, const do
       uniq += __shfl_xor_sync(0xffffffffu, uniq, o);
       comm += __shfl_xor_sync(0xffffffffu, comm, o);
     }
-    if (lane == 0) out[off] = uniq / (uniq + comm);
+    if (lane == 0) store_fixed(out, off, uniq / (uniq + comm), first, ex);
   }
 }
 
@@ -413,27 +405,34 @@ struct BitsOperands {
   double unit;
 };
 
-BitsOperands* bits_operands_create(const uint32_t* bitsS, int64_t np, int32_t kp, const uint8_t* qa,
-                                   const uint8_t* qh, const uint8_t* ql, const TcChunks& chunks,
-                                   const double* len_col, const double* flag_u, const long long* r_int,
-                                   double unit, std::string* err) {
-  static PFN_tmapEncodeTiled encode = nullptr;
-  if (!encode) {
+static PFN_tmapEncodeTiled g_bits_encode = nullptr;
+
+bool bits_setup(std::string* err) {
+  if (!g_bits_encode) {  // process-wide: the driver entry point
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
     if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
       if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
-      return nullptr;
+      return false;
     }
-    encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
-    e = cudaFuncSetAttribute(k_unweighted_bits2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) {
-      if (err) *err = std::string("cudaFuncSetAttribute(k_unweighted_bits2): ") + cudaGetErrorString(e);
-      encode = nullptr;
-      return nullptr;
-    }
+    g_bits_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
   }
+  // per device context
+  cudaError_t e = cudaFuncSetAttribute(k_unweighted_bits2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("cudaFuncSetAttribute(k_unweighted_bits2): ") + cudaGetErrorString(e);
+    return false;
+  }
+  return true;
+}
+
+BitsOperands* bits_operands_create(const uint32_t* bitsS, int64_t np, int32_t kp, const uint8_t* qa,
+                                   const uint8_t* qh, const uint8_t* ql, const TcChunks& chunks,
+                                   const double* len_col, const double* flag_u, const long long* r_int,
+                                   double unit, std::string* err) {
+  PFN_tmapEncodeTiled encode = g_bits_encode;
+  if (!encode) { if (err) *err = "bits_setup has not run on this device context"; return nullptr; }
   BitsOperands* o = new BitsOperands();
   o->bitsS = bitsS; o->qa = qa; o->qh = qh; o->ql = ql; o->kp = kp; o->chunks = chunks;
   o->len_col = len_col; o->flag_u = flag_u; o->r_int = r_int; o->unit = unit;
@@ -454,7 +453,7 @@ BitsOperands* bits_operands_create(const uint32_t* bitsS, int64_t np, int32_t kp
 void bits_operands_destroy(BitsOperands* o) { delete o; }
 
 int launch_unweighted_bits(const BitsOperands* ops, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
-                           int64_t first, double* out, uint32_t* flagged, unsigned long long* n_flagged,
+                           int64_t first, float* out, uint32_t* flagged, unsigned long long* n_flagged,
                            int num_sms, cudaStream_t s) {
   if (n_tiles <= 0) return 0;
   const int pairs = num_sms / 2;
@@ -467,10 +466,10 @@ int launch_unweighted_bits(const BitsOperands* ops, const Tile* tiles, int32_t n
 }
 
 int launch_unweighted_fixup_bits(const BitsOperands* ops, const uint32_t* flagged, const unsigned long long* n_flagged,
-                                 unsigned long long* count_host, int64_t first, double* out, int num_sms,
-                                 cudaStream_t s) {
+                                 unsigned long long* count_host, int64_t first, float* out, const Exceptions& ex,
+                                 int num_sms, cudaStream_t s) {
   k_unweighted_fixup_bits<<<num_sms * 4, 256, 0, s>>>(ops->bitsS, ops->kp, ops->len_col, flagged, n_flagged, count_host,
-                                                      first, out);
+                                                      first, out, ex);
   return 1;
 }
 

@@ -18,24 +18,8 @@
 //                        scales span more than 2^16.
 //   k_unweighted_tc2<0>  bf16 operands (P exact, len = hi + lo planes), kind::f16 K16, fp32
 //                        accumulators restarted every K-chunk (FRC_FLAG_UW_BF16; negative lengths).
-//   k_unweighted_tc      the first kernel of the round: one CTA per tile, bf16, M128 x N256
-//                        (FRC_TC_CTAS=1; kept as a cross-check), described below.
 //   k_unweighted_fixup   exact fp64 recompute of the pairs the epilogues flag.
 //
-// Single-CTA bf16 kernel (one CTA per SM, persistent over a tile list):
-//   warp 0     TMA producer: per 64-node block loads A = P[j-tile] and, stacked
-//              right behind each other, Bh = (P*hi)[i-tile] and Bl = (P*lo)[i-tile]
-//              (128-byte swizzle) into a 4-stage ring, mbarrier complete_tx.
-//   warp 1     allocates TMEM and issues tcgen05.mma M128 N256 K16 (bf16 -> fp32):
-//              the stacked [Bh; Bl] is ONE 256-row B operand, so A is read from
-//              shared memory once per k-step and the accumulator holds the hi-plane
-//              sums in columns [0,128) and the lo-plane sums in [128,256).
-//              tcgen05.commit frees the stage; one commit per K-chunk publishes
-//              the accumulator buffer.
-//   warps 2-9  epilogue (8 warps = 4 TMEM lane quarters x 2 column halves):
-//              tcgen05.ld the partial sums of each K-chunk and add them into fp32
-//              registers, then the fused ratio epilogue in fp64 and stores into the
-//              flat lower-triangle band buffer (TMEM lane = column sample: coalesced).
 // bf16: why two accumulator halves and K-chunks: the tensor core's fp32 accumulate
 // loses the addend bits below the accumulator's ulp (measured: a bias, not
 // noise).  hi-plane addends are 8-bit significands, so they add EXACTLY while the
@@ -55,186 +39,18 @@
 
 #include "frc_internal.h"
 #include "ptx.cuh"
+#include "wire.cuh"
 
 namespace frc {
 
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
-constexpr int NUM_BARS = 2 * STAGES + 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_BARS * 8 + 16 + 1024;
-constexpr int EPI_WARPS = 8;
 constexpr int EPI_WARP0 = 2;                // warp 0: TMA producer, warp 1: MMA issuer
-constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int DN = 2 * BN;                 // accumulator columns: [hi | lo]
 constexpr uint32_t TMEM_COLS = 2 * DN;    // two buffers: all 512 columns
-
-__global__ void __launch_bounds__(THREADS, 1)
-k_unweighted_tc(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapBh,
-                const __grid_constant__ CUtensorMap mapBl, int32_t n_kblocks, int32_t chunk_kblocks,
-                const double* __restrict__ r, const Tile* __restrict__ tiles, int32_t n_tiles,
-                int64_t n_samples, int64_t first, double* __restrict__ out, double flag_below,
-                uint32_t* __restrict__ flagged, unsigned long long* __restrict__ n_flagged) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = ptx::smem_u32(smem_raw);
-  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
-  uint8_t* smem = smem_raw + pad;
-  const uint32_t smem_base = raw + pad;  // 1024-aligned: required by SWIZZLE_128B
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
-  volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + NUM_BARS * 8);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&mapP);
-    ptx::prefetch_tensormap(&mapBh);
-    ptx::prefetch_tensormap(&mapBl);
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(tfull_bar(b), 1);
-      ptx::mbar_init(tempty_bar(b), EPI_WARPS);  // one arrival per epilogue warp
-    }
-    ptx::fence_barrier_init();
-    ptx::fence_proxy_async();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc<1>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
-    ptx::tmem_relinquish<1>();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int n_chunks = (n_kblocks + chunk_kblocks - 1) / chunk_kblocks;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const Tile tile = tiles[t];
-        const int row_a = tile.tj * BM, row_b = tile.ti * BN;  // lanes = column samples j (coalesced stores)
-        for (int kb = 0; kb < n_kblocks; ++kb) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          ptx::mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          ptx::tma_load_2d(sa, &mapP, full_bar(stage), kb * BK, row_a);
-          ptx::tma_load_2d(sa + A_BYTES, &mapBh, full_bar(stage), kb * BK, row_b);
-          ptx::tma_load_2d(sa + A_BYTES + B_BYTES, &mapBl, full_bar(stage), kb * BK, row_b);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, DN);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t chunk = 0;  // running chunk counter over all tiles of this CTA
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
-          const uint32_t buf = chunk & 1u;
-          ptx::mbar_wait(tempty_bar(buf), ((chunk >> 1) & 1u) ^ 1u);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * DN;
-          const int kb_end = min(n_kblocks, (ch + 1) * chunk_kblocks);
-          for (int kb = ch * chunk_kblocks; kb < kb_end; ++kb) {
-            ptx::mbar_wait(full_bar(stage), phase);
-            ptx::tc_fence_after();
-            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            const uint64_t da = ptx::umma_desc_k_sw128(sa);
-            // Bh and Bl sit back to back: one 256-row K-major operand
-            const uint64_t db = ptx::umma_desc_k_sw128(sa + A_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / UK; ++k) {
-              // advancing 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the
-              // (>>4) start-address field
-              ptx::umma_bf16<1>(d_tmem, da + 2u * k, db + 2u * k, idesc,
-                                (kb > ch * chunk_kblocks || k > 0) ? 1u : 0u);
-            }
-            ptx::umma_commit(empty_bar(stage));  // stage reusable once these MMAs retire
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          }
-          ptx::umma_commit(tfull_bar(buf));  // accumulator of this chunk complete
-        }
-      }
-    }
-  } else if (warp >= EPI_WARP0) {
-    // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int half = (warp - EPI_WARP0) >> 2;  // which 64 columns of each plane it owns
-    uint32_t chunk = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const Tile tile = tiles[t];
-      float acc[64];
-#pragma unroll
-      for (int n = 0; n < 64; ++n) acc[n] = 0.f;
-      for (int ch = 0; ch < n_chunks; ++ch, ++chunk) {
-        const uint32_t buf = chunk & 1u;
-        ptx::mbar_wait(tfull_bar(buf), (chunk >> 1) & 1u);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * DN + half * 64;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t v[16], w[16];
-          ptx::tmem_ld_32x16(taddr + cc * 16, v);
-          ptx::tmem_ld_32x16(taddr + BN + cc * 16, w);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int x = 0; x < 16; ++x)  // round-to-nearest adds: unbiased
-            acc[cc * 16 + x] += __uint_as_float(v[x]) + __uint_as_float(w[x]);
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tempty_bar(buf));
-      }
-      // fused ratio epilogue, fp64: lane = column sample j, registers = 64 row samples i
-      const int64_t j = static_cast<int64_t>(tile.tj) * BM + q * 32 + lane;
-      const int64_t i0 = static_cast<int64_t>(tile.ti) * BN + half * 64;
-      if (j < n_samples && j < i0 + 64) {
-        const double rj = r[j];
-#pragma unroll
-        for (int n = 0; n < 64; ++n) {
-          const int64_t i = i0 + n;
-          if (i < n_samples && j < i) {
-            const double R = r[i] + rj;
-            const double s = static_cast<double>(acc[n]);
-            const double d = (R - 2.0 * s) / (R - s);
-            const int64_t off = i * (i - 1) / 2 - first + j;
-            out[off] = d;
-            if (d < flag_below) {
-              unsigned long long slot = atomicAdd(n_flagged, 1ULL);
-              flagged[slot] = static_cast<uint32_t>(off);
-            }
-          }
-        }
-      }
-    }
-  }
-
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    ptx::tmem_dealloc<1>(tmem_base, TMEM_COLS);
-  }
-}
-
 
 // ----------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): two CTAs of a cluster (one TPC) compute two
@@ -294,22 +110,6 @@ constexpr int EPI2_WARPS = 16;
 constexpr int EPI2_COLS = 128 / (EPI2_WARPS / 4);  // accumulator columns per thread and plane
 constexpr int THREADS2 = 32 * (EPI_WARP0 + EPI2_WARPS);
 
-// Exact float -> double widening with integer instructions only.  On B200 every fp64-pipe
-// instruction (DADD/DFMA/F2F) costs an SM ~4 cycles per warp (measured: the fp64 ratio epilogue
-// took 54k cycles per tile, more than half of the u8 mainloop), so the epilogue keeps fp64 for
-// the one cancellation that needs it (U = R - 2s) and does the rest in fp32 / integers.
-// f is 0, NaN (0/0, A8) or a normal number in [2^-3, 1] here; smaller values are overwritten by
-// the exact fix-up pass.
-__device__ __forceinline__ double widen_f32(float f) {
-  const uint32_t u = __float_as_uint(f);
-  const uint32_t e = (u >> 23) & 0xFFu;
-  uint32_t hi = (u & 0x80000000u) | (((u & 0x7FFFFFFFu) >> 3) + 0x38000000u);
-  uint32_t lo = u << 29;
-  if (e == 0u) { hi = u & 0x80000000u; lo = 0u; }
-  if (e == 0xFFu) { hi = 0x7FF80000u; lo = 0u; }
-  return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
-}
-
 // kMode: 0 = bf16 planes (fp32 accumulators), 1 = u8 planes with fp64 chunk accumulation (chunk scales
 // spanning more than 2^16), 2 = u8 planes with 64-bit INTEGER accumulation and an integer / fp32 ratio
 // epilogue: no fp64 instruction at all (every DADD/DFMA stalls its warp for tens of cycles on B200:
@@ -321,7 +121,7 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
                  const double* __restrict__ chunk_scale, const int32_t* __restrict__ chunk_shift,
                  int32_t n_chunks, int32_t biased, const double* __restrict__ r,
                  const long long* __restrict__ r_int, double unit, const Tile* __restrict__ tiles, int32_t n_tiles,
-                 int64_t n_samples, int64_t first, double* __restrict__ out, double flag_below,
+                 int64_t n_samples, int64_t first, float* __restrict__ out, double flag_below,
                  const double* __restrict__ flag_u_ptr, uint32_t* __restrict__ flagged,
                  unsigned long long* __restrict__ n_flagged, int dbg) {
   (void)dbg;
@@ -540,12 +340,12 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
       TL(const long long c2 = clock64();)
       // this thread's TMEM lane is a COLUMN sample j of the output; its registers run over
       // EPI2_COLS ROW samples i.  For a fixed register the 32 lanes of the warp therefore write
-      // 32 consecutive doubles of one row of the flat triangle: fully coalesced 256-byte stores.
+      // 32 consecutive floats of one row of the flat triangle: fully coalesced 128-byte stores.
       const int64_t j = static_cast<int64_t>(tile.tj + static_cast<int>(cta)) * BM + q * 32 + lane;
       const int64_t i0 = static_cast<int64_t>(tile.ti) * BN + cg * EPI2_COLS;
       static_assert(EPI2_COLS == 32, "r[i] is broadcast from lane n");
       if (TL_ON(4)) {
-        if (acc[0] == static_cast<Acc>(-1.5)) out[0] = 0.0;
+        if (acc[0] == static_cast<Acc>(-1.5)) out[0] = 0.f;
       } else if (static_cast<int64_t>(tile.tj + static_cast<int>(cta)) * BM + q * 32 < i0 + EPI2_COLS) {  // warp-uniform
         int64_t off = i0 * (i0 - 1) / 2 - first + j;  // flat index of (i0, j) relative to the band
         // r is padded to a multiple of the tile size: the loads are in range and coalesced.
@@ -576,7 +376,7 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
             for (int x = 0; x < 8; ++x) {
               const int64_t i = i0 + n0 + x;
               if (i < n_samples && j < i) {
-                out[off] = widen_f32(dv[x]);
+                out[off] = dv[x];  // fp32 is what the ratio is; the host widens (wire.cu)
                 // U and V are exact integer sums of the quantised lengths: no cancellation error, so a
                 // small d needs no recompute here (identical samples give U = 0 exactly); only the
                 // absolute-error rule of the merged small-length columns applies
@@ -607,7 +407,7 @@ k_unweighted_tc2(const __grid_constant__ CUtensorMap mapP, const __grid_constant
             for (int x = 0; x < 8; ++x) {
               const int64_t i = i0 + n0 + x;
               if (i < n_samples && j < i) {
-                out[off] = widen_f32(dv[x]);
+                out[off] = dv[x];  // fp32 is what the ratio is; the host widens (wire.cu)
                 if (dv[x] < flag_d || uv[x] < flag_u) {
                   unsigned long long slot = atomicAdd(n_flagged, 1ULL);
                   flagged[slot] = static_cast<uint32_t>(off);
@@ -644,7 +444,8 @@ template <bool kI8>
 __global__ void __launch_bounds__(256)
 k_unweighted_fixup(const void* __restrict__ Pv, int32_t kp, const double* __restrict__ len_col,
                    const uint32_t* __restrict__ flagged, const unsigned long long* __restrict__ n_flagged,
-                   unsigned long long* __restrict__ count_host, int64_t first, double* __restrict__ out) {
+                   unsigned long long* __restrict__ count_host, int64_t first, float* __restrict__ out,
+                   const Exceptions ex) {
   constexpr int kPer = kI8 ? 16 : 8;  // operand columns per 16-byte load
   const unsigned long long total = *n_flagged;
   if (blockIdx.x == 0 && threadIdx.x == 0) *count_host = total;  // mapped pinned memory
@@ -685,7 +486,7 @@ k_unweighted_fixup(const void* __restrict__ Pv, int32_t kp, const double* __rest
       uniq += __shfl_xor_sync(0xffffffffu, uniq, o);
       comm += __shfl_xor_sync(0xffffffffu, comm, o);
     }
-    if (lane == 0) out[off] = uniq / (uniq + comm);
+    if (lane == 0) store_fixed(out, off, uniq / (uniq + comm), first, ex);
   }
 }
 
@@ -726,28 +527,28 @@ struct TcOperands {
   const double* flag_u;  // device scalar (u8) or null
   const long long* r_int = nullptr;  // u8 integer mode: row sums in units of `unit`
   double unit = 1.0;
+  int dbg = 0;  // FRC_TC_DEBUG (timeline builds), read once per job
 };
 
 bool tc_setup(std::string* err) {
-  if (g_encode) return true;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
-    if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
-    return false;
+  if (!g_encode) {  // process-wide: the driver entry point
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+      if (err) *err = "cuTensorMapEncodeTiled is not available from the driver";
+      return false;
+    }
+    g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
   }
-  g_encode = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
-  e = cudaFuncSetAttribute(k_unweighted_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_unweighted_tc2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+  // per device (function attributes live in the device's context): called once per device context
+  cudaError_t e = cudaFuncSetAttribute(k_unweighted_tc2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_unweighted_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_unweighted_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
   if (e != cudaSuccess) {
-    if (err) *err = std::string("cudaFuncSetAttribute(k_unweighted_tc): ") + cudaGetErrorString(e);
-    g_encode = nullptr;
+    if (err) *err = std::string("cudaFuncSetAttribute(k_unweighted_tc2): ") + cudaGetErrorString(e);
     return false;
   }
   return true;
@@ -756,8 +557,9 @@ bool tc_setup(std::string* err) {
 TcOperands* tc_operands_create(const void* P, const void* Bh, const void* Bl, int64_t np, int32_t kp,
                                bool i8, const TcChunks& chunks, const double* len_col, const double* flag_u,
                                std::string* err) {
-  if (!tc_setup(err)) return nullptr;
+  if (!g_encode) { if (err) *err = "tc_setup has not run on this device context"; return nullptr; }
   TcOperands* o = new TcOperands();
+  if (const char* de = getenv("FRC_TC_DEBUG")) o->dbg = atoi(de);
   o->P = P;
   o->i8 = i8;
   o->kp = kp;
@@ -795,40 +597,31 @@ int tc_chunk_kblocks() {
 }
 
 int launch_unweighted_tc(const TcOperands* ops, const double* r, const Tile* tiles, int32_t n_tiles,
-                         int64_t n_samples, int64_t first, double* out, double flag_below,
-                         uint32_t* flagged, unsigned long long* n_flagged, int num_sms, int ctas,
-                         cudaStream_t s) {
+                         int64_t n_samples, int64_t first, float* out, double flag_below,
+                         uint32_t* flagged, unsigned long long* n_flagged, int num_sms, cudaStream_t s) {
   if (n_tiles <= 0) return 0;
-  if (ctas == 2) {  // `tiles` lists pair tiles (ti even): one cluster of two CTAs each
-    int pairs = num_sms / 2;
-    int grid = 2 * (n_tiles < pairs ? n_tiles : pairs);
-    const TcChunks& c = ops->chunks;
-    const char* de = getenv("FRC_TC_DEBUG");
-    const int dbg = de ? atoi(de) : 0;
+  // `tiles` lists pair tiles (tj even): one cluster of two CTAs each
+  const int pairs = num_sms / 2;
+  const int grid = 2 * (n_tiles < pairs ? n_tiles : pairs);
+  const TcChunks& c = ops->chunks;
 #define FRC_TC2_ARGS ops->mapP, ops->mapBh, ops->mapBl, c.end, c.scale, c.shift, c.n, c.biased ? 1 : 0, r, ops->r_int, \
-                     ops->unit, tiles, n_tiles, n_samples, first, out, flag_below, ops->flag_u, flagged, n_flagged, dbg
-    if (ops->i8 && ops->r_int) k_unweighted_tc2<2><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
-    else if (ops->i8) k_unweighted_tc2<1><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
-    else k_unweighted_tc2<0><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
+                     ops->unit, tiles, n_tiles, n_samples, first, out, flag_below, ops->flag_u, flagged, n_flagged, ops->dbg
+  if (ops->i8 && ops->r_int) k_unweighted_tc2<2><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
+  else if (ops->i8) k_unweighted_tc2<1><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
+  else k_unweighted_tc2<0><<<grid, THREADS2, SMEM2_BYTES, s>>>(FRC_TC2_ARGS);
 #undef FRC_TC2_ARGS
-    return 1;
-  }
-  int grid = n_tiles < num_sms ? n_tiles : num_sms;
-  k_unweighted_tc<<<grid, THREADS, SMEM_BYTES, s>>>(ops->mapP, ops->mapBh, ops->mapBl, ops->kp / BK,
-                                                    tc_chunk_kblocks(), r, tiles, n_tiles, n_samples,
-                                                    first, out, flag_below, flagged, n_flagged);
   return 1;
 }
 
 int launch_unweighted_fixup(const TcOperands* ops, const uint32_t* flagged, const unsigned long long* n_flagged,
-                            unsigned long long* count_host, int64_t first, double* out, int num_sms,
-                            cudaStream_t s) {
+                            unsigned long long* count_host, int64_t first, float* out, const Exceptions& ex,
+                            int num_sms, cudaStream_t s) {
   if (ops->i8)
     k_unweighted_fixup<true><<<num_sms * 4, 256, 0, s>>>(ops->P, ops->kp, ops->len_col, flagged, n_flagged,
-                                                         count_host, first, out);
+                                                         count_host, first, out, ex);
   else
     k_unweighted_fixup<false><<<num_sms * 4, 256, 0, s>>>(ops->P, ops->kp, ops->len_col, flagged, n_flagged,
-                                                          count_host, first, out);
+                                                          count_host, first, out, ex);
   return 1;
 }
 

@@ -19,6 +19,7 @@
 // running sums into 64 totals every 256 nodes) to keep fp32 summation error
 // well under the 1e-5 budget for contractions of 10^5..10^6 nodes.
 #include "frc_internal.h"
+#include "wire.cuh"
 
 namespace frc {
 namespace {
@@ -48,7 +49,7 @@ template <bool kPrescaled>
 __global__ void __launch_bounds__(256, 1)
 k_weighted_tiles(const float* __restrict__ A, int64_t ld, int32_t kp, const float* __restrict__ lenf,
                  const double* __restrict__ W, const Tile* __restrict__ tiles, int64_t n_samples,
-                 int64_t first, double* __restrict__ out, double flag_below, uint32_t* __restrict__ flagged,
+                 int64_t first, float* __restrict__ out, double flag_below, uint32_t* __restrict__ flagged,
                  unsigned long long* __restrict__ n_flagged) {
   extern __shared__ __align__(16) float smem[];
   const Tile tile = tiles[blockIdx.x];
@@ -128,13 +129,13 @@ k_weighted_tiles(const float* __restrict__ A, int64_t ld, int32_t kp, const floa
     const int64_t i = i0 + (a < 4 ? ty * 4 + a : 64 + ty * 4 + (a - 4));
     if (i >= n_samples) continue;
     const double wi = W[i];
-    double* orow = out + (i * (i - 1) / 2 - first);
+    float* orow = out + (i * (i - 1) / 2 - first);
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
       const int64_t j = j0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + (b - 4));
       if (j < i) {
         const double d = static_cast<double>(tot[a][b] + acc[a][b]) / (wi + W[j]);
-        orow[j] = d;
+        orow[j] = static_cast<float>(d);  // fp32 numerator: fp32 is what the value carries (wire.cu)
         // fp32 operands carry 6e-8 relative error each, so the L1 numerator is off by up to
         // 6e-8 * (W_i + W_j) = 6e-8 / d relative: small distances are recomputed (k_weighted_fixup)
         if (d < flag_below) {
@@ -158,7 +159,7 @@ k_weighted_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict_
                  const double* __restrict__ length, int32_t n_nodes, const double* __restrict__ total,
                  const double* __restrict__ W, const uint32_t* __restrict__ flagged,
                  const unsigned long long* __restrict__ n_flagged, unsigned long long* __restrict__ count_host,
-                 int64_t first, long long* __restrict__ ws, double* __restrict__ out) {
+                 int64_t first, long long* __restrict__ ws, float* __restrict__ out, const Exceptions ex) {
   __shared__ double red[8];
   const unsigned long long n = *n_flagged;
   if (blockIdx.x == 0 && threadIdx.x == 0) *count_host = n;  // mapped pinned memory
@@ -217,7 +218,7 @@ k_weighted_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict_
     if (threadIdx.x == 0) {
       double tot = 0.0;
       for (int k = 0; k < 8; ++k) tot += red[k];
-      out[off] = tot / (W[i] + W[j]);
+      store_fixed(out, off, tot / (W[i] + W[j]), first, ex);
     }
     __syncthreads();
   }
@@ -227,10 +228,10 @@ k_weighted_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict_
 
 int launch_weighted_fixup(const DevCsr& a, const DevTree& t, const double* total, const double* W,
                           const uint32_t* flagged, const unsigned long long* n_flagged,
-                          unsigned long long* count_host, int64_t first, long long* ws, int ws_ctas, double* out,
-                          cudaStream_t s) {
+                          unsigned long long* count_host, int64_t first, long long* ws, int ws_ctas, float* out,
+                          const Exceptions& ex, cudaStream_t s) {
   k_weighted_fixup<<<ws_ctas, 256, 0, s>>>(a.row_ptr, a.col, a.val, t.parent, t.length, t.n_nodes, total, W, flagged,
-                                           n_flagged, count_host, first, ws, out);
+                                           n_flagged, count_host, first, ws, out, ex);
   return 1;
 }
 
@@ -241,8 +242,9 @@ void weighted_setup() {
 
 int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
                           const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
-                          int64_t first, double* out, double flag_below, uint32_t* flagged,
-                          unsigned long long* n_flagged, cudaStream_t s) {
+                          int64_t first, float* out, double flag_below, uint32_t* flagged,
+                          unsigned long long* n_flagged, int num_sms, cudaStream_t s) {
+  (void)num_sms;
   if (n_tiles <= 0) return 0;
   if (prescaled)
     k_weighted_tiles<true><<<n_tiles, 256, SMEM_BYTES, s>>>(A, ld, kp, lenf, W, tiles, n_samples, first, out,

@@ -25,9 +25,11 @@ FLAG_SHARD_EMBED = 4
 FLAG_UW_BITS = 8
 COMM_ID_BYTES = 128
 
-EXPORTS = ["frc_abi_version", "frc_ctx_create", "frc_ctx_destroy", "frc_create", "frc_next",
-           "frc_restart", "frc_job_info", "frc_destroy", "frc_last_error", "frc_plan_bands",
-           "frc_comm_unique_id", "frc_ctx_comm_init"]
+NORM_L_AS_CODED, NORM_DEFAULT, NORM_L_DOCUMENTED = 0, 1, 2  # frc_opts_t.normalize
+
+EXPORTS = ["frc_abi_version", "frc_ctx_create", "frc_ctx_create_multi", "frc_ctx_destroy", "frc_create", "frc_next",
+           "frc_next_f32", "frc_chunk_exceptions", "frc_restart", "frc_job_info", "frc_destroy", "frc_last_error",
+           "frc_plan_bands", "frc_comm_unique_id", "frc_ctx_comm_init"]
 
 
 class FrcError(RuntimeError):
@@ -48,7 +50,8 @@ class _Csr(C.Structure):
 class _Opts(C.Structure):
     _fields_ = [("mode", C.c_int32), ("normalize", C.c_int32), ("path", C.c_int32),
                 ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("band_rows", C.c_int64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("band_rows", C.c_int64), ("flags", C.c_uint32), ("n_devices", C.c_int32),
+                ("devices", C.c_void_p)]
 
 
 class _Info(C.Structure):
@@ -58,7 +61,8 @@ class _Info(C.Structure):
                 ("embed_ms", C.c_double), ("pairs_ms", C.c_double), ("fixup_ms", C.c_double),
                 ("run_ms", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("embed_bytes", C.c_int64), ("flagged_pairs", C.c_int64),
-                ("operand_kind", C.c_int64), ("gather_bytes", C.c_int64)]
+                ("operand_kind", C.c_int64), ("gather_bytes", C.c_int64), ("n_devices", C.c_int32),
+                ("value_bytes", C.c_int32), ("exceptions", C.c_int64), ("create_ms", C.c_double)]
 
 
 @dataclass
@@ -82,6 +86,10 @@ class JobInfo:
     flagged_pairs: int
     operand_kind: int
     gather_bytes: int
+    n_devices: int
+    value_bytes: int
+    exceptions: int
+    create_ms: float
 
 
 _lib = None
@@ -97,11 +105,14 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.frc_abi_version.restype = C.c_int
         L.frc_ctx_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
+        L.frc_ctx_create_multi.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
         L.frc_ctx_destroy.argtypes = [C.c_void_p]
         L.frc_ctx_destroy.restype = None
         L.frc_create.argtypes = [C.c_void_p, C.POINTER(_Tree), C.POINTER(_Csr), C.POINTER(_Opts),
                                  C.POINTER(C.c_void_p)]
         L.frc_next.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.frc_next_f32.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.frc_chunk_exceptions.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.frc_restart.argtypes = [C.c_void_p]
         L.frc_job_info.argtypes = [C.c_void_p, C.POINTER(_Info)]
         L.frc_destroy.argtypes = [C.c_void_p]
@@ -118,16 +129,23 @@ def lib():
 
 
 class Context:
-    """Reusable device context (streams + memory pools)."""
+    """Reusable context (streams + memory pools) over one GPU, or over several GPUs of this process
+    (`devices`: a list of ordinals, or -1 for every visible sm_100 device)."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device: int = -1, devices=None):
         # several ranks on one host (torchrun): split the host cores between their worker pools
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-        if local_world > 1 and "FRC_HOST_THREADS" not in os.environ:
+        if local_world > 1 and "FRC_HOST_THREADS" not in os.environ and devices is None:
             cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             os.environ["FRC_HOST_THREADS"] = str(max(2, min(16, cores // local_world)))
         h = C.c_void_p()
-        rc = lib().frc_ctx_create(device, C.byref(h))
+        if devices is None:
+            rc = lib().frc_ctx_create(device, C.byref(h))
+        elif devices == -1:
+            rc = lib().frc_ctx_create_multi(-1, None, C.byref(h))
+        else:
+            ids = np.ascontiguousarray(devices, np.int32)
+            rc = lib().frc_ctx_create_multi(len(ids), ids.ctypes.data, C.byref(h))
         if rc:
             raise FrcError(rc, lib().frc_last_error(None).decode())
         self.h = h
@@ -162,9 +180,12 @@ def comm_unique_id() -> bytes:
 class Job:
     """One unifrac() call.  Iterate `chunks()` for (first_index, ndarray) runs."""
 
-    def __init__(self, parent, length, row_ptr, col, val, *, weighted: bool, normalize: bool = True,
+    def __init__(self, parent, length, row_ptr, col, val, *, weighted: bool, normalize=True,
                  path: int = PATH_AUTO, ctx: Context | None = None, device: int = -1, rank: int = 0,
-                 world: int = 1, band_rows: int = 0, flags: int = 0):
+                 world: int = 1, band_rows: int = 0, flags: int = 0, devices=None):
+        """normalize: True / 1 = default; False / 0 = flag -l as CODED in the reference (unsorted merge-join,
+        exact path only); 2 = flag -l as documented.  devices: None = one GPU (`device` or the context's);
+        a list of ordinals or -1 (all) = this process drives several GPUs, one ordered stream."""
         self._keep = [np.ascontiguousarray(parent, np.int32), np.ascontiguousarray(length, np.float64),
                       np.ascontiguousarray(row_ptr, np.int64), np.ascontiguousarray(col, np.int32),
                       np.ascontiguousarray(val, np.float64)]
@@ -175,8 +196,16 @@ class Job:
             raise ValueError("CSR arrays are inconsistent")
         t = _Tree(len(p), p.ctypes.data, l.ctypes.data)
         a = _Csr(max(len(rp) - 1, 0), rp.ctypes.data if len(rp) else None, c.ctypes.data, v.ctypes.data)
-        o = _Opts(WEIGHTED if weighted else UNWEIGHTED, 1 if normalize else 0, path, device, rank, world,
-                  band_rows, flags, 0)
+        norm = int(normalize) if not isinstance(normalize, bool) else (1 if normalize else 0)
+        ids = None
+        if devices is None:
+            nd, dp = 0, None
+        elif devices == -1:
+            nd, dp = -1, None
+        else:
+            ids = np.ascontiguousarray(devices, np.int32)
+            nd, dp = len(ids), ids.ctypes.data
+        o = _Opts(WEIGHTED if weighted else UNWEIGHTED, norm, path, device, rank, world, band_rows, flags, nd, dp)
         self.h = C.c_void_p()
         self.flags = flags
         self.ctx = ctx
@@ -187,12 +216,31 @@ class Job:
         self._keep = None  # inputs were copied
 
     def next_raw(self):
-        """(address, first_index, count) of the next chunk; count == 0 at the end."""
+        """(address, first_index, count) of the next float64 chunk; count == 0 at the end."""
         d, f, n = C.c_void_p(), C.c_int64(), C.c_int64()
         rc = lib().frc_next(self.h, C.byref(d), C.byref(f), C.byref(n))
         if rc:
             raise FrcError(rc, lib().frc_last_error(self.h).decode())
         return d.value, f.value, n.value
+
+    def next_raw_f32(self):
+        """(address, first_index, count) of the next float32 band (fast paths); count == 0 at the end."""
+        d, f, n = C.c_void_p(), C.c_int64(), C.c_int64()
+        rc = lib().frc_next_f32(self.h, C.byref(d), C.byref(f), C.byref(n))
+        if rc:
+            raise FrcError(rc, lib().frc_last_error(self.h).decode())
+        return d.value, f.value, n.value
+
+    def exceptions(self):
+        """(flat indices, float64 values) of the last float32 band that fp32 could not carry."""
+        i, v, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        rc = lib().frc_chunk_exceptions(self.h, C.byref(i), C.byref(v), C.byref(n))
+        if rc:
+            raise FrcError(rc, lib().frc_last_error(self.h).decode())
+        if n.value == 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.float64)
+        return (np.ctypeslib.as_array(C.cast(i, C.POINTER(C.c_int64)), shape=(n.value,)).copy(),
+                np.ctypeslib.as_array(C.cast(v, C.POINTER(C.c_double)), shape=(n.value,)).copy())
 
     def chunks(self, copy: bool = True):
         if self.flags & FLAG_NO_D2H:
@@ -204,11 +252,26 @@ class Job:
             a = np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_double)), shape=(n,))
             yield first, (a.copy() if copy else a)
 
-    def drain(self) -> int:
-        """Runs the stream to its end without touching the data; returns pairs seen."""
+    def chunks_f32(self, copy: bool = True):
+        """Float32 bands of a fast-path job straight from the pinned ring (no host widening pass)."""
+        if self.flags & FLAG_NO_D2H:
+            raise RuntimeError("chunks_f32() needs host output; this job keeps distances in HBM")
+        while True:
+            addr, first, n = self.next_raw_f32()
+            if n == 0:
+                return
+            a = np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_float)), shape=(n,))
+            yield first, (a.copy() if copy else a)
+
+    def drain(self, f32=None) -> int:
+        """Runs the stream to its end without touching the data; returns pairs seen.  f32: which call
+        to drain with (default: the job's native format: float32 on the fast paths)."""
+        if f32 is None:
+            f32 = self.info().value_bytes == 4
+        nxt = self.next_raw_f32 if f32 else self.next_raw
         total = 0
         while True:
-            _, _, n = self.next_raw()
+            _, _, n = nxt()
             if n == 0:
                 return total
             total += n
@@ -252,7 +315,7 @@ def plan_bands(n_samples: int, rank: int = 0, world: int = 1, band_rows: int = 0
     return first, count
 
 
-def unifrac(parent, length, row_ptr, col, val, weighted: bool, normalize: bool = True, **kw) -> np.ndarray:
+def unifrac(parent, length, row_ptr, col, val, weighted: bool, normalize=True, **kw) -> np.ndarray:
     """All n(n-1)/2 distances (this rank's bands; zeros elsewhere when world > 1)."""
     n = max(len(row_ptr) - 1, 0)
     out = np.zeros(n * (n - 1) // 2 if n >= 2 else 0, np.float64)

@@ -3,6 +3,7 @@
 // this image has no Go toolchain; INTEGRATION.md shows the cgo patch that makes
 // the real Go main call the same C ABI.  The only thing replaced is the body
 // of unifrac() (frcfrc.go:58): it now pulls ordered chunks from libfrcfrc_cuda.
+#include <algorithm>
 #include <cerrno>
 #include <chrono>
 #include <cstdio>
@@ -128,23 +129,43 @@ int main(int argc, char** argv) {
     frc_csr_t fc{tab.n_samples(), csr.row_ptr.data(), csr.col.data(), csr.val.data()};
     frc_opts_t fo{};
     fo.mode = fl.wgt ? FRC_WEIGHTED : FRC_UNWEIGHTED;
+    // -l: the reference's behaviour as coded (normalize = 0: unifrac.go:108-110 skips the id-sort together with
+    // the normalisation).  FRCFRC_L=documented selects what the flag's help text says (sorted lists, raw values).
     fo.normalize = fl.nnorm ? 0 : 1;
+    if (fl.nnorm)
+      if (const char* e = getenv("FRCFRC_L")) fo.normalize = !strcmp(e, "documented") ? 2 : 0;
     fo.path = FRC_PATH_AUTO;
     if (const char* e = getenv("FRCFRC_PATH")) fo.path = !strcmp(e, "exact") ? FRC_PATH_EXACT : !strcmp(e, "fast") ? FRC_PATH_FAST : FRC_PATH_AUTO;
     fo.device = -1;
     fo.world = 1;
+    // every visible B200 works on the job; the engine hands their bands out as ONE ordered stream
+    // (FRCFRC_DEVICES=n limits it to the first n; tiny inputs are not worth more than one context)
+    fo.n_devices = -1;
+    if (const char* e = getenv("FRCFRC_DEVICES")) fo.n_devices = std::max(1, atoi(e));
+    else if (static_cast<double>(tab.n_samples()) * static_cast<double>(tab.n_samples()) * static_cast<double>(tree.parent.size()) < 4e12)
+      fo.n_devices = 1;
     frc_job_t* job = nullptr;
     if (frc_create(nullptr, &ft, &fc, &fo, &job) != FRC_OK) die(frc_last_error(nullptr));
     lap("frc_create (+ CUDA init)");
     fputs("Calculating distances\n", stderr);
+    frc_info_t info;
+    frc_job_info(job, &info);
+    const bool f32 = info.value_bytes == 4;  // fast paths deliver fp32: format straight from the pinned ring
     std::vector<std::string> parts;  // one formatted piece per -p worker, written in order
     for (;;) {
-      const double* d; int64_t first, n;
+      const double* d = nullptr; const float* f = nullptr; int64_t first, n;
       auto a0 = std::chrono::steady_clock::now();
-      if (frc_next(job, &d, &first, &n) != FRC_OK) { std::string m = frc_last_error(job); frc_destroy(job); die(m); }
+      const int rc = f32 ? frc_next_f32(job, &f, &first, &n) : frc_next(job, &d, &first, &n);
+      if (rc != FRC_OK) { std::string m = frc_last_error(job); frc_destroy(job); die(m); }
       if (n == 0) break;
       auto a1 = std::chrono::steady_clock::now();
-      frchost::format_parts_parallel(d, n, static_cast<int>(fl.nt), parts);  // -p threads format, one writer
+      if (f32) {
+        const int64_t* xi = nullptr; const double* xv = nullptr; int64_t nx = 0;
+        frc_chunk_exceptions(job, &xi, &xv, &nx);
+        frchost::format_parts_parallel_f32(f, n, first, xi, xv, nx, static_cast<int>(fl.nt), parts);
+      } else {
+        frchost::format_parts_parallel(d, n, static_cast<int>(fl.nt), parts);  // -p threads format, one writer
+      }
       auto a2 = std::chrono::steady_clock::now();
       std::string werr;
       try {

@@ -508,34 +508,54 @@ int format_go(double v, char* buf) {
   return o;
 }
 
-void append_lines(const double* d, int64_t n, std::string& out) {
+template <class T>
+static void append_lines_t(const T* d, int64_t n, std::string& out) {
   // formatted in blocks on the stack: one append per ~200 values instead of one per line
   char b[8192];
   size_t o = 0;
   for (int64_t k = 0; k < n; ++k) {
     if (o + 40 > sizeof b) { out.append(b, o); o = 0; }
-    o += static_cast<size_t>(format_go(d[k], b + o));
+    o += static_cast<size_t>(format_go(static_cast<double>(d[k]), b + o));  // (float: widened exactly, as Go's float64(f))
     b[o++] = '\n';
   }
   out.append(b, o);
 }
 
-void format_parts_parallel(const double* d, int64_t n, int threads, std::vector<std::string>& parts) {
+void append_lines(const double* d, int64_t n, std::string& out) { append_lines_t(d, n, out); }
+
+template <class T>
+static void format_parts_parallel_t(const T* d, int64_t n, int threads, std::vector<std::string>& parts) {
   if (threads < 1) threads = 1;
   if (n < 4096) threads = 1;
   threads = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(threads, n / 2048)));
   if (static_cast<int>(parts.size()) < threads) parts.resize(threads);
   for (auto& p : parts) p.clear();  // (capacity is kept: a caller that reuses `parts` allocates once)
-  if (threads == 1) { append_lines(d, n, parts[0]); return; }
+  if (threads == 1) { append_lines_t(d, n, parts[0]); return; }
   std::vector<std::thread> th;
   for (int t = 0; t < threads; ++t) {
     const int64_t b = n * t / threads, e = n * (t + 1) / threads;
     th.emplace_back([&, t, b, e] {
       parts[t].reserve(static_cast<size_t>(e - b) * 20);
-      append_lines(d + b, e - b, parts[t]);
+      append_lines_t(d + b, e - b, parts[t]);
     });
   }
   for (auto& x : th) x.join();
+}
+
+void format_parts_parallel(const double* d, int64_t n, int threads, std::vector<std::string>& parts) {
+  format_parts_parallel_t(d, n, threads, parts);
+}
+
+void format_parts_parallel_f32(const float* d, int64_t n, int64_t first_index, const int64_t* ex_index,
+                               const double* ex_value, int64_t n_ex, int threads, std::vector<std::string>& parts) {
+  if (n_ex <= 0) { format_parts_parallel_t(d, n, threads, parts); return; }
+  // (rare: distances below fp32's range travel beside the band as doubles)
+  std::vector<double> wide(d, d + n);
+  for (int64_t k = 0; k < n_ex; ++k) {
+    const int64_t at = ex_index[k] - first_index;
+    if (at >= 0 && at < n) wide[at] = ex_value[k];
+  }
+  format_parts_parallel_t(wide.data(), n, threads, parts);
 }
 
 void format_lines_parallel(const double* d, int64_t n, int threads, std::string& out) {

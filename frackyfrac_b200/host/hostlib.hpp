@@ -64,6 +64,11 @@ void format_lines_parallel(const double* d, int64_t n, int threads, std::string&
 // as it is, which spares a single-threaded concatenation of the whole band (250 MB of text at cfg2).
 // Unused trailing entries of `parts` are left empty; reusing `parts` across calls reuses its buffers.
 void format_parts_parallel(const double* d, int64_t n, int threads, std::vector<std::string>& parts);
+// The same for a float32 band of the fast paths (frc_next_f32): every value is widened exactly (Go's float64(f))
+// and printed as that double, i.e. the bytes `frc_next` + format_parts_parallel would give, without the widening
+// pass over memory.  ex_* are the band's fp32 exceptions (frc_chunk_exceptions; usually none).
+void format_parts_parallel_f32(const float* d, int64_t n, int64_t first_index, const int64_t* ex_index,
+                               const double* ex_value, int64_t n_ex, int threads, std::vector<std::string>& parts);
 
 // aio.Open stand-in (frcfrc.go:93,109): the whole file, decoded by suffix (".gz", ".zst"); "" = stdin.
 std::string read_file(const std::string& path);

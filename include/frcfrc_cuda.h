@@ -18,6 +18,13 @@
  *     no CPU fallback anywhere behind this ABI.
  *   - entry points of one job/context must be called from one host thread at a
  *     time.
+ *   - the calling thread's current CUDA device is the same after every call as
+ *     before it (a job may drive several devices).
+ *
+ * ABI v2 (this file) over v1: frc_opts_t gained n_devices / devices (one process,
+ * several GPUs, ONE ordered stream), `normalize` gained the value 2, frc_next_f32 /
+ * frc_chunk_exceptions deliver the fast paths' native fp32 distances without the
+ * host widening pass, frc_ctx_create_multi.
  */
 #ifndef FRCFRC_CUDA_H
 #define FRCFRC_CUDA_H
@@ -29,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FRC_ABI_VERSION 1
+#define FRC_ABI_VERSION 2
 
 typedef enum {
   FRC_OK = 0,
@@ -97,15 +104,28 @@ typedef struct {
 
 typedef struct {
   int32_t mode;       /* frc_mode                                               */
-  int32_t normalize;  /* 1 = default; 0 = flag -l (frcfrc.go:25, unifrac.go:108) */
+  int32_t normalize;  /* flag -l (frcfrc.go:25):
+                         1 = no -l: sort + divide by the all-node total (unifrac.go:56-67)
+                         0 = -l AS CODED in the reference: normalizeFlatNodes is skipped
+                             (unifrac.go:108-110) and with it the id-sort (:57), so the
+                             merge-join (:178-203) walks POST-ORDER lists and mis-pairs nodes;
+                             reproduced bit for bit by a dedicated kernel (csrc/exact.cu)
+                         2 = -l as documented: id-sorted lists, raw values
+                         0 and 2 need mode == FRC_WEIGHTED (frcfrc.go:84-86)            */
   int32_t path;       /* frc_path                                               */
-  int32_t device;     /* CUDA device ordinal; -1 = current device               */
-  int32_t rank;       /* tile-band sharding over `world` processes (one per GPU): */
-  int32_t world;      /*   bands are dealt 0..G-1,G-1..0,...; 0/1 = all bands     */
+  int32_t device;     /* CUDA device ordinal; -1 = current device (n_devices <= 1) */
+  int32_t rank;       /* tile-band sharding over `world` PROCESSES (one per GPU):  */
+  int32_t world;      /*   bands are dealt to the least loaded rank; 0/1 = all bands */
   int64_t band_rows;  /* rows of the lower triangle per output chunk; 0 = auto
                          (bands of equal pair count, see frc_plan_bands)        */
   uint32_t flags;     /* FRC_FLAG_*                                             */
-  uint32_t reserved;
+  int32_t n_devices;  /* 0 / 1: one GPU (`device`).  > 1: THIS process drives that many GPUs:
+                         one validation + staging pass, per-device uploads / embedding / tile
+                         bands / pinned rings, and frc_next hands the bands out in flat-index
+                         order from their owners' rings -- one ordered stream behind the seam
+                         (frcfrc.go:58-62).  -1 = every visible sm_100 device.  Needs
+                         world <= 1.  Ignored when `ctx` is given (the context's devices).  */
+  const int32_t *devices; /* [n_devices] ordinals; NULL = 0 .. n_devices-1      */
 } frc_opts_t;
 
 typedef struct frc_ctx frc_ctx_t; /* device + streams + reusable memory pools  */
@@ -122,8 +142,11 @@ typedef struct {
   int64_t n_nodes_padded;  /* contraction length the pair kernel runs over      */
   int64_t kernel_launches; /* kernels of this library launched so far           */
   double h2d_ms, embed_ms;  /* device time (CUDA events) of the upload / embedding */
-  double pairs_ms;          /* sum over delivered bands of the pair kernel's time  */
-  double fixup_ms;          /* same for the exact fix-up pass (fast unweighted)    */
+  double pairs_ms;          /* sum over delivered bands of (band start -> pair kernel end) on the band's
+                               stream: the kernel's own time when the job runs ONE band with
+                               FRC_FLAG_NO_D2H (bench.py's roofline leg); with several bands in flight
+                               the spans overlap and the sum is only an upper bound        */
+  double fixup_ms;          /* same for (pair kernel end -> fix-up end)                   */
   double run_ms;            /* embedding start -> last band (and its D2H) done;
                                valid once the stream has been read to its end      */
   int64_t h2d_bytes, d2h_bytes;
@@ -131,7 +154,11 @@ typedef struct {
   int64_t flagged_pairs;   /* fast unweighted: pairs recomputed exactly (d tiny) */
   int64_t operand_kind;    /* fast unweighted: 1 = bf16 hi/lo planes, 2 = u8 block floating
                               point, 3 = u8 expanded in-kernel from bits; 0 otherwise */
-  int64_t gather_bytes;    /* bytes this rank received in the embedding all-gather  */
+  int64_t gather_bytes;    /* bytes this rank received in the embedding exchange    */
+  int32_t n_devices;       /* GPUs this job drives (1 unless opts.n_devices > 1)     */
+  int32_t value_bytes;     /* bytes per distance on PCIe / in HBM: 4 (fast paths, fp32) or 8 (exact) */
+  int64_t exceptions;      /* distances delivered so far that fp32 could not carry (frc_chunk_exceptions) */
+  double create_ms;        /* host wall clock of frc_create                          */
 } frc_info_t;
 
 int frc_abi_version(void);
@@ -139,6 +166,11 @@ int frc_abi_version(void);
 /* Optional reusable context.  A job created with ctx == NULL owns a private
  * one.  Reusing a context across jobs reuses its device / pinned allocations. */
 int frc_ctx_create(int32_t device, frc_ctx_t **out);
+/* A context over several GPUs of this process (opts.n_devices semantics: n_devices == -1 = all
+ * visible sm_100 devices, devices == NULL = ordinals 0..n-1).  Peer access between the devices is
+ * enabled when the hardware allows it (the sharded embedding then stores its bit columns straight
+ * into every device's HBM over NVLink); without it every device rebuilds the whole embedding. */
+int frc_ctx_create_multi(int32_t n_devices, const int32_t *devices, frc_ctx_t **out);
 void frc_ctx_destroy(frc_ctx_t *ctx);
 
 /* Multi-GPU, one process per GPU.  frc_comm_unique_id produces the 128-byte NCCL id on one
@@ -162,8 +194,23 @@ int frc_create(frc_ctx_t *ctx, const frc_tree_t *tree, const frc_csr_t *abnd,
  * until the next call on this job.  *count == 0 means the stream has ended.
  * A run is one tile band of the plan (frc_plan_bands) or, for the fast paths on
  * the host route, a piece of one of at most 2^21 values: those distances cross
- * PCIe as fp32 and are widened here into a cache-sized buffer (csrc/wire.cu). */
+ * PCIe as fp32 and are widened here into a cache-sized buffer (csrc/wire.cu).
+ * With FRC_FLAG_NO_D2H only exact-path jobs can be read through this call (device
+ * doubles); fast-path jobs keep fp32 in HBM: frc_next_f32. */
 int frc_next(frc_job_t *job, const double **data, int64_t *first_index, int64_t *count);
+
+/* The same stream in the fast paths' native precision.  The tensor-core and FP32 tile kernels
+ * produce fp32 ratios and store them as fp32, a band crosses PCIe as 4 bytes per pair, and this call
+ * hands out the pinned landing buffer itself: one run per band, no host pass over the data.  (frc_next
+ * on a fast-path job widens the same fp32 values into doubles on the host, so both calls deliver the
+ * same numbers.)  Exact-path jobs are float64 only: FRC_ERR_STATE.  The two calls may not be mixed
+ * on one pass of a job.  With FRC_FLAG_NO_D2H `*data` is a device pointer. */
+int frc_next_f32(frc_job_t *job, const float **data, int64_t *first_index, int64_t *count);
+
+/* Distances of the run returned by the LAST frc_next_f32 call that fp32 cannot carry to 2^-23
+ * relative (|d| < 1.2e-38, only ever produced by the exact fix-up passes on pathological trees):
+ * their flat indices and float64 values.  frc_next applies them itself.  Usually *count == 0. */
+int frc_chunk_exceptions(frc_job_t *job, const int64_t **index, const double **value, int64_t *count);
 
 /* Re-runs embedding + pair stage on the inputs already resident in HBM
  * (benchmarking the device path without the host→device copy). */

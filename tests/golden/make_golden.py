@@ -33,7 +33,9 @@ def answers(stem, tree_text, table_text, sparse):
     tree = orc.Tree.parse(tree_text)
     tab = orc.Table.parse(table_text, sparse)
     orc.validate_species(tab, tree)
-    for tag, weighted, normalize in (("uw", False, 1), ("w", True, 1), ("wl", True, 2)):
+    # wl = flag -l as CODED in the reference (normalize 0: post-order lists, unifrac.go:57,108-110) -- what `frcfrc -w -l`
+    # prints; wl2 = flag -l as documented (normalize 2: sorted lists, raw values)
+    for tag, weighted, normalize in (("uw", False, 1), ("w", True, 1), ("wl", True, 0), ("wl2", True, 2)):
         d = orc.unifrac(tab, tree, weighted, normalize, 1)
         write(f"{stem}.{tag}.want", "".join(orc.format_go(float(v)) + "\n" for v in d))
 

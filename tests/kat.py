@@ -24,10 +24,11 @@ def sparse_text(abnd):
     return "".join("\t".join(f"{k}:{v}" for k, v in m.items()) + "\n" for m in abnd)
 
 
-# (fixture, table suffix, sparse, want tag, weighted, unnormalised): tests/golden/make_golden.py (oracle answers on
-# seeded synthetic inputs, committed)
-SYNTH = [("synth_a", ".sparse", True, "uw", False, False), ("synth_a", ".dense", False, "uw", False, False),
-         ("synth_a", ".sparse", True, "w", True, False), ("synth_a", ".dense", False, "w", True, False),
-         ("synth_a", ".sparse", True, "wl", True, True),
-         ("synth_b", ".sparse", True, "uw", False, False), ("synth_b", ".sparse", True, "w", True, False),
-         ("synth_b", ".sparse", True, "wl", True, True)]
+# (fixture, table suffix, sparse, want tag, weighted, normalize): tests/golden/make_golden.py (oracle answers on
+# seeded synthetic inputs, committed).  normalize: 1 = default, 0 = flag -l as coded in the reference (what the CLI
+# prints for -l), 2 = flag -l as documented (FRCFRC_L=documented)
+SYNTH = [("synth_a", ".sparse", True, "uw", False, 1), ("synth_a", ".dense", False, "uw", False, 1),
+         ("synth_a", ".sparse", True, "w", True, 1), ("synth_a", ".dense", False, "w", True, 1),
+         ("synth_a", ".sparse", True, "wl", True, 0), ("synth_a", ".sparse", True, "wl2", True, 2),
+         ("synth_b", ".sparse", True, "uw", False, 1), ("synth_b", ".sparse", True, "w", True, 1),
+         ("synth_b", ".sparse", True, "wl", True, 0), ("synth_b", ".sparse", True, "wl2", True, 2)]

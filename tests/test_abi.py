@@ -17,12 +17,12 @@ def test_exports_every_declared_symbol(built):
 
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    declared = sorted(set(re.findall(r"\b(frc_[a-z_]+)\s*\(", src)))
+    declared = sorted(set(re.findall(r"\b(frc_[a-z_0-9]+)\s*\(", src)))
     assert set(declared) == set(engine.EXPORTS)
     L = engine.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.frc_abi_version() == 1
+    assert L.frc_abi_version() == 2
 
 
 def test_struct_layout_matches_binding(built, tmp_path):

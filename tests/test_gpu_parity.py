@@ -61,24 +61,34 @@ def test_cli_binary_golden(built, tmp_path, fixture, sparse, weighted):
     assert out.read_text() == _read(fixture + ".want")
 
 
-@pytest.mark.parametrize("fixture,suffix,sparse,tag,weighted,nnorm", kat.SYNTH)
-def test_synthetic_golden_through_the_gpu(built, gpu_ctx, tmp_path, fixture, suffix, sparse, tag, weighted, nnorm):
+@pytest.mark.parametrize("fixture,suffix,sparse,tag,weighted,normalize", kat.SYNTH)
+def test_synthetic_golden_through_the_gpu(built, gpu_ctx, tmp_path, fixture, suffix, sparse, tag, weighted, normalize):
     """Committed synthetic fixtures (tests/golden/make_golden.py): the CLI stand-in reproduces the bytes (these sizes
-    take the exact fp64 kernel), and the fast kernels land within 1e-5 of the committed values."""
+    take the exact fp64 kernels; `-l` prints what the reference prints, FRCFRC_L=documented the documented variant),
+    and the fast kernels land within 1e-5 of the committed values."""
     from frackyfrac_b200 import engine, hostlib
 
     want_text = _read(f"{fixture}.{tag}.want")
     out = tmp_path / "got"
     cmd = [hostlib.CLI_PATH, "-t", os.path.join(GOLDEN, fixture + ".tree"), "-i", os.path.join(GOLDEN, fixture + suffix),
            "-o", str(out)]
-    cmd += (["-s"] if sparse else []) + (["-w"] if weighted else []) + (["-l"] if nnorm else [])
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    cmd += (["-s"] if sparse else []) + (["-w"] if weighted else []) + (["-l"] if normalize != 1 else [])
+    env = dict(os.environ, FRCFRC_L="documented") if normalize == 2 else dict(os.environ)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     assert out.read_text() == want_text
     tree = hostlib.Tree(_read(fixture + ".tree"))
     rp, col, val = hostlib.Table(_read(fixture + suffix), sparse=sparse).resolve(tree)
     want = np.array([float(x) for x in want_text.split()])
-    got = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, not nnorm, path=engine.PATH_FAST, ctx=gpu_ctx)
+    # through the ABI: bit-identical on the exact path in every mode ...
+    exact = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, normalize, path=engine.PATH_EXACT, ctx=gpu_ctx)
+    assert "".join(hostlib.format_go(v) + "\n" for v in exact) == want_text
+    if normalize == 0:
+        # ... and the reference's -l (unsorted merge-join) has no fast kernel: asking for one is an error
+        with pytest.raises(engine.FrcError, match="as coded"):
+            engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, 0, path=engine.PATH_FAST, ctx=gpu_ctx)
+        return
+    got = engine.unifrac(tree.parent, tree.length, rp, col, val, weighted, normalize, path=engine.PATH_FAST, ctx=gpu_ctx)
     assert rel_err(got, want).max() < 1e-5
     assert (got[want == 0] == 0).all()
 
@@ -113,7 +123,7 @@ def test_cli_binary_compressed_files(built, tmp_path):
 
 
 # ------------------------------------------------------------------ exact path
-@pytest.mark.parametrize("weighted,normalize", [(False, 1), (True, 1), (True, 2)])
+@pytest.mark.parametrize("weighted,normalize", [(False, 1), (True, 1), (True, 2), (True, 0)])
 @pytest.mark.parametrize("shape", ["random", "caterpillar", "balanced"])
 def test_exact_path_bit_identical(gpu_ctx, weighted, normalize, shape):
     from frackyfrac_b200 import engine, synth
@@ -121,7 +131,7 @@ def test_exact_path_bit_identical(gpu_ctx, weighted, normalize, shape):
     tree = synth.random_tree(300, 11, shape=shape)
     csr = synth.random_table(tree, 40, 0.05, 12, integer_counts=False)
     want = oracle_flat(tree, csr, weighted, normalize)
-    got = gpu_flat(tree, csr, weighted, normalize == 1, path=engine.PATH_EXACT, ctx=gpu_ctx)
+    got = gpu_flat(tree, csr, weighted, normalize, path=engine.PATH_EXACT, ctx=gpu_ctx)
     assert np.array_equal(got, want), f"max rel err {rel_err(got, want).max()}"
 
 
@@ -176,7 +186,7 @@ def test_fast_path_within_tolerance(gpu_ctx, weighted, normalize, uw):
     tree = synth.random_tree(1000, 21)
     csr = synth.random_table(tree, 300, 0.02, 22)
     want = oracle_flat(tree, csr, weighted, normalize)
-    got = gpu_flat(tree, csr, weighted, normalize == 1, path=engine.PATH_FAST, ctx=gpu_ctx, flags=uw[1])
+    got = gpu_flat(tree, csr, weighted, normalize, path=engine.PATH_FAST, ctx=gpu_ctx, flags=uw[1])
     e = rel_err(got, want)
     assert e.max() < 1e-5, f"max rel err {e.max():.3e}"
 
@@ -245,7 +255,7 @@ def test_fast_weighted_small_distances(gpu_ctx, normalize):
         col[k * m:(k + 1) * m] = col[:m]
         val[k * m:(k + 1) * m] = val[:m] * (1.0 + eps * rng.random(m) * (rng.random(m) < 0.2))
     want = oracle_flat(tree, (rp, col, val), True, normalize)
-    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=True, normalize=normalize == 1,
+    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=True, normalize=normalize,
                     path=engine.PATH_FAST, ctx=gpu_ctx) as job:
         got = np.concatenate([a for _, a in job.chunks()])
         flagged = job.info().flagged_pairs
@@ -257,10 +267,22 @@ def test_fast_weighted_small_distances(gpu_ctx, normalize):
     assert (np.abs(got[:21] - want[:21]) <= 1.2e-7 * want[:21] + 1e-15).all()
 
 
+def _f32_stream(job):
+    """The job's float32 bands (frc_next_f32) with their exceptions applied, as one float64 vector."""
+    out = []
+    for first, a in job.chunks_f32():
+        d = a.astype(np.float64)
+        xi, xv = job.exceptions()
+        d[xi - first] = xv
+        out.append(d)
+    return np.concatenate(out) if out else np.zeros(0)
+
+
 @pytest.mark.parametrize("weighted", [False, True])
-def test_fp32_wire_against_f64_wire(gpu_ctx, monkeypatch, weighted):
-    """Fast-path distances cross PCIe as fp32 and are widened on the host (wire.cu).  Against doubles on the
-    bus: half the bytes, identical values (the doubles route rounds in place on the device)."""
+def test_f32_stream_equals_f64_stream(gpu_ctx, weighted):
+    """Fast-path kernels store fp32; a band crosses PCIe as 4 bytes per pair.  frc_next_f32 hands the pinned
+    slot out as it is, frc_next widens the same values on the host: both streams carry identical numbers, and
+    neither depends on the band decomposition."""
     from frackyfrac_b200 import engine, synth
 
     tree = synth.random_tree(1500, 301)
@@ -271,34 +293,38 @@ def test_fp32_wire_against_f64_wire(gpu_ctx, monkeypatch, weighted):
     col[2 * m:3 * m] = col[:m]
     val[2 * m:3 * m] = val[:m] * (1.0 + 1e-3 * (np.arange(m) % 5 == 0))
 
-    def run(band_rows=0):
+    def run(f32, band_rows=0):
         with engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=gpu_ctx,
                         band_rows=band_rows) as job:
-            got = np.concatenate([a for _, a in job.chunks()])
+            got = _f32_stream(job) if f32 else np.concatenate([a for _, a in job.chunks()])
             return got, job.info()
 
-    monkeypatch.setenv("FRC_WIRE", "f32")   # (the default picks it when the rank has >= 8 host threads)
-    narrow, ni = run()
-    ragged, _ = run(band_rows=128)       # many small bands, odd lengths and alignments
-    monkeypatch.setenv("FRC_WIRE", "f64")
-    wide, wi = run()
+    narrow, ni = run(True)
+    ragged, _ = run(True, band_rows=128)       # many small bands, odd lengths and alignments
+    wide, wi = run(False)
     pairs = 1100 * 1099 // 2
-    assert ni.d2h_bytes == 4 * pairs and wi.d2h_bytes == 8 * pairs
+    assert ni.d2h_bytes == 4 * pairs and wi.d2h_bytes == 4 * pairs and ni.value_bytes == 4
     assert narrow[0] == 0.0 and wide[0] == 0.0
     assert np.array_equal(narrow, ragged)
-    # the bus format must not show in the output (ranks with few host threads keep doubles on the bus, and the
-    # stream has to be byte-identical for 1, 2, 4 and 8 GPUs: SURVEY 8e) - the doubles are rounded the same way
     assert np.array_equal(narrow, wide, equal_nan=True)
     assert np.array_equal(narrow, narrow.astype(np.float32).astype(np.float64))
     assert rel_err(narrow, oracle_flat(tree, (rp, col, val), weighted)).max() < 1e-5
+    # the two calls cannot be mixed on one pass; the exact path is float64 only
+    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=gpu_ctx) as job:
+        job.next_raw()
+        with pytest.raises(engine.FrcError, match="mixed"):
+            job.next_raw_f32()
+    with engine.Job(tree.parent, tree.length, rp[:4], col[:rp[3]], val[:rp[3]], weighted=weighted, path=engine.PATH_EXACT,
+                    ctx=gpu_ctx) as job:
+        assert job.info().value_bytes == 8
+        with pytest.raises(engine.FrcError, match="exact path"):
+            job.next_raw_f32()
 
 
-def test_fp32_wire_delivers_large_bands_in_pieces(gpu_ctx, monkeypatch):
-    """A band larger than the host widening buffer (2 M pairs) arrives over several frc_next calls: contiguous,
-    in order, and with the same values as the default band plan."""
+def test_f64_stream_delivers_large_bands_in_pieces(gpu_ctx):
+    """frc_next widens into a cache-sized buffer: a band larger than it (2 M pairs) arrives over several calls,
+    contiguous, in order, and with the same values as the default band plan; frc_next_f32 hands it out whole."""
     from frackyfrac_b200 import engine, synth
-
-    monkeypatch.setenv("FRC_WIRE", "f32")
 
     tree = synth.random_tree(300, 311)
     rp, col, val = synth.random_table(tree, 2500, 0.05, 312)
@@ -312,13 +338,16 @@ def test_fp32_wire_delivers_large_bands_in_pieces(gpu_ctx, monkeypatch):
     one_band = np.concatenate([a for _, a in runs])
     assert np.array_equal(one_band, gpu_flat(tree, (rp, col, val), False, path=engine.PATH_FAST, ctx=gpu_ctx))
     assert rel_err(one_band, oracle_flat(tree, (rp, col, val), False)).max() < 1e-5
+    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx,
+                    band_rows=4096) as job:
+        whole = [(first, a) for first, a in job.chunks_f32()]
+    assert len(whole) == 1 and whole[0][0] == 0 and np.array_equal(whole[0][1].astype(np.float64), one_band)
 
 
-def test_fp32_wire_falls_back_when_a_value_underflows(gpu_ctx, monkeypatch):
-    """A distance below fp32's range must still arrive: the band is then fetched as doubles."""
+def test_values_below_fp32_range_travel_as_exceptions(gpu_ctx):
+    """A distance below fp32's range must still arrive: the exact fix-up pass reports it beside the fp32 band
+    (wire.cuh), frc_next patches it into the doubles and frc_chunk_exceptions hands it to fp32 consumers."""
     from frackyfrac_b200 import engine, hostlib
-
-    monkeypatch.setenv("FRC_WIRE", "f32")
 
     tree = hostlib.Tree("((a:1e-60,b:1e-60):1,(c:1,d:2):0.5);")
     tab = hostlib.Table("a:1\tc:1\nb:1\tc:1\nc:1\td:1\na:1\td:3\n", sparse=True)
@@ -330,7 +359,65 @@ def test_fp32_wire_falls_back_when_a_value_underflows(gpu_ctx, monkeypatch):
     assert 0 < want[0] < 1e-59
     assert abs(got[0] - want[0]) <= 1e-5 * want[0]
     assert rel_err(got, want).max() < 1e-5
-    assert info.d2h_bytes == 4 * 6 + 8 * 6   # the fp32 band, then the same band as doubles
+    assert info.d2h_bytes == 4 * 6 and info.exceptions >= 1
+    with engine.Job(tree.parent, tree.length, rp, col, val, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx) as job:
+        (first, a), = list(job.chunks_f32())
+        xi, xv = job.exceptions()
+    assert first == 0 and a[0] == 0.0 and 0 in xi.tolist() and abs(xv[xi.tolist().index(0)] - want[0]) <= 1e-5 * want[0]
+
+
+def test_fast_weighted_fixups_in_concurrent_bands(gpu_ctx):
+    """Near-duplicate samples spread over MANY bands: consecutive bands run on two streams, so their fix-up
+    kernels overlap and must not share a workspace (each stream has its own)."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(900, 185)
+    n = 1400
+    rp, col, val = synth.random_table(tree, n, 0.04, 186, integer_counts=False)
+    m = rp[1]
+    rng = np.random.default_rng(187)
+    # every 64th sample is a near copy of sample 0: flagged pairs (d < 1/32) in every band of 128 rows
+    copies = list(range(64, n, 64))
+    for k in copies:
+        col[k * m:(k + 1) * m] = col[:m]
+        val[k * m:(k + 1) * m] = val[:m] * (1.0 + 1e-4 * rng.random(m) * (rng.random(m) < 0.3))
+    want = oracle_flat(tree, (rp, col, val), True)
+    for rep in range(3):
+        with engine.Job(tree.parent, tree.length, rp, col, val, weighted=True, path=engine.PATH_FAST, ctx=gpu_ctx,
+                        band_rows=128) as job:
+            got = np.concatenate([a for _, a in job.chunks()])
+            info = job.info()
+        assert info.n_bands_mine == 11 and info.flagged_pairs >= len(copies) * (len(copies) + 1) // 2
+        e = rel_err(got, want)
+        assert e.max() < 1e-5, f"rep {rep}: max rel err {e.max():.3e}"
+        idx = [i * (i - 1) // 2 + j for i in copies for j in [0] + [c for c in copies if c < i]]
+        assert (np.abs(got[idx] - want[idx]) <= 1.2e-7 * want[idx] + 1e-15).all()
+
+
+def test_flagged_pairs_are_deterministic(gpu_ctx):
+    """The exact-recompute threshold of the u8 path (flag_u) is summed in a fixed order on the device: the same
+    pairs are flagged on every run and for every band / owner layout."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(1500, 91)
+    L = np.exp(np.random.default_rng(92).normal(-3.0, 4.0, tree.n_nodes))   # heavy tail: merged small-length columns
+    L[0] = 0.0
+    tree = synth.Tree(tree.parent, L, tree.leaf_ids, tree.names)
+    csr = synth.random_table(tree, 520, 0.03, 93)
+    counts, outs = [], []
+    for kw in (dict(), dict(), dict(band_rows=128), dict(band_rows=256)):
+        with engine.Job(tree.parent, tree.length, *csr, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx, **kw) as job:
+            outs.append(np.concatenate([a for _, a in job.chunks()]))
+            counts.append(job.info().flagged_pairs)
+    parts = []
+    for r in range(2):
+        with engine.Job(tree.parent, tree.length, *csr, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx, band_rows=128,
+                        rank=r, world=2) as job:
+            for _ in job.chunks():
+                pass
+            parts.append(job.info().flagged_pairs)
+    assert len(set(counts)) == 1 and sum(parts) == counts[0], (counts, parts)
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
 
 
 @pytest.mark.parametrize("slab", [128, 256])

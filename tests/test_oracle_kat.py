@@ -44,8 +44,8 @@ def test_cli_golden(built, fixture, sparse, weighted):
     assert r.returncode == 0 and r.stdout == _read(fixture + ".want")
 
 
-@pytest.mark.parametrize("fixture,suffix,sparse,tag,weighted,nnorm", kat.SYNTH)
-def test_synthetic_golden_bytes(built, fixture, suffix, sparse, tag, weighted, nnorm):
+@pytest.mark.parametrize("fixture,suffix,sparse,tag,weighted,normalize", kat.SYNTH)
+def test_synthetic_golden_bytes(built, fixture, suffix, sparse, tag, weighted, normalize):
     """The committed synthetic fixtures (tests/golden/make_golden.py): the oracle, through its library and its
     CLI, must keep producing exactly these bytes — a change to the checker cannot move the target unnoticed."""
     from oracle import oracle as orc
@@ -55,13 +55,13 @@ def test_synthetic_golden_bytes(built, fixture, suffix, sparse, tag, weighted, n
     orc.validate_species(tab, tree)
     want = _read(f"{fixture}.{tag}.want")
     for threads in (1, 3):
-        d = orc.unifrac(tab, tree, weighted, 2 if nnorm else 1, threads)
+        d = orc.unifrac(tab, tree, weighted, normalize, threads)
         assert "".join(orc.format_go(float(v)) + "\n" for v in d) == want
-    if nnorm:
-        return  # the oracle's CLI restates the reference's -l literally (unsorted lists, normalize=0); the fixture
-                # holds -l as documented (normalize=2), which is what the engine implements (DESIGN.md, A-notes)
+    if normalize == 2:
+        return  # the oracle's CLI restates the reference's -l literally (unsorted lists, normalize = 0: the `wl`
+                # fixtures); -l as documented (normalize = 2, `wl2`) is only reachable through the library
     cmd = [orc.CLI_PATH, "-t", os.path.join(GOLDEN, fixture + ".tree"), "-i", os.path.join(GOLDEN, fixture + suffix)]
-    cmd += (["-s"] if sparse else []) + (["-w"] if weighted else [])
+    cmd += (["-s"] if sparse else []) + (["-w"] if weighted else []) + (["-l"] if normalize == 0 else [])
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout == want
 
@@ -164,8 +164,8 @@ def test_l_flag_reference_quirk(built):
     """With -l the reference never sorts its node lists (the sort lives inside
     normalizeFlatNodes, unifrac.go:57), so its merge-join runs over post-order
     lists.  The oracle restates that faithfully as normalize=0; normalize=2 is -l
-    as documented (sorted lists, raw values), which is what the CUDA engine computes.
-    This test pins the difference so the divergence stays visible."""
+    as documented (sorted lists, raw values).  The CUDA engine implements both (frc_opts_t.normalize 0 / 2;
+    the CLI's -l is 0, like the reference).  This test pins the difference between the two."""
     from oracle import oracle as orc
 
     tree = orc.Tree.parse("((s1:1,s2:3):2,(s3:2,s4:5):1);")
