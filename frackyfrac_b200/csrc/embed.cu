@@ -265,57 +265,78 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
   for (int32_t v = tid; v < n_nodes; v += 512) colw[v] = 0u;
   if (tid < 128 && tid <= height + 1) lptr[tid] = level_ptr[tid];
   __syncthreads();
-  // phase 1
-  for (int sl = warp; sl < 32; sl += 16) {
-    const int64_t s = static_cast<int64_t>(w) * 32 + sl;
-    if (s < n_samples) {
-      const int64_t b = row_ptr[s], e = row_ptr[s + 1];
-      for (int64_t k = b + lane; k < e; k += 128) {  // four loads in flight per lane
-        int32_t c[4];
+  // phase 1: two CSR rows per warp; both rows' bounds are fetched before either row's entries
+  {
+    int64_t rb[2], re[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = k + 32 * u < e ? col[k + 32 * u] : -1;
+    for (int u = 0; u < 2; ++u) {
+      const int64_t s = static_cast<int64_t>(w) * 32 + warp + 16 * u;
+      rb[u] = s < n_samples ? row_ptr[s] : 0;
+      re[u] = s < n_samples ? row_ptr[s + 1] : 0;
+    }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (c[u] >= 0) atomicOr(colw + c[u], 1u << sl);
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t bit = 1u << (warp + 16 * u);
+      for (int64_t k = rb[u] + lane; k < re[u]; k += 256) {  // eight loads in flight per lane
+        int32_t c[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) c[x] = k + 32 * x < re[u] ? col[k + 32 * x] : -1;
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+          if (c[x] >= 0) atomicOr(colw + c[x], bit);
       }
     }
   }
   __syncthreads();
   // phase 2: every node ORs its (final) word into its parent, one tree level at a time from the
-  // leaves up.  level_nodes / level_parent are read coalesced, and the first 512 entries of the
-  // NEXT level are fetched before this level's barrier: the deep levels of a tree hold few nodes,
-  // so without the prefetch every level paid a full global-load latency on top of its barrier.
+  // leaves up.  The kernel is latency-bound (157 CTAs at cfg2, DRAM 1.4 %): what a level costs is the
+  // round trip of its index loads (level_nodes / level_parent, L2), so the loads are batched:
+  //   wide levels (near the leaves): eight independent index pairs in flight per thread;
+  //   narrow levels (<= 512 nodes, one per thread; level sizes never grow towards the root): the
+  //   indices of EIGHT levels are fetched at once, then the eight levels run on shared memory alone
+  //   (read, atomicOr, barrier) -- one load round trip per eight levels instead of one per level.
   auto lp = [&](int32_t h) { return h < 128 ? lptr[h] : level_ptr[h]; };
-  int32_t b = lp(0), e = lp(1);
-  int32_t pn = -1, pp = 0;
-  if (height > 0 && b + tid < e) { pn = level_nodes[b + tid]; pp = level_parent[b + tid]; }
-  for (int32_t h = 0; h < height; ++h) {
-    const int32_t nb = e, ne = h + 1 < height ? lp(h + 2) : e;
-    int32_t qn = -1, qp = 0;
-    if (nb + tid < ne) { qn = level_nodes[nb + tid]; qp = level_parent[nb + tid]; }
-    if (pn >= 0) {
-      const uint32_t x = colw[pn];
-      if (x) atomicOr(colw + pp, x);
-    }
-    // the wide levels near the leaves: four independent index loads in flight per thread (one load
-    // at a time made this loop the bulk of the kernel: ~40 dependent L2 round trips per thread)
-    for (int32_t idx = b + tid + 512; idx < e; idx += 2048) {
-      int32_t n[4], p[4];
+  int32_t h = 0;
+  for (; h < height; ++h) {
+    const int32_t b = lp(h), e = lp(h + 1);
+    if (e - b <= 512) break;
+    for (int32_t idx = b + tid; idx < e; idx += 4096) {
+      int32_t n[8], p[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int32_t k = idx + u * 512;
         n[u] = k < e ? level_nodes[k] : -1;
         p[u] = k < e ? level_parent[k] : 0;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
         if (n[u] >= 0) {
           const uint32_t x = colw[n[u]];
           if (x) atomicOr(colw + p[u], x);
         }
     }
     __syncthreads();
-    b = nb; e = ne; pn = qn; pp = qp;
+  }
+  for (; h < height; h += 8) {
+    int32_t n[8], p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      n[u] = -1; p[u] = 0;
+      if (h + u < height) {
+        const int32_t k = lp(h + u) + tid;
+        if (k < lp(h + u + 1)) { n[u] = level_nodes[k]; p[u] = level_parent[k]; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (h + u < height) {  // (block-uniform)
+        if (n[u] >= 0) {
+          const uint32_t x = colw[n[u]];
+          if (x) atomicOr(colw + p[u], x);
+        }
+        __syncthreads();
+      }
+    }
   }
   // phase 3
   uint32_t* dst = bitsT + static_cast<int64_t>(w) * kp;
@@ -324,6 +345,7 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
     // ones as plain stores over NVLink (visible to the peers once this kernel has completed; the
     // ranks meet at the small NCCL all-gather of the row sums before anyone reads bitsT)
     const int64_t at = static_cast<int64_t>(w) * kp;
+#pragma unroll 4
     for (int32_t k = tid; k < kp; k += 512) {
       const int32_t v = order[k];
       const uint32_t x = v >= 0 ? colw[v] : 0u;
@@ -332,7 +354,7 @@ k_embed_presence_fused(const int64_t* __restrict__ row_ptr, const int32_t* __res
         if (pr < peers.n) peers.p[pr][at + k] = x;
     }
   } else {
-#pragma unroll 4
+#pragma unroll 8
     for (int32_t k = tid; k < kp; k += 512) {
       const int32_t v = order[k];
       dst[k] = v >= 0 ? colw[v] : 0u;
@@ -472,12 +494,20 @@ k_expand_operands_t(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
 
 // Same for the u8 operands: block = 128 columns x 256 samples, 4 columns (one 32-bit store per
 // operand) per thread and sample; 3 * np * kp bytes written.
+// r_int != null (integer mode): the block also adds its share of the row sums r_s = sum_k q_k P_ks -- the
+// words are in shared memory anyway, so bitsT is read ONCE by the whole stage (the separate row-sum pass
+// cost 35 us at cfg2, a third of the stage).  Thread = sample for that part: q[k] = a*m < 2^24, 128 columns
+// sum exactly in 32 bits, the block's one power-of-two scale becomes a shift and the partial sum goes to
+// r_int with a 64-bit integer atomic (order-independent: deterministic).
 __global__ void __launch_bounds__(256)
 k_expand_operands_u8(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp, int64_t np,
                      const uint8_t* __restrict__ qa, const uint8_t* __restrict__ qh,
                      const uint8_t* __restrict__ ql, uint8_t* __restrict__ A, uint8_t* __restrict__ Bh,
-                     uint8_t* __restrict__ Bl, const uint8_t* __restrict__ need) {
+                     uint8_t* __restrict__ Bl, const uint8_t* __restrict__ need,
+                     const uint32_t* __restrict__ qam, const int32_t* __restrict__ col_exp, int32_t e_min,
+                     long long* __restrict__ r_int) {
   __shared__ __align__(16) uint32_t words[8][128];
+  __shared__ __align__(16) uint32_t sq[128];
   const int32_t v0 = blockIdx.x * 128;
   const int32_t w0 = blockIdx.y * 8;
   // need[block of 256 samples]: bit 0 = these samples occur as columns (A), bit 1 = as rows (Bh, Bl)
@@ -490,6 +520,7 @@ k_expand_operands_u8(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
     if (w0 + word < nw) x = bitsT[static_cast<int64_t>(w0 + word) * kp + v0 + node];
     words[word][node] = x;
   }
+  if (r_int != nullptr && threadIdx.x < 128) sq[threadIdx.x] = qam[v0 + threadIdx.x];
   __syncthreads();
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t va = v0 + 4 * lane;
@@ -511,6 +542,25 @@ k_expand_operands_u8(const uint32_t* __restrict__ bitsT, int32_t nw, int32_t kp,
       *reinterpret_cast<uint32_t*>(Bh + o) = h4 & m;
       *reinterpret_cast<uint32_t*>(Bl + o) = l4 & m;
     }
+  }
+  if (r_int != nullptr) {
+    // lane = sample of word wi; every read below is a shared-memory broadcast
+    const uint32_t m = 1u << lane;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 8
+    for (int k = 0; k < 128; k += 4) {
+      const uint4 w = *reinterpret_cast<const uint4*>(&words[wi][k]);
+      const uint4 q = *reinterpret_cast<const uint4*>(&sq[k]);
+      a0 += (w.x & m) ? q.x : 0u;
+      a1 += (w.y & m) ? q.y : 0u;
+      a2 += (w.z & m) ? q.z : 0u;
+      a3 += (w.w & m) ? q.w : 0u;
+    }
+    const uint32_t sum = (a0 + a1) + (a2 + a3);  // < 2^31
+    const int64_t s = s0 + lane;
+    if (sum != 0u && s < np)
+      atomicAdd(reinterpret_cast<unsigned long long*>(r_int) + s,
+                static_cast<unsigned long long>(sum) << (col_exp[v0] - e_min));
   }
 }
 
@@ -746,13 +796,15 @@ int launch_presence_rowsum_t(const uint32_t* bitsT, int32_t n_nodes, int32_t nw,
 
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
                              const void* q0, const void* q1, const void* q2, void* P, void* Bh, void* Bl,
-                             const uint8_t* need, cudaStream_t s) {
+                             const uint8_t* need, const uint32_t* qam, const int32_t* col_exp, int32_t e_min,
+                             long long* r_int, cudaStream_t s) {
   if (i8) {
+    if (r_int) cudaMemsetAsync(r_int, 0, sizeof(long long) * np, s);
     dim3 grid(kp / 128, static_cast<unsigned>((np + 255) / 256));
     k_expand_operands_u8<<<grid, 256, 0, s>>>(bitsT, nw, kp, np, static_cast<const uint8_t*>(q0),
                                               static_cast<const uint8_t*>(q1), static_cast<const uint8_t*>(q2),
                                               static_cast<uint8_t*>(P), static_cast<uint8_t*>(Bh),
-                                              static_cast<uint8_t*>(Bl), need);
+                                              static_cast<uint8_t*>(Bl), need, qam, col_exp, e_min, r_int);
   } else {
     (void)q0;
     dim3 grid(kp / 64, static_cast<unsigned>((np + 255) / 256));

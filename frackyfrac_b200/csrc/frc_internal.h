@@ -126,9 +126,12 @@ int launch_presence_rowsum_t(const uint32_t* bitsT, int32_t n_nodes, int32_t nw,
                              double* partial, double* r, int32_t e_min, long long* r_int, cudaStream_t s);
 // need[np / 256] (device, may be null = everything): bit 0 = write the A rows of that block of 256
 // samples, bit 1 = write its Bh / Bl rows.
+// r_int != null (u8 integer mode): the expansion also produces the exact integer row sums (units of 2^e_min) of
+// every sample block it touches, from the words it already holds -- no separate row-sum pass over bitsT.
 int launch_expand_operands_t(const uint32_t* bitsT, int32_t nw, int32_t kp, int64_t np, bool i8,
                              const void* q0, const void* q1, const void* q2, void* P, void* Bh, void* Bl,
-                             const uint8_t* need, cudaStream_t s);
+                             const uint8_t* need, const uint32_t* qam, const int32_t* col_exp, int32_t e_min,
+                             long long* r_int, cudaStream_t s);
 // u8 block floating point: for operand column k with true length len_col[k] >= 0 and chunk
 // exponent col_exp[k], find the 8-bit a and 16-bit m = 256*qh + ql minimising
 // |a * m * 2^e - len| ; lenq[k] = a * m * 2^e (exact in fp64).

@@ -490,30 +490,41 @@ int embed_stage1(Part* p) {
     }
     launches += launch_embed_presence_fused(p->dtree, p->d_level_ptr, p->dcsr, sh.nw, p->shard_w0, p->shard_nw,
                                             sh.kp, p->d_order, p->d_node_scratch, p->d_bits, p->d_bitsS, peers, s);
-    // the row sums (integer-ALU-bound) and the operand expansion (HBM-bound) both only read the bit
-    // columns: they run side by side on the two compute streams unless an exchange sits between
-    const bool split = sh.exchange == Shared::kNone;
+    // Row sums.  Integer mode with materialised operands (the default): the operand expansion of stage 2
+    // produces them for every sample from the words it holds anyway -- nothing to do here, nothing to
+    // exchange but the bit columns.  Otherwise (fp64 row sums of the bf16 / wide-scale modes, bits-fed kernel)
+    // a separate pass over this part's shard: it runs beside the expansion on the second compute stream
+    // unless an exchange sits between.
+    const bool rowsum_in_expand = sh.cols.intacc && !sh.bits_feed;
+    const bool split = sh.exchange == Shared::kNone && !rowsum_in_expand;
     cudaStream_t rs = split ? dc->stream[1] : s;
     if (split) {
       PART_CUDA(p, cudaEventRecord(p->ev_bits, s));
       PART_CUDA(p, cudaStreamWaitEvent(rs, p->ev_bits, 0));
     }
-    launches += launch_presence_rowsum_t(p->d_bits, sh.B, sh.nw, p->shard_w0, p->shard_nw, sh.kp, p->d_lenq,
-                                         sh.cols.i8 ? p->d_qam : nullptr, p->d_col_exp, p->d_scratch, p->d_r,
-                                         sh.cols.e_min, sh.cols.intacc ? p->d_r_int : nullptr, rs);
-    const size_t rbytes = static_cast<size_t>(p->shard_nw) * 32 * sizeof(double);
+    if (!rowsum_in_expand)
+      launches += launch_presence_rowsum_t(p->d_bits, sh.B, sh.nw, p->shard_w0, p->shard_nw, sh.kp, p->d_lenq,
+                                           sh.cols.i8 ? p->d_qam : nullptr, p->d_col_exp, p->d_scratch, p->d_r,
+                                           sh.cols.e_min, sh.cols.intacc ? p->d_r_int : nullptr, rs);
+    const size_t rbytes = rowsum_in_expand ? 0 : static_cast<size_t>(p->shard_nw) * 32 * sizeof(double);
     const size_t bbytes = static_cast<size_t>(p->shard_nw) * sh.kp * sizeof(uint32_t);
     if (sh.exchange == Shared::kNccl) {
-      // the one exchange step of the path: presence bit columns + row sums of every rank's sample
+      // the one exchange step of the path: presence bit columns (+ row sums) of every rank's sample
       // shard, concatenated over NVLink (2.5 GB at cfg4 instead of 120 GB of operands)
       // (bits-fed kernel: the sample-major bit rows are what is exchanged, same size)
-      void* bufs[2] = {sh.cols.intacc ? static_cast<void*>(p->d_r_int) : static_cast<void*>(p->d_r),
-                       sh.bits_feed ? p->d_bitsS : p->d_bits};
-      const size_t bytes[2] = {rbytes, bbytes};
+      void* bufs[2];
+      size_t bytes[2];
+      int nb = 0;
+      if (!rowsum_in_expand) {
+        bufs[nb] = sh.cols.intacc ? static_cast<void*>(p->d_r_int) : static_cast<void*>(p->d_r);
+        bytes[nb++] = rbytes;
+      }
       // peer_push: the bit columns already sit in every rank's bitsT (stored there by the embedding
-      // kernel itself); the small all-gather of the row sums is also the point where the ranks meet
+      // kernel itself); the ranks then only have to MEET before anyone reads bitsT
+      if (!p->peer_push) { bufs[nb] = sh.bits_feed ? p->d_bitsS : p->d_bits; bytes[nb++] = bbytes; }
       std::string cerr;
-      if (!comm_all_gather_inplace(c->comm, bufs, bytes, p->peer_push ? 1 : 2, s, &cerr)) return pfail(p, FRC_ERR_CUDA, cerr);
+      if (nb > 0 ? !comm_all_gather_inplace(c->comm, bufs, bytes, nb, s, &cerr) : !comm_barrier(c->comm, s, &cerr))
+        return pfail(p, FRC_ERR_CUDA, cerr);
       p->info.gather_bytes = static_cast<int64_t>(rbytes + bbytes) * (sh.world - 1);
     } else if (inproc) {
       // row sums of the shard (8 bytes per sample) and, for the bits-fed kernel, the shard's bit rows:
@@ -522,10 +533,12 @@ int embed_stage1(Part* p) {
       for (int q = 0; q < n_parts; ++q) {
         if (q == p->index) continue;
         Part* o = p->job->parts[q].get();
-        if (sh.cols.intacc)
+        if (rowsum_in_expand) {
+        } else if (sh.cols.intacc) {
           PART_CUDA(p, cudaMemcpyPeerAsync(o->d_r_int + s_begin, o->dc->device, p->d_r_int + s_begin, dc->device, rbytes, s));
-        else
+        } else {
           PART_CUDA(p, cudaMemcpyPeerAsync(o->d_r + s_begin, o->dc->device, p->d_r + s_begin, dc->device, rbytes, s));
+        }
         if (sh.bits_feed) {
           const size_t roww = static_cast<size_t>(sh.kp / 32);
           PART_CUDA(p, cudaMemcpyPeerAsync(o->d_bitsS + s_begin * roww, o->dc->device, p->d_bitsS + s_begin * roww,
@@ -534,7 +547,7 @@ int embed_stage1(Part* p) {
       }
       p->info.gather_bytes = static_cast<int64_t>(rbytes + bbytes) * (n_parts - 1);
     }
-    if (!split) {
+    if (sh.exchange != Shared::kNone) {
       // bits written + read once per level pass (+ CSR cols): this part's shard
       p->info.embed_bytes = 2LL * sh.B * p->shard_nw * 4 + 4LL * (p->csr_k1 - p->csr_k0);
     }
@@ -556,12 +569,16 @@ int embed_stage2(Part* p) {
       if (o.get() != p) PART_CUDA(p, cudaStreamWaitEvent(s, o->ev_shard, 0));
   if (!sh.exact && !sh.weighted) {
     if (sh.fused_embed) {
+      const bool rowsum_in_expand = sh.cols.intacc && !sh.bits_feed;
       if (!sh.bits_feed)
         launches += launch_expand_operands_t(p->d_bits, sh.nw, sh.kp, sh.np, sh.cols.i8, p->d_q0, p->d_q1, p->d_q2,
-                                             p->d_P, p->d_Bh, p->d_Bl, p->d_need, s);
+                                             p->d_P, p->d_Bh, p->d_Bl, p->d_need, p->d_qam, p->d_col_exp, sh.cols.e_min,
+                                             rowsum_in_expand ? p->d_r_int : nullptr, s);
       if (sh.exchange == Shared::kNone) {
-        PART_CUDA(p, cudaEventRecord(p->ev_rsum, dc->stream[1]));
-        PART_CUDA(p, cudaStreamWaitEvent(s, p->ev_rsum, 0));
+        if (!rowsum_in_expand) {
+          PART_CUDA(p, cudaEventRecord(p->ev_rsum, dc->stream[1]));
+          PART_CUDA(p, cudaStreamWaitEvent(s, p->ev_rsum, 0));
+        }
         p->info.embed_bytes = 2LL * sh.B * sh.nw * 4 + 4LL * sh.nnz;
       }
       // + three operands written once, the bit columns read once more

@@ -133,19 +133,25 @@ class Context:
     (`devices`: a list of ordinals, or -1 for every visible sm_100 device)."""
 
     def __init__(self, device: int = -1, devices=None):
-        # several ranks on one host (torchrun): split the host cores between their worker pools
+        # several ranks on one host (torchrun): split the host cores between their worker pools (a context over
+        # several devices is the only worker of its process group while it runs: it keeps the library's default)
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-        if local_world > 1 and "FRC_HOST_THREADS" not in os.environ and devices is None:
+        saved = os.environ.get("FRC_HOST_THREADS")
+        if saved is None and local_world > 1 and devices is None:
             cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             os.environ["FRC_HOST_THREADS"] = str(max(2, min(16, cores // local_world)))
         h = C.c_void_p()
-        if devices is None:
-            rc = lib().frc_ctx_create(device, C.byref(h))
-        elif devices == -1:
-            rc = lib().frc_ctx_create_multi(-1, None, C.byref(h))
-        else:
-            ids = np.ascontiguousarray(devices, np.int32)
-            rc = lib().frc_ctx_create_multi(len(ids), ids.ctypes.data, C.byref(h))
+        try:
+            if devices is None:
+                rc = lib().frc_ctx_create(device, C.byref(h))
+            elif devices == -1:
+                rc = lib().frc_ctx_create_multi(-1, None, C.byref(h))
+            else:
+                ids = np.ascontiguousarray(devices, np.int32)
+                rc = lib().frc_ctx_create_multi(len(ids), ids.ctypes.data, C.byref(h))
+        finally:
+            if saved is None:
+                os.environ.pop("FRC_HOST_THREADS", None)
         if rc:
             raise FrcError(rc, lib().frc_last_error(None).decode())
         self.h = h

@@ -81,33 +81,86 @@ func unifrac(abnd []map[string]float64, tree *newick.Node, weighted bool) iter.S
 			p.Pin(&val[0])
 		}
 	}
-	o := C.frc_opts_t{mode: C.FRC_UNWEIGHTED, normalize: 1, path: C.FRC_PATH_AUTO, device: -1, world: 1}
+	// n_devices = -1: every visible B200 works on the job; the engine validates and stages the inputs once and
+	// hands the bands of all devices out as ONE ordered stream, so this function stays the single iter.Seq the
+	// caller ranges over (frcfrc.go:58-62).
+	o := C.frc_opts_t{mode: C.FRC_UNWEIGHTED, normalize: 1, path: C.FRC_PATH_AUTO, device: -1, world: 1, n_devices: -1}
 	if weighted {
 		o.mode = C.FRC_WEIGHTED
 	}
-	if *nnorm { // flag -l (frcfrc.go:25)
-		o.normalize = 0
+	if *nnorm { // flag -l (frcfrc.go:25): 0 = what unifrac.go:108-110 does (normalizeFlatNodes skipped, and with it
+		o.normalize = 0 // the id-sort of :57); 2 would be the documented behaviour (sorted lists, raw values)
 	}
 	// *nt (flag -p) has no meaning on the device; it keeps sizing the parsers' goroutine pools.
 
 	return func(yield func(float64) bool) {
+		// frc_last_error(NULL) reads a thread-local of the C library: the create call and the read of its
+		// message must run on the same OS thread
+		runtime.LockOSThread()
 		var job *C.frc_job_t
 		var pin runtime.Pinner
 		pinInputs(&pin)
 		rc := C.frc_create(nil, &t, &a, &o, &job)
 		pin.Unpin() // everything was copied
 		if rc != C.FRC_OK {
-			fmt.Fprintln(os.Stderr, "ERROR:", C.GoString(C.frc_last_error(nil))) // common.ExitIfError
+			msg := C.GoString(C.frc_last_error(nil))
+			runtime.UnlockOSThread()
+			fmt.Fprintln(os.Stderr, "ERROR:", msg) // common.ExitIfError
 			os.Exit(2)
 		}
+		runtime.UnlockOSThread()
 		defer C.frc_destroy(job) // legal mid-stream: the consumer's `break` (frcfrc.go:59-61)
 		fmt.Fprintln(os.Stderr, "Calculating distances")
-		for {
+		var info C.frc_info_t
+		C.frc_job_info(job, &info)
+		fail := func() {
+			fmt.Fprintln(os.Stderr, "ERROR:", C.GoString(C.frc_last_error(job)))
+			os.Exit(2)
+		}
+		if info.value_bytes == 4 {
+			// fast paths: the kernels produce fp32 ratios; take the pinned fp32 bands as they are and widen
+			// per value here (float64(f) is exact), instead of a widening pass over memory inside the library
+			for {
+				var data *C.float
+				var first, n C.int64_t
+				if rc := C.frc_next_f32(job, &data, &first, &n); rc != C.FRC_OK {
+					fail()
+				}
+				if n == 0 {
+					return
+				}
+				band := unsafe.Slice((*float32)(unsafe.Pointer(data)), int(n))
+				// distances below fp32's range (pathological trees only) travel beside the band as float64
+				var xi *C.int64_t
+				var xv *C.double
+				var nx C.int64_t
+				C.frc_chunk_exceptions(job, &xi, &xv, &nx)
+				patch := map[int]float64{}
+				if nx > 0 {
+					idx := unsafe.Slice((*int64)(unsafe.Pointer(xi)), int(nx))
+					val := unsafe.Slice((*float64)(unsafe.Pointer(xv)), int(nx))
+					for k := range idx {
+						patch[int(idx[k]-int64(first))] = val[k]
+					}
+				}
+				for k, f := range band {
+					v := float64(f)
+					if nx > 0 {
+						if p, ok := patch[k]; ok {
+							v = p
+						}
+					}
+					if !yield(v) { // pinned memory stays valid until the next frc_next_f32
+						return
+					}
+				}
+			}
+		}
+		for { // exact path: bit-exact float64
 			var data *C.double
 			var first, n C.int64_t
 			if rc := C.frc_next(job, &data, &first, &n); rc != C.FRC_OK {
-				fmt.Fprintln(os.Stderr, "ERROR:", C.GoString(C.frc_last_error(job)))
-				os.Exit(2)
+				fail()
 			}
 			if n == 0 {
 				return

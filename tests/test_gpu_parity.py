@@ -361,8 +361,10 @@ def test_values_below_fp32_range_travel_as_exceptions(gpu_ctx):
     assert rel_err(got, want).max() < 1e-5
     assert info.d2h_bytes == 4 * 6 and info.exceptions >= 1
     with engine.Job(tree.parent, tree.length, rp, col, val, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx) as job:
-        (first, a), = list(job.chunks_f32())
-        xi, xv = job.exceptions()
+        gen = job.chunks_f32()
+        first, a = next(gen)
+        xi, xv = job.exceptions()      # (of the band just handed out: valid until the next call)
+        assert next(gen, None) is None
     assert first == 0 and a[0] == 0.0 and 0 in xi.tolist() and abs(xv[xi.tolist().index(0)] - want[0]) <= 1e-5 * want[0]
 
 
