@@ -97,7 +97,7 @@ float bf16_to_float(uint16_t h) {
 }
 
 constexpr int64_t kWidePiece = 2LL << 20;        // frc_next on a fast path: pairs widened per call (16 MB of doubles: cache-resident)
-constexpr int kSlots = 8;                       // output ring: enough for the compute to run ahead of the D2H
+constexpr int kSlots = 12;                      // output ring: a part's 8 bands all fit, so nothing is launched while the stream is read
 constexpr int kMinSlots = 3;
 constexpr int64_t kSlotBytesBudget = 1LL << 30;  // bytes the output ring may take beyond kMinSlots (pinned allocation is slow: ~0.4 s per GB)
 constexpr double kFlagBelow = 0.125;            // fast unweighted (fp64 / bf16 modes): recompute d below this exactly
@@ -1577,10 +1577,14 @@ int part_wait_band(Part* p, size_t idx, Slot** out) {
   const auto tn0 = std::chrono::steady_clock::now();
   PART_CUDA(p, cudaEventSynchronize(sl.done));
   float ms = 0.f;
-  PART_CUDA(p, cudaEventElapsedTime(&ms, sl.k0, sl.k1));
-  p->info.pairs_ms += ms;
-  PART_CUDA(p, cudaEventElapsedTime(&ms, sl.k1, sl.k2));
-  p->info.fixup_ms += ms;
+  if (p->mine.size() <= 2 || sh.knobs.trace) {
+    // per-band kernel spans (info.pairs_ms / fixup_ms): meaningful for a job of one or two bands (bench.py's
+    // roofline leg); a many-band stream skips the four driver calls per band on the consumer's thread
+    PART_CUDA(p, cudaEventElapsedTime(&ms, sl.k0, sl.k1));
+    p->info.pairs_ms += ms;
+    PART_CUDA(p, cudaEventElapsedTime(&ms, sl.k1, sl.k2));
+    p->info.fixup_ms += ms;
+  }
   if (idx + 1 == p->mine.size() && !p->run_timed) {
     PART_CUDA(p, cudaEventSynchronize(p->ev_run1));
     PART_CUDA(p, cudaEventElapsedTime(&ms, p->ev_embed0, p->ev_run1));

@@ -8,10 +8,10 @@
 
 namespace frc {
 
-std::vector<int> band_owners(const std::vector<int64_t>& rows, int world) {
+// Largest-first onto the least loaded owner: the best balance, any order.
+static std::vector<int> band_owners_lpt(const std::vector<int64_t>& rows, int world) {
   const size_t n = rows.size() > 0 ? rows.size() - 1 : 0;
   std::vector<int> owner(n, 0);
-  if (world <= 1) return owner;
   std::vector<size_t> order(n);
   std::vector<int64_t> cnt(n);
   for (size_t k = 0; k < n; ++k) {
@@ -26,6 +26,39 @@ std::vector<int> band_owners(const std::vector<int64_t>& rows, int world) {
       if (load[r] < load[best]) best = r;
     owner[k] = best;
     load[best] += cnt[k];
+  }
+  return owner;
+}
+
+std::vector<int> band_owners(const std::vector<int64_t>& rows, int world) {
+  // Few bands (at most 8 per owner: the automatic plan of a triangle that fits the rings): every owner queues
+  // ALL its bands at once, so the order in which the consumer reads them cannot stall anybody and the
+  // assignment only has to balance: largest first onto the least loaded owner (within ~1 %).
+  if (world > 1 && rows.size() >= 1 && rows.size() - 1 <= 8 * static_cast<size_t>(world)) return band_owners_lpt(rows, world);
+  // More bands than the rings hold: dealt in ROUNDS of G consecutive bands, every owner exactly one band per round: a consumer reading the
+  // stream in flat-index order then drains every owner's ring (and PCIe link) at the same pace, whatever the
+  // ring size (a largest-first assignment over all bands balances better but hands one owner runs of
+  // consecutive bands: the others' rings fill up and their GPUs idle until the consumer gets to them).
+  // Inside a round the largest band goes to the owner with the smallest load so far (tile-row rounding makes
+  // band sizes differ by ~10 % on small triangles; the greedy match keeps the owners within ~2 %).
+  const size_t n = rows.size() > 0 ? rows.size() - 1 : 0;
+  std::vector<int> owner(n, 0);
+  if (world <= 1) return owner;
+  std::vector<int64_t> load(world, 0);
+  std::vector<int> who(world);
+  std::vector<size_t> idx;
+  for (size_t k0 = 0; k0 < n; k0 += world) {
+    const size_t k1 = std::min(n, k0 + world);
+    idx.clear();
+    for (size_t k = k0; k < k1; ++k) idx.push_back(k);
+    auto cnt = [&](size_t k) { return tri(rows[k + 1]) - (rows[k] >= 2 ? tri(rows[k]) : 0); };
+    std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return cnt(a) > cnt(b); });
+    for (int r = 0; r < world; ++r) who[r] = r;
+    std::stable_sort(who.begin(), who.end(), [&](int a, int b) { return load[a] < load[b]; });
+    for (size_t t = 0; t < idx.size(); ++t) {
+      owner[idx[t]] = who[t];
+      load[who[t]] += cnt(idx[t]);
+    }
   }
   return owner;
 }

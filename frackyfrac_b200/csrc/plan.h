@@ -30,7 +30,8 @@ struct Band {
 //                   one or two per rank when the distances stay in HBM; more when a band would exceed
 //                   96 MB (streamed) / 1.5 GB (kept in HBM).
 std::vector<int64_t> band_boundaries(int64_t N, int64_t requested, int world, bool d2h, int per_rank, int value_bytes);
-// Largest-first onto the least loaded rank (deterministic; the same in every process).
+// One band per owner in every round of G consecutive bands, greedily balanced (deterministic; the same in
+// every process).
 std::vector<int> band_owners(const std::vector<int64_t>& rows, int world);
 // Every non-empty band of the triangle, in flat-index order, with its owner.
 std::vector<Band> make_bands(int64_t N, int64_t requested, int world, bool d2h, int per_rank, int value_bytes);

@@ -115,7 +115,7 @@ typedef struct {
   int32_t path;       /* frc_path                                               */
   int32_t device;     /* CUDA device ordinal; -1 = current device (n_devices <= 1) */
   int32_t rank;       /* tile-band sharding over `world` PROCESSES (one per GPU):  */
-  int32_t world;      /*   bands are dealt to the least loaded rank; 0/1 = all bands */
+  int32_t world;      /*   every G consecutive bands go to G different ranks; 0/1 = all  */
   int64_t band_rows;  /* rows of the lower triangle per output chunk; 0 = auto
                          (bands of equal pair count, see frc_plan_bands)        */
   uint32_t flags;     /* FRC_FLAG_*                                             */
