@@ -357,6 +357,38 @@ def host_leg(tree, csr, weighted, flags, steps, warmup, ctx=None, devices=None, 
     return dt, info, flat
 
 
+def d2h_floor(n_devices, bytes_total, chunk_bytes, reps=5):
+    """The host-link bound of `e2e`: the same bytes, in band-sized chunks, copied device -> pinned host from all
+    `n_devices` GPUs at once with plain cudaMemcpyAsync (torch), nothing else running.  On this pool's 8-GPU box the
+    GPUs share the host links: the aggregate saturates near 95 GB/s, not 8 x 55."""
+    import torch
+
+    per = max(chunk_bytes, bytes_total // n_devices)
+    n_chunks = max(1, per // max(chunk_bytes, 1))
+    src, dst, streams = [], [], []
+    for d in range(n_devices):
+        with torch.cuda.device(d):
+            src.append(torch.empty(chunk_bytes, dtype=torch.uint8, device=f"cuda:{d}"))
+            dst.append(torch.empty(chunk_bytes * min(n_chunks, 8), dtype=torch.uint8).pin_memory())
+            streams.append(torch.cuda.Stream(device=d))
+    best = 1e9
+    for _ in range(reps + 1):
+        for d in range(n_devices):
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        for c in range(n_chunks):
+            for d in range(n_devices):
+                with torch.cuda.stream(streams[d]):
+                    k = c % min(n_chunks, 8)
+                    dst[d][k * chunk_bytes:(k + 1) * chunk_bytes].copy_(src[d], non_blocking=True)
+        for d in range(n_devices):
+            streams[d].synchronize()
+        best = min(best, time.perf_counter() - t0)
+    moved = n_chunks * chunk_bytes * n_devices
+    return {"ms": 1e3 * best * bytes_total / moved, "aggregate_gbs": moved / best / 1e9, "per_device_gbs": moved / best / 1e9 / n_devices,
+            "how": f"{n_chunks} x {chunk_bytes} B per device, {n_devices} device(s) at once, cudaMemcpyAsync to pinned host, best of {reps}"}
+
+
 def kernel_roofline(ctx, tree, csr, weighted, flags, config, total_pairs, samples, peaks, peaks_kind, reps):
     """The dominant kernel timed alone: one band over the whole triangle, nothing else on the device."""
     from frackyfrac_b200 import engine
@@ -549,6 +581,10 @@ def run_ours(args, world, rank, local_rank):
                             (f"; one process, {world} GPUs, one ordered stream (opts.n_devices)" if world > 1 else "")}
             if mctx is not ctx:
                 mctx.close()
+            if not args.quick:
+                fl = d2h_floor(world, int(ei.d2h_bytes), max(1 << 20, int(ei.d2h_bytes) // max(1, int(ei.n_bands_total))))
+                e2e["d2h_floor"] = fl
+                e2e["frac_of_d2h_floor"] = fl["ms"] / e2e["ms_per_step"]
         h.cpu_barrier()
     clocks = sampler.stop()
 

@@ -178,9 +178,20 @@ int launch_unsorted_pairs(const int64_t* list_ptr, const int32_t* list_id, const
 void widen_band(const float* src, double* dst, int64_t n, bool stream_stores);  // host
 
 // ---- weighted.cu ------------------------------------------------------------
-// A is the tile-panel operand Ap[np/128][kp][128].
+// Where the fp32 tile panels of the weighted operand live.  Resident (n_dev == 0): one array
+// Ap[np/128][kp][128] in this device's HBM.  Capacity mode (n_dev = G > 1: the panels of all samples exceed one
+// GPU's HBM -- BASELINE config 5 is 320 GB): the samples are cut into 2G shards of `tiles_per_shard` tiles,
+// device d keeps the panels of shards d and 2G-1-d (slots 0 and 1 of base[d]) and NOTHING is gathered: a pair
+// tile reads its row panel from local HBM and its column panel from whichever device holds it, over NVLink,
+// through the same cp.async ring (peer access; the kernel is FP32-issue-bound, the loads hide behind it).
+struct PanelMap {
+  const float* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int32_t n_dev = 0;
+  int32_t tiles_per_shard = 0;
+};
+// A is the tile-panel operand (see PanelMap; resident: Ap[np/128][kp][128]).
 // Pairs with d < flag_below are appended to flagged[] for the fix-up pass (as the unweighted kernel).
-int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
+int launch_weighted_tiles(const PanelMap& A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
                           const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
                           int64_t first, float* out, double flag_below, uint32_t* flagged,
                           unsigned long long* n_flagged, int num_sms, cudaStream_t s);

@@ -121,6 +121,7 @@ struct Knobs {
   int peer_push = -1;         // FRC_PEER_PUSH (multi-process sharding: 0 = NCCL all-gather of the bits)
   int group_binades = 3;      // FRC_U8_GROUP_BINADES
   int shard = -1;             // FRC_SHARD (in-process multi-GPU: 0 = every device rebuilds the embedding)
+  int capacity = -1;          // FRC_CAPACITY (in-process multi-GPU, fast weighted: 1 / 0 = force / forbid the sharded-panel mode)
   static Knobs read() {
     Knobs k;
     auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; };
@@ -136,6 +137,7 @@ struct Knobs {
     k.peer_push = num("FRC_PEER_PUSH", -1);
     k.group_binades = num("FRC_U8_GROUP_BINADES", 3);
     k.shard = num("FRC_SHARD", -1);
+    k.capacity = num("FRC_CAPACITY", -1);
     return k;
   }
 };
@@ -205,6 +207,8 @@ struct Shared {
   int world = 1, rank0 = 0;   // band ownership: `world` owners; part p owns owner id rank0 + p
   enum Exchange { kNone, kInProcess, kNccl } exchange = kNone;  // how the sample shards of the embedding meet
   bool fused_embed = true, bits_feed = false;
+  bool capacity = false;      // fast weighted over several devices: panels stay sharded (PanelMap), tiles read peers' HBM
+  int64_t shard_rows = 0;     // capacity: samples per shard (np / 2G)
   ColumnPlan cols;
   std::vector<Band> bands;   // whole triangle (owners filled in)
   std::vector<int32_t> level_ptr;
@@ -243,6 +247,11 @@ struct Part {
   // sample shard of the embedding this part builds (word columns of 32 samples; everything unless sharded)
   int32_t shard_w0 = 0, shard_nw = 0;
   int64_t csr_k0 = 0, csr_k1 = 0;  // CSR entries this part uploads
+  // fast weighted: the sample ranges whose panels this part builds, and where their first tile sits in d_A
+  struct Range { int64_t s0, s1, slot0; };
+  std::vector<Range> ranges;
+  PanelMap pm;
+  int64_t remote_panel_bytes = 0;  // capacity: column panels its tiles read from other devices per pass
 
   DevTree dtree;
   DevCsr dcsr;
@@ -439,37 +448,58 @@ int embed_stage1(Part* p) {
     // <= 2 GB whatever the sample count) and leaves as the fp32 tile-panel operand + denominators;
     // a part of a sharded job only builds the slabs of its own sample shard
     const bool norm = sh.opts.normalize == 1;
-    const int64_t s_begin = static_cast<int64_t>(p->shard_w0) * 32, s_stop = s_begin + static_cast<int64_t>(p->shard_nw) * 32;
-    for (int64_t sb = s_begin; sb < s_stop; sb += p->ws_slab) {
-      const int64_t ld = std::min<int64_t>(p->ws_slab, s_stop - sb);
-      launches += launch_embed_f64(p->dtree, sh.level_ptr.data(), p->dcsr, p->d_E, ld, sb, s);
-      if (norm) launches += launch_totals_fast_f64(p->d_E, sh.B, ld, p->d_total + sb, p->d_scratch, s);
-      launches += launch_weighted_operand_panels(p->d_E, p->dtree.length, sh.B, sh.kp, ld, sb,
-                                                 norm ? p->d_total + sb : nullptr, sh.prescale, p->d_A, p->d_W,
-                                                 p->d_scratch, s);
-    }
-    const size_t per = static_cast<size_t>(p->shard_nw) * 32;
-    const size_t bytes[3] = {per * sh.kp * sizeof(float), per * sizeof(double), per * sizeof(double)};
-    if (sh.exchange == Shared::kNccl) {
-      void* bufs[3] = {p->d_A, p->d_W, p->d_total};
-      std::string cerr;
-      if (!comm_all_gather_inplace(c->comm, bufs, bytes, norm ? 3 : 2, s, &cerr)) return pfail(p, FRC_ERR_CUDA, cerr);
-      p->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (norm ? bytes[2] : 0)) * (sh.world - 1);
-    } else if (inproc) {
-      // the shard's panels, denominators and normalisers go to the same place in every other device's
-      // HBM: device-to-device copies over NVLink on the copy engines
-      for (int q = 0; q < n_parts; ++q) {
-        if (q == p->index) continue;
-        Part* o = p->job->parts[q].get();
-        PART_CUDA(p, cudaMemcpyPeerAsync(o->d_A + s_begin * sh.kp, o->dc->device, p->d_A + s_begin * sh.kp, dc->device, bytes[0], s));
-        PART_CUDA(p, cudaMemcpyPeerAsync(o->d_W + s_begin, o->dc->device, p->d_W + s_begin, dc->device, bytes[1], s));
-        if (norm)
-          PART_CUDA(p, cudaMemcpyPeerAsync(o->d_total + s_begin, o->dc->device, p->d_total + s_begin, dc->device, bytes[2], s));
+    int64_t built = 0;
+    p->info.gather_bytes = 0;
+    for (const Part::Range& rg : p->ranges) {
+      const int64_t s_begin = rg.s0, s_stop = rg.s1;
+      built += s_stop - s_begin;
+      // panels are addressed by GLOBAL sample tile inside the kernel: shift the base so that the range's
+      // first tile lands in its local slot (resident: slot == global tile, no shift)
+      float* Ap = p->d_A + (rg.slot0 - s_begin / kTile) * static_cast<int64_t>(sh.kp) * kTile;
+      for (int64_t sb = s_begin; sb < s_stop; sb += p->ws_slab) {
+        const int64_t ld = std::min<int64_t>(p->ws_slab, s_stop - sb);
+        launches += launch_embed_f64(p->dtree, sh.level_ptr.data(), p->dcsr, p->d_E, ld, sb, s);
+        if (norm) launches += launch_totals_fast_f64(p->d_E, sh.B, ld, p->d_total + sb, p->d_scratch, s);
+        launches += launch_weighted_operand_panels(p->d_E, p->dtree.length, sh.B, sh.kp, ld, sb,
+                                                   norm ? p->d_total + sb : nullptr, sh.prescale, Ap, p->d_W,
+                                                   p->d_scratch, s);
       }
-      p->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (norm ? bytes[2] : 0)) * (n_parts - 1);
+      const size_t per = static_cast<size_t>(s_stop - s_begin);
+      const size_t bytes[3] = {per * sh.kp * sizeof(float), per * sizeof(double), per * sizeof(double)};
+      if (sh.exchange == Shared::kNccl) {
+        void* bufs[3] = {p->d_A, p->d_W, p->d_total};
+        std::string cerr;
+        if (!comm_all_gather_inplace(c->comm, bufs, bytes, norm ? 3 : 2, s, &cerr)) return pfail(p, FRC_ERR_CUDA, cerr);
+        p->info.gather_bytes = static_cast<int64_t>(bytes[0] + bytes[1] + (norm ? bytes[2] : 0)) * (sh.world - 1);
+      } else if (inproc) {
+        // the shard's denominators and normalisers -- and, unless the panels stay sharded (capacity mode), the
+        // panels themselves -- go to the same place in every other device's HBM: device-to-device copies over
+        // NVLink on the copy engines
+        for (int q = 0; q < n_parts; ++q) {
+          if (q == p->index) continue;
+          Part* o = p->job->parts[q].get();
+          if (!sh.capacity)
+            PART_CUDA(p, cudaMemcpyPeerAsync(o->d_A + s_begin * sh.kp, o->dc->device, p->d_A + s_begin * sh.kp, dc->device, bytes[0], s));
+          PART_CUDA(p, cudaMemcpyPeerAsync(o->d_W + s_begin, o->dc->device, p->d_W + s_begin, dc->device, bytes[1], s));
+          if (norm)
+            PART_CUDA(p, cudaMemcpyPeerAsync(o->d_total + s_begin, o->dc->device, p->d_total + s_begin, dc->device, bytes[2], s));
+        }
+        p->info.gather_bytes += static_cast<int64_t>((sh.capacity ? 0 : bytes[0]) + bytes[1] + (norm ? bytes[2] : 0)) * (n_parts - 1);
+      }
+    }
+    if (sh.capacity) {
+      // the panel map: slot arrays of every device (all prepared by now); what crosses NVLink instead of a
+      // gather is the column panels the tiles read from their owners while they compute
+      p->pm.n_dev = n_parts;
+      p->pm.tiles_per_shard = static_cast<int32_t>(sh.shard_rows / kTile);
+      for (int q = 0; q < n_parts; ++q) p->pm.base[q] = p->job->parts[q]->d_A;
+      p->info.gather_bytes += p->remote_panel_bytes;
+    } else {
+      p->pm = PanelMap{};
+      p->pm.base[0] = p->d_A;
     }
     // write each element once, read it once when folded into its parent (+ CSR)
-    p->info.embed_bytes = 2LL * sh.B * (static_cast<int64_t>(p->shard_nw) * 32) * 8 + 12LL * (p->csr_k1 - p->csr_k0);
+    p->info.embed_bytes = 2LL * sh.B * built * 8 + 12LL * (p->csr_k1 - p->csr_k0);
   } else if (sh.fused_embed) {
     const int cur = static_cast<int>(p->run_count & 1);
     if (p->peer_push) {
@@ -629,7 +659,7 @@ int enqueue_band(Part* p, size_t idx) {
     unsigned long long* cnt = p->d_flag_counts + idx;
     *sl.ex.count = 0;  // (the slot's previous band has been delivered)
     if (sh.weighted) {
-      launches += launch_weighted_tiles(p->d_A, sh.np, sh.kp, p->d_lenf, sh.prescale, p->d_W, p->d_tiles + b.tile_off,
+      launches += launch_weighted_tiles(p->pm, sh.np, sh.kp, p->d_lenf, sh.prescale, p->d_W, p->d_tiles + b.tile_off,
                                         b.n_tiles, sh.N, b.first, sl.dev32, kFlagBelowW, sl.flagged, cnt, dc->num_sms, s);
       PART_CUDA(p, cudaEventRecord(sl.k1, s));
       // (one workspace per compute stream: consecutive bands run their fix-ups concurrently)
@@ -1000,9 +1030,27 @@ int plan_job(frc_job* j, const frc_tree_t* tree, bool neg_len) {
       sh.exchange = Shared::kNccl;
     }
   }
-  const int shards = sh.exchange == Shared::kInProcess ? n_parts : sh.exchange == Shared::kNccl ? sh.world : 1;
+  int shards = sh.exchange == Shared::kInProcess ? n_parts : sh.exchange == Shared::kNccl ? sh.world : 1;
+  // Capacity mode of the fast weighted path: the fp32 panels of ALL samples (kp x np x 4 bytes: 320 GB at
+  // BASELINE config 5) would not fit one device -> they stay sharded where they are built (two shards per
+  // device) and the pair tiles read remote column panels over NVLink (PanelMap, weighted.cu).
+  if (sh.exchange == Shared::kInProcess && sh.weighted && sh.knobs.capacity != 0 && sh.N >= 2) {
+    bool want = sh.knobs.capacity == 1;
+    if (!want) {
+      const double panels = 4.0 * static_cast<double>(round_up(sh.B, kKBlock)) * static_cast<double>(round_up(sh.N, kTile * 2LL * n_parts));
+      if (panels > 24.0 * (1 << 30)) {  // (cudaMemGetInfo costs milliseconds: only asked when it can matter)
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(c->devs[0]->device);
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && panels > 0.55 * static_cast<double>(free_b)) want = true;
+        cudaGetLastError();
+      }
+    }
+    sh.capacity = want;
+    if (want) shards = 2 * n_parts;
+  }
   // sharded: every owner builds np / shards samples, a whole number of tiles
   sh.np = std::max<int64_t>(kTile, round_up(sh.N, kTile * static_cast<int64_t>(shards)));
+  sh.shard_rows = sh.capacity ? sh.np / shards : 0;
   sh.nw = static_cast<int32_t>(sh.np / 32);
   sh.kp = static_cast<int32_t>(round_up(sh.B, kKBlock));
   sh.prescale = !neg_len;
@@ -1025,7 +1073,8 @@ int plan_job(frc_job* j, const frc_tree_t* tree, bool neg_len) {
     }
   }
   const int owners = sh.n_parts > 1 ? sh.n_parts : sh.world;
-  sh.bands = make_bands(sh.N, sh.opts.band_rows, owners, sh.d2h, sh.knobs.bands_per_rank, 8);
+  sh.bands = sh.capacity ? make_bands_capacity(sh.N, sh.np, n_parts, sh.opts.band_rows, sh.d2h)
+                         : make_bands(sh.N, sh.opts.band_rows, owners, sh.d2h, sh.knobs.bands_per_rank, 8);
   for (const Band& b : sh.bands)
     if (b.count >= (1LL << 32)) return fail(j, FRC_ERR_UNSUPPORTED, "band too large; lower band_rows");
   return FRC_OK;
@@ -1091,6 +1140,21 @@ int prepare_part(Part* p) {
   const int shards = sh.exchange == Shared::kNone ? 1 : owners;
   p->shard_nw = sh.nw / shards;
   p->shard_w0 = sh.exchange == Shared::kNone ? 0 : p->owner * p->shard_nw;
+  if (sh.capacity) {
+    // two shards per device (d and 2G-1-d: balanced pair counts), panels in slots 0 and 1 of the local array
+    const int64_t R = sh.shard_rows;
+    const int64_t a = p->owner, b = 2LL * sh.n_parts - 1 - p->owner;
+    p->ranges = {{a * R, (a + 1) * R, 0}, {b * R, (b + 1) * R, R / kTile}};
+    p->shard_nw = static_cast<int32_t>(R / 32);  // (slab sizing below)
+    for (const Tile& t : p->tiles) {
+      const int64_t sh_j = static_cast<int64_t>(t.tj) * kTile / R;
+      const int64_t dev_j = sh_j < sh.n_parts ? sh_j : 2LL * sh.n_parts - 1 - sh_j;
+      if (dev_j != p->owner) p->remote_panel_bytes += static_cast<int64_t>(sh.kp) * kTile * sizeof(float);
+    }
+  } else {
+    p->ranges = {{static_cast<int64_t>(p->shard_w0) * 32, (static_cast<int64_t>(p->shard_w0) + p->shard_nw) * 32,
+                  static_cast<int64_t>(p->shard_w0) * 32 / kTile}};
+  }
   // CSR entries this part uploads: its own rows when only the embedding reads the table (the weighted
   // fix-up walks the rows of any flagged pair, so weighted parts keep the whole table)
   p->csr_k0 = 0; p->csr_k1 = sh.nnz;
@@ -1166,7 +1230,9 @@ int prepare_part(Part* p) {
     if (!(p->d_total = dev_alloc<double>(p, sh.np))) return p->rc;
     if (sh.unsorted_l && !(p->d_list_ptr = dev_alloc<int64_t>(p, sh.N + 2))) return p->rc;
     if (!sh.exact) {
-      if (!(p->d_A = dev_alloc<float>(p, static_cast<size_t>(sh.kp) * sh.np))) return p->rc;
+      // resident: the panels of all samples; capacity: of this device's two shards only
+      const size_t a_samples = sh.capacity ? static_cast<size_t>(2 * sh.shard_rows) : static_cast<size_t>(sh.np);
+      if (!(p->d_A = dev_alloc<float>(p, static_cast<size_t>(sh.kp) * a_samples))) return p->rc;
       if (!(p->d_W = dev_alloc<double>(p, sh.np))) return p->rc;
       if (!(p->d_scratch = dev_alloc<double>(p, static_cast<size_t>(chunks) * sh.np))) return p->rc;
       if (!(p->d_flag_counts = dev_alloc<unsigned long long>(p, p->mine.size() + 1))) return p->rc;

@@ -109,6 +109,47 @@ std::vector<Band> make_bands(int64_t N, int64_t requested, int world, bool d2h, 
   return bands;
 }
 
+std::vector<Band> make_bands_capacity(int64_t N, int64_t np, int G, int64_t requested, bool d2h) {
+  std::vector<Band> bands;
+  if (N < 2 || G < 1) return bands;
+  const int64_t R = np / (2 * static_cast<int64_t>(G));  // rows per shard, a multiple of the tile size
+  const double band_cap = (d2h ? 96.0 : 1536.0) * 1024 * 1024 / 8.0;  // pairs per band, as in band_boundaries
+  for (int s = 0; s < 2 * G; ++s) {
+    const int64_t r0 = s * R, r1 = std::min<int64_t>(N, (s + 1) * R);
+    if (r0 >= r1) break;
+    const int owner = s < G ? s : 2 * G - 1 - s;
+    std::vector<int64_t> rows;
+    rows.push_back(r0);
+    if (requested > 0) {
+      const int64_t step = round_up(requested, kTile);
+      for (int64_t r = r0 + step; r < r1; r += step) rows.push_back(r);
+    } else {
+      const int64_t t0 = r0 >= 2 ? tri(r0) : 0, pairs = tri(r1) - t0;
+      const int64_t tile_rows = (r1 - r0 + kTile - 1) / kTile;
+      int64_t nb = std::max<int64_t>(d2h ? 4 : 1, static_cast<int64_t>(std::ceil(static_cast<double>(pairs) / band_cap)));
+      nb = std::max<int64_t>(1, std::min(nb, tile_rows));
+      for (int64_t k = 1; k < nb; ++k) {
+        // row r with tri(r) = t0 + pairs * k / nb
+        const double target = static_cast<double>(t0) + static_cast<double>(pairs) * k / nb;
+        int64_t r = static_cast<int64_t>(std::llround((0.5 + std::sqrt(0.25 + 2.0 * target)) / kTile)) * kTile;
+        r = std::max(r, rows.back() + kTile);
+        if (r >= r1) break;
+        rows.push_back(r);
+      }
+    }
+    rows.push_back(r1);
+    for (size_t k = 0; k + 1 < rows.size(); ++k) {
+      Band b;
+      b.row0 = rows[k]; b.row1 = rows[k + 1];
+      b.first = b.row0 >= 2 ? tri(b.row0) : 0;
+      b.count = tri(b.row1) - b.first;
+      b.owner = owner;
+      if (b.count > 0) bands.push_back(b);
+    }
+  }
+  return bands;
+}
+
 // Column k of the K-major operands holds node col_order[k] (-1: padding).  bf16: identity order,
 // uniform accumulation chunks.  u8: nodes grouped by binade triples of their length so that one
 // power-of-two scale per chunk leaves every length a 21..24-bit integer a * m (zero-length nodes
@@ -308,6 +349,17 @@ extern "C" {
 int64_t frc_debug_bands(int64_t n_samples, int64_t band_rows, int32_t world, int32_t d2h, int32_t per_rank,
                         int32_t value_bytes, int64_t* out5, int64_t cap) {
   const std::vector<frc::Band> bands = frc::make_bands(n_samples, band_rows, world, d2h != 0, per_rank, value_bytes);
+  for (size_t k = 0; k < bands.size() && static_cast<int64_t>(k) < cap; ++k) {
+    out5[5 * k] = bands[k].row0; out5[5 * k + 1] = bands[k].row1; out5[5 * k + 2] = bands[k].first;
+    out5[5 * k + 3] = bands[k].count; out5[5 * k + 4] = bands[k].owner;
+  }
+  return static_cast<int64_t>(bands.size());
+}
+
+// Capacity-mode bands (2G row shards, owner s or 2G-1-s): same output layout as frc_debug_bands.
+int64_t frc_debug_bands_capacity(int64_t n_samples, int64_t np, int32_t n_dev, int64_t band_rows, int32_t d2h,
+                                 int64_t* out5, int64_t cap) {
+  const std::vector<frc::Band> bands = frc::make_bands_capacity(n_samples, np, n_dev, band_rows, d2h != 0);
   for (size_t k = 0; k < bands.size() && static_cast<int64_t>(k) < cap; ++k) {
     out5[5 * k] = bands[k].row0; out5[5 * k + 1] = bands[k].row1; out5[5 * k + 2] = bands[k].first;
     out5[5 * k + 3] = bands[k].count; out5[5 * k + 4] = bands[k].owner;

@@ -36,6 +36,11 @@ std::vector<int> band_owners(const std::vector<int64_t>& rows, int world);
 // Every non-empty band of the triangle, in flat-index order, with its owner.
 std::vector<Band> make_bands(int64_t N, int64_t requested, int world, bool d2h, int per_rank, int value_bytes);
 
+// Capacity mode of the fast weighted path (PanelMap in frc_internal.h): the padded sample range [0, np) is cut
+// into 2G shards of np / 2G rows; shard s belongs to device s (s < G) or 2G-1-s, which balances the pair counts
+// (row r has r columns: the two shards of a device add up to the same total).  Bands never straddle a shard.
+std::vector<Band> make_bands_capacity(int64_t N, int64_t np, int G, int64_t requested, bool d2h);
+
 // Fast unweighted path: which node sits in which column of the K-major operands and how the
 // columns group into TMEM accumulation chunks.
 struct ColumnPlan {

@@ -45,9 +45,19 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Panel of sample tile t (PanelMap in frc_internal.h): local array, or slot 0 / 1 of the device that keeps
+// the tile's shard.
+__device__ __forceinline__ const float* panel_of(const PanelMap& m, int32_t t, int32_t kp) {
+  if (m.n_dev == 0) return m.base[0] + static_cast<int64_t>(t) * kp * kTile;
+  const int32_t s = t / m.tiles_per_shard, r = t - s * m.tiles_per_shard;
+  const int32_t dev = s < m.n_dev ? s : 2 * m.n_dev - 1 - s;
+  const int32_t slot = (s < m.n_dev ? 0 : m.tiles_per_shard) + r;
+  return m.base[dev] + static_cast<int64_t>(slot) * kp * kTile;
+}
+
 template <bool kPrescaled>
 __global__ void __launch_bounds__(256, 1)
-k_weighted_tiles(const float* __restrict__ A, int64_t ld, int32_t kp, const float* __restrict__ lenf,
+k_weighted_tiles(const PanelMap A, int64_t ld, int32_t kp, const float* __restrict__ lenf,
                  const double* __restrict__ W, const Tile* __restrict__ tiles, int64_t n_samples,
                  int64_t first, float* __restrict__ out, double flag_below, uint32_t* __restrict__ flagged,
                  unsigned long long* __restrict__ n_flagged) {
@@ -59,12 +69,14 @@ k_weighted_tiles(const float* __restrict__ A, int64_t ld, int32_t kp, const floa
   const int tx = tid & 15, ty = tid >> 4;
   const int n_slabs = kp / KT;
 
+  // tile-panel layout [kp][128] per sample tile: a slab of 32 nodes x 128 samples is 16 contiguous KB
+  const float* const pa = panel_of(A, tile.ti, kp);  // row samples: always local
+  const float* const pb = panel_of(A, tile.tj, kp);  // column samples: local, or a peer's HBM over NVLink
   auto load_slab = [&](int slab, int stage) {
     float* sa = smem + stage * STAGE_FLOATS;
     float* sb = sa + SLAB_FLOATS;
-    // tile-panel layout Ap[tile][kp][128]: a slab of 32 nodes x 128 samples is 16 contiguous KB
-    const float* ga = A + (static_cast<int64_t>(tile.ti) * kp + static_cast<int64_t>(slab) * KT) * kTile;
-    const float* gb = A + (static_cast<int64_t>(tile.tj) * kp + static_cast<int64_t>(slab) * KT) * kTile;
+    const float* ga = pa + static_cast<int64_t>(slab) * KT * kTile;
+    const float* gb = pb + static_cast<int64_t>(slab) * KT * kTile;
 #pragma unroll
     for (int c = tid; c < KT * (kTile / 4); c += 256) {
       cp_async16(sa + c * 4, ga + c * 4);
@@ -240,7 +252,7 @@ void weighted_setup() {
   cudaFuncSetAttribute(k_weighted_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 }
 
-int launch_weighted_tiles(const float* A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
+int launch_weighted_tiles(const PanelMap& A, int64_t ld, int32_t kp, const float* lenf, bool prescaled,
                           const double* W, const Tile* tiles, int32_t n_tiles, int64_t n_samples,
                           int64_t first, float* out, double flag_below, uint32_t* flagged,
                           unsigned long long* n_flagged, int num_sms, cudaStream_t s) {
