@@ -49,6 +49,10 @@ CONFIGS = {
     "cfg4w": ("weighted", 100_000, 100_000, 0.02, 1004, 2004),
     # 150 GB of u8 operands: more than one GPU holds -> the pair kernel expands its tiles from the bit rows
     "cfg4x": ("unweighted", 100_000, 250_000, 0.02, 1004, 2004),
+    # BASELINE config 5: 320 GB of fp32 panels -> capacity mode over 8 GPUs (panels stay sharded, tiles read peers' HBM);
+    # cfg5h is the same tree with half the samples (160 GB of panels: still more than one GPU holds)
+    "cfg5": ("weighted", 200_000, 200_000, 0.02, 1005, 2005),
+    "cfg5h": ("weighted", 200_000, 100_000, 0.02, 1005, 2005),
     "tiny": ("unweighted", 1_000, 512, 0.02, 1009, 2009),
     "tinyw": ("weighted", 1_000, 512, 0.02, 1009, 2009),
 }

@@ -1,5 +1,10 @@
-"""Runs one BASELINE config at full size on one GPU through the C ABI (host buffers -> pinned host
-distances), checks the last rows of the triangle against the oracle, prints throughput."""
+"""Runs one BASELINE config at full size through the C ABI (host buffers -> pinned host distances, streamed),
+checks the last rows of the triangle against the oracle, prints throughput.
+
+  python scripts/run_big.py cfg4 [--no-d2h]            one GPU
+  python scripts/run_big.py cfg5h --devices 8          one process driving 8 GPUs (opts.n_devices): the weighted
+                                                       panels exceed one GPU -> capacity mode (PanelMap)
+"""
 import argparse, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,6 +17,7 @@ ap.add_argument("config")
 ap.add_argument("--check-rows", type=int, default=16)
 ap.add_argument("--no-d2h", action="store_true")
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--devices", type=int, default=1)
 a = ap.parse_args()
 mode, leaves, samples, density, ts, bs = bench.CONFIGS[a.config]
 weighted = mode == "weighted"
@@ -20,7 +26,9 @@ tree = synth.random_tree(leaves, ts)
 rp, col, val = synth.random_table(tree, samples, density, bs)
 print(f"{a.config}: {mode}, {leaves} leaves ({tree.n_nodes} nodes) x {samples} samples, nnz {len(col)}; generated in {time.perf_counter() - t0:.1f}s", flush=True)
 import torch
-ctx = engine.Context(0)
+t0 = time.perf_counter()
+ctx = engine.Context(devices=list(range(a.devices))) if a.devices > 1 else engine.Context(0)
+print(f"context over {a.devices} device(s) in {time.perf_counter() - t0:.1f}s", flush=True)
 n = samples
 total = n * (n - 1) // 2
 r0 = n - a.check_rows
@@ -30,24 +38,33 @@ t0 = time.perf_counter()
 job = engine.Job(tree.parent, tree.length, rp, col, val, weighted=weighted, path=engine.PATH_FAST, ctx=ctx,
                  flags=a.flags | (engine.FLAG_NO_D2H if a.no_d2h else 0))
 t1 = time.perf_counter()
-seen = 0
+seen, chunks, expect = 0, 0, 0
 if a.no_d2h:
     seen = job.drain()
 else:
-    for first, arr in job.chunks(copy=False):
+    for first, arr in job.chunks_f32(copy=False):   # fp32 bands straight from the pinned rings, in flat-index order
+        assert first == expect
+        expect += len(arr)
         seen += len(arr)
+        chunks += 1
         lo = max(first, first_checked)
         if first + len(arr) > lo:
             tail[lo - first_checked: first + len(arr) - first_checked] = arr[lo - first:]
 t2 = time.perf_counter()
 info = job.info()
-free, tot = torch.cuda.mem_get_info(0)
+mem = [torch.cuda.mem_get_info(d) for d in range(a.devices)]
 job.close()
 assert seen == total, (seen, total)
-print(f"create {t1 - t0:.3f}s  stream {t2 - t1:.3f}s  device: h2d {info.h2d_ms:.1f} ms embed {info.embed_ms:.1f} ms pair kernels {info.pairs_ms:.1f} ms "
-      f"fixup {info.fixup_ms:.1f} ms run {info.run_ms:.1f} ms | bands {info.n_bands_total} flagged {info.flagged_pairs} kp {info.n_nodes_padded} "
-      f"| HBM in use {(tot - free) / 2**30:.1f} GiB", flush=True)
-print(f"pairs/s: device {total / (info.run_ms / 1e3):.3e}  pair-kernels-only {total / (info.pairs_ms / 1e3):.3e}  end-to-end {total / (t2 - t0):.3e}", flush=True)
+print(f"create {t1 - t0:.3f}s  stream {t2 - t1:.3f}s ({chunks} chunks)  device: h2d {info.h2d_ms:.1f} ms embed {info.embed_ms:.1f} ms "
+      f"run {info.run_ms:.1f} ms | devices {info.n_devices} bands {info.n_bands_total} flagged {info.flagged_pairs} kp {info.n_nodes_padded} "
+      f"| h2d {info.h2d_bytes / 2**30:.2f} GiB d2h {info.d2h_bytes / 2**30:.2f} GiB exchanged between devices {info.gather_bytes / 2**30:.2f} GiB "
+      f"({info.gather_bytes / 2**30 / max(1, info.n_devices):.2f} GiB per device) "
+      f"| HBM in use per device {[round((t - f) / 2**30, 1) for f, t in mem]} GiB", flush=True)
+print(f"pairs/s: device {total / (info.run_ms / 1e3):.3e}  end-to-end {total / (t2 - t0):.3e}", flush=True)
+if weighted:
+    lane = total * 2.0 * tree.n_nodes / (info.run_ms / 1e3) / 1e12
+    print(f"FP32 lane-ops: {lane:.1f} T/s over {info.n_devices} device(s) = {lane / info.n_devices / 37.22:.3f} of 148 SM x 128 lanes x 1.965 GHz per device "
+          f"(whole pass incl. embedding)", flush=True)
 if not a.no_d2h:
     ot, tab = orc.Tree.from_flat(tree.parent, tree.length), orc.Table.from_csr(rp, col, val)
     t0 = time.perf_counter()

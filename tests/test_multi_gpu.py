@@ -92,6 +92,52 @@ def test_one_process_many_gpus_one_ordered_stream(built, monkeypatch):
         assert np.array_equal(_stream(job), ref[(False, 0, engine.PATH_FAST)]) and job.info().n_devices == min(n_gpu, 8)
 
 
+def test_weighted_capacity_mode_reads_panels_from_peers(built, monkeypatch):
+    """BASELINE config 5 in the small: when the fp32 panels of all samples do not fit one GPU they stay sharded over
+    the devices (two shards each) and the pair tiles read their column panels from the owners' HBM over NVLink
+    (PanelMap, csrc/weighted.cu).  Forced here with FRC_CAPACITY=1: the stream must be the resident path's, byte
+    for byte -- same arithmetic, only the address of a panel changes."""
+    import numpy as np
+    import torch
+
+    from frackyfrac_b200 import engine, synth
+    from tests.helpers import oracle_flat, rel_err
+
+    n_gpu = torch.cuda.device_count()
+    if n_gpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    tree = synth.random_tree(900, 401)
+    rp, col, val = synth.random_table(tree, 1300, 0.04, 402, integer_counts=False)
+    m = rp[1]
+    col[9 * m:10 * m] = col[:m]; val[9 * m:10 * m] = val[:m] * (1 + 1e-4 * (np.arange(m) % 3 == 0))   # fix-up territory
+    one = engine.Context(0)
+    ref = {}
+    for normalize in (1, 2):
+        with engine.Job(tree.parent, tree.length, rp, col, val, weighted=True, normalize=normalize, path=engine.PATH_FAST, ctx=one) as job:
+            ref[normalize] = _stream(job)
+    one.close()
+    want = oracle_flat(tree, (rp, col, val), True)
+    assert rel_err(ref[1], want).max() < 1e-5
+    for nd in [k for k in (2, 4, 8) if k <= n_gpu]:
+        ctx = engine.Context(devices=list(range(nd)))
+        monkeypatch.setenv("FRC_CAPACITY", "1")
+        for normalize in (1, 2):
+            for band_rows, slab in ((0, "0"), (128, "128")):
+                monkeypatch.setenv("FRC_WS_SLAB", slab)
+                with engine.Job(tree.parent, tree.length, rp, col, val, weighted=True, normalize=normalize, path=engine.PATH_FAST,
+                                ctx=ctx, band_rows=band_rows) as job:
+                    got = _stream(job)
+                    info = job.info()
+                # remote column panels: a sizeable share of all panel reads crossed NVLink
+                assert info.n_devices == nd and info.gather_bytes > 4 * tree.n_nodes * 128 * nd
+                assert np.array_equal(got, ref[normalize], equal_nan=True), (nd, normalize, band_rows)
+        monkeypatch.setenv("FRC_CAPACITY", "0")
+        monkeypatch.delenv("FRC_WS_SLAB")
+        with engine.Job(tree.parent, tree.length, rp, col, val, weighted=True, path=engine.PATH_FAST, ctx=ctx) as job:
+            assert np.array_equal(_stream(job), ref[1], equal_nan=True)
+        ctx.close()
+
+
 def test_cli_on_all_gpus_reproduces_the_reference_fixtures(built, tmp_path):
     """The CLI stand-in with every visible GPU behind it: the six testdata/*.want files, byte for byte."""
     import torch

@@ -180,3 +180,26 @@ def test_tree_walk_levels_children_post_order(L):
     assert L.frc_debug_tree(bad.ctypes.data, 4, *[a.ctypes.data for a in z]) == -1 - 3
     bad = np.array([-1, 0, 5, 1, 1, 1], np.int32)
     assert L.frc_debug_tree(bad.ctypes.data, 6, *[a.ctypes.data for a in z]) == -1 - 2
+
+
+def test_capacity_bands_respect_the_shards(L):
+    """Capacity mode of the weighted path: 2G row shards, shard s on device s or 2G-1-s; no band straddles a shard,
+    the triangle is covered once and the devices' pair counts are balanced."""
+    L.frc_debug_bands_capacity.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int64]
+    L.frc_debug_bands_capacity.restype = C.c_int64
+    for n, G in ((1100, 2), (5000, 4), (20000, 8), (200_000, 8), (300, 2)):
+        np_ = -(-n // (256 * G)) * 256 * G
+        R = np_ // (2 * G)
+        for d2h in (0, 1):
+            for band_rows in (0, 128):
+                out = np.zeros((1 << 14, 5), np.int64)
+                k = L.frc_debug_bands_capacity(n, np_, G, band_rows, d2h, out.ctypes.data, len(out))
+                b = out[:k]
+                assert b[0, 0] == 0 and b[-1, 1] == n and (b[1:, 0] == b[:-1, 1]).all()
+                assert (b[1:, 2] == np.cumsum(b[:-1, 3])).all() and b[:, 3].sum() == n * (n - 1) // 2
+                shard = b[:, 0] // R
+                assert (shard == (b[:, 1] - 1) // R).all()
+                assert (b[:, 4] == np.where(shard < G, shard, 2 * G - 1 - shard)).all()
+                if n >= 5000:
+                    load = np.bincount(b[:, 4], weights=b[:, 3], minlength=G)
+                    assert load.max() / load.mean() < 1.06, (n, G, load)
