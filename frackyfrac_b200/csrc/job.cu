@@ -381,14 +381,19 @@ int for_parts(frc_job* j, const std::function<int(Part*)>& fn) {
 
 // Multi-process sharding: maps the blocks of the symmetric heap that the peers have not seen yet (collective:
 // every rank allocates the same sequence, so every rank gains the same blocks at the same time).
-int sym_sync(Part* p) {
+// *usable = false when SOME rank could not map a peer's block (no P2P between the GPUs, IPC unavailable in a
+// container): the ranks agree on that with one more tiny exchange, and the caller falls back to the NCCL
+// all-gather of the bit columns on every rank -- the decision has to be collective.
+int sym_sync(Part* p, bool* usable) {
   frc_ctx* c = p->job->ctx;
   DevCtx* dc = p->dc;
   const int world = comm_world(c->comm), rank = comm_rank(c->comm);
+  char failed = 0;
   while (c->sym_peer.size() < dc->sym.blocks.size()) {
     const size_t b = c->sym_peer.size();
     cudaIpcMemHandle_t mine;
-    PART_CUDA(p, cudaIpcGetMemHandle(&mine, dc->sym.blocks[b].p));
+    memset(&mine, 0, sizeof(mine));
+    if (cudaIpcGetMemHandle(&mine, dc->sym.blocks[b].p) != cudaSuccess) { cudaGetLastError(); failed = 1; }
     std::vector<cudaIpcMemHandle_t> all(world);
     std::string cerr;
     if (!comm_all_gather_host(c->comm, &mine, sizeof(mine), all.data(), dc->stream[0], &cerr))
@@ -397,11 +402,23 @@ int sym_sync(Part* p) {
     for (int r = 0; r < world; ++r) {
       if (r == rank) { bases[r] = dc->sym.blocks[b].p; continue; }
       void* q = nullptr;
-      PART_CUDA(p, cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess));
+      if (failed || cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        failed = 1;
+        q = nullptr;
+      }
       bases[r] = static_cast<char*>(q);
     }
     c->sym_peer.push_back(bases);
   }
+  for (auto& blk : c->sym_peer)
+    for (char* base : blk)
+      if (!base) failed = 1;  // (a block that could not be mapped for an earlier job)
+  std::vector<char> flags(world, 0);
+  std::string cerr;
+  if (!comm_all_gather_host(c->comm, &failed, 1, flags.data(), dc->stream[0], &cerr)) return pfail(p, FRC_ERR_CUDA, cerr);
+  *usable = true;
+  for (char f : flags) if (f) *usable = false;
   return FRC_OK;
 }
 
@@ -1254,7 +1271,11 @@ int prepare_part(Part* p) {
         p->d_bits2[k] = static_cast<uint32_t*>(dc->sym.alloc(words * sizeof(uint32_t), &e));
         if (!p->d_bits2[k]) return pfail(p, FRC_ERR_OOM, std::string("symmetric heap: ") + cudaGetErrorString(e));
       }
-      if (sym_sync(p) != FRC_OK) return p->rc;
+      bool usable = true;
+      if (sym_sync(p, &usable) != FRC_OK) return p->rc;
+      if (!usable) p->peer_push = false;  // every rank takes the NCCL all-gather of the bit columns instead
+    }
+    if (p->peer_push) {
       for (int k = 0; k < 2; ++k) {
         size_t blk = 0;
         for (; blk < dc->sym.blocks.size(); ++blk) {

@@ -91,6 +91,12 @@ std::vector<int64_t> band_boundaries(int64_t N, int64_t requested, int world, bo
     rows.push_back(r);
   }
   rows.push_back(N);
+  if (d2h && world == 1 && rows.size() > 2) {
+    // one device, streamed: the D2H chain (the bound of an end-to-end call) can only start when the FIRST band
+    // is done, so that one is cut again: a quarter of a band first, the rest of it second
+    const int64_t r = static_cast<int64_t>(std::llround(static_cast<double>(N) * std::sqrt(0.25 / static_cast<double>(n)) / kTile)) * kTile;
+    if (r >= kTile && r < rows[1]) rows.insert(rows.begin() + 1, r);
+  }
   return rows;
 }
 

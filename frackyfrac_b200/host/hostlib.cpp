@@ -128,15 +128,61 @@ struct SpaceLut {
 constexpr SpaceLut kSpace;
 inline bool go_space(unsigned char c) { return kSpace.t[c]; }
 
+// Syntax of strconv.ParseFloat beyond plain decimals (strconv/atof.go: special, readFloat, underscoreOK):
+//   [+-] inf | infinity | nan (any case; nan unsigned)
+//   [+-] digits [. digits] [e|E [+-] digits]          at least one mantissa digit, exponent digits required
+//   [+-] 0x hexdigits [. hexdigits] p|P [+-] digits    the p exponent is REQUIRED
+//   underscores may separate digits (and follow the base prefix), nowhere else ("1_000", not "1__0", "_1", "1_")
+// Returns false for anything else (what strtod would still take: "0x1A", "nan(1)", "1e", leading space ...);
+// on success `clean` holds the token without its underscores, ready for strtod.
+bool go_float_syntax(const char* s, size_t n, std::string& clean) {
+  auto lower = [](char c) { return static_cast<char>(c | 0x20); };
+  size_t i = 0;
+  if (i < n && (s[i] == '+' || s[i] == '-')) ++i;
+  const size_t body = i;
+  auto ieq = [&](const char* w) {
+    size_t k = 0;
+    for (; w[k]; ++k)
+      if (body + k >= n || lower(s[body + k]) != w[k]) return false;
+    return body + k == n;
+  };
+  if (ieq("inf") || ieq("infinity") || (body == 0 && ieq("nan"))) { clean.assign(s, n); return true; }
+  bool hex = false;
+  if (i + 1 < n && s[i] == '0' && lower(s[i + 1]) == 'x') { hex = true; i += 2; }
+  // underscore placement: '^' start, '0' digit or base prefix, '_' underscore, '!' anything else
+  char saw = hex ? '0' : '^';
+  bool digits = false, dot = false, exp = false, underscores = false;
+  for (; i < n; ++i) {
+    const char c = s[i];
+    const bool dig = (c >= '0' && c <= '9') || (hex && !exp && lower(c) >= 'a' && lower(c) <= 'f');
+    if (dig) { digits = true; saw = '0'; continue; }
+    if (c == '_') { if (saw != '0') return false; saw = '_'; underscores = true; continue; }
+    if (saw == '_') return false;
+    saw = '!';
+    if (c == '.' && !dot && !exp) { dot = true; continue; }
+    if (!exp && digits && (hex ? lower(c) == 'p' : lower(c) == 'e')) {
+      exp = true;
+      if (i + 1 < n && (s[i + 1] == '+' || s[i + 1] == '-')) ++i;
+      if (i + 1 >= n || s[i + 1] < '0' || s[i + 1] > '9') return false;  // exponent digits required
+      continue;
+    }
+    return false;
+  }
+  if (!digits || saw == '_' || (hex && !exp)) return false;
+  clean.assign(s, n);
+  if (underscores) clean.erase(std::remove(clean.begin(), clean.end(), '_'), clean.end());
+  return true;
+}
+
 // strconv.ParseFloat(s, 64).  Fast path: std::from_chars (correctly rounded, no allocation, no
-// locale); anything it does not consume entirely (hex floats, "+1", "infinity", ...) goes through
-// the strtod path the first version used for every token.
+// locale) for plain decimals; every other spelling is checked against Go's syntax (go_float_syntax)
+// and then converted by strtod.
 bool parse_float(const char* s, size_t n, double* out) {
   if (n == 0) return false;
   if (n == 1 && s[0] >= '0' && s[0] <= '9') { *out = s[0] - '0'; return true; }  // dense tables are mostly "0"
   {
     double v;
-    auto r = std::from_chars(s, s + n, v);  // general format; rejects a leading '+'
+    auto r = std::from_chars(s, s + n, v);  // general format; rejects a leading '+', underscores, hex
     if (r.ec == std::errc() && r.ptr == s + n && !(s[0] == 'i' || s[0] == 'I' || s[0] == 'n' || s[0] == 'N') &&
         !(n > 1 && (s[1] == 'i' || s[1] == 'I' || s[1] == 'n' || s[1] == 'N'))) {
       *out = v;
@@ -150,18 +196,12 @@ bool parse_float(const char* s, size_t n, double* out) {
       if (!neg_exp) return false;
     }
   }
-  unsigned char c0 = static_cast<unsigned char>(s[0]);
-  if (!(std::isdigit(c0) || c0 == '+' || c0 == '-' || c0 == '.' || c0 == 'i' || c0 == 'I' || c0 == 'n' || c0 == 'N'))
-    return false;
-  char small[64];
-  std::string big;
-  const char* z;
-  if (n < sizeof(small)) { memcpy(small, s, n); small[n] = 0; z = small; }
-  else { big.assign(s, n); z = big.c_str(); }
+  std::string clean;
+  if (!go_float_syntax(s, n, clean)) return false;
   char* end = nullptr;
   errno = 0;
-  double v = strtod(z, &end);
-  if (end == z || *end) return false;
+  const double v = strtod(clean.c_str(), &end);
+  if (end == clean.c_str() || *end) return false;
   if (errno == ERANGE && std::isinf(v)) return false;  // Go: value out of range
   *out = v;
   return true;

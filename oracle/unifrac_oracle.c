@@ -35,6 +35,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 #include <time.h>
 
 /* ------------------------------------------------------------------ errors */
@@ -353,18 +354,53 @@ double orc_table_entry_value(const orc_table *t, int64_t s, int64_t k) { return 
 /* Go regexp \s is [\t\n\f\r ] (parser.go:17 splits on \S+). */
 static int go_space(int c) { return c == '\t' || c == '\n' || c == '\f' || c == '\r' || c == ' '; }
 
+/* The spellings strconv.ParseFloat accepts (strconv/atof.go: special(), readFloat(), underscoreOK()):
+ * inf / infinity / nan in any case (inf signed), decimal mantissa with optional e-exponent, hex mantissa with a
+ * REQUIRED p-exponent, underscores only between digits or right after the 0x prefix.  Copies the token without
+ * underscores into buf (n + 1 bytes) and returns 0, or -1 for anything Go calls a syntax error. */
+static int go_float_token(const char *s, size_t n, char *buf) {
+  size_t i = 0, k = 0;
+  if (i < n && (s[i] == '+' || s[i] == '-')) buf[k++] = s[i++];
+  size_t rest = n - i;
+  if ((rest == 3 && !strncasecmp(s + i, "inf", 3)) || (rest == 8 && !strncasecmp(s + i, "infinity", 8)) ||
+      (i == 0 && rest == 3 && !strncasecmp(s, "nan", 3))) {
+    memcpy(buf, s, n); buf[n] = 0;
+    return 0;
+  }
+  int hex = 0;
+  if (i + 1 < n && s[i] == '0' && (s[i + 1] == 'x' || s[i + 1] == 'X')) { hex = 1; buf[k++] = s[i++]; buf[k++] = s[i++]; }
+  int prev_digit = hex, prev_us = 0, digits = 0, dot = 0, in_exp = 0;
+  for (; i < n; i++) {
+    char c = s[i];
+    int dig = isdigit((unsigned char)c) || (hex && !in_exp && isxdigit((unsigned char)c));
+    if (c == '_') {
+      if (!prev_digit) return -1;
+      prev_us = 1; prev_digit = 0;
+      continue;
+    }
+    if (dig) { digits = 1; prev_digit = 1; prev_us = 0; buf[k++] = c; continue; }
+    if (prev_us) return -1;
+    prev_digit = 0;
+    if (c == '.' && !dot && !in_exp) { dot = 1; buf[k++] = c; continue; }
+    if (!in_exp && digits && (hex ? (c == 'p' || c == 'P') : (c == 'e' || c == 'E'))) {
+      in_exp = 1; buf[k++] = c;
+      if (i + 1 < n && (s[i + 1] == '+' || s[i + 1] == '-')) buf[k++] = s[++i];
+      if (i + 1 >= n || !isdigit((unsigned char)s[i + 1])) return -1;
+      continue;
+    }
+    return -1;
+  }
+  if (!digits || prev_us || (hex && !in_exp)) return -1;
+  buf[k] = 0;
+  return 0;
+}
+
 /* strconv.ParseFloat(tok, 64): nil error required. */
 static int parse_float(const char *s, size_t n, double *out) {
   char small[64], *buf = small;
   if (n == 0) return -1;
   if (n + 1 > sizeof small) buf = malloc(n + 1);
-  memcpy(buf, s, n); buf[n] = 0;
-  int ok = 0;
-  /* strtod accepts leading space and a few spellings Go rejects; tokens never
-   * start with space, and every such spelling is a non-finite value that is
-   * rejected right after (parser.go:71,117). */
-  if (!(isdigit((unsigned char)buf[0]) || buf[0] == '+' || buf[0] == '-' || buf[0] == '.' ||
-        buf[0] == 'i' || buf[0] == 'I' || buf[0] == 'n' || buf[0] == 'N')) ok = -1;
+  int ok = go_float_token(s, n, buf);
   if (ok == 0) {
     char *end;
     errno = 0;

@@ -102,6 +102,57 @@ def test_cfg2w_rows_match_oracle(gpu_ctx):
         assert rel_err(flat[r0 * (r0 - 1) // 2: r1 * (r1 - 1) // 2], want).max() < 1e-5
 
 
+def _rows_against_oracle(tree, csr, weighted, flat, blocks):
+    from oracle import oracle as orc
+
+    rp, col, val = csr
+    ot, tab = orc.Tree.from_flat(tree.parent, tree.length), orc.Table.from_csr(rp, col, val)
+    worst = 0.0
+    for r0, r1 in blocks:
+        want, _, _ = orc.unifrac_rows(tab, ot, weighted, 1, os.cpu_count() or 1, r0, r1)
+        worst = max(worst, rel_err(flat[r0 * (r0 - 1) // 2: r1 * (r1 - 1) // 2], want).max())
+    return worst
+
+
+def test_cfg3_weighted_rows_match_oracle(gpu_ctx):
+    """BASELINE config 3 at full size (weighted, 50k-leaf tree x 20k samples, 2e8 pairs, 8 GB of fp32 panels):
+    sampled rows of the fp32 stream against the oracle, and the properties the size does not change."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(50_000, 1003)
+    csr = synth.random_table(tree, 20_000, 0.02, 2003)
+    n = 20_000
+    flat = np.empty(n * (n - 1) // 2, np.float32)
+    with engine.Job(tree.parent, tree.length, *csr, weighted=True, path=engine.PATH_FAST, ctx=gpu_ctx) as job:
+        expect = 0
+        for first, a in job.chunks_f32(copy=False):
+            assert first == expect
+            flat[first:first + len(a)] = a
+            expect += len(a)
+        info = job.info()
+    assert expect == len(flat) and info.path_taken == engine.PATH_FAST and info.exceptions == 0
+    assert np.isfinite(flat).all() and flat.min() >= 0.0 and flat.max() <= 1.0
+    assert _rows_against_oracle(tree, csr, True, flat, ((1, 12), (9995, 10003), (19992, 20000))) < 1e-5
+
+
+def test_cfg4s_unweighted_rows_match_oracle(gpu_ctx):
+    """A sub-block of BASELINE config 4 (unweighted, 100k-leaf tree, 30k of its samples, 4.5e8 pairs): the tensor-core
+    path at the north-star tree size (kp = 2e5: 1563 K blocks, several TMEM accumulation chunks) against the oracle."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(100_000, 1004)
+    csr = synth.random_table(tree, 30_000, 0.02, 2004)
+    n = 30_000
+    flat = np.empty(n * (n - 1) // 2, np.float32)
+    with engine.Job(tree.parent, tree.length, *csr, weighted=False, path=engine.PATH_FAST, ctx=gpu_ctx) as job:
+        for first, a in job.chunks_f32(copy=False):
+            flat[first:first + len(a)] = a
+        info = job.info()
+    assert info.operand_kind == 2 and info.exceptions == 0
+    assert np.isfinite(flat).all() and flat.min() >= 0.0 and flat.max() <= 1.0
+    assert _rows_against_oracle(tree, csr, False, flat, ((1, 10), (14996, 15002), (29994, 30000))) < 1e-5
+
+
 # ------------------------------------------------------------------ randomised parity
 def _random_case(seed):
     """Random multifurcating tree in pre-order + random sparse table with empty and tiny samples."""

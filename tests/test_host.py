@@ -243,7 +243,23 @@ def test_float_token_forms_match_the_oracle_parser(built):
     from oracle import oracle as orc
 
     tokens = ["7", "0", "+5", "-0", ".5", "5.", "1e3", "1E-3", "0x1p-2", "1_000", "1e999", "1e-999", "inf", "Inf",
-              "+Infinity", "nan", "NaN", "-1", "abc", "1.5e", "--1", "0x", "1e+400", "4.9e-324", "1.7976931348623157e308"]
+              "+Infinity", "nan", "NaN", "-1", "abc", "1.5e", "--1", "0x", "1e+400", "4.9e-324", "1.7976931348623157e308",
+              "0x1A", "0X1.8P+1", "0x_1p0", "0xp1", "nan(1)", "NAN(abc)", "+nan", "1__0", "_1", "1_", "1_.5", "1._5", "1e1_0", "1e_5",
+              "1e5e3", ".e5", ".", "+", "1p3", "0x1e3p1", "infinit", "1_0.2_5e0_1"]
+    # strconv.ParseFloat's own rules (strconv/atof.go), independent of what the C library's strtod would take:
+    # underscores may separate digits, a hex mantissa needs its p exponent, nan takes no payload
+    go_accepts = {"1_000": 1000.0, "0x1p-2": 0.25, "0X1.8P+1": 3.0, "0x_1p0": 1.0, "1e1_0": 1e10, "0x1e3p1": 966.0,
+                  "1_0.2_5e0_1": 102.5, "+5": 5.0, "5.": 5.0, ".5": 0.5}
+    go_rejects = ["0x1A", "0xp1", "nan(1)", "NAN(abc)", "1__0", "_1", "1_", "1_.5", "1._5", "1e_5", "1e5e3", ".e5", ".", "+",
+                  "1p3", "infinit", "0x", "1.5e", "1e999"]
+    for tok, want in go_accepts.items():
+        assert hostlib.Table(f"a:{tok}\n", True, 1).maps() == [{"a": want}], tok
+        assert orc.Table.parse(f"a:{tok}\n", True).maps() == [{"a": want}], tok
+    for tok in go_rejects:
+        with pytest.raises(hostlib.HostError):
+            hostlib.Table(f"a:{tok}\n", True, 1)
+        with pytest.raises(orc.OracleError):
+            orc.Table.parse(f"a:{tok}\n", True)
     for tok in tokens:
         outcomes = []
         for parse in (lambda t: hostlib.Table(t, True, 1).maps(), lambda t: orc.Table.parse(t, True).maps()):

@@ -58,7 +58,7 @@ def test_bands_partition_the_triangle_and_balance_the_owners(L):
         f, c = engine.plan_bands(14142, r, 8)
         mine = b[b[:, 4] == r]
         assert f.tolist() == mine[:, 2].tolist() and c.tolist() == mine[:, 3].tolist()
-    assert len(_bands(L, 5000, per_rank=3)) == 3
+    assert len(_bands(L, 5000, per_rank=3)) == 3 + 1   # (one device, streamed: the first band is cut again)
 
 
 @pytest.mark.parametrize("pair", [0, 1])
