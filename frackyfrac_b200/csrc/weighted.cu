@@ -15,35 +15,22 @@
 // Tiling: CTA = 128 x 128 pairs, 256 threads, each an 8 x 8 register block
 // (two 4-wide groups per side, so every shared-memory read is a conflict-free
 // LDS.128).  The contraction is staged through shared memory in 32-node slabs
-// with a 3-deep cp.async ring.  Accumulation is two-level (flush the 64
+// with a 6-deep ring of TMA bulk copies (one 16 KB copy per operand slab).  Accumulation is two-level (flush the 64
 // running sums into 64 totals every 256 nodes) to keep fp32 summation error
 // well under the 1e-5 budget for contractions of 10^5..10^6 nodes.
 #include "frc_internal.h"
+#include "ptx.cuh"
 #include "wire.cuh"
 
 namespace frc {
 namespace {
 
 constexpr int KT = 32;        // nodes per smem slab
-constexpr int STAGES = 3;
+constexpr int STAGES = 6;     // ring depth: 5 slabs (160 KB) in flight per CTA, enough to cover NVLink latency in capacity mode
 constexpr int FLUSH = 8;      // slabs between flushes (256 nodes)
-constexpr int SLAB_FLOATS = KT * kTile;           // one operand side
-constexpr int STAGE_FLOATS = 2 * SLAB_FLOATS + KT;  // + per-node lengths
-constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4;
-
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-  uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
+constexpr int SLAB_FLOATS = KT * kTile;             // one operand side: 16 KB
+constexpr int STAGE_FLOATS = 2 * SLAB_FLOATS + KT;  // + per-node lengths (128 B)
+constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4 + STAGES * 8 + 128;
 
 // Panel of sample tile t (PanelMap in frc_internal.h): local array, or slot 0 / 1 of the device that keeps
 // the tile's shard.
@@ -55,35 +42,47 @@ __device__ __forceinline__ const float* panel_of(const PanelMap& m, int32_t t, i
   return m.base[dev] + static_cast<int64_t>(slot) * kp * kTile;
 }
 
+// Operand staging: one thread issues TMA bulk copies (cp.async.bulk, 16 KB per operand slab: the tile-panel
+// layout makes a slab of 32 nodes x 128 samples contiguous) that complete on an mbarrier per stage.  The
+// FP32-issue-bound inner loop spends no slot on copies, and the copy engine keeps the whole ring in flight --
+// which is what a column panel read from a PEER's HBM over NVLink needs (capacity mode): per-thread cp.async
+// with two slabs in flight ran the remote loads latency-bound at a fifth of the local speed.
 template <bool kPrescaled>
 __global__ void __launch_bounds__(256, 1)
 k_weighted_tiles(const PanelMap A, int64_t ld, int32_t kp, const float* __restrict__ lenf,
                  const double* __restrict__ W, const Tile* __restrict__ tiles, int64_t n_samples,
                  int64_t first, float* __restrict__ out, double flag_below, uint32_t* __restrict__ flagged,
                  unsigned long long* __restrict__ n_flagged) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const Tile tile = tiles[blockIdx.x];
   const int64_t i0 = static_cast<int64_t>(tile.ti) * kTile;
   const int64_t j0 = static_cast<int64_t>(tile.tj) * kTile;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int n_slabs = kp / KT;
+  const uint32_t bar0 = ptx::smem_u32(smem + STAGES * STAGE_FLOATS);
+  (void)ld;
 
-  // tile-panel layout [kp][128] per sample tile: a slab of 32 nodes x 128 samples is 16 contiguous KB
+  // tile-panel layout [kp][128] per sample tile
   const float* const pa = panel_of(A, tile.ti, kp);  // row samples: always local
   const float* const pb = panel_of(A, tile.tj, kp);  // column samples: local, or a peer's HBM over NVLink
-  auto load_slab = [&](int slab, int stage) {
+  auto issue = [&](int slab) {  // thread 0 only
+    const int stage = slab % STAGES;
     float* sa = smem + stage * STAGE_FLOATS;
-    float* sb = sa + SLAB_FLOATS;
-    const float* ga = pa + static_cast<int64_t>(slab) * KT * kTile;
-    const float* gb = pb + static_cast<int64_t>(slab) * KT * kTile;
-#pragma unroll
-    for (int c = tid; c < KT * (kTile / 4); c += 256) {
-      cp_async16(sa + c * 4, ga + c * 4);
-      cp_async16(sb + c * 4, gb + c * 4);
-    }
-    if (!kPrescaled && tid < KT) cp_async4(sb + SLAB_FLOATS + tid, lenf + slab * KT + tid);
+    const uint32_t bar = bar0 + 8u * stage;
+    constexpr uint32_t kSlabBytes = SLAB_FLOATS * 4;
+    ptx::mbar_expect_tx(bar, 2 * kSlabBytes + (kPrescaled ? 0u : KT * 4u));
+    ptx::bulk_load_1d(ptx::smem_u32(sa), pa + static_cast<int64_t>(slab) * SLAB_FLOATS, kSlabBytes, bar);
+    ptx::bulk_load_1d(ptx::smem_u32(sa + SLAB_FLOATS), pb + static_cast<int64_t>(slab) * SLAB_FLOATS, kSlabBytes, bar);
+    if (!kPrescaled) ptx::bulk_load_1d(ptx::smem_u32(sa + 2 * SLAB_FLOATS), lenf + slab * KT, KT * 4u, bar);
   };
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(bar0 + 8u * s, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int p = 0; p < STAGES - 1 && p < n_slabs; ++p) issue(p);
 
   float acc[8][8], tot[8][8];
 #pragma unroll
@@ -91,19 +90,12 @@ k_weighted_tiles(const PanelMap A, int64_t ld, int32_t kp, const float* __restri
 #pragma unroll
     for (int b = 0; b < 8; ++b) { acc[a][b] = 0.f; tot[a][b] = 0.f; }
 
-  for (int p = 0; p < STAGES - 1; ++p) {
-    if (p < n_slabs) load_slab(p, p);
-    cp_async_commit();
-  }
   for (int slab = 0; slab < n_slabs; ++slab) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      int nxt = slab + STAGES - 1;
-      if (nxt < n_slabs) load_slab(nxt, nxt % STAGES);
-      cp_async_commit();
-    }
-    const float* sa = smem + (slab % STAGES) * STAGE_FLOATS;
+    // the stage that slab + STAGES - 1 goes to was read in the previous iteration (barrier at its end)
+    if (tid == 0 && slab + STAGES - 1 < n_slabs) issue(slab + STAGES - 1);
+    const int stage = slab % STAGES;
+    ptx::mbar_wait(bar0 + 8u * stage, static_cast<uint32_t>((slab / STAGES) & 1));
+    const float* sa = smem + stage * STAGE_FLOATS;
     const float* sb = sa + SLAB_FLOATS;
     const float* sl = sb + SLAB_FLOATS;
 #pragma unroll 4
@@ -133,8 +125,8 @@ k_weighted_tiles(const PanelMap A, int64_t ld, int32_t kp, const float* __restri
 #pragma unroll
         for (int b = 0; b < 8; ++b) { tot[a][b] += acc[a][b]; acc[a][b] = 0.f; }
     }
+    __syncthreads();  // every thread is done with this stage: it may be refilled
   }
-  cp_async_wait<0>();
 
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
