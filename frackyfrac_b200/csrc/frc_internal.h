@@ -178,15 +178,17 @@ int launch_unsorted_pairs(const int64_t* list_ptr, const int32_t* list_id, const
 void widen_band(const float* src, double* dst, int64_t n, bool stream_stores);  // host
 
 // ---- weighted.cu ------------------------------------------------------------
-// Where the fp32 tile panels of the weighted operand live.  Resident (n_dev == 0): one array
-// Ap[np/128][kp][128] in this device's HBM.  Capacity mode (n_dev = G > 1: the panels of all samples exceed one
+// Where the fp32 tile panels of the weighted operand live.  Resident (n_shards == 0): one array
+// Ap[np/128][kp][128] in this device's HBM (shard[0]).  Capacity mode (the panels of all samples exceed one
 // GPU's HBM -- BASELINE config 5 is 320 GB): the samples are cut into 2G shards of `tiles_per_shard` tiles,
-// device d keeps the panels of shards d and 2G-1-d (slots 0 and 1 of base[d]) and NOTHING is gathered: a pair
-// tile reads its row panel from local HBM and its column panel from whichever device holds it, over NVLink,
-// through the same cp.async ring (peer access; the kernel is FP32-issue-bound, the loads hide behind it).
+// device d builds and keeps the panels of shards d and 2G-1-d, and the OTHER shards visit it one at a time:
+// shard[s] points at wherever shard s currently sits in THIS device's HBM (its own slot, or one of two visiting
+// buffers that the copy engines fill from the owner over NVLink while the previous shard is being used).  A
+// launch only touches the shards of its tiles' rows (own) and of its one column shard.
 struct PanelMap {
-  const float* base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int32_t n_dev = 0;
+  const float* shard[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int32_t n_shards = 0;
   int32_t tiles_per_shard = 0;
 };
 // A is the tile-panel operand (see PanelMap; resident: Ap[np/128][kp][128]).

@@ -155,7 +155,7 @@ struct DeviceGuard {
 struct DevCtx {
   int device = 0;
   int num_sms = 0;
-  cudaStream_t stream[3] = {nullptr, nullptr, nullptr};  // two compute streams + one copy (D2H) stream
+  cudaStream_t stream[4] = {nullptr, nullptr, nullptr, nullptr};  // two compute streams, one D2H stream, one device-to-device (visiting shards) stream
   Arena dev, pin, sym;
 };
 
@@ -251,7 +251,20 @@ struct Part {
   struct Range { int64_t s0, s1, slot0; };
   std::vector<Range> ranges;
   PanelMap pm;
-  int64_t remote_panel_bytes = 0;  // capacity: column panels its tiles read from other devices per pass
+  // capacity mode: every band of this part keeps its own output buffer for the whole pass (the column shards visit
+  // one at a time, so all bands advance together); pinned ring slots only carry the D2H
+  struct CapBand {
+    float* out = nullptr;
+    uint32_t* flagged = nullptr;
+    unsigned long long* n_flagged_host = nullptr;
+    Exceptions ex;
+    cudaEvent_t done = nullptr;
+    int shard = 0;
+    std::vector<int32_t> coff;  // tile offset (inside the band's list) of every column shard, + end
+  };
+  std::vector<CapBand> cap;
+  float* d_V[2] = {nullptr, nullptr};          // visiting buffers: one shard of panels each
+  std::vector<cudaEvent_t> ev_fetch, ev_used;  // per column shard: "has arrived" / "no launch reads it any more"
 
   DevTree dtree;
   DevCsr dcsr;
@@ -504,16 +517,15 @@ int embed_stage1(Part* p) {
         p->info.gather_bytes += static_cast<int64_t>((sh.capacity ? 0 : bytes[0]) + bytes[1] + (norm ? bytes[2] : 0)) * (n_parts - 1);
       }
     }
+    p->pm = PanelMap{};
     if (sh.capacity) {
-      // the panel map: slot arrays of every device (all prepared by now); what crosses NVLink instead of a
-      // gather is the column panels the tiles read from their owners while they compute
-      p->pm.n_dev = n_parts;
+      // own shards in their slots; the visiting shards are filled in by the rotation (start_pairs_capacity)
+      p->pm.n_shards = 2 * n_parts;
       p->pm.tiles_per_shard = static_cast<int32_t>(sh.shard_rows / kTile);
-      for (int q = 0; q < n_parts; ++q) p->pm.base[q] = p->job->parts[q]->d_A;
-      p->info.gather_bytes += p->remote_panel_bytes;
+      for (const Part::Range& rg : p->ranges)
+        p->pm.shard[rg.s0 / sh.shard_rows] = p->d_A + rg.slot0 * static_cast<int64_t>(sh.kp) * kTile;
     } else {
-      p->pm = PanelMap{};
-      p->pm.base[0] = p->d_A;
+      p->pm.shard[0] = p->d_A;
     }
     // write each element once, read it once when folded into its parent (+ CSR)
     p->info.embed_bytes = 2LL * sh.B * built * 8 + 12LL * (p->csr_k1 - p->csr_k0);
@@ -661,6 +673,24 @@ int enqueue_band(Part* p, size_t idx) {
   cudaStream_t s = dc->stream[si];
   sl.band = static_cast<int>(idx);
   int launches = 0;
+  if (sh.capacity) {
+    // the band was (or is being) computed by the rotation; what is queued here is its way to the host
+    Part::CapBand& cb = p->cap[idx];
+    cudaStream_t cs = dc->stream[2];
+    sl.dev32 = cb.out; sl.flagged = cb.flagged; sl.n_flagged_host = cb.n_flagged_host; sl.ex = cb.ex;
+    PART_CUDA(p, cudaStreamWaitEvent(cs, cb.done, 0));
+    for (cudaEvent_t e : {sl.k0, sl.k1, sl.k2}) PART_CUDA(p, cudaEventRecord(e, cs));
+    if (sh.d2h) {
+      PART_CUDA(p, cudaMemcpyAsync(sl.host32, cb.out, sizeof(float) * b.count, cudaMemcpyDeviceToHost, cs));
+      p->info.d2h_bytes += static_cast<int64_t>(sizeof(float)) * b.count;
+    }
+    PART_CUDA(p, cudaEventRecord(sl.done, cs));
+    if (idx + 1 == p->mine.size()) {
+      PART_CUDA(p, cudaStreamWaitEvent(dc->stream[0], sl.done, 0));
+      PART_CUDA(p, cudaEventRecord(p->ev_run1, dc->stream[0]));
+    }
+    return FRC_OK;
+  }
   PART_CUDA(p, cudaEventRecord(sl.k0, s));
   if (sh.exact) {
     if (sh.unsorted_l)
@@ -726,6 +756,64 @@ int enqueue_band(Part* p, size_t idx) {
   return FRC_OK;
 }
 
+// Capacity mode of the fast weighted path: queue the WHOLE pair stage of this part.  The column shards
+// 0, 1, ... visit the device one at a time: a shard of another device is copied into one of two visiting buffers
+// by the copy engines (device-to-device over NVLink, on its own stream, while the previous shard is in use), and
+// for every visiting shard c one launch per band covers the tiles (rows of the band) x (columns of shard c).  A
+// band is complete -- fix-up, then its `done` event -- once the shard of its own rows has passed.  Every remote
+// shard crosses NVLink exactly once per device and pass; the tile kernel itself only ever reads local HBM.
+int start_pairs_capacity(Part* p) {
+  const Shared& sh = *p->sh;
+  DevCtx* dc = p->dc;
+  cudaStream_t s = dc->stream[0], cin = dc->stream[3];
+  const int G = sh.n_parts, n_shards = 2 * G;
+  const int64_t T = sh.shard_rows / kTile;
+  const size_t shard_floats = static_cast<size_t>(T) * kTile * sh.kp;
+  int launches = 0, n_remote = 0, last_c = 0;
+  for (const Part::CapBand& cb : p->cap) last_c = std::max(last_c, cb.shard);
+  PanelMap pm = p->pm;  // own shards set by the embedding stage
+  int prev_user[2] = {-1, -1};
+  int64_t fetched = 0;
+  for (Part::CapBand& cb : p->cap) *cb.ex.count = 0;
+  for (int c = 0; c <= last_c; ++c) {
+    const int owner = c < G ? c : n_shards - 1 - c;
+    bool remote = owner != p->index;
+    if (remote) {
+      const int buf = n_remote++ & 1;
+      Part* o = p->job->parts[owner].get();
+      const float* src = o->d_A + (c < G ? 0 : shard_floats);
+      if (prev_user[buf] >= 0) PART_CUDA(p, cudaStreamWaitEvent(cin, p->ev_used[prev_user[buf]], 0));
+      PART_CUDA(p, cudaStreamWaitEvent(cin, o->ev_shard, 0));  // the owner has built it
+      PART_CUDA(p, cudaMemcpyPeerAsync(p->d_V[buf], dc->device, src, o->dc->device, shard_floats * sizeof(float), cin));
+      PART_CUDA(p, cudaEventRecord(p->ev_fetch[c], cin));
+      PART_CUDA(p, cudaStreamWaitEvent(s, p->ev_fetch[c], 0));
+      pm.shard[c] = p->d_V[buf];
+      prev_user[buf] = c;
+      fetched += static_cast<int64_t>(shard_floats * sizeof(float));
+    }
+    for (size_t idx = 0; idx < p->cap.size(); ++idx) {
+      Part::CapBand& cb = p->cap[idx];
+      if (cb.shard < c) continue;
+      const Band& b = p->bands[idx];
+      const int32_t t0 = cb.coff[c], n = cb.coff[c + 1] - cb.coff[c];
+      unsigned long long* cnt = p->d_flag_counts + idx;
+      launches += launch_weighted_tiles(pm, sh.np, sh.kp, p->d_lenf, sh.prescale, p->d_W, p->d_tiles + b.tile_off + t0, n,
+                                        sh.N, b.first, cb.out, kFlagBelowW, cb.flagged, cnt, dc->num_sms, s);
+      if (cb.shard == c) {
+        launches += launch_weighted_fixup(p->dcsr, p->dtree, sh.opts.normalize == 1 ? p->d_total : nullptr, p->d_W,
+                                          cb.flagged, cnt, cb.n_flagged_host, b.first, p->d_fix_ws[0], kFixupCtas,
+                                          cb.out, cb.ex, s);
+        PART_CUDA(p, cudaEventRecord(cb.done, s));
+      }
+    }
+    PART_CUDA(p, cudaGetLastError());
+    if (remote) PART_CUDA(p, cudaEventRecord(p->ev_used[c], s));
+  }
+  p->info.gather_bytes += fetched;
+  p->info.kernel_launches += launches;
+  return FRC_OK;
+}
+
 int start_pairs(Part* p) {
   p->next_enqueue = p->next_deliver = 0;
   p->info.pairs_ms = 0;
@@ -739,6 +827,7 @@ int start_pairs(Part* p) {
     PART_CUDA(p, cudaEventRecord(p->ev_run1, p->dc->stream[0]));
     return FRC_OK;
   }
+  if (p->sh->capacity && start_pairs_capacity(p)) return p->rc;
   // keep one slot free for the band the caller is still reading
   while (p->next_enqueue < p->mine.size() && p->next_enqueue < static_cast<size_t>(p->n_slots - 1)) {
     if (enqueue_band(p, p->next_enqueue)) return p->rc;
@@ -763,6 +852,9 @@ void destroy_part(Part* p) {
   for (cudaEvent_t e : {p->ev_h2d0, p->ev_h2d1, p->ev_embed0, p->ev_embed1, p->ev_run1, p->ev_join, p->ev_bits,
                         p->ev_rsum, p->ev_shard})
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->ev_fetch) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->ev_used) if (e) cudaEventDestroy(e);
+  for (auto& cb : p->cap) if (cb.done) cudaEventDestroy(cb.done);
   tc_operands_destroy(p->tc);
   bits_operands_destroy(p->bo);
   if (p->dc) {
@@ -1148,8 +1240,28 @@ int prepare_part(Part* p) {
       p->max_band = std::max(p->max_band, sh.bands[k].count);
     }
   const bool fast_uw = !sh.exact && !sh.weighted;
-  if (!sh.exact)
+  if (sh.capacity) {
+    // tiles of a band grouped by COLUMN SHARD (the order the shards visit in), column-major inside a group
+    const int64_t T = sh.shard_rows / kTile;
+    p->cap.resize(p->bands.size());
+    for (size_t k = 0; k < p->bands.size(); ++k) {
+      Band& b = p->bands[k];
+      Part::CapBand& cb = p->cap[k];
+      const int32_t t0 = static_cast<int32_t>(b.row0 / kTile), t1 = static_cast<int32_t>((b.row1 - 1) / kTile);
+      cb.shard = static_cast<int>(t0 / T);
+      b.tile_off = static_cast<int32_t>(p->tiles.size());
+      cb.coff.assign(2 * sh.n_parts + 1, 0);
+      for (int c = 0; c <= cb.shard; ++c) {
+        cb.coff[c] = static_cast<int32_t>(p->tiles.size()) - b.tile_off;
+        for (int32_t tj = static_cast<int32_t>(c * T); tj < static_cast<int32_t>((c + 1) * T) && tj <= t1; ++tj)
+          for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) p->tiles.push_back({ti, tj});
+      }
+      for (int c = cb.shard + 1; c <= 2 * sh.n_parts; ++c) cb.coff[c] = static_cast<int32_t>(p->tiles.size()) - b.tile_off;
+      b.n_tiles = static_cast<int32_t>(p->tiles.size()) - b.tile_off;
+    }
+  } else if (!sh.exact) {
     for (Band& b : p->bands) append_band_tiles(b, fast_uw, p->tiles);
+  }
   const int owners = sh.n_parts > 1 ? sh.n_parts : sh.world;
   std::vector<uint8_t> need;
   if (fast_uw && owners > 1 && sh.fused_embed) need = operand_need_blocks(p->tiles, sh.np, true);
@@ -1163,11 +1275,6 @@ int prepare_part(Part* p) {
     const int64_t a = p->owner, b = 2LL * sh.n_parts - 1 - p->owner;
     p->ranges = {{a * R, (a + 1) * R, 0}, {b * R, (b + 1) * R, R / kTile}};
     p->shard_nw = static_cast<int32_t>(R / 32);  // (slab sizing below)
-    for (const Tile& t : p->tiles) {
-      const int64_t sh_j = static_cast<int64_t>(t.tj) * kTile / R;
-      const int64_t dev_j = sh_j < sh.n_parts ? sh_j : 2LL * sh.n_parts - 1 - sh_j;
-      if (dev_j != p->owner) p->remote_panel_bytes += static_cast<int64_t>(sh.kp) * kTile * sizeof(float);
-    }
   } else {
     p->ranges = {{static_cast<int64_t>(p->shard_w0) * 32, (static_cast<int64_t>(p->shard_w0) + p->shard_nw) * 32,
                   static_cast<int64_t>(p->shard_w0) * 32 / kTile}};
@@ -1250,6 +1357,30 @@ int prepare_part(Part* p) {
       // resident: the panels of all samples; capacity: of this device's two shards only
       const size_t a_samples = sh.capacity ? static_cast<size_t>(2 * sh.shard_rows) : static_cast<size_t>(sh.np);
       if (!(p->d_A = dev_alloc<float>(p, static_cast<size_t>(sh.kp) * a_samples))) return p->rc;
+      if (sh.capacity) {
+        for (int k = 0; k < 2; ++k)
+          if (!(p->d_V[k] = dev_alloc<float>(p, static_cast<size_t>(sh.kp) * sh.shard_rows))) return p->rc;
+        p->ev_fetch.assign(2 * sh.n_parts, nullptr);
+        p->ev_used.assign(2 * sh.n_parts, nullptr);
+        for (int k = 0; k < 2 * sh.n_parts; ++k) {
+          PART_CUDA(p, cudaEventCreateWithFlags(&p->ev_fetch[k], cudaEventDisableTiming));
+          PART_CUDA(p, cudaEventCreateWithFlags(&p->ev_used[k], cudaEventDisableTiming));
+        }
+        for (size_t k = 0; k < p->cap.size(); ++k) {
+          Part::CapBand& cb = p->cap[k];
+          const size_t cnt = static_cast<size_t>(p->bands[k].count);
+          if (!(cb.out = dev_alloc<float>(p, cnt))) return p->rc;
+          if (!(cb.flagged = dev_alloc<uint32_t>(p, cnt))) return p->rc;
+          if (!(cb.n_flagged_host = pin_alloc<unsigned long long>(p, 1))) return p->rc;
+          *cb.n_flagged_host = 0;
+          if (!(cb.ex.count = pin_alloc<unsigned long long>(p, 1))) return p->rc;
+          if (!(cb.ex.index = pin_alloc<int64_t>(p, kMaxExceptions))) return p->rc;
+          if (!(cb.ex.value = pin_alloc<double>(p, kMaxExceptions))) return p->rc;
+          cb.ex.cap = kMaxExceptions;
+          *cb.ex.count = 0;
+          PART_CUDA(p, cudaEventCreateWithFlags(&cb.done, cudaEventDisableTiming));
+        }
+      }
       if (!(p->d_W = dev_alloc<double>(p, sh.np))) return p->rc;
       if (!(p->d_scratch = dev_alloc<double>(p, static_cast<size_t>(chunks) * sh.np))) return p->rc;
       if (!(p->d_flag_counts = dev_alloc<unsigned long long>(p, p->mine.size() + 1))) return p->rc;
@@ -1333,6 +1464,9 @@ int prepare_part(Part* p) {
     if (sh.exact) {
       if (!(sl.dev64 = dev_alloc<double>(p, p->max_band))) return p->rc;
       if (sh.d2h && !(sl.host64 = pin_alloc<double>(p, p->max_band))) return p->rc;
+    } else if (sh.capacity) {
+      // (device buffers, flag lists and exception lists belong to the bands: Part::CapBand)
+      if (sh.d2h && !(sl.host32 = pin_alloc<float>(p, p->max_band))) return p->rc;
     } else {
       if (!(sl.dev32 = dev_alloc<float>(p, p->max_band))) return p->rc;
       if (sh.d2h && !(sl.host32 = pin_alloc<float>(p, p->max_band))) return p->rc;

@@ -32,21 +32,17 @@ constexpr int SLAB_FLOATS = KT * kTile;             // one operand side: 16 KB
 constexpr int STAGE_FLOATS = 2 * SLAB_FLOATS + KT;  // + per-node lengths (128 B)
 constexpr int SMEM_BYTES = STAGES * STAGE_FLOATS * 4 + STAGES * 8 + 128;
 
-// Panel of sample tile t (PanelMap in frc_internal.h): local array, or slot 0 / 1 of the device that keeps
-// the tile's shard.
+// Panel of sample tile t (PanelMap in frc_internal.h): the one local array, or the place its shard currently
+// occupies in this device's HBM.
 __device__ __forceinline__ const float* panel_of(const PanelMap& m, int32_t t, int32_t kp) {
-  if (m.n_dev == 0) return m.base[0] + static_cast<int64_t>(t) * kp * kTile;
+  if (m.n_shards == 0) return m.shard[0] + static_cast<int64_t>(t) * kp * kTile;
   const int32_t s = t / m.tiles_per_shard, r = t - s * m.tiles_per_shard;
-  const int32_t dev = s < m.n_dev ? s : 2 * m.n_dev - 1 - s;
-  const int32_t slot = (s < m.n_dev ? 0 : m.tiles_per_shard) + r;
-  return m.base[dev] + static_cast<int64_t>(slot) * kp * kTile;
+  return m.shard[s] + static_cast<int64_t>(r) * kp * kTile;
 }
 
 // Operand staging: one thread issues TMA bulk copies (cp.async.bulk, 16 KB per operand slab: the tile-panel
 // layout makes a slab of 32 nodes x 128 samples contiguous) that complete on an mbarrier per stage.  The
-// FP32-issue-bound inner loop spends no slot on copies, and the copy engine keeps the whole ring in flight --
-// which is what a column panel read from a PEER's HBM over NVLink needs (capacity mode): per-thread cp.async
-// with two slabs in flight ran the remote loads latency-bound at a fifth of the local speed.
+// FP32-issue-bound inner loop spends no slot on copies and the copy engine keeps the whole ring in flight.
 template <bool kPrescaled>
 __global__ void __launch_bounds__(256, 1)
 k_weighted_tiles(const PanelMap A, int64_t ld, int32_t kp, const float* __restrict__ lenf,
@@ -64,8 +60,8 @@ k_weighted_tiles(const PanelMap A, int64_t ld, int32_t kp, const float* __restri
   (void)ld;
 
   // tile-panel layout [kp][128] per sample tile
-  const float* const pa = panel_of(A, tile.ti, kp);  // row samples: always local
-  const float* const pb = panel_of(A, tile.tj, kp);  // column samples: local, or a peer's HBM over NVLink
+  const float* const pa = panel_of(A, tile.ti, kp);  // row samples: this device's own shard
+  const float* const pb = panel_of(A, tile.tj, kp);  // column samples: own shard or the visiting one
   auto issue = [&](int slab) {  // thread 0 only
     const int stage = slab % STAGES;
     float* sa = smem + stage * STAGE_FLOATS;
