@@ -251,18 +251,26 @@ struct Part {
   struct Range { int64_t s0, s1, slot0; };
   std::vector<Range> ranges;
   PanelMap pm;
-  // capacity mode: every band of this part keeps its own output buffer for the whole pass (the column shards visit
-  // one at a time, so all bands advance together); pinned ring slots only carry the D2H
-  struct CapBand {
+  // capacity mode: the rows of each of this part's (two) shards form one GROUP with one output buffer for the whole
+  // pass (the column shards visit one at a time, so all rows advance together) and ONE launch per visiting shard:
+  // thousands of tiles each -- per-band launches of 50-100 tiles left two thirds of the SMs idle at cfg5 sizes,
+  // where the 48 MB band cap makes a band one or two tile rows thin.  Bands are sub-ranges of their group's
+  // buffer; the pinned ring slots only carry the D2H.
+  struct CapGroup {
+    int shard = 0;                 // row shard (also the last column shard its tiles need)
+    int64_t first = 0, count = 0;  // flat range of the group's rows
+    int32_t tile_off = 0;          // into the part's tile list
+    std::vector<int32_t> coff;     // tile offset (inside the group's list) of every column shard, + end
     float* out = nullptr;
     uint32_t* flagged = nullptr;
+    unsigned long long* cnt = nullptr;  // device counter of flagged pairs
     unsigned long long* n_flagged_host = nullptr;
     Exceptions ex;
     cudaEvent_t done = nullptr;
-    int shard = 0;
-    std::vector<int32_t> coff;  // tile offset (inside the band's list) of every column shard, + end
+    bool counted = false;          // its flagged / exception counts have been added to the job's info
   };
-  std::vector<CapBand> cap;
+  std::vector<CapGroup> cap;
+  std::vector<int> band_group;     // per band of this part: index into cap
   float* d_V[2] = {nullptr, nullptr};          // visiting buffers: one shard of panels each
   std::vector<cudaEvent_t> ev_fetch, ev_used;  // per column shard: "has arrived" / "no launch reads it any more"
 
@@ -327,6 +335,9 @@ struct frc_job {
   size_t next_item = 0;
   int held_part = -1;   // part whose slot the caller currently reads
   int held_slot = -1;
+  int64_t held_first = 0, held_count = 0;  // flat range of the run handed out last
+  std::vector<int64_t> ex_index;           // frc_chunk_exceptions: the entries inside that range
+  std::vector<double> ex_value;
   int read_mode = 0;    // 0 = not decided, 1 = frc_next (float64), 2 = frc_next_f32
   double* wide = nullptr;  // frc_next on a fast path: the one double buffer handed out (<= kWidePiece values)
   int64_t piece_first = 0, piece_off = 0, piece_end = 0;
@@ -675,13 +686,16 @@ int enqueue_band(Part* p, size_t idx) {
   int launches = 0;
   if (sh.capacity) {
     // the band was (or is being) computed by the rotation; what is queued here is its way to the host
-    Part::CapBand& cb = p->cap[idx];
+    Part::CapGroup& cb = p->cap[p->band_group[idx]];
     cudaStream_t cs = dc->stream[2];
-    sl.dev32 = cb.out; sl.flagged = cb.flagged; sl.n_flagged_host = cb.n_flagged_host; sl.ex = cb.ex;
+    float* band_out = cb.out + (b.first - cb.first);
+    sl.dev32 = band_out; sl.flagged = cb.flagged; sl.ex = cb.ex;
+    sl.n_flagged_host = cb.counted ? nullptr : cb.n_flagged_host;  // (a group's count is reported once)
+    cb.counted = true;
     PART_CUDA(p, cudaStreamWaitEvent(cs, cb.done, 0));
     for (cudaEvent_t e : {sl.k0, sl.k1, sl.k2}) PART_CUDA(p, cudaEventRecord(e, cs));
     if (sh.d2h) {
-      PART_CUDA(p, cudaMemcpyAsync(sl.host32, cb.out, sizeof(float) * b.count, cudaMemcpyDeviceToHost, cs));
+      PART_CUDA(p, cudaMemcpyAsync(sl.host32, band_out, sizeof(float) * b.count, cudaMemcpyDeviceToHost, cs));
       p->info.d2h_bytes += static_cast<int64_t>(sizeof(float)) * b.count;
     }
     PART_CUDA(p, cudaEventRecord(sl.done, cs));
@@ -770,11 +784,12 @@ int start_pairs_capacity(Part* p) {
   const int64_t T = sh.shard_rows / kTile;
   const size_t shard_floats = static_cast<size_t>(T) * kTile * sh.kp;
   int launches = 0, n_remote = 0, last_c = 0;
-  for (const Part::CapBand& cb : p->cap) last_c = std::max(last_c, cb.shard);
+  for (const Part::CapGroup& cb : p->cap) last_c = std::max(last_c, cb.shard);
   PanelMap pm = p->pm;  // own shards set by the embedding stage
   int prev_user[2] = {-1, -1};
   int64_t fetched = 0;
-  for (Part::CapBand& cb : p->cap) *cb.ex.count = 0;
+  for (Part::CapGroup& cb : p->cap) { *cb.ex.count = 0; cb.counted = false; }
+  PART_CUDA(p, cudaMemsetAsync(p->cap[0].cnt, 0, sizeof(unsigned long long) * p->cap.size(), s));
   for (int c = 0; c <= last_c; ++c) {
     const int owner = c < G ? c : n_shards - 1 - c;
     bool remote = owner != p->index;
@@ -791,17 +806,14 @@ int start_pairs_capacity(Part* p) {
       prev_user[buf] = c;
       fetched += static_cast<int64_t>(shard_floats * sizeof(float));
     }
-    for (size_t idx = 0; idx < p->cap.size(); ++idx) {
-      Part::CapBand& cb = p->cap[idx];
+    for (Part::CapGroup& cb : p->cap) {
       if (cb.shard < c) continue;
-      const Band& b = p->bands[idx];
       const int32_t t0 = cb.coff[c], n = cb.coff[c + 1] - cb.coff[c];
-      unsigned long long* cnt = p->d_flag_counts + idx;
-      launches += launch_weighted_tiles(pm, sh.np, sh.kp, p->d_lenf, sh.prescale, p->d_W, p->d_tiles + b.tile_off + t0, n,
-                                        sh.N, b.first, cb.out, kFlagBelowW, cb.flagged, cnt, dc->num_sms, s);
+      launches += launch_weighted_tiles(pm, sh.np, sh.kp, p->d_lenf, sh.prescale, p->d_W, p->d_tiles + cb.tile_off + t0, n,
+                                        sh.N, cb.first, cb.out, kFlagBelowW, cb.flagged, cb.cnt, dc->num_sms, s);
       if (cb.shard == c) {
         launches += launch_weighted_fixup(p->dcsr, p->dtree, sh.opts.normalize == 1 ? p->d_total : nullptr, p->d_W,
-                                          cb.flagged, cnt, cb.n_flagged_host, b.first, p->d_fix_ws[0], kFixupCtas,
+                                          cb.flagged, cb.cnt, cb.n_flagged_host, cb.first, p->d_fix_ws[0], kFixupCtas,
                                           cb.out, cb.ex, s);
         PART_CUDA(p, cudaEventRecord(cb.done, s));
       }
@@ -1241,23 +1253,33 @@ int prepare_part(Part* p) {
     }
   const bool fast_uw = !sh.exact && !sh.weighted;
   if (sh.capacity) {
-    // tiles of a band grouped by COLUMN SHARD (the order the shards visit in), column-major inside a group
+    // one group per row shard of this part: its bands, and its tiles grouped by COLUMN SHARD (the order the
+    // shards visit in), column-major inside a column shard (the CTAs of a wave share one or two column panels)
     const int64_t T = sh.shard_rows / kTile;
-    p->cap.resize(p->bands.size());
     for (size_t k = 0; k < p->bands.size(); ++k) {
-      Band& b = p->bands[k];
-      Part::CapBand& cb = p->cap[k];
-      const int32_t t0 = static_cast<int32_t>(b.row0 / kTile), t1 = static_cast<int32_t>((b.row1 - 1) / kTile);
-      cb.shard = static_cast<int>(t0 / T);
-      b.tile_off = static_cast<int32_t>(p->tiles.size());
-      cb.coff.assign(2 * sh.n_parts + 1, 0);
-      for (int c = 0; c <= cb.shard; ++c) {
-        cb.coff[c] = static_cast<int32_t>(p->tiles.size()) - b.tile_off;
+      const Band& b = p->bands[k];
+      const int shard = static_cast<int>(b.row0 / sh.shard_rows);
+      if (p->cap.empty() || p->cap.back().shard != shard) {
+        Part::CapGroup g;
+        g.shard = shard;
+        g.first = b.first;
+        p->cap.push_back(g);
+      }
+      p->cap.back().count = b.first + b.count - p->cap.back().first;
+      p->band_group.push_back(static_cast<int>(p->cap.size()) - 1);
+    }
+    for (Part::CapGroup& g : p->cap) {
+      if (g.count >= (1LL << 32)) return pfail(p, FRC_ERR_UNSUPPORTED, "capacity mode: a row shard holds 2^32 pairs or more");
+      const int64_t r0 = static_cast<int64_t>(g.shard) * sh.shard_rows, r1 = std::min<int64_t>(sh.N, r0 + sh.shard_rows);
+      const int32_t t0 = static_cast<int32_t>(r0 / kTile), t1 = static_cast<int32_t>((r1 - 1) / kTile);
+      g.tile_off = static_cast<int32_t>(p->tiles.size());
+      g.coff.assign(2 * sh.n_parts + 1, 0);
+      for (int c = 0; c <= g.shard; ++c) {
+        g.coff[c] = static_cast<int32_t>(p->tiles.size()) - g.tile_off;
         for (int32_t tj = static_cast<int32_t>(c * T); tj < static_cast<int32_t>((c + 1) * T) && tj <= t1; ++tj)
           for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) p->tiles.push_back({ti, tj});
       }
-      for (int c = cb.shard + 1; c <= 2 * sh.n_parts; ++c) cb.coff[c] = static_cast<int32_t>(p->tiles.size()) - b.tile_off;
-      b.n_tiles = static_cast<int32_t>(p->tiles.size()) - b.tile_off;
+      for (int c = g.shard + 1; c <= 2 * sh.n_parts; ++c) g.coff[c] = static_cast<int32_t>(p->tiles.size()) - g.tile_off;
     }
   } else if (!sh.exact) {
     for (Band& b : p->bands) append_band_tiles(b, fast_uw, p->tiles);
@@ -1366,9 +1388,12 @@ int prepare_part(Part* p) {
           PART_CUDA(p, cudaEventCreateWithFlags(&p->ev_fetch[k], cudaEventDisableTiming));
           PART_CUDA(p, cudaEventCreateWithFlags(&p->ev_used[k], cudaEventDisableTiming));
         }
+        unsigned long long* cnts = dev_alloc<unsigned long long>(p, p->cap.size() + 1);
+        if (!cnts) return p->rc;
         for (size_t k = 0; k < p->cap.size(); ++k) {
-          Part::CapBand& cb = p->cap[k];
-          const size_t cnt = static_cast<size_t>(p->bands[k].count);
+          Part::CapGroup& cb = p->cap[k];
+          const size_t cnt = static_cast<size_t>(cb.count);
+          cb.cnt = cnts + k;
           if (!(cb.out = dev_alloc<float>(p, cnt))) return p->rc;
           if (!(cb.flagged = dev_alloc<uint32_t>(p, cnt))) return p->rc;
           if (!(cb.n_flagged_host = pin_alloc<unsigned long long>(p, 1))) return p->rc;
@@ -1465,7 +1490,7 @@ int prepare_part(Part* p) {
       if (!(sl.dev64 = dev_alloc<double>(p, p->max_band))) return p->rc;
       if (sh.d2h && !(sl.host64 = pin_alloc<double>(p, p->max_band))) return p->rc;
     } else if (sh.capacity) {
-      // (device buffers, flag lists and exception lists belong to the bands: Part::CapBand)
+      // (device buffers, flag lists and exception lists belong to the row-shard groups: Part::CapGroup)
       if (sh.d2h && !(sl.host32 = pin_alloc<float>(p, p->max_band))) return p->rc;
     } else {
       if (!(sl.dev32 = dev_alloc<float>(p, p->max_band))) return p->rc;
@@ -1818,7 +1843,7 @@ int part_wait_band(Part* p, size_t idx, Slot** out) {
     if (n > static_cast<unsigned long long>(sl.ex.cap))
       return pfail(p, FRC_ERR_UNSUPPORTED, "more than " + std::to_string(sl.ex.cap) + " distances of one band lie below "
                                            "fp32's range (|d| < 1.2e-38): run this input with path = FRC_PATH_EXACT");
-    p->info.exceptions += static_cast<int64_t>(n);
+    if (!sh.capacity || sl.n_flagged_host) p->info.exceptions += static_cast<int64_t>(n);  // (capacity: once per group)
   }
   if (sh.knobs.trace) {
     float a = 0, b = 0, c2 = 0, d = 0;
@@ -1919,6 +1944,7 @@ int next_chunk(frc_job* j, int mode, const void** data, int64_t* first_index, in
   }
   *first_index = b.first;
   *count = deliver_n;
+  j->held_first = b.first; j->held_count = b.count;
   j->held_part = it.part;
   j->held_slot = static_cast<int>(it.idx % p->n_slots);
   ++p->next_deliver;
@@ -1951,9 +1977,18 @@ int frc_chunk_exceptions(frc_job_t* j, const int64_t** index, const double** val
   *index = nullptr; *value = nullptr; *count = 0;
   if (j->held_part < 0 || j->sh.exact) return FRC_OK;
   const Slot& sl = j->parts[j->held_part]->slots[j->held_slot];
-  *index = sl.ex.index;
-  *value = sl.ex.value;
-  *count = std::min<int64_t>(static_cast<int64_t>(*sl.ex.count), sl.ex.cap);
+  const int64_t n = std::min<int64_t>(static_cast<int64_t>(*sl.ex.count), sl.ex.cap);
+  if (n == 0) return FRC_OK;
+  // (a list may cover more than this run: the capacity mode keeps one per row shard)
+  j->ex_index.clear(); j->ex_value.clear();
+  for (int64_t k = 0; k < n; ++k)
+    if (sl.ex.index[k] >= j->held_first && sl.ex.index[k] < j->held_first + j->held_count) {
+      j->ex_index.push_back(sl.ex.index[k]);
+      j->ex_value.push_back(sl.ex.value[k]);
+    }
+  *index = j->ex_index.data();
+  *value = j->ex_value.data();
+  *count = static_cast<int64_t>(j->ex_index.size());
   return FRC_OK;
 }
 

@@ -94,9 +94,10 @@ def test_one_process_many_gpus_one_ordered_stream(built, monkeypatch):
 
 def test_weighted_capacity_mode_reads_panels_from_peers(built, monkeypatch):
     """BASELINE config 5 in the small: when the fp32 panels of all samples do not fit one GPU they stay sharded over
-    the devices (two shards each) and the pair tiles read their column panels from the owners' HBM over NVLink
-    (PanelMap, csrc/weighted.cu).  Forced here with FRC_CAPACITY=1: the stream must be the resident path's, byte
-    for byte -- same arithmetic, only the address of a panel changes."""
+    the devices (two shards each) and the column shards visit every device in turn through two visiting buffers filled
+    over NVLink (start_pairs_capacity in csrc/job.cu, PanelMap in csrc/weighted.cu).  Forced here with FRC_CAPACITY=1:
+    the stream must be the resident path's, byte for byte -- same tiles, same arithmetic, only the address of a panel
+    changes."""
     import numpy as np
     import torch
 
@@ -128,7 +129,7 @@ def test_weighted_capacity_mode_reads_panels_from_peers(built, monkeypatch):
                                 ctx=ctx, band_rows=band_rows) as job:
                     got = _stream(job)
                     info = job.info()
-                # remote column panels: a sizeable share of all panel reads crossed NVLink
+                # the other devices' shards visited this one: their panels crossed NVLink
                 assert info.n_devices == nd and info.gather_bytes > 4 * tree.n_nodes * 128 * nd
                 assert np.array_equal(got, ref[normalize], equal_nan=True), (nd, normalize, band_rows)
         monkeypatch.setenv("FRC_CAPACITY", "0")
