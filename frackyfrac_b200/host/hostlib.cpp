@@ -689,6 +689,21 @@ char* frch_format_lines(const double* d, int64_t n, int threads, size_t* len) {
   *len = out.size();
   return p;
 }
+// The CLI's fp32 route: a float32 band (frc_next_f32) + its exceptions -> the same text.
+char* frch_format_lines_f32(const float* d, int64_t n, int64_t first_index, const int64_t* ex_index, const double* ex_value,
+                            int64_t n_ex, int threads, size_t* len) {
+  std::vector<std::string> parts;
+  frchost::format_parts_parallel_f32(d, n, first_index, ex_index, ex_value, n_ex, threads, parts);
+  size_t total = 0;
+  for (const std::string& x : parts) total += x.size();
+  char* p = static_cast<char*>(malloc(total + 1));
+  size_t o = 0;
+  for (const std::string& x : parts) { memcpy(p + o, x.data(), x.size()); o += x.size(); }
+  p[total] = 0;
+  *len = total;
+  return p;
+}
+
 void frch_free(void* p) { free(p); }
 
 // Dense table text -> sparse table text (sprspr); malloc'd, free with frch_free; NULL + frch_last_error on bad input.

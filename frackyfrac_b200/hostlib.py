@@ -72,6 +72,9 @@ def lib():
         L.frch_format_go.argtypes = [C.c_double, C.c_char_p]
         L.frch_format_lines.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_size_t)]
         L.frch_format_lines.restype = C.c_void_p
+        L.frch_format_lines_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                            C.POINTER(C.c_size_t)]
+        L.frch_format_lines_f32.restype = C.c_void_p
         L.frch_free.argtypes = [C.c_void_p]
         L.frch_to_sparse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
         L.frch_to_sparse.restype = C.c_void_p
@@ -162,6 +165,21 @@ def format_lines(values, threads: int = 1) -> bytes:
     a = np.ascontiguousarray(values, np.float64)
     n = C.c_size_t()
     p = lib().frch_format_lines(a.ctypes.data, len(a), threads, C.byref(n))
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        lib().frch_free(p)
+
+
+def format_lines_f32(values, first_index: int = 0, ex_index=None, ex_value=None, threads: int = 1) -> bytes:
+    """The same text from a float32 band of the fast paths (frc_next_f32) and its exceptions
+    (frc_chunk_exceptions): every value widened exactly, as Go's float64(f), then printed with %v."""
+    a = np.ascontiguousarray(values, np.float32)
+    xi = np.ascontiguousarray(ex_index if ex_index is not None else [], np.int64)
+    xv = np.ascontiguousarray(ex_value if ex_value is not None else [], np.float64)
+    n = C.c_size_t()
+    p = lib().frch_format_lines_f32(a.ctypes.data, len(a), first_index, xi.ctypes.data, xv.ctypes.data, len(xi), threads,
+                                    C.byref(n))
     try:
         return C.string_at(p, n.value)
     finally:

@@ -304,3 +304,24 @@ def test_sprspr_converter_follows_the_reference_test(built, tmp_path):
     assert sparse == hostlib.to_sparse(dense, threads=1)
     r = subprocess.run([hostlib.SPRSPR_PATH], input="a b\n1\n", capture_output=True, text=True)
     assert r.returncode == 2 and r.stderr.rstrip().split("\n")[-1].startswith("ERROR: ")
+
+
+def test_fp32_bands_format_like_their_widened_doubles(built):
+    """The CLI formats fast-path distances straight from the fp32 bands (frc_next_f32): the text must be what Go's
+    fmt.Fprintln prints for float64(f) -- i.e. the double formatter applied to the exactly widened value -- for any
+    thread count, and a band's exceptions (distances below fp32's range) replace their fp32 stand-ins."""
+    from frackyfrac_b200 import hostlib
+
+    rng = np.random.default_rng(5)
+    f = np.concatenate([rng.random(20_000, dtype=np.float32), np.array([0.0, 1.0, np.nan, 1e-5, 3e-39, 0.6111111], np.float32)])
+    want = hostlib.format_lines(f.astype(np.float64), 1)
+    for threads in (1, 3, 8):
+        assert hostlib.format_lines_f32(f, threads=threads) == want
+    assert b"0.6111111044883728\n" in want and want.splitlines()[-4] == b"NaN"
+    # exceptions: flat indices relative to the band's first index; entries outside the band are ignored
+    first = 1_000_000
+    xi, xv = np.array([first + 3, first + len(f) - 5, first - 1, first + len(f)], np.int64), np.array([1e-60, 2.5e-45, 9.0, 9.0])
+    d = f.astype(np.float64)
+    d[3], d[len(f) - 5] = 1e-60, 2.5e-45
+    for threads in (1, 4):
+        assert hostlib.format_lines_f32(f, first, xi, xv, threads) == hostlib.format_lines(d, 1)
