@@ -90,13 +90,16 @@ typedef struct {
                               kernel instead of the default u8 block-floating-point
                               (kind::i8, exact integer accumulation) one             */
 
-#define FRC_FLAG_SHARD_EMBED 4u /* world > 1: build the embedding for this rank's sample
-                                  shard only and exchange the compact form (presence bit
-                                  columns + row sums) with one NCCL all-gather; needs a
-                                  context with a communicator (frc_ctx_comm_init).  Every
-                                  rank of the communicator must create its job with the
-                                  same inputs (the call is collective).  Without the flag
-                                  each rank rebuilds the whole embedding.              */
+#define FRC_FLAG_SHARD_EMBED 4u /* world > 1 (one process per GPU): build the embedding for this rank's
+                                  sample shard only and exchange the compact form: the presence bit
+                                  columns are stored into every rank's HBM by the kernel that produces
+                                  them (CUDA IPC mappings over NVLink; NCCL all-gather when IPC is not
+                                  available), weighted panels are all-gathered with NCCL.  Needs a
+                                  context with a communicator (frc_ctx_comm_init).  Every rank of the
+                                  communicator must create its job with the same inputs (the call is
+                                  collective).  Without the flag each rank rebuilds the whole embedding.
+                                  (Jobs over several devices of ONE process, opts.n_devices, shard and
+                                  exchange over peer memory by themselves.)                          */
 
 #define FRC_FLAG_UW_BITS 8u /* fast unweighted, u8 integer mode: expand the operand tiles inside
                               the pair kernel from the presence bits instead of materialising
