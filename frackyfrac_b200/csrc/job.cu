@@ -1253,33 +1253,15 @@ int prepare_part(Part* p) {
     }
   const bool fast_uw = !sh.exact && !sh.weighted;
   if (sh.capacity) {
-    // one group per row shard of this part: its bands, and its tiles grouped by COLUMN SHARD (the order the
-    // shards visit in), column-major inside a column shard (the CTAs of a wave share one or two column panels)
-    const int64_t T = sh.shard_rows / kTile;
-    for (size_t k = 0; k < p->bands.size(); ++k) {
-      const Band& b = p->bands[k];
-      const int shard = static_cast<int>(b.row0 / sh.shard_rows);
-      if (p->cap.empty() || p->cap.back().shard != shard) {
-        Part::CapGroup g;
-        g.shard = shard;
-        g.first = b.first;
-        p->cap.push_back(g);
-      }
-      p->cap.back().count = b.first + b.count - p->cap.back().first;
-      p->band_group.push_back(static_cast<int>(p->cap.size()) - 1);
-    }
-    for (Part::CapGroup& g : p->cap) {
-      if (g.count >= (1LL << 32)) return pfail(p, FRC_ERR_UNSUPPORTED, "capacity mode: a row shard holds 2^32 pairs or more");
-      const int64_t r0 = static_cast<int64_t>(g.shard) * sh.shard_rows, r1 = std::min<int64_t>(sh.N, r0 + sh.shard_rows);
-      const int32_t t0 = static_cast<int32_t>(r0 / kTile), t1 = static_cast<int32_t>((r1 - 1) / kTile);
-      g.tile_off = static_cast<int32_t>(p->tiles.size());
-      g.coff.assign(2 * sh.n_parts + 1, 0);
-      for (int c = 0; c <= g.shard; ++c) {
-        g.coff[c] = static_cast<int32_t>(p->tiles.size()) - g.tile_off;
-        for (int32_t tj = static_cast<int32_t>(c * T); tj < static_cast<int32_t>((c + 1) * T) && tj <= t1; ++tj)
-          for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) p->tiles.push_back({ti, tj});
-      }
-      for (int c = g.shard + 1; c <= 2 * sh.n_parts; ++c) g.coff[c] = static_cast<int32_t>(p->tiles.size()) - g.tile_off;
+    // one group per row shard of this part (csrc/plan.cpp): its bands, and its tiles grouped by COLUMN SHARD (the
+    // order the shards visit in), column-major inside a column shard (the CTAs of a wave share a column panel)
+    const std::vector<CapGroupPlan> groups =
+        plan_capacity_groups(p->bands, sh.N, sh.shard_rows, 2 * sh.n_parts, p->tiles, p->band_group);
+    for (const CapGroupPlan& gp : groups) {
+      if (gp.count >= (1LL << 32)) return pfail(p, FRC_ERR_UNSUPPORTED, "capacity mode: a row shard holds 2^32 pairs or more");
+      Part::CapGroup g;
+      g.shard = gp.shard; g.first = gp.first; g.count = gp.count; g.tile_off = gp.tile_off; g.coff = gp.coff;
+      p->cap.push_back(g);
     }
   } else if (!sh.exact) {
     for (Band& b : p->bands) append_band_tiles(b, fast_uw, p->tiles);

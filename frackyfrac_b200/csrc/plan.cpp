@@ -156,6 +156,37 @@ std::vector<Band> make_bands_capacity(int64_t N, int64_t np, int G, int64_t requ
   return bands;
 }
 
+std::vector<CapGroupPlan> plan_capacity_groups(const std::vector<Band>& bands, int64_t N, int64_t shard_rows, int n_shards,
+                                               std::vector<Tile>& tiles, std::vector<int>& band_group) {
+  std::vector<CapGroupPlan> groups;
+  band_group.clear();
+  const int64_t T = shard_rows / kTile;
+  for (const Band& b : bands) {
+    const int shard = static_cast<int>(b.row0 / shard_rows);
+    if (groups.empty() || groups.back().shard != shard) {
+      CapGroupPlan g;
+      g.shard = shard;
+      g.first = b.first;
+      groups.push_back(g);
+    }
+    groups.back().count = b.first + b.count - groups.back().first;
+    band_group.push_back(static_cast<int>(groups.size()) - 1);
+  }
+  for (CapGroupPlan& g : groups) {
+    const int64_t r0 = static_cast<int64_t>(g.shard) * shard_rows, r1 = std::min<int64_t>(N, r0 + shard_rows);
+    const int32_t t0 = static_cast<int32_t>(r0 / kTile), t1 = static_cast<int32_t>((r1 - 1) / kTile);
+    g.tile_off = static_cast<int32_t>(tiles.size());
+    g.coff.assign(n_shards + 1, 0);
+    for (int c = 0; c <= g.shard; ++c) {
+      g.coff[c] = static_cast<int32_t>(tiles.size()) - g.tile_off;
+      for (int32_t tj = static_cast<int32_t>(c * T); tj < static_cast<int32_t>((c + 1) * T) && tj <= t1; ++tj)
+        for (int32_t ti = std::max(tj, t0); ti <= t1; ++ti) tiles.push_back({ti, tj});
+    }
+    for (int c = g.shard + 1; c <= n_shards; ++c) g.coff[c] = static_cast<int32_t>(tiles.size()) - g.tile_off;
+  }
+  return groups;
+}
+
 // Column k of the K-major operands holds node col_order[k] (-1: padding).  bf16: identity order,
 // uniform accumulation chunks.  u8: nodes grouped by binade triples of their length so that one
 // power-of-two scale per chunk leaves every length a 21..24-bit integer a * m (zero-length nodes
@@ -371,6 +402,29 @@ int64_t frc_debug_bands_capacity(int64_t n_samples, int64_t np, int32_t n_dev, i
     out5[5 * k + 3] = bands[k].count; out5[5 * k + 4] = bands[k].owner;
   }
   return static_cast<int64_t>(bands.size());
+}
+
+// Capacity-mode groups of device `dev`: out_groups holds (shard, first, count, tile_off) quadruples, out_coff
+// (n_shards + 1) offsets per group, out_tiles (ti, tj) pairs; returns the number of groups, *n_tiles the tile count
+// (negative: a cap was too small).
+int64_t frc_debug_capacity_groups(int64_t n_samples, int64_t np, int32_t n_dev, int32_t dev, int64_t band_rows, int32_t d2h,
+                                  int64_t* out_groups, int32_t* out_coff, int64_t cap_groups, int32_t* out_tiles,
+                                  int64_t cap_tiles, int64_t* n_tiles) {
+  const std::vector<frc::Band> all = frc::make_bands_capacity(n_samples, np, n_dev, band_rows, d2h != 0);
+  std::vector<frc::Band> mine;
+  for (const frc::Band& b : all)
+    if (b.owner == dev) mine.push_back(b);
+  std::vector<frc::Tile> tiles;
+  std::vector<int> band_group;
+  const std::vector<frc::CapGroupPlan> g = frc::plan_capacity_groups(mine, n_samples, np / (2 * n_dev), 2 * n_dev, tiles, band_group);
+  *n_tiles = static_cast<int64_t>(tiles.size());
+  if (static_cast<int64_t>(g.size()) > cap_groups || static_cast<int64_t>(tiles.size()) > cap_tiles) return -1;
+  for (size_t k = 0; k < g.size(); ++k) {
+    out_groups[4 * k] = g[k].shard; out_groups[4 * k + 1] = g[k].first; out_groups[4 * k + 2] = g[k].count; out_groups[4 * k + 3] = g[k].tile_off;
+    for (int c = 0; c <= 2 * n_dev; ++c) out_coff[k * (2 * n_dev + 1) + c] = g[k].coff[c];
+  }
+  for (size_t k = 0; k < tiles.size(); ++k) { out_tiles[2 * k] = tiles[k].ti; out_tiles[2 * k + 1] = tiles[k].tj; }
+  return static_cast<int64_t>(g.size());
 }
 
 // Tiles of the band [row0, row1): writes up to `cap` (ti, tj) pairs; returns the count.

@@ -41,6 +41,18 @@ std::vector<Band> make_bands(int64_t N, int64_t requested, int world, bool d2h, 
 // (row r has r columns: the two shards of a device add up to the same total).  Bands never straddle a shard.
 std::vector<Band> make_bands_capacity(int64_t N, int64_t np, int G, int64_t requested, bool d2h);
 
+// Capacity mode, one device: its bands (in row order) grouped by row shard, and per group the tile list ordered by
+// the COLUMN shard the tiles read (the order the shards visit in), column-major inside a column shard.
+struct CapGroupPlan {
+  int shard = 0;                 // row shard (also the last column shard its tiles need)
+  int64_t first = 0, count = 0;  // flat range of the group's rows
+  int32_t tile_off = 0;          // into `tiles`
+  std::vector<int32_t> coff;     // [n_shards + 1] tile offset (inside the group's list) of every column shard
+};
+// `bands`: the device's bands; appends the groups' tiles to `tiles`; band_group[k] = group of bands[k].
+std::vector<CapGroupPlan> plan_capacity_groups(const std::vector<Band>& bands, int64_t N, int64_t shard_rows, int n_shards,
+                                               std::vector<Tile>& tiles, std::vector<int>& band_group);
+
 // Fast unweighted path: which node sits in which column of the K-major operands and how the
 // columns group into TMEM accumulation chunks.
 struct ColumnPlan {

@@ -203,3 +203,41 @@ def test_capacity_bands_respect_the_shards(L):
                 if n >= 5000:
                     load = np.bincount(b[:, 4], weights=b[:, 3], minlength=G)
                     assert load.max() / load.mean() < 1.06, (n, G, load)
+
+
+def test_capacity_groups_cover_every_tile_once_in_visiting_order(L):
+    """Capacity mode, per device: the rows of each of its two shards form a group whose tiles are listed by the column
+    shard they read (the order the shards visit in).  Over all devices every tile of the triangle appears exactly
+    once, every tile sits in the segment of its own column shard, and rows only ever belong to the device's shards."""
+    L.frc_debug_capacity_groups.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    L.frc_debug_capacity_groups.restype = C.c_int64
+    for n, G in ((1300, 2), (5000, 4), (9000, 8), (300, 2)):
+        np_ = -(-n // (256 * G)) * 256 * G
+        R, T, S = np_ // (2 * G), np_ // (2 * G) // 128, 2 * G
+        seen = {}
+        pairs = 0
+        for dev in range(G):
+            groups = np.zeros((4, 4), np.int64)
+            coff = np.zeros((4, S + 1), np.int32)
+            tiles = np.zeros((1 << 20, 2), np.int32)
+            nt = C.c_int64()
+            k = L.frc_debug_capacity_groups(n, np_, G, dev, 0, 1, groups.ctypes.data, coff.ctypes.data, 4, tiles.ctypes.data,
+                                            len(tiles), C.byref(nt))
+            assert 1 <= k <= 2
+            for g in range(k):
+                shard, first, count, off = groups[g].tolist()
+                assert shard in (dev, S - 1 - dev)
+                r0, r1 = shard * R, min(n, (shard + 1) * R)
+                assert first == (r0 * (r0 - 1) // 2 if r0 >= 2 else 0) and count == r1 * (r1 - 1) // 2 - first
+                pairs += count
+                assert coff[g][0] == 0 and (np.diff(coff[g]) >= 0).all() and (coff[g][shard + 1:] == coff[g][shard + 1]).all()
+                for c in range(S):
+                    seg = tiles[off + coff[g][c]: off + coff[g][c + 1]]
+                    for ti, tj in seg.tolist():
+                        assert tj // T == c and ti // T == shard and tj <= ti and ti * 128 < n
+                        assert (ti, tj) not in seen
+                        seen[(ti, tj)] = dev
+        nt_rows = (n + 127) // 128
+        assert pairs == n * (n - 1) // 2
+        assert set(seen) == {(ti, tj) for ti in range(nt_rows) for tj in range(ti + 1)}
