@@ -325,3 +325,27 @@ def test_fp32_bands_format_like_their_widened_doubles(built):
     d[3], d[len(f) - 5] = 1e-60, 2.5e-45
     for threads in (1, 4):
         assert hostlib.format_lines_f32(f, first, xi, xv, threads) == hostlib.format_lines(d, 1)
+
+
+def test_float_token_grammar_differential(built):
+    """Random tokens over the alphabet of Go's float syntax (digits, '.', '_', exponents, hex prefix, signs, inf / nan
+    letters): the C++ host reader and the C oracle implement strconv.ParseFloat's grammar independently
+    (hostlib.cpp go_float_syntax, unifrac_oracle.c go_float_token) and must agree on accept / reject and on the value."""
+    from frackyfrac_b200 import hostlib
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(11)
+    alphabet = list("0123456789") * 3 + list("..__eEpPxX+-") + list("abfnNiIt")
+    accepted = 0
+    for _ in range(6000):
+        tok = "".join(rng.choice(alphabet, size=int(rng.integers(1, 9))))
+        res = []
+        for parse, err in ((lambda t: hostlib.Table(t, True, 1).maps(), hostlib.HostError),
+                           (lambda t: orc.Table.parse(t, True).maps(), orc.OracleError)):
+            try:
+                res.append(parse(f"a:{tok}\n"))
+            except err:
+                res.append("error")
+        assert res[0] == res[1], (tok, res)
+        accepted += res[0] != "error"
+    assert accepted > 300   # (the generator does produce plenty of valid spellings)
