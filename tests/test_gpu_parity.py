@@ -521,6 +521,25 @@ def test_stream_order_and_early_destroy(gpu_ctx):
     assert len(again) == 600 * 599 // 2
 
 
+def test_fewer_than_two_samples_give_an_empty_stream(gpu_ctx):
+    """A9: IterPairs over fewer than two samples yields nothing (common/common.go:21-31): the job is valid, the stream
+    ends at once, on every path."""
+    from frackyfrac_b200 import engine, synth
+
+    tree = synth.random_tree(40, 63)
+    rp, col, val = synth.random_table(tree, 1, 0.2, 64)
+    for n in (0, 1):
+        for weighted in (False, True):
+            for path in (engine.PATH_AUTO, engine.PATH_FAST, engine.PATH_EXACT):
+                with engine.Job(tree.parent, tree.length, rp[:n + 1], col[:rp[n]], val[:rp[n]], weighted=weighted, path=path,
+                                ctx=gpu_ctx) as job:
+                    assert list(job.chunks()) == []
+                    info = job.info()
+                    assert info.n_pairs_total == 0 and info.n_bands_total == 0
+                got = engine.unifrac(tree.parent, tree.length, rp[:n + 1], col[:rp[n]], val[:rp[n]], weighted, path=path, ctx=gpu_ctx)
+                assert len(got) == 0
+
+
 def test_bad_arguments_are_errors(gpu_ctx):
     from frackyfrac_b200 import engine, synth
 
